@@ -1,0 +1,603 @@
+// Thin C-ABI CUDA layer of the B200 backend (see include/acb200.h for the contract and the
+// reference interfaces each entry point replaces).
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "acb200_common.cuh"
+#include "acb200_ffma.cuh"
+#include "acb200_pixel.cuh"
+
+namespace
+{
+    using namespace acb;
+
+    std::atomic<unsigned long long> g_launches{ 0 };
+
+    // ------------------------------------------------------------------------------------------------
+    // model: host copy of the flat arrays + the segment chain they are consumed by
+    // ------------------------------------------------------------------------------------------------
+    enum SegKind
+    {
+        SEG_LEGACY_FULL,    // <LEGACY, head, 7, tail>
+        SEG_ACNET_B4,       // <ACNET, head, 4, tail>
+        SEG_ACNET_B8,       // <ACNET, head, 8, tail>
+        SEG_ACNET_B18_A,    // <ACNET, head, 9, ->
+        SEG_ACNET_B18_B,    // <ACNET, -, 9, tail>
+        SEG_ARNET_FIRST,    // <ARNET, head, 8, ->
+        SEG_ARNET_MID,      // <ARNET, -, 8, ->
+        SEG_ARNET_LAST,     // <ARNET, -, 6, tail>
+    };
+    using SegLegacyFull = Seg<ACB200_FAMILY_ACNET_LEGACY, true, 7, true>;
+    using SegAcnetB4 = Seg<ACB200_FAMILY_ACNET, true, 4, true>;
+    using SegAcnetB8 = Seg<ACB200_FAMILY_ACNET, true, 8, true>;
+    using SegAcnetB18A = Seg<ACB200_FAMILY_ACNET, true, 9, false>;
+    using SegAcnetB18B = Seg<ACB200_FAMILY_ACNET, false, 9, true>;
+    using SegArnetFirst = Seg<ACB200_FAMILY_ARNET, true, 8, false>;
+    using SegArnetMid = Seg<ACB200_FAMILY_ARNET, false, 8, false>;
+    using SegArnetLast = Seg<ACB200_FAMILY_ARNET, false, 6, true>;
+
+    struct SegSpec
+    {
+        SegKind kind;
+        int koff, boff, aoff;   // slice starts inside the model's flat arrays (contiguous by construction)
+    };
+}
+
+struct acb200_model
+{
+    int family = 0, blocks = 0;
+    std::vector<float> k, b, a;
+    std::vector<SegSpec> chain;
+};
+
+namespace
+{
+    bool expected_lengths(int family, int blocks, int& nk, int& nb, int& na)
+    {
+        switch (family)
+        {
+        case ACB200_FAMILY_ACNET_LEGACY: // core/include/AC/Core/Model/ACNet.hpp:34-37
+            nk = 72 + 576 * blocks + 32; nb = 8 + 8 * blocks; na = 0;
+            return blocks == 8;
+        case ACB200_FAMILY_ACNET: // ACNet.hpp:78-83
+            nk = 72 + 576 * blocks + 288; nb = 8 + 8 * blocks + 4; na = 8 * (blocks + 1);
+            return blocks == 4 || blocks == 8 || blocks == 18;
+        case ACB200_FAMILY_ARNET: // ARNet.hpp:32-37
+            nk = 72 + 576 * blocks * 2 + 64 + 288; nb = 8 + 8 * (blocks * 2 + 1) + 4; na = 8 * (blocks + 1);
+            return blocks >= 8 && (blocks % 4) == 0;
+        default:
+            return false;
+        }
+    }
+
+    void build_chain(acb200_model& m)
+    {
+        m.chain.clear();
+        if (m.family == ACB200_FAMILY_ACNET_LEGACY) m.chain.push_back({ SEG_LEGACY_FULL, 0, 0, 0 });
+        else if (m.family == ACB200_FAMILY_ACNET)
+        {
+            if (m.blocks == 4) m.chain.push_back({ SEG_ACNET_B4, 0, 0, 0 });
+            else if (m.blocks == 8) m.chain.push_back({ SEG_ACNET_B8, 0, 0, 0 });
+            else
+            {
+                m.chain.push_back({ SEG_ACNET_B18_A, 0, 0, 0 });
+                m.chain.push_back({ SEG_ACNET_B18_B, 72 + 576 * 9, 8 + 8 * 9, 8 + 8 * 9 });
+            }
+        }
+        else
+        {
+            // 2(B-1) body convs ahead of the last block: 8 with the head, 8 per middle segment, 6 in the tail segment
+            const int body = 2 * (m.blocks - 1);
+            m.chain.push_back({ SEG_ARNET_FIRST, 0, 0, 0 });
+            int c0 = 8;
+            for (; c0 + 6 < body; c0 += 8) m.chain.push_back({ SEG_ARNET_MID, 72 + 576 * c0, 8 + 8 * c0, (c0 / 2) * 8 });
+            m.chain.push_back({ SEG_ARNET_LAST, 72 + 576 * c0, 8 + 8 * c0, (c0 / 2) * 8 });
+        }
+    }
+
+    // ------------------------------------------------------------------------------------------------
+    // Catmull-Rom contributor tables (stb_image_resize2 gather upsample as called from
+    // core/src/ImageResize.cpp:167-272: centre (n+0.5)/scale, support 2, coefficients normalised, CLAMP edge
+    // folded onto the border pixel).  Kernel polynomial: ImageResize.cpp:58-83 with b = 0, c = 1/2.
+    // ------------------------------------------------------------------------------------------------
+    float catmull_rom(float v)
+    {
+        volatile float x = std::fabs(v); // volatile: keep every intermediate rounded to fp32, no contraction
+        auto poly3 = [](float x, float c0, float c1, float c2, float c3) {
+            volatile float t = x * c3; t = c2 + t; t = x * t; t = c1 + t; t = x * t; t = c0 + t; return static_cast<float>(t);
+        };
+        if (x < 1.0f) return poly3(x, 1.0f, 0.0f, -2.5f, 1.5f);
+        if (x < 2.0f) return poly3(x, 2.0f, -4.0f, 2.5f, -0.5f);
+        return 0.0f;
+    }
+    bool make_contribs(std::vector<Contrib>& out, int in_size, int out_size)
+    {
+        out.resize(out_size);
+        const float scale = static_cast<float>(out_size) / static_cast<float>(in_size);
+        const float inv_scale = 1.0f / scale, out_radius = 2.0f * scale;
+        for (int n = 0; n < out_size; n++)
+        {
+            volatile float out_center = static_cast<float>(n) + 0.5f;
+            volatile float in_center = out_center * inv_scale;
+            volatile float lo = out_center - out_radius; lo = lo * inv_scale;
+            volatile float hi = out_center + out_radius; hi = hi * inv_scale;
+            int first = static_cast<int>(std::floor(lo + 0.5f)), last = static_cast<int>(std::floor(hi - 0.5f));
+            if (last < first) last = first;
+            if (last - first > 10) last = first + 10;
+            float raw[12];
+            volatile float total = 0.0f;
+            for (int i = 0; i <= last - first; i++)
+            {
+                volatile float pc = static_cast<float>(first + i) + 0.5f;
+                raw[i] = catmull_rom(in_center - pc);
+                total = total + raw[i];
+            }
+            volatile float fs = 1.0f / total;
+            for (int i = 0; i <= last - first; i++) { volatile float t = raw[i] * fs; raw[i] = t; }
+            int n0 = std::max(first, 0), n1 = std::min(last, in_size - 1);
+            if (n1 < n0) n1 = n0 = (first < 0 ? 0 : in_size - 1);
+            float c[12] = {};
+            for (int i = 0; i <= last - first; i++) { int p = first + i; if (p >= n0 && p <= n1) c[p - n0] = raw[i]; }
+            for (int i = 0; i <= last - first; i++)
+            {
+                int p = first + i;
+                if (p < n0) { volatile float t = c[0] + raw[i]; c[0] = t; }
+                else if (p > n1) { volatile float t = c[n1 - n0] + raw[i]; c[n1 - n0] = t; }
+            }
+            // drop leading / trailing zero taps so the device loop stays within 6
+            while (n1 > n0 && c[n1 - n0] == 0.0f) n1--;
+            int lead = 0;
+            while (lead < n1 - n0 && c[lead] == 0.0f) lead++;
+            Contrib& o = out[n];
+            o.n0 = n0 + lead; o.cnt = n1 - n0 + 1 - lead;
+            if (o.cnt > 6) return false;
+            for (int i = 0; i < 6; i++) o.c[i] = i < o.cnt ? c[lead + i] : 0.0f;
+        }
+        return true;
+    }
+}
+
+struct acb200_session
+{
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    int engine = 0;
+    std::string error = "NO ERROR";
+    // grow-only device scratch
+    struct Buf { void* p = nullptr; size_t cap = 0; };
+    Buf src, dst, y[2], uv, map[2], feat, htab, vtab;
+    int tab_in_w = 0, tab_in_h = 0, tab_out_w = 0, tab_out_h = 0;
+    int smem_configured = 0;
+};
+
+namespace
+{
+    int fail(acb200_session* s, int code, const char* what, cudaError_t e = cudaSuccess)
+    {
+        if (s)
+        {
+            s->error = what;
+            if (e != cudaSuccess) { s->error += ": "; s->error += cudaGetErrorString(e); }
+        }
+        return code;
+    }
+#define ACB_CUDA(s, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail((s), ACB200_ECUDA, #call, e__); } while (0)
+
+    int ensure(acb200_session* s, acb200_session::Buf& b, size_t bytes)
+    {
+        if (b.cap >= bytes) return ACB200_OK;
+        // stream-ordered so an in-flight kernel still using the old block finishes first
+        if (b.p) ACB_CUDA(s, cudaFreeAsync(b.p, s->stream));
+        b.p = nullptr; b.cap = 0;
+        ACB_CUDA(s, cudaMallocAsync(&b.p, bytes, s->stream));
+        b.cap = bytes;
+        return ACB200_OK;
+    }
+    size_t pitch_of(int w, int c, int es) { return (static_cast<size_t>(w) * c * es + 255) & ~static_cast<size_t>(255); }
+
+    template<class S>
+    int launch_segment(acb200_session* s, cudaStream_t st, const acb200_model& m, const SegSpec& spec,
+                       const void* src, int src_pitch, void* dst, int dst_pitch, int w, int h, int type,
+                       const float* map_in, float* map_out, float* feat)
+    {
+        static_assert(sizeof(SegParams<S>) <= 32764, "kernel parameter block too large");
+        SegParams<S> prm;
+        prm.src = src; prm.map_in = map_in; prm.map_out = map_out; prm.feat_in = feat; prm.feat_out = feat; prm.dst = dst;
+        prm.src_pitch = src_pitch; prm.dst_pitch = dst_pitch; prm.w = w; prm.h = h; prm.type = type;
+        prm.tiles_x = (w + S::T - 1) / S::T;
+        const int tiles_y = (h + S::T - 1) / S::T;
+        std::memcpy(prm.k, m.k.data() + spec.koff, sizeof(float) * S::NK);
+        std::memcpy(prm.b, m.b.data() + spec.boff, sizeof(float) * S::NB);
+        if (S::NA > 0) std::memcpy(prm.a, m.a.data() + spec.aoff, sizeof(float) * S::NA);
+        else prm.a[0] = 0.0f;
+        static std::once_flag once[16];
+        cudaError_t attr_err = cudaSuccess;
+        // the attribute is per device: set it each time the device changes (cheap)
+        attr_err = cudaFuncSetAttribute(segment_ffma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(FFMA_SMEM_BYTES));
+        if (attr_err != cudaSuccess) return fail(s, ACB200_ECUDA, "cudaFuncSetAttribute(max dynamic smem)", attr_err);
+        (void)once;
+        segment_ffma_kernel<S><<<prm.tiles_x * tiles_y, FFMA_THREADS, FFMA_SMEM_BYTES, st>>>(prm);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        ACB_CUDA(s, cudaGetLastError());
+        return ACB200_OK;
+    }
+
+    // one 2x luma pass: src (w x h) -> dst (2w x 2h), both planes in HBM
+    int luma_pass(acb200_session* s, cudaStream_t st, const acb200_model& m, const void* src, int src_pitch,
+                  void* dst, int dst_pitch, int w, int h, int type)
+    {
+        float* maps[2] = { nullptr, nullptr };
+        float* feat = nullptr;
+        if (m.chain.size() > 1)
+        {
+            const size_t bytes = static_cast<size_t>(w) * h * 8 * sizeof(float);
+            int rc;
+            if ((rc = ensure(s, s->map[0], bytes)) != ACB200_OK) return rc;
+            if ((rc = ensure(s, s->map[1], bytes)) != ACB200_OK) return rc;
+            maps[0] = static_cast<float*>(s->map[0].p); maps[1] = static_cast<float*>(s->map[1].p);
+            if (m.family == ACB200_FAMILY_ARNET)
+            {
+                if ((rc = ensure(s, s->feat, bytes)) != ACB200_OK) return rc;
+                feat = static_cast<float*>(s->feat.p);
+            }
+        }
+        int cur = 0;
+        for (size_t i = 0; i < m.chain.size(); i++)
+        {
+            const SegSpec& sp = m.chain[i];
+            const float* in = maps[cur];
+            float* out = maps[cur ^ 1];
+            int rc = ACB200_EINVAL;
+            switch (sp.kind)
+            {
+            case SEG_LEGACY_FULL: rc = launch_segment<SegLegacyFull>(s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, nullptr, nullptr, nullptr); break;
+            case SEG_ACNET_B4: rc = launch_segment<SegAcnetB4>(s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, nullptr, nullptr, nullptr); break;
+            case SEG_ACNET_B8: rc = launch_segment<SegAcnetB8>(s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, nullptr, nullptr, nullptr); break;
+            case SEG_ACNET_B18_A: rc = launch_segment<SegAcnetB18A>(s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, nullptr, out, nullptr); break;
+            case SEG_ACNET_B18_B: rc = launch_segment<SegAcnetB18B>(s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, in, nullptr, nullptr); break;
+            case SEG_ARNET_FIRST: rc = launch_segment<SegArnetFirst>(s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, nullptr, out, feat); break;
+            case SEG_ARNET_MID: rc = launch_segment<SegArnetMid>(s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, in, out, feat); break;
+            case SEG_ARNET_LAST: rc = launch_segment<SegArnetLast>(s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, in, nullptr, feat); break;
+            }
+            if (rc != ACB200_OK) return rc;
+            cur ^= 1;
+        }
+        return ACB200_OK;
+    }
+
+    int ensure_tables(acb200_session* s, cudaStream_t st, int w, int h, int ow, int oh)
+    {
+        if (s->tab_in_w == w && s->tab_in_h == h && s->tab_out_w == ow && s->tab_out_h == oh) return ACB200_OK;
+        std::vector<Contrib> ht, vt;
+        if (!make_contribs(ht, w, ow) || !make_contribs(vt, h, oh)) return fail(s, ACB200_EINVAL, "resize: unsupported scale");
+        int rc;
+        if ((rc = ensure(s, s->htab, ht.size() * sizeof(Contrib))) != ACB200_OK) return rc;
+        if ((rc = ensure(s, s->vtab, vt.size() * sizeof(Contrib))) != ACB200_OK) return rc;
+        // pageable -> device: the copy is staged before the call returns, so the vectors may die
+        ACB_CUDA(s, cudaMemcpyAsync(s->htab.p, ht.data(), ht.size() * sizeof(Contrib), cudaMemcpyHostToDevice, st));
+        ACB_CUDA(s, cudaMemcpyAsync(s->vtab.p, vt.data(), vt.size() * sizeof(Contrib), cudaMemcpyHostToDevice, st));
+        ACB_CUDA(s, cudaStreamSynchronize(st));
+        s->tab_in_w = w; s->tab_in_h = h; s->tab_out_w = ow; s->tab_out_h = oh;
+        return ACB200_OK;
+    }
+
+    bool valid_type(int t) { return t == ACB200_UINT8 || t == ACB200_UINT16 || t == ACB200_FLOAT16 || t == ACB200_FLOAT32; }
+
+    // factor -> number of 2x passes; only powers of two (fxy == 1, Processor.cpp:204-205)
+    int passes_for(double factor)
+    {
+        for (int p = 1; p <= 6; p++) if (factor == static_cast<double>(1 << p)) return p;
+        return 0;
+    }
+
+    // The whole Processor::process on device-resident planes (Processor.cpp:199-276).
+    int process_on_device(acb200_session* s, const acb200_model* m, cudaStream_t st,
+                          const void* d_src, int w, int h, int c, int src_pitch, int type, int power, void* d_dst, int dst_pitch)
+    {
+        const int es = type & 0xff;
+        const dim3 blk(32, 8);
+        const void* cur = d_src;
+        int cur_pitch = src_pitch, cw = w, ch = h, rc;
+        if (c > 1)
+        {
+            const size_t yp = pitch_of(w, 1, es), uvp = pitch_of(w, c - 1, es);
+            if ((rc = ensure(s, s->y[0], yp * h)) != ACB200_OK) return rc;
+            if ((rc = ensure(s, s->uv, uvp * h)) != ACB200_OK) return rc;
+            rgb2yuv_kernel<<<dim3((w + 31) / 32, (h + 7) / 8), blk, 0, st>>>(d_src, src_pitch, w, h, c, type, s->y[0].p, static_cast<int>(yp), 1, s->uv.p, static_cast<int>(uvp), c - 1);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            ACB_CUDA(s, cudaGetLastError());
+            cur = s->y[0].p; cur_pitch = static_cast<int>(yp);
+        }
+        int slot = 1;
+        for (int i = 0; i < power; i++)
+        {
+            const int nw = cw * 2, nh = ch * 2;
+            const bool to_dst = (c == 1) && (i == power - 1);
+            void* out; int out_pitch;
+            if (to_dst) { out = d_dst; out_pitch = dst_pitch; }
+            else
+            {
+                const size_t p = pitch_of(nw, 1, es);
+                if ((rc = ensure(s, s->y[slot], p * nh)) != ACB200_OK) return rc;
+                out = s->y[slot].p; out_pitch = static_cast<int>(p);
+                slot ^= 1;
+            }
+            if ((rc = luma_pass(s, st, *m, cur, cur_pitch, out, out_pitch, cw, ch, type)) != ACB200_OK) return rc;
+            cur = out; cur_pitch = out_pitch; cw = nw; ch = nh;
+        }
+        if (c > 1)
+        {
+            if ((rc = ensure_tables(s, st, w, h, cw, ch)) != ACB200_OK) return rc;
+            chroma_merge_kernel<<<dim3((cw + 31) / 32, (ch + 7) / 8), blk, 0, st>>>(cur, cur_pitch, s->uv.p, static_cast<int>(pitch_of(w, c - 1, es)),
+                static_cast<const Contrib*>(s->htab.p), static_cast<const Contrib*>(s->vtab.p), cw, ch, c, type, d_dst, dst_pitch);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            ACB_CUDA(s, cudaGetLastError());
+        }
+        return ACB200_OK;
+    }
+
+    int check_args(acb200_session* s, const acb200_model* m, const void* src, int w, int h, int c, int type, double factor, void* dst, int& power)
+    {
+        if (!s) return ACB200_EINVAL;
+        if (!m || !src || !dst) return fail(s, ACB200_EINVAL, "null argument");
+        if (w <= 0 || h <= 0 || !(c == 1 || c == 3 || c == 4) || !valid_type(type)) return fail(s, ACB200_EINVAL, "unsupported image shape or element type");
+        power = passes_for(factor);
+        if (!power) return fail(s, ACB200_EINVAL, "factor must be a power of two >= 2");
+        if ((static_cast<long long>(w) << power) > 0x7fffffffLL / 16 || (static_cast<long long>(h) << power) > 0x7fffffffLL / 16) return fail(s, ACB200_EINVAL, "image too large");
+        return ACB200_OK;
+    }
+}
+
+extern "C"
+{
+    int acb200_device_count(void)
+    {
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+        return n;
+    }
+    int acb200_device_info(int device, char* name, int name_len, size_t* vram_bytes, int* cc, int* sm_count, int* clock_khz)
+    {
+        if (device < 0 || device >= acb200_device_count()) return ACB200_ENODEVICE;
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, device) != cudaSuccess) { cudaGetLastError(); return ACB200_ECUDA; }
+        if (name && name_len > 0) { std::strncpy(name, p.name, name_len - 1); name[name_len - 1] = 0; }
+        if (vram_bytes) *vram_bytes = p.totalGlobalMem;
+        if (cc) *cc = p.major * 10 + p.minor;
+        if (sm_count) *sm_count = p.multiProcessorCount;
+        if (clock_khz) { int khz = 0; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device); *clock_khz = khz; }
+        return ACB200_OK;
+    }
+
+    int acb200_model_create(int family, int blocks, const float* kernels, int n_kernels, const float* biases, int n_biases,
+                            const float* alphas, int n_alphas, acb200_model** out)
+    {
+        if (!out || !kernels || !biases) return ACB200_EINVAL;
+        int nk, nb, na;
+        if (!expected_lengths(family, blocks, nk, nb, na)) return ACB200_EINVAL;
+        if (n_kernels != nk || n_biases != nb || n_alphas != na || (na > 0 && !alphas)) return ACB200_EINVAL;
+        acb200_model* m = new (std::nothrow) acb200_model;
+        if (!m) return ACB200_ENOMEM;
+        m->family = family; m->blocks = blocks;
+        m->k.assign(kernels, kernels + nk);
+        m->b.assign(biases, biases + nb);
+        if (na) m->a.assign(alphas, alphas + na);
+        build_chain(*m);
+        *out = m;
+        return ACB200_OK;
+    }
+    void acb200_model_destroy(acb200_model* model) { delete model; }
+
+    int acb200_session_create(int device, acb200_session** out)
+    {
+        if (!out) return ACB200_EINVAL;
+        *out = nullptr;
+        if (device < 0 || device >= acb200_device_count()) return ACB200_ENODEVICE;
+        acb200_session* s = new (std::nothrow) acb200_session;
+        if (!s) return ACB200_ENOMEM;
+        s->device = device;
+        if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess)
+        {
+            cudaGetLastError();
+            delete s;
+            return ACB200_ECUDA;
+        }
+        // keep freed scratch in the pool instead of returning it to the OS between frames
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
+        {
+            unsigned long long thr = ~0ULL;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        *out = s;
+        return ACB200_OK;
+    }
+    void acb200_session_destroy(acb200_session* s)
+    {
+        if (!s) return;
+        cudaSetDevice(s->device);
+        cudaStreamSynchronize(s->stream);
+        acb200_session::Buf* bufs[] = { &s->src, &s->dst, &s->y[0], &s->y[1], &s->uv, &s->map[0], &s->map[1], &s->feat, &s->htab, &s->vtab };
+        for (auto* b : bufs) if (b->p) cudaFreeAsync(b->p, s->stream);
+        cudaStreamSynchronize(s->stream);
+        cudaEventDestroy(s->ev0); cudaEventDestroy(s->ev1);
+        cudaStreamDestroy(s->stream);
+        cudaGetLastError();
+        delete s;
+    }
+    int acb200_session_device(const acb200_session* s) { return s ? s->device : ACB200_EINVAL; }
+    const char* acb200_session_error(const acb200_session* s) { return s ? s->error.c_str() : "invalid session"; }
+    void acb200_session_clear_error(acb200_session* s) { if (s) s->error = "NO ERROR"; }
+    int acb200_session_set_engine(acb200_session* s, int engine) { if (!s || engine < 0 || engine > 1) return ACB200_EINVAL; s->engine = engine; return ACB200_OK; }
+
+    int acb200_process_device(acb200_session* s, const acb200_model* m, const void* d_src, int w, int h, int c, int src_stride, int type,
+                              double factor, void* d_dst, int dst_stride, void* stream)
+    {
+        int power, rc;
+        if ((rc = check_args(s, m, d_src, w, h, c, type, factor, d_dst, power)) != ACB200_OK) return rc;
+        ACB_CUDA(s, cudaSetDevice(s->device));
+        cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : s->stream;
+        const int es = type & 0xff;
+        if (src_stride < w * c * es) src_stride = w * c * es;
+        if (dst_stride < (w << power) * c * es) dst_stride = (w << power) * c * es;
+        return process_on_device(s, m, st, d_src, w, h, c, src_stride, type, power, d_dst, dst_stride);
+    }
+
+    int acb200_process_host(acb200_session* s, const acb200_model* m, const void* src, int w, int h, int c, int src_stride, int type,
+                            double factor, void* dst, int dst_stride)
+    {
+        int power, rc;
+        if ((rc = check_args(s, m, src, w, h, c, type, factor, dst, power)) != ACB200_OK) return rc;
+        ACB_CUDA(s, cudaSetDevice(s->device));
+        const int es = type & 0xff, ow = w << power, oh = h << power;
+        const size_t line_in = static_cast<size_t>(w) * c * es, line_out = static_cast<size_t>(ow) * c * es;
+        if (src_stride < static_cast<int>(line_in)) src_stride = static_cast<int>(line_in);
+        if (dst_stride < static_cast<int>(line_out)) dst_stride = static_cast<int>(line_out);
+        const size_t sp = pitch_of(w, c, es), dp = pitch_of(ow, c, es);
+        if ((rc = ensure(s, s->src, sp * h)) != ACB200_OK) return rc;
+        if ((rc = ensure(s, s->dst, dp * oh)) != ACB200_OK) return rc;
+        ACB_CUDA(s, cudaMemcpy2DAsync(s->src.p, sp, src, src_stride, line_in, h, cudaMemcpyHostToDevice, s->stream));
+        ACB_CUDA(s, cudaEventRecord(s->ev0, s->stream));
+        if ((rc = process_on_device(s, m, s->stream, s->src.p, w, h, c, static_cast<int>(sp), type, power, s->dst.p, static_cast<int>(dp))) != ACB200_OK) return rc;
+        ACB_CUDA(s, cudaEventRecord(s->ev1, s->stream));
+        s->timed = true;
+        ACB_CUDA(s, cudaMemcpy2DAsync(dst, dst_stride, s->dst.p, dp, line_out, oh, cudaMemcpyDeviceToHost, s->stream));
+        ACB_CUDA(s, cudaStreamSynchronize(s->stream));
+        return ACB200_OK;
+    }
+    int acb200_session_sync(acb200_session* s)
+    {
+        if (!s) return ACB200_EINVAL;
+        ACB_CUDA(s, cudaSetDevice(s->device));
+        ACB_CUDA(s, cudaStreamSynchronize(s->stream));
+        return ACB200_OK;
+    }
+    float acb200_session_last_kernel_ms(acb200_session* s)
+    {
+        float ms = -1.0f;
+        if (s && s->timed && cudaEventElapsedTime(&ms, s->ev0, s->ev1) != cudaSuccess) { cudaGetLastError(); ms = -1.0f; }
+        return ms;
+    }
+
+    // packed != 0: `y` is a packed YUV[A] image (c channels) and `uv` is ignored (1-plane forms,
+    // core/src/ImageProcess.cpp:15-37,87-112); otherwise the 2-plane forms (:38-61,113-138)
+    static int rgb2yuv_host_impl(acb200_session* s, const void* src, int w, int h, int c, int src_stride, int type, void* y, int y_stride, void* uv, int uv_stride, bool packed)
+    {
+        if (!s) return ACB200_EINVAL;
+        if (!src || !y || (!packed && !uv) || w <= 0 || h <= 0 || !(c == 3 || c == 4) || !valid_type(type)) return fail(s, ACB200_EINVAL, "rgb2yuv: bad argument");
+        ACB_CUDA(s, cudaSetDevice(s->device));
+        const int es = type & 0xff;
+        const size_t line = static_cast<size_t>(w) * c * es;
+        const size_t sp = pitch_of(w, c, es), yp = pitch_of(w, packed ? c : 1, es), uvp = pitch_of(w, c - 1, es);
+        int rc;
+        if ((rc = ensure(s, s->src, sp * h)) != ACB200_OK) return rc;
+        if ((rc = ensure(s, s->y[0], yp * h)) != ACB200_OK) return rc;
+        if (!packed && (rc = ensure(s, s->uv, uvp * h)) != ACB200_OK) return rc;
+        ACB_CUDA(s, cudaMemcpy2DAsync(s->src.p, sp, src, std::max<size_t>(src_stride, line), line, h, cudaMemcpyHostToDevice, s->stream));
+        if (packed)
+            rgb2yuv_kernel<<<dim3((w + 31) / 32, (h + 7) / 8), dim3(32, 8), 0, s->stream>>>(s->src.p, static_cast<int>(sp), w, h, c, type,
+                s->y[0].p, static_cast<int>(yp), c, static_cast<uint8_t*>(s->y[0].p) + es, static_cast<int>(yp), c);
+        else
+            rgb2yuv_kernel<<<dim3((w + 31) / 32, (h + 7) / 8), dim3(32, 8), 0, s->stream>>>(s->src.p, static_cast<int>(sp), w, h, c, type,
+                s->y[0].p, static_cast<int>(yp), 1, s->uv.p, static_cast<int>(uvp), c - 1);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        ACB_CUDA(s, cudaGetLastError());
+        const size_t yline = static_cast<size_t>(w) * (packed ? c : 1) * es;
+        ACB_CUDA(s, cudaMemcpy2DAsync(y, std::max<size_t>(y_stride, yline), s->y[0].p, yp, yline, h, cudaMemcpyDeviceToHost, s->stream));
+        if (!packed)
+            ACB_CUDA(s, cudaMemcpy2DAsync(uv, std::max<size_t>(uv_stride, static_cast<size_t>(w) * (c - 1) * es), s->uv.p, uvp, static_cast<size_t>(w) * (c - 1) * es, h, cudaMemcpyDeviceToHost, s->stream));
+        ACB_CUDA(s, cudaStreamSynchronize(s->stream));
+        return ACB200_OK;
+    }
+    static int yuv2rgb_host_impl(acb200_session* s, const void* y, int y_stride, const void* uv, int uv_stride, int w, int h, int c, int type, void* dst, int dst_stride, bool packed)
+    {
+        if (!s) return ACB200_EINVAL;
+        if (!dst || !y || (!packed && !uv) || w <= 0 || h <= 0 || !(c == 3 || c == 4) || !valid_type(type)) return fail(s, ACB200_EINVAL, "yuv2rgb: bad argument");
+        ACB_CUDA(s, cudaSetDevice(s->device));
+        const int es = type & 0xff;
+        const size_t dp = pitch_of(w, c, es), yp = pitch_of(w, packed ? c : 1, es), uvp = pitch_of(w, c - 1, es);
+        int rc;
+        if ((rc = ensure(s, s->dst, dp * h)) != ACB200_OK) return rc;
+        if ((rc = ensure(s, s->y[0], yp * h)) != ACB200_OK) return rc;
+        if (!packed && (rc = ensure(s, s->uv, uvp * h)) != ACB200_OK) return rc;
+        const size_t yline = static_cast<size_t>(w) * (packed ? c : 1) * es;
+        ACB_CUDA(s, cudaMemcpy2DAsync(s->y[0].p, yp, y, std::max<size_t>(y_stride, yline), yline, h, cudaMemcpyHostToDevice, s->stream));
+        if (packed)
+            yuv2rgb_kernel<<<dim3((w + 31) / 32, (h + 7) / 8), dim3(32, 8), 0, s->stream>>>(s->y[0].p, static_cast<int>(yp), c,
+                static_cast<uint8_t*>(s->y[0].p) + es, static_cast<int>(yp), c, w, h, c, type, s->dst.p, static_cast<int>(dp));
+        else
+        {
+            ACB_CUDA(s, cudaMemcpy2DAsync(s->uv.p, uvp, uv, std::max<size_t>(uv_stride, static_cast<size_t>(w) * (c - 1) * es), static_cast<size_t>(w) * (c - 1) * es, h, cudaMemcpyHostToDevice, s->stream));
+            yuv2rgb_kernel<<<dim3((w + 31) / 32, (h + 7) / 8), dim3(32, 8), 0, s->stream>>>(s->y[0].p, static_cast<int>(yp), 1, s->uv.p, static_cast<int>(uvp), c - 1,
+                w, h, c, type, s->dst.p, static_cast<int>(dp));
+        }
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        ACB_CUDA(s, cudaGetLastError());
+        ACB_CUDA(s, cudaMemcpy2DAsync(dst, std::max<size_t>(dst_stride, static_cast<size_t>(w) * c * es), s->dst.p, dp, static_cast<size_t>(w) * c * es, h, cudaMemcpyDeviceToHost, s->stream));
+        ACB_CUDA(s, cudaStreamSynchronize(s->stream));
+        return ACB200_OK;
+    }
+    int acb200_rgb2yuv_host(acb200_session* s, const void* src, int w, int h, int c, int src_stride, int type, void* y, int y_stride, void* uv, int uv_stride)
+    {
+        return rgb2yuv_host_impl(s, src, w, h, c, src_stride, type, y, y_stride, uv, uv_stride, false);
+    }
+    int acb200_rgb2yuv_packed_host(acb200_session* s, const void* src, int w, int h, int c, int src_stride, int type, void* yuv, int yuv_stride)
+    {
+        return rgb2yuv_host_impl(s, src, w, h, c, src_stride, type, yuv, yuv_stride, nullptr, 0, true);
+    }
+    int acb200_yuv2rgb_host(acb200_session* s, const void* y, int y_stride, const void* uv, int uv_stride, int w, int h, int c, int type, void* dst, int dst_stride)
+    {
+        return yuv2rgb_host_impl(s, y, y_stride, uv, uv_stride, w, h, c, type, dst, dst_stride, false);
+    }
+    int acb200_yuv2rgb_packed_host(acb200_session* s, const void* yuv, int yuv_stride, int w, int h, int c, int type, void* dst, int dst_stride)
+    {
+        return yuv2rgb_host_impl(s, yuv, yuv_stride, nullptr, 0, w, h, c, type, dst, dst_stride, true);
+    }
+    int acb200_resize_catmull_rom_host(acb200_session* s, const void* src, int w, int h, int c, int src_stride, int type, void* dst, int ow, int oh, int dst_stride)
+    {
+        if (!s) return ACB200_EINVAL;
+        if (!src || !dst || w <= 0 || h <= 0 || c < 1 || c > 4 || !valid_type(type) || ow < w || oh < h) return fail(s, ACB200_EINVAL, "resize: bad argument (upscale only)");
+        ACB_CUDA(s, cudaSetDevice(s->device));
+        const int es = type & 0xff;
+        const size_t sp = pitch_of(w, c, es), dp = pitch_of(ow, c, es);
+        int rc;
+        if ((rc = ensure(s, s->src, sp * h)) != ACB200_OK) return rc;
+        if ((rc = ensure(s, s->dst, dp * oh)) != ACB200_OK) return rc;
+        if ((rc = ensure_tables(s, s->stream, w, h, ow, oh)) != ACB200_OK) return rc;
+        ACB_CUDA(s, cudaMemcpy2DAsync(s->src.p, sp, src, std::max<size_t>(src_stride, static_cast<size_t>(w) * c * es), static_cast<size_t>(w) * c * es, h, cudaMemcpyHostToDevice, s->stream));
+        resize_catmull_kernel<<<dim3((ow + 31) / 32, (oh + 7) / 8), dim3(32, 8), 0, s->stream>>>(s->src.p, static_cast<int>(sp), c, type,
+            static_cast<const Contrib*>(s->htab.p), static_cast<const Contrib*>(s->vtab.p), s->dst.p, ow, oh, static_cast<int>(dp));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        ACB_CUDA(s, cudaGetLastError());
+        ACB_CUDA(s, cudaMemcpy2DAsync(dst, std::max<size_t>(dst_stride, static_cast<size_t>(ow) * c * es), s->dst.p, dp, static_cast<size_t>(ow) * c * es, oh, cudaMemcpyDeviceToHost, s->stream));
+        ACB_CUDA(s, cudaStreamSynchronize(s->stream));
+        return ACB200_OK;
+    }
+
+    unsigned long long acb200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+    const char* acb200_error_string(int code)
+    {
+        switch (code)
+        {
+        case ACB200_OK: return "success";
+        case ACB200_EINVAL: return "invalid argument";
+        case ACB200_ENODEVICE: return "no CUDA device";
+        case ACB200_ENOMEM: return "out of memory";
+        case ACB200_ECUDA: return "CUDA error";
+        default: return "unknown error";
+        }
+    }
+    const char* acb200_version(void) { return "acb200 0.1 (sm_100a)"; }
+}

@@ -1,0 +1,181 @@
+// Colour split / merge and Catmull-Rom resize kernels of the hot path (HBM-bound, elementwise).
+//
+// Reference semantics:
+//   rgb2yuv / rgba2yuva (2-plane)   core/src/ImageProcess.cpp:38-61, 113-138
+//   yuv2rgb / yuva2rgba (2-plane)   core/src/ImageProcess.cpp:191-215, 275-308
+//   resize(..., RESIZE_CATMULL_ROM) core/src/ImageResize.cpp:136-272 -> stb_image_resize2 gather upsample
+// Every multiply/add below that the reference rounds separately uses __fmul_rn/__fadd_rn so nvcc cannot
+// contract it into an FMA: the quantised planes must come out bit-identical to the CPU processor's.
+#pragma once
+
+#include "acb200_common.cuh"
+
+namespace acb
+{
+    // one output sample's taps along one axis (already edge-folded): src index n0 .. n0+cnt-1
+    struct Contrib
+    {
+        int n0, cnt;
+        float c[6];
+    };
+
+    struct YuvFromRgb { float y, u, v; };
+    __device__ __forceinline__ YuvFromRgb rgb_to_yuv(float r, float g, float b)
+    {
+        YuvFromRgb o;
+        o.y = __fadd_rn(__fadd_rn(__fmul_rn(0.299f, r), __fmul_rn(0.587f, g)), __fmul_rn(0.114f, b));
+        o.u = __fadd_rn(__fmul_rn(0.564f, __fsub_rn(b, o.y)), 0.5f);
+        o.v = __fadd_rn(__fmul_rn(0.713f, __fsub_rn(r, o.y)), 0.5f);
+        return o;
+    }
+
+    // ystep / uvstep: element distance between horizontally adjacent samples of the Y and (U,V[,A]) outputs:
+    // 1 and c-1 for the 2-plane form, c and c (uvp = yp + 1 element) for the packed YUV[A] form.
+    __global__ void rgb2yuv_kernel(const void* __restrict__ src, int src_pitch, int w, int h, int c, int type,
+                                   void* __restrict__ yp, int y_pitch, int ystep, void* __restrict__ uvp, int uv_pitch, int uvstep)
+    {
+        const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+        if (x >= w || y >= h) return;
+        const uint8_t* in = static_cast<const uint8_t*>(src) + static_cast<size_t>(y) * src_pitch;
+        float r = load_elem(in, x * c + 0, type), g = load_elem(in, x * c + 1, type), b = load_elem(in, x * c + 2, type);
+        float a = 1.0f;
+        if (c == 4)
+        {
+            a = load_elem(in, x * c + 3, type);
+            r = __fmul_rn(r, a); g = __fmul_rn(g, a); b = __fmul_rn(b, a);
+        }
+        const YuvFromRgb o = rgb_to_yuv(r, g, b);
+        uint8_t* yo = static_cast<uint8_t*>(yp) + static_cast<size_t>(y) * y_pitch;
+        uint8_t* uvo = static_cast<uint8_t*>(uvp) + static_cast<size_t>(y) * uv_pitch;
+        store_elem(yo, x * ystep, type, o.y);
+        store_elem(uvo, x * uvstep + 0, type, o.u);
+        store_elem(uvo, x * uvstep + 1, type, o.v);
+        if (c == 4) store_elem(uvo, x * uvstep + 2, type, a);
+    }
+
+    // r,g,b (+a) from y and the already-decoded u,v(,a) of the same element type
+    __device__ __forceinline__ void yuv_to_rgb_store(void* out_row, int x, int c, int type, float y, float uq, float vq, float aq)
+    {
+        const float u = __fsub_rn(uq, 0.5f), v = __fsub_rn(vq, 0.5f);
+        float r = __fadd_rn(y, __fmul_rn(1.403f, v));
+        float g = __fsub_rn(__fsub_rn(y, __fmul_rn(0.344f, u)), __fmul_rn(0.714f, v));
+        float b = __fadd_rn(y, __fmul_rn(1.773f, u));
+        if (c == 4)
+        {
+            if (aq > 1e-6f) { r = __fdiv_rn(r, aq); g = __fdiv_rn(g, aq); b = __fdiv_rn(b, aq); }
+            else r = g = b = 0.0f;
+            store_elem(out_row, x * c + 3, type, aq);
+        }
+        store_elem(out_row, x * c + 0, type, r);
+        store_elem(out_row, x * c + 1, type, g);
+        store_elem(out_row, x * c + 2, type, b);
+    }
+
+    __global__ void yuv2rgb_kernel(const void* __restrict__ yp, int y_pitch, int ystep, const void* __restrict__ uvp, int uv_pitch, int uvstep,
+                                   int w, int h, int c, int type, void* __restrict__ dst, int dst_pitch)
+    {
+        const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+        if (x >= w || y >= h) return;
+        const uint8_t* yi = static_cast<const uint8_t*>(yp) + static_cast<size_t>(y) * y_pitch;
+        const uint8_t* uvi = static_cast<const uint8_t*>(uvp) + static_cast<size_t>(y) * uv_pitch;
+        const float a = c == 4 ? load_elem(uvi, x * uvstep + 2, type) : 1.0f;
+        yuv_to_rgb_store(static_cast<uint8_t*>(dst) + static_cast<size_t>(y) * dst_pitch, x, c, type,
+                         load_elem(yi, x * ystep, type), load_elem(uvi, x * uvstep + 0, type), load_elem(uvi, x * uvstep + 1, type), a);
+    }
+
+    // stb_image_resize2 decode: integers are scaled by a reciprocal *multiply* (unlike toFloat's division)
+    __device__ __forceinline__ float resize_decode(const void* row, int x, int type)
+    {
+        switch (type)
+        {
+        case ACB200_UINT8: return __fmul_rn(static_cast<float>(static_cast<const uint8_t*>(row)[x]), 1.0f / 255.0f);
+        case ACB200_UINT16: return __fmul_rn(static_cast<float>(static_cast<const uint16_t*>(row)[x]), 1.0f / 65535.0f);
+        case ACB200_FLOAT16: return __half2float(static_cast<const __half*>(row)[x]);
+        default: return static_cast<const float*>(row)[x];
+        }
+    }
+    // stb encode: v*max + 0.5, clamp to [0,max], truncate; floats are stored unclamped.
+    // Returns the value as the next stage's toFloat() will read it back.
+    __device__ __forceinline__ float resize_encode_store(void* row, int x, int type, float s, bool do_store)
+    {
+        switch (type)
+        {
+        case ACB200_UINT8:
+        {
+            float f = __fadd_rn(__fmul_rn(s, 255.0f), 0.5f);
+            f = f < 0.0f ? 0.0f : (f > 255.0f ? 255.0f : f);
+            const uint8_t q = static_cast<uint8_t>(f);
+            if (do_store) static_cast<uint8_t*>(row)[x] = q;
+            return __fdiv_rn(static_cast<float>(q), 255.0f);
+        }
+        case ACB200_UINT16:
+        {
+            float f = __fadd_rn(__fmul_rn(s, 65535.0f), 0.5f);
+            f = f < 0.0f ? 0.0f : (f > 65535.0f ? 65535.0f : f);
+            const uint16_t q = static_cast<uint16_t>(f);
+            if (do_store) static_cast<uint16_t*>(row)[x] = q;
+            return __fdiv_rn(static_cast<float>(q), 65535.0f);
+        }
+        case ACB200_FLOAT16:
+        {
+            const __half q = __float2half_rn(s);
+            if (do_store) static_cast<__half*>(row)[x] = q;
+            return __half2float(q);
+        }
+        default:
+            if (do_store) static_cast<float*>(row)[x] = s;
+            return s;
+        }
+    }
+
+    // horizontal pass then vertical pass for one output sample of channel `ch` (left-to-right sums,
+    // products and sums rounded separately, as the CPU restatement does)
+    __device__ __forceinline__ float catmull_sample(const void* __restrict__ src, int src_pitch, int c, int ch, int type,
+                                                    const Contrib& hc, const Contrib& vc)
+    {
+        float s = 0.0f;
+        for (int i = 0; i < vc.cnt; i++)
+        {
+            const uint8_t* row = static_cast<const uint8_t*>(src) + static_cast<size_t>(vc.n0 + i) * src_pitch;
+            float hsum = 0.0f;
+            for (int j = 0; j < hc.cnt; j++)
+            {
+                const float t = __fmul_rn(hc.c[j], resize_decode(row, (hc.n0 + j) * c + ch, type));
+                hsum = j == 0 ? t : __fadd_rn(hsum, t);
+            }
+            const float t = __fmul_rn(vc.c[i], hsum);
+            s = i == 0 ? t : __fadd_rn(s, t);
+        }
+        return s;
+    }
+
+    __global__ void resize_catmull_kernel(const void* __restrict__ src, int src_pitch, int c, int type,
+                                          const Contrib* __restrict__ htab, const Contrib* __restrict__ vtab,
+                                          void* __restrict__ dst, int ow, int oh, int dst_pitch)
+    {
+        const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+        if (x >= ow || y >= oh) return;
+        const Contrib hc = htab[x], vc = vtab[y];
+        void* row = static_cast<uint8_t*>(dst) + static_cast<size_t>(y) * dst_pitch;
+        for (int ch = 0; ch < c; ch++)
+            resize_encode_store(row, x * c + ch, type, catmull_sample(src, src_pitch, c, ch, type, hc, vc), true);
+    }
+
+    // Processor.cpp:251-253 fused: Catmull-Rom upscale of the (u,v[,a]) plane by the full factor, re-quantised to
+    // the element type exactly where the reference materialises the resized plane, then YUV->RGB merge with the
+    // network's luma.
+    __global__ void chroma_merge_kernel(const void* __restrict__ yp, int y_pitch, const void* __restrict__ uvp, int uv_pitch,
+                                        const Contrib* __restrict__ htab, const Contrib* __restrict__ vtab,
+                                        int ow, int oh, int c, int type, void* __restrict__ dst, int dst_pitch)
+    {
+        const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+        if (x >= ow || y >= oh) return;
+        const Contrib hc = htab[x], vc = vtab[y];
+        const int uvc = c - 1;
+        float q[3] = { 0.0f, 0.0f, 1.0f };
+        for (int ch = 0; ch < uvc; ch++)
+            q[ch] = resize_encode_store(nullptr, 0, type, catmull_sample(uvp, uv_pitch, uvc, ch, type, hc, vc), false);
+        const float yv = load_elem(static_cast<const uint8_t*>(yp) + static_cast<size_t>(y) * y_pitch, x, type);
+        yuv_to_rgb_store(static_cast<uint8_t*>(dst) + static_cast<size_t>(y) * dst_pitch, x, c, type, yv, q[0], q[1], q[2]);
+    }
+}

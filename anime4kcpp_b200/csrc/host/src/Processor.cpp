@@ -1,0 +1,315 @@
+// The processor front door and the B200 CUDA backend's host class.
+//
+// Front door: type / model string parsing, create dispatch and listInfo follow the reference's
+// core/src/processor/Processor.cpp (findProcessorType :12-25, findModel :26-187, create :286-317, listInfo
+// :319-333).  Backend host class: device choice, sticky per-thread status and naming follow
+// core/src/processor/cuda/CUDAProcessor.cpp (:45-50 performance score, :233-251 device index rule, :260-283).
+//
+// There is no CPU or OpenCL backend in this library and no fallback to one: `create("cpu", ...)` yields a
+// processor whose ok() is false.
+#include <algorithm>
+#include <cctype>
+#include <map>
+#include <mutex>
+#include <shared_mutex>
+#include <sstream>
+#include <string>
+#include <thread>
+
+#include "AC/Core/Model.hpp"
+#include "AC/Core/Processor.hpp"
+
+#include "../../../../include/acb200.h"
+#include "Internal.hpp"
+
+namespace
+{
+    using namespace ac::core;
+
+    std::string lower(const char* s)
+    {
+        std::string out = s ? s : "";
+        for (char& ch : out) ch = static_cast<char>(std::tolower(static_cast<unsigned char>(ch)));
+        return out;
+    }
+    bool has(const std::string& s, const char* needle) { return s.find(needle) != std::string::npos; }
+
+    int parseType(const char* type)
+    {
+        const std::string t = lower(type);
+        if (t == "auto") return -1;
+        if (t == "opencl") return Processor::OpenCL;
+        if (t == "cuda") return Processor::CUDA;
+        return Processor::CPU;
+    }
+
+    struct ModelChoice
+    {
+        int family;     // ACB200_FAMILY_*, or -1 for a family this build does not carry
+        int variant;    // index into the family's Variant enum
+    };
+    // first size token present wins, in the reference's test order
+    int firstOf(const std::string& s, std::initializer_list<const char*> tokens, int fallback)
+    {
+        int i = 0;
+        for (const char* t : tokens) { if (has(s, t)) return i; i++; }
+        return fallback;
+    }
+    ModelChoice parseModel(const char* model)
+    {
+        const std::string m = lower(model);
+        if (model)
+        {
+            if (has(m, "fsrcnnx") || has(m, "artcnn")) return { -1, 0 };
+            const int flavour = (has(m, "box") ? 2 : 0) + (has(m, "hdn") ? 1 : 0);   // NORMAL, HDN, BOX, BOX_HDN
+            if (has(m, "arnet")) return { ACB200_FAMILY_ARNET, firstOf(m, { "b8", "b16", "b32", "b64" }, 0) * 4 + flavour };
+            if (has(m, "acnet"))
+            {
+                if (has(m, "legacy"))
+                {
+                    if (!has(m, "hdn")) return { ACB200_FAMILY_ACNET_LEGACY, 0 };   // GAN
+                    for (char ch : m) if (ch >= '0' && ch <= '3') return { ACB200_FAMILY_ACNET_LEGACY, 1 + (ch - '0') };
+                    return { ACB200_FAMILY_ACNET_LEGACY, 1 };                          // HDN0
+                }
+                return { ACB200_FAMILY_ACNET, firstOf(m, { "b4", "b8", "b18" }, 1) * 4 + flavour };
+            }
+        }
+        return { ACB200_FAMILY_ACNET_LEGACY, 0 };
+    }
+
+    // ---- a processor that only reports why it cannot run ---------------------------------------------------------
+    class UnavailableProcessor final : public Processor
+    {
+    public:
+        UnavailableProcessor(int type, const char* why) : kind(type), reason(why) {}
+        bool ok() noexcept override { return false; }
+        const char* error() noexcept override { return reason.c_str(); }
+        const char* name() const noexcept override { return "unavailable"; }
+        int type() const noexcept override { return kind; }
+        const char* typeName() const noexcept override { return kind == Processor::CPU ? "CPU" : kind == Processor::OpenCL ? "OpenCL" : "CUDA"; }
+    protected:
+        void processImage(const Image&, Image&, double) override {}
+    private:
+        int kind;
+        std::string reason;
+    };
+
+    // ---- the B200 backend ----------------------------------------------------------------------------------------
+    class B200Processor final : public Processor
+    {
+    public:
+        B200Processor(int device, int family, int blocks, const float* k, int nk, const float* b, int nb, const float* a, int na)
+        {
+            const int count = acb200_device_count();
+            if (count <= 0) { createError = "no CUDA device"; return; }
+            idx = device;
+            if (!(device >= 0 && device < count))
+            {
+                // out-of-range index = fastest device by clock x SM count
+                long long best = -1;
+                for (int i = 0; i < count; i++)
+                {
+                    int sms = 0, khz = 0;
+                    if (acb200_device_info(i, nullptr, 0, nullptr, nullptr, &sms, &khz) != ACB200_OK) continue;
+                    const long long score = static_cast<long long>(sms) * khz;
+                    if (score > best) { best = score; idx = i; }
+                }
+            }
+            char buf[256] = {};
+            if (acb200_device_info(idx, buf, sizeof(buf), nullptr, nullptr, nullptr, nullptr) != ACB200_OK) { createError = "cannot query CUDA device"; return; }
+            deviceName = buf;
+            const int rc = acb200_model_create(family, blocks, k, nk, b, nb, a, na, &model);
+            if (rc != ACB200_OK) { createError = std::string("model rejected: ") + acb200_error_string(rc); model = nullptr; return; }
+            // touch the device once so construction-time failures surface through ok(), as in the reference
+            State& st = local();
+            if (!st.session && createError.empty()) createError = st.error;
+        }
+        ~B200Processor() override
+        {
+            for (auto& kv : states) if (kv.second.session) acb200_session_destroy(kv.second.session);
+            if (model) acb200_model_destroy(model);
+        }
+
+        bool ok() noexcept override
+        {
+            if (!createError.empty()) return false;
+            return local().good;
+        }
+        const char* error() noexcept override
+        {
+            if (!createError.empty()) return createError.c_str();
+            State& st = local();
+            return st.good ? "NO ERROR" : st.error.c_str();
+        }
+        const char* name() const noexcept override { return deviceName.c_str(); }
+        int type() const noexcept override { return Processor::CUDA; }
+        const char* typeName() const noexcept override { return "CUDA"; }
+
+    protected:
+        void processImage(const Image& src, Image& dst, const double factor) override
+        {
+            if (!createError.empty()) return;
+            State& st = local();
+            if (!st.session) return;
+            const int rc = acb200_process_host(st.session, model, src.ptr(), src.width(), src.height(), src.channels(), src.stride(), src.type(),
+                                               factor, dst.ptr(), dst.stride());
+            st.good = rc == ACB200_OK;
+            if (!st.good) st.error = acb200_session_error(st.session);
+        }
+
+    private:
+        // one session (stream + scratch) and one sticky status per calling thread, like the reference's
+        // util::ThreadLocal members (CUDAProcessor.cpp:284, :374-377)
+        struct State
+        {
+            acb200_session* session = nullptr;
+            bool good = true;
+            std::string error = "NO ERROR";
+        };
+        State& local()
+        {
+            const auto id = std::this_thread::get_id();
+            {
+                std::shared_lock<std::shared_mutex> lock(mutex);
+                auto it = states.find(id);
+                if (it != states.end()) return it->second;
+            }
+            std::unique_lock<std::shared_mutex> lock(mutex);
+            State& st = states[id];
+            if (!st.session)
+            {
+                const int rc = acb200_session_create(idx, &st.session);
+                if (rc != ACB200_OK) { st.session = nullptr; st.good = false; st.error = std::string("cannot create CUDA session: ") + acb200_error_string(rc); }
+            }
+            return st;
+        }
+
+        std::string deviceName = "unavailable";
+        std::string createError;
+        acb200_model* model = nullptr;
+        std::shared_mutex mutex;
+        std::map<std::thread::id, State> states;
+    };
+
+    template<typename Model>
+    std::shared_ptr<Processor> makeB200(int device, int family, const Model& m)
+    {
+        if (!m.kernel()) return std::make_shared<UnavailableProcessor>(Processor::CUDA, "model weights are not available in this build");
+        return std::make_shared<B200Processor>(device, family, m.blocks(), m.kernel(), m.kernelLength(), m.bias(), m.biasLength(),
+                                               m.alphaLength() ? m.alpha() : nullptr, m.alphaLength());
+    }
+}
+
+ac::core::Processor::Processor() noexcept : idx(0) {}
+ac::core::Processor::~Processor() = default;
+
+ac::core::Image ac::core::Processor::process(const Image& src, const double factor)
+{
+    Image dst{};
+    process(src, dst, factor);
+    return dst;
+}
+void ac::core::Processor::process(const Image& src, Image& dst, const double factor)
+{
+    if (src.empty()) return;
+    // an empty dst is allocated to (int)(w*factor) x (int)(h*factor); a non-empty one is trusted (Processor.hpp:27-29)
+    if (dst.empty()) dst.create(static_cast<int>(src.width() * factor), static_cast<int>(src.height() * factor), src.channels(), src.type());
+    processImage(src, dst, factor);
+}
+bool ac::core::Processor::ok() noexcept { return true; }
+const char* ac::core::Processor::error() noexcept { return "NO ERROR"; }
+
+template<> AC_CORE_EXPORT std::shared_ptr<ac::core::Processor> ac::core::Processor::create<ac::core::Processor::CUDA, ac::core::model::ACNetLegacy>(const int idx, const model::ACNetLegacy& model)
+{
+    return makeB200(idx, ACB200_FAMILY_ACNET_LEGACY, model);
+}
+template<> AC_CORE_EXPORT std::shared_ptr<ac::core::Processor> ac::core::Processor::create<ac::core::Processor::CUDA, ac::core::model::ACNet<8>>(const int idx, const model::ACNet<8>& model)
+{
+    return makeB200(idx, ACB200_FAMILY_ACNET, model);
+}
+template<> AC_CORE_EXPORT std::shared_ptr<ac::core::Processor> ac::core::Processor::create<ac::core::Processor::CUDA, ac::core::model::ARNet<8>>(const int idx, const model::ARNet<8>& model)
+{
+    return makeB200(idx, ACB200_FAMILY_ARNET, model);
+}
+
+std::shared_ptr<ac::core::Processor> ac::core::Processor::create(const char* type, const int device, const char* const model)
+{
+    const int kind = parseType(type);
+    if (kind == Processor::CPU) return std::make_shared<UnavailableProcessor>(Processor::CPU, "the B200 drop-in carries no CPU backend (use \"cuda\" or \"auto\")");
+    if (kind == Processor::OpenCL) return std::make_shared<UnavailableProcessor>(Processor::OpenCL, "the B200 drop-in carries no OpenCL backend (use \"cuda\" or \"auto\")");
+    const int dev = kind == Processor::CUDA ? device : -1;   // auto = fastest device
+    const ModelChoice choice = parseModel(model);
+    switch (choice.family)
+    {
+    case ACB200_FAMILY_ACNET_LEGACY: return create<Processor::CUDA>(dev, model::ACNetLegacy{ static_cast<model::ACNetLegacy::Variant>(choice.variant) });
+    case ACB200_FAMILY_ACNET: return create<Processor::CUDA>(dev, model::ACNet<8>{ static_cast<model::ACNet<8>::Variant>(choice.variant) });
+    case ACB200_FAMILY_ARNET: return create<Processor::CUDA>(dev, model::ARNet<8>{ static_cast<model::ARNet<8>::Variant>(choice.variant) });
+    default: return std::make_shared<UnavailableProcessor>(Processor::CUDA, "model family (ArtCNN / FSRCNNX) is outside the B200 drop-in's scope");
+    }
+}
+
+template<> AC_CORE_EXPORT const char* ac::core::Processor::info<ac::core::Processor::CUDA>()
+{
+    static const std::string text = []() {
+        std::ostringstream out;
+        out << "CUDA:\n";
+        const int count = acb200_device_count();
+        for (int i = 0; i < count; i++)
+        {
+            char name[256] = {};
+            std::size_t vram = 0;
+            int cc = 0;
+            if (acb200_device_info(i, name, sizeof(name), &vram, &cc, nullptr, nullptr) != ACB200_OK) continue;
+            out << "  [" << i << "] " << name << " (" << (vram >> 20) << "MB, CC " << cc / 10.0 << ")\n";
+        }
+        return out.str();
+    }();
+    return text.c_str();
+}
+template<> AC_CORE_EXPORT const char* ac::core::Processor::info<ac::core::Processor::CPU>()
+{
+    return "CPU:\n  (no CPU backend in the B200 drop-in)\n";
+}
+template<> AC_CORE_EXPORT const char* ac::core::Processor::info<ac::core::Processor::OpenCL>()
+{
+    return "OpenCL:\n  (no OpenCL backend in the B200 drop-in)\n";
+}
+const char* ac::core::Processor::listInfo()
+{
+    static const std::string text = std::string(info<Processor::CPU>()) + info<Processor::CUDA>();
+    return text.c_str();
+}
+
+// exported for bindings / tests: the canonical name a model string resolves to (empty = out of scope)
+extern "C" AC_CORE_EXPORT const char* ac_b200_resolve_model(const char* model)
+{
+    const ModelChoice c = parseModel(model);
+    switch (c.family)
+    {
+    case ACB200_FAMILY_ACNET_LEGACY: return model::ACNetLegacy{ static_cast<model::ACNetLegacy::Variant>(c.variant) }.name();
+    case ACB200_FAMILY_ACNET: return model::ACNet<8>{ static_cast<model::ACNet<8>::Variant>(c.variant) }.name();
+    case ACB200_FAMILY_ARNET: return model::ARNet<8>{ static_cast<model::ARNet<8>::Variant>(c.variant) }.name();
+    default: return "";
+    }
+}
+
+// exported for bindings / tests: the flat weight arrays behind a model string, exactly as handed to the CUDA layer.
+// Returns the ACB200_FAMILY_* code, or -1 when the family is out of scope.
+extern "C" AC_CORE_EXPORT int ac_b200_model_arrays(const char* model, int* blocks, const float** k, int* nk, const float** b, int* nb, const float** a, int* na)
+{
+    const ModelChoice c = parseModel(model);
+    auto fill = [&](const auto& m) {
+        if (blocks) *blocks = m.blocks();
+        if (k) *k = m.kernel(); if (nk) *nk = m.kernelLength();
+        if (b) *b = m.bias(); if (nb) *nb = m.biasLength();
+        if (a) *a = m.alphaLength() ? m.alpha() : nullptr; if (na) *na = m.alphaLength();
+    };
+    switch (c.family)
+    {
+    case ACB200_FAMILY_ACNET_LEGACY: fill(model::ACNetLegacy{ static_cast<model::ACNetLegacy::Variant>(c.variant) }); break;
+    case ACB200_FAMILY_ACNET: fill(model::ACNet<8>{ static_cast<model::ACNet<8>::Variant>(c.variant) }); break;
+    case ACB200_FAMILY_ARNET: fill(model::ARNet<8>{ static_cast<model::ARNet<8>::Variant>(c.variant) }); break;
+    default: return -1;
+    }
+    return c.family;
+}

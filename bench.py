@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""Benchmark of the B200 backend on BASELINE.json's metric: output megapixels/s (and 1080p->4K frames/s) of the
+CNN upscaling hot path, with the kernel roofline and the reference CPU processor timed beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--model M] [--batch B]
+
+A "step" is one pass of the hot path -- Processor::process(frame, 2.0): RGB->YUV split, the fused luma network,
+Catmull-Rom chroma resize, YUV->RGB merge -- over one batch of B synthetic 1920x1080 RGB u8 frames.
+ * value : whole-job output MP/s with the batch already resident in HBM (device-resident C-ABI entry, CUDA events
+           on the launching stream, max over ranks).
+ * e2e   : the same metric through the reference-facing C binding (ac_processor_process) with HOST buffers: pinned
+           host images in, pinned host images out, H2D and D2H inside the timed region, caller threads sharing one
+           processor exactly as tools/benchmark does.
+ * roofline : the luma-network kernel, algorithmic FLOPs (2 x kernelLength() per input pixel) over
+           its CUDA-event launch duration, against the measured peaks in MEASURED_PEAKS.json.
+ * cpu_baseline : the reference's CPU processor (oracle/_ref, auto-ISA backend, OpenMP) on the box's host cores.
+Multi-GPU (torchrun, one rank per GPU): frames are independent, every rank upscales its own batch, no data-path
+collective (weak scaling); NCCL is used only for the timing barrier / max-reduce.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+W, H, CH = 1920, 1080, 3
+FACTOR = 2.0
+OUT_MP = (W * 2) * (H * 2) / 1e6
+MACS_PER_PIXEL = {"acnet-legacy": 4712, "acnet-f8b4": 2664, "acnet-f8b8": 4968, "acnet-f8b18": 10728,
+                  "arnet-f8b8": 9640, "arnet-f8b16": 18856, "arnet-f8b32": 37288, "arnet-f8b64": 74152}
+
+
+def macs_for(model):
+    for k, v in sorted(MACS_PER_PIXEL.items(), key=lambda kv: -len(kv[0])):
+        if model.startswith(k):
+            return v
+    raise KeyError(model)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index),
+                 "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
+                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arms: the reference's own CPU processor (oracle/_ref) when it travelled with the repo, else the oracle port
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_time_frames(model, frames, threads_in_flight=1):
+    """Seconds for `frames` 1080p RGB u8 frames through Processor::process(img, 2.0) on the host cores."""
+    import numpy as np
+    import oracle_lib as O
+    ref = O.ref()
+    if ref is not None:
+        t = ref.ref_benchmark(model.encode(), 0, W, H, CH, frames, threads_in_flight, 1234)
+        return t, "reference", ref.ref_processor_name(model.encode(), 0).decode()
+    img = O.noise_u8(H, W, CH, seed=1234)
+    O.oracle_process(model, img[:64, :64], FACTOR)
+    t0 = time.perf_counter()
+    for _ in range(frames):
+        O.oracle_process(model, img, FACTOR)
+    return time.perf_counter() - t0, "port", "oracle/ac_oracle.c (Generic order)"
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    frames_per_step = 1
+    for _ in range(max(args.warmup, 0)):
+        cpu_time_frames(args.model, frames_per_step)
+    t, kind, backend = cpu_time_frames(args.model, frames_per_step * args.steps)
+    value = OUT_MP * frames_per_step * args.steps / t
+    line = {
+        "impl": "reference", "metric": "output megapixels/s, 1080p->2160p RGB u8, 2x", "value": value, "unit": "MP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s 2x on synthetic 1920x1080 RGB u8 frames (BASELINE configs[1])" % args.model, "frames_per_step": frames_per_step,
+                   "fps": frames_per_step * args.steps / t},
+        "cpu_baseline": {"value": value, "unit": "MP/s", "cores": cores, "kind": kind, "sample": "%d frame(s) per step, %d steps, backend %s, OpenMP rows over all host threads"
+                         % (frames_per_step, args.steps, backend)},
+        "e2e": {"value": value, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------------
+class ACImage(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("channels", C.c_int), ("stride", C.c_int), ("element_type", C.c_int),
+                ("ptr", C.c_void_p), ("hptr", C.c_void_p)]
+
+
+class ACProcessor(C.Structure):
+    _fields_ = [("device", C.c_int), ("type", C.c_char_p), ("model", C.c_char_p), ("hptr", C.c_void_p)]
+
+
+def map_image(lib, arr):
+    lib.ac_image_alloc.restype = C.POINTER(ACImage)
+    img = lib.ac_image_alloc()
+    h, w = arr.shape[:2]
+    img.contents.width, img.contents.height, img.contents.channels = w, h, (1 if arr.ndim == 2 else arr.shape[2])
+    img.contents.element_type, img.contents.stride, img.contents.ptr = 1, arr.strides[0], arr.ctypes.data
+    assert lib.ac_image_map(img) == 0
+    return img
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import anime4kcpp_b200 as A
+    import oracle_lib as O
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert A.device_count() > local, "no CUDA device: the B200 backend has no CPU fallback"
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    lib = A.lib()
+    B = args.batch
+    model = A.Model(args.model)
+    sess = A.Session(local)
+    sess.set_engine(args.engine)
+    rs = np.random.RandomState(1234 + rank)
+    host_frames = rs.randint(0, 256, size=(B, H, W, CH), dtype=np.uint8)
+    d_in = torch.from_numpy(host_frames).cuda()
+    d_out = torch.empty((B, 2 * H, 2 * W, CH), dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        for i in range(B):
+            sess.process_device(model, d_in[i], FACTOR, out=d_out[i], stream=stream)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = A.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = A.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    frames_total = B * args.steps * world
+    value = OUT_MP * frames_total / (ms_max / 1e3)
+
+    # ---- spot parity inside the bench: a crop of the first output frame against the CPU oracle ---------------------
+    parity = None
+    if rank == 0:
+        crop = host_frames[0, :96, :128]
+        got = sess.process_host(model, np.ascontiguousarray(crop), FACTOR)
+        mx, exact = O.compare_u8(got, O.oracle_process(args.model, np.ascontiguousarray(crop), FACTOR))
+        parity = {"max_lsb": mx, "bit_exact_frac": exact}
+
+    # ---- dominant kernel alone: the luma network on a device-resident 1080p Y plane (what the RGB path launches) ----
+    y_in = d_in[:, :, :, 0].contiguous()
+    y_out = torch.empty((2 * H, 2 * W), dtype=torch.uint8, device="cuda")
+    for i in range(3):
+        sess.process_device(model, y_in[i % B], FACTOR, out=y_out, stream=stream)
+    torch.cuda.synchronize()
+    l0 = A.launch_count()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = max(8, min(64, B * args.steps))
+    k0.record()
+    for i in range(reps):
+        sess.process_device(model, y_in[i % B], FACTOR, out=y_out, stream=stream)
+    k1.record()
+    torch.cuda.synchronize()
+    kernel_ms = k0.elapsed_time(k1) / reps
+    launches_per_pass = (A.launch_count() - l0) / reps
+    peaks = load_peaks()
+    flop_frame = 2.0 * macs_for(args.model) * W * H
+    achieved_tf = flop_frame / (kernel_ms / 1e3) / 1e12
+    fp32_peak_tf = 148 * 128 * 2 * 1.965e9 / 1e12
+    # bytes that must cross HBM per RGB frame (in + out) -- the other roofline candidate; compute dominates
+    bytes_frame = W * H * CH + 4 * W * H * CH
+    t_roof_ms = max(flop_frame / (peaks["bf16_tflops_sustained"] * 1e12), bytes_frame / (peaks["hbm_gbs"] * 1e9)) * 1e3
+
+    # ---- end to end through the C binding with host buffers ---------------------------------------------------------
+    e2e = None
+    n_threads = args.threads
+    pin_in = torch.from_numpy(host_frames).pin_memory()
+    pin_out = torch.empty((B, 2 * H, 2 * W, CH), dtype=torch.uint8).pin_memory()
+    lib.ac_processor_alloc.restype = C.POINTER(ACProcessor)
+    lib.ac_processor_error.restype = C.c_char_p
+    proc = lib.ac_processor_alloc()
+    proc.contents.type, proc.contents.model, proc.contents.device = b"cuda", args.model.encode(), local
+    assert lib.ac_processor_create(proc) == 0, lib.ac_processor_error(proc)
+    np_in, np_out = pin_in.numpy(), pin_out.numpy()
+    srcs = [map_image(lib, np_in[i]) for i in range(B)]
+    dsts = [map_image(lib, np_out[i]) for i in range(B)]
+
+    def e2e_step():
+        nxt = [0]
+        lock = threading.Lock()
+
+        def worker():
+            while True:
+                with lock:
+                    i = nxt[0]
+                    nxt[0] += 1
+                if i >= B:
+                    return
+                rc = lib.ac_processor_process(proc, srcs[i], dsts[i], C.c_double(FACTOR))
+                assert rc == 0, lib.ac_processor_error(proc)
+        ts = [threading.Thread(target=worker) for _ in range(n_threads)]
+        [x.start() for x in ts]
+        [x.join() for x in ts]
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    te = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = OUT_MP * frames_total / float(te.item())
+    if rank == 0:
+        want = d_out[0].cpu().numpy()
+        assert np.array_equal(np_out[0], want), "host path and device path disagree"
+    e2e = {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": B * W * H * CH, "d2h_bytes_per_step": B * 4 * W * H * CH,
+           "fps": frames_total / float(te.item()), "caller_threads": n_threads, "api": "ac_processor_process (libac_c binding), pinned host images"}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        frames = args.cpu_frames
+        tc, kind, backend = cpu_time_frames(args.model, frames)
+        cpu = {"value": OUT_MP * frames / tc, "unit": "MP/s", "cores": os.cpu_count() or 1, "kind": kind,
+               "sample": "%d 1080p RGB frames, backend %s, one frame at a time with OpenMP over all host threads" % (frames, backend),
+               "fps": frames / tc}
+
+    if rank == 0:
+        line = {
+            "metric": "output megapixels/s, 1080p->2160p RGB u8, 2x", "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%s 2x on a batch of %d synthetic 1920x1080 RGB u8 frames per GPU (BASELINE configs[1])" % (args.model, B),
+                       "frames_per_step_per_gpu": B, "fps": frames_total / (ms_max / 1e3), "engine": args.engine,
+                       "cache": "inputs larger than L2: %d MB in + %d MB out per step" % (B * W * H * CH >> 20, B * 4 * W * H * CH >> 20),
+                       "parity_spot_check": parity},
+            "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": achieved_tf / peaks["bf16_tflops_sustained"], "traffic": None,
+                         "kernel": "fused luma network (segment kernel), 1920x1080 Y -> 3840x2160 Y", "kernel_ms": kernel_ms,
+                         "launches_per_pass": launches_per_pass, "flop_per_launch": flop_frame, "peak_source": peaks["source"],
+                         "pipe": "fp32 FFMA (CUDA cores)" if args.engine == 0 else "split-fp16 tensor-core MMA",
+                         "fp32_ffma_peak_tflops_nominal": fp32_peak_tf, "frac_of_fp32_ffma_peak": achieved_tf / fp32_peak_tf,
+                         "frame_roofline_ms": t_roof_ms, "frame_frac": t_roof_ms / (ms_max / (B * args.steps))},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="acnet-legacy-hdn0")
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--threads", type=int, default=4, help="caller threads sharing the processor in the e2e leg")
+    ap.add_argument("--engine", type=int, default=0)
+    ap.add_argument("--cpu-frames", type=int, default=12)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

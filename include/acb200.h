@@ -1,0 +1,141 @@
+/*
+ * acb200.h -- thin C-ABI CUDA layer of the B200 (sm_100a) backend for Anime4KCPP v3's
+ * CNN upscaling hot path.
+ *
+ * This is the seam the C++ host (`ac::core::Processor` re-creation, src/host/) talks to, and the
+ * boundary a reference maintainer would bind instead of core/src/processor/cuda/{Kernel.cu,
+ * CUDAProcessor.cpp}.  Plain pointers and sizes only; no C++/torch types.  Entry points and what
+ * they replace in the reference:
+ *
+ *   acb200_device_count / acb200_device_info   <- CUDAProcessor.cpp:68-83 (ContextList), :882-892 (info<CUDA>)
+ *   acb200_model_create / _destroy             <- CUDAProcessor.cpp:291-326 (per-layer cudaMalloc+cudaMemcpy of
+ *                                                 model.kernel(l)/bias(l)/alpha(l))
+ *   acb200_session_create / _destroy           <- CUDAProcessor.cpp:96-228 (per-thread stream, pool allocator,
+ *                                                 scratch images), :374-377
+ *   acb200_process_host                        <- Processor.cpp:199-276 (colour split, 2x passes, chroma
+ *                                                 resize, merge) + CUDAProcessor.cpp:383-422/:451-490/:520-566
+ *                                                 (H2D, layer launches, D2H, sync) in ONE submission
+ *   acb200_process_device                      <- same, for frames already resident in HBM (no copies)
+ *   acb200_session_sync / acb200_error_string  <- CUDAProcessor.cpp:260-267 (sticky cudaError_t + string)
+ *
+ * Image memory layout is the reference's `ac::core::Image` (core/include/AC/Core/Image.hpp:359-419):
+ * interleaved HWC rows, `stride` in BYTES, element type code = (kind << 8) | bytes.
+ *
+ * Every function returns 0 on success or a negative code (ACB200_E*); nothing throws or aborts.
+ * There is no CPU fallback: without a usable CUDA device every compute entry fails with
+ * ACB200_ENODEVICE.
+ */
+#ifndef ACB200_H
+#define ACB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#   define ACB200_API __attribute__((visibility("default")))
+#else
+#   define ACB200_API
+#endif
+
+/* element types, core/include/AC/Core/Image.hpp:365-370 */
+#define ACB200_UINT8   0x001
+#define ACB200_UINT16  0x002
+#define ACB200_FLOAT16 0x202
+#define ACB200_FLOAT32 0x204
+
+/* model families on the hot path, core/src/processor/Processor.cpp:26-187 */
+#define ACB200_FAMILY_ACNET_LEGACY 0   /* model::ACNetLegacy: ReLU, 2x2 deconvolution tail */
+#define ACB200_FAMILY_ACNET        1   /* model::ACNet<8>:   PReLU, pixel-shuffle + nearest residual tail */
+#define ACB200_FAMILY_ARNET        2   /* model::ARNet<8>:   residual blocks, 1x1 fuse, pixel-shuffle tail */
+
+#define ACB200_OK          0
+#define ACB200_EINVAL     (-22)   /* bad argument / unsupported shape */
+#define ACB200_ENODEVICE  (-19)   /* no CUDA device, or device index out of range */
+#define ACB200_ENOMEM     (-12)
+#define ACB200_ECUDA      (-256)  /* a CUDA call failed; acb200_session_error()/acb200_last_error() has the text */
+
+typedef struct acb200_model acb200_model;
+typedef struct acb200_session acb200_session;
+
+ACB200_API int acb200_device_count(void);
+/* name: device name (NUL-terminated, truncated to name_len); vram in bytes; cc = major*10+minor */
+ACB200_API int acb200_device_info(int device, char* name, int name_len, size_t* vram_bytes, int* cc, int* sm_count, int* clock_khz);
+
+/*
+ * Flat fp32 arrays exactly as the reference's model objects expose them
+ * (core/include/AC/Core/Model/ACNet.hpp:34-60,78-115, ARNet.hpp:32-71): kernels `[cout][ky*3+kx][cin]`
+ * per layer, layers concatenated.  Lengths are validated against family/blocks.
+ * The model is host-side and device-independent; sessions upload it lazily per device.
+ */
+ACB200_API int acb200_model_create(int family, int blocks,
+                                   const float* kernels, int n_kernels,
+                                   const float* biases, int n_biases,
+                                   const float* alphas, int n_alphas,
+                                   acb200_model** out);
+ACB200_API void acb200_model_destroy(acb200_model* model);
+
+/*
+ * A session owns one CUDA stream, its scratch planes in HBM and pinned staging buffers on `device`.
+ * One session per calling thread (the reference keeps the same state per thread,
+ * CUDAProcessor.cpp:374-377); a session must not be used from two threads at once.
+ */
+ACB200_API int acb200_session_create(int device, acb200_session** out);
+ACB200_API void acb200_session_destroy(acb200_session* session);
+ACB200_API int acb200_session_device(const acb200_session* session);
+/* sticky error text of the last failure on this session ("NO ERROR" when none) */
+ACB200_API const char* acb200_session_error(const acb200_session* session);
+ACB200_API void acb200_session_clear_error(acb200_session* session);
+
+/*
+ * Processor::process(src, dst, factor) for HOST images: H2D, RGB->YUV split (c = 3/4), ceil(log2(factor))
+ * 2x luma passes, Catmull-Rom chroma resize by `factor`, YUV->RGB merge, D2H, stream sync.
+ * dst must be preallocated: (int)(w*factor) x (int)(h*factor) x c, same element type.
+ * `factor` must be a power of two >= 2 (fxy == 1 in Processor.cpp:204-205); others -> ACB200_EINVAL.
+ */
+ACB200_API int acb200_process_host(acb200_session* session, const acb200_model* model,
+                                   const void* src, int w, int h, int c, int src_stride, int elem_type,
+                                   double factor, void* dst, int dst_stride);
+/*
+ * Same work on frames already resident in this device's HBM; enqueued on the session stream
+ * (or on `stream` if non-NULL: a cudaStream_t), returns without synchronising.
+ */
+ACB200_API int acb200_process_device(acb200_session* session, const acb200_model* model,
+                                     const void* d_src, int w, int h, int c, int src_stride, int elem_type,
+                                     double factor, void* d_dst, int dst_stride, void* stream);
+ACB200_API int acb200_session_sync(acb200_session* session);
+
+/*
+ * Stand-alone image ops of the hot path on HOST images (reference: core/src/ImageProcess.cpp:38-61,
+ * 113-138,191-215,275-308 and the Catmull-Rom upscale of core/src/ImageResize.cpp:136-272).
+ */
+ACB200_API int acb200_rgb2yuv_host(acb200_session* session, const void* src, int w, int h, int c, int src_stride, int elem_type,
+                                   void* y, int y_stride, void* uv, int uv_stride);
+ACB200_API int acb200_yuv2rgb_host(acb200_session* session, const void* y, int y_stride, const void* uv, int uv_stride,
+                                   int w, int h, int c, int elem_type, void* dst, int dst_stride);
+/* packed 1-plane forms YUV[A] <-> RGB[A] (core/src/ImageProcess.cpp:15-37, 87-112, 166-190, 243-274) */
+ACB200_API int acb200_rgb2yuv_packed_host(acb200_session* session, const void* src, int w, int h, int c, int src_stride, int elem_type,
+                                          void* yuv, int yuv_stride);
+ACB200_API int acb200_yuv2rgb_packed_host(acb200_session* session, const void* yuv, int yuv_stride, int w, int h, int c, int elem_type,
+                                          void* dst, int dst_stride);
+ACB200_API int acb200_resize_catmull_rom_host(acb200_session* session, const void* src, int w, int h, int c, int src_stride,
+                                              int elem_type, void* dst, int ow, int oh, int dst_stride);
+
+/* number of kernels this library has launched since load (all sessions); for bench.py's gpu_launches */
+ACB200_API unsigned long long acb200_launch_count(void);
+/* elapsed GPU milliseconds of the most recent process_* call's kernels on this session (CUDA events) */
+ACB200_API float acb200_session_last_kernel_ms(acb200_session* session);
+/* select the luma-network engine: 0 = fp32 FFMA (CUDA cores), 1 = split-fp16 tensor-core MMA; default best */
+ACB200_API int acb200_session_set_engine(acb200_session* session, int engine);
+
+ACB200_API const char* acb200_error_string(int code);
+ACB200_API const char* acb200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

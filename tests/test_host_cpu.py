@@ -1,0 +1,150 @@
+"""CPU suite, part 2: the native library loads, exports every symbol include/*.h declares, and its host logic
+(model strings, weight tables, Image semantics through the C binding, loud failure without a device) behaves like
+the reference's.  No compute call is made here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import anime4kcpp_b200 as A
+import oracle_lib as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    names = set()
+    for path in ("include/acb200.h", "include/AC/Core/Image.h", "include/AC/Core/Processor.h"):
+        text = open(os.path.join(ROOT, path)).read()
+        names |= set(re.findall(r"(?:ACB200_API|AC_C_API)\s+[\w\s\*]+?\b(acb200_\w+|ac_\w+)\s*\(", text))
+    return sorted(names)
+
+
+def test_library_exports_every_declared_symbol():
+    lib = A.lib()
+    syms = _declared_symbols()
+    assert len(syms) >= 45
+    for s in syms:
+        assert hasattr(lib, s), "missing export: " + s
+
+
+def test_weights_in_library_match_blob_and_synth():
+    for name in list(O.models().keys()) + ["arnet-f8b8", "arnet-f8b32-box-hdn"]:
+        fam, blocks, k, b, a = A.model_arrays(name)
+        ofam, oblocks, ok, ob, oa = O.model(name)
+        assert (fam, blocks) == (ofam, oblocks)
+        assert np.array_equal(k.view(np.uint32), ok.view(np.uint32))
+        assert np.array_equal(b.view(np.uint32), ob.view(np.uint32))
+        assert np.array_equal(a.view(np.uint32), oa.view(np.uint32))
+
+
+@pytest.mark.parametrize("s", ["acnet-hdn", "ACNet-Legacy-HDN2", "acnet-legacy", "acnet-legacy-hdn", "arnet-f8b16-box", "arnet", "ARNET-B64-hdn",
+                               "acnet-f8b18-box-hdn", "acnet-b4", "unknown", "", "acnet-f8b8-box"])
+def test_model_string_resolution_matches_reference_rules(s):
+    assert A.resolve_model(s) == O.canonical(s)
+
+
+def test_out_of_scope_families_are_reported():
+    assert A.resolve_model("fsrcnnx-f8b4") == "" and A.resolve_model("artcnn-c4f16") == ""
+
+
+def test_model_create_validates_lengths():
+    fam, blocks, k, b, a = A.model_arrays("acnet-f8b4")
+    A.Model(family=fam, blocks=blocks, kernels=k, biases=b, alphas=a)
+    with pytest.raises(A.Acb200Error):
+        A.Model(family=fam, blocks=blocks, kernels=k[:-1], biases=b, alphas=a)
+    with pytest.raises(A.Acb200Error):
+        A.Model(family=fam, blocks=5, kernels=k, biases=b, alphas=a)
+
+
+class ACImage(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("channels", C.c_int), ("stride", C.c_int), ("element_type", C.c_int),
+                ("ptr", C.c_void_p), ("hptr", C.c_void_p)]
+
+
+class ACProcessor(C.Structure):
+    _fields_ = [("device", C.c_int), ("type", C.c_char_p), ("model", C.c_char_p), ("hptr", C.c_void_p)]
+
+
+def _cimage(lib, w, h, c, t, stride=0):
+    lib.ac_image_alloc.restype = C.POINTER(ACImage)
+    img = lib.ac_image_alloc()
+    img.contents.width, img.contents.height, img.contents.channels, img.contents.element_type, img.contents.stride = w, h, c, t, stride
+    return img
+
+
+def test_c_binding_image_semantics():
+    # reference tests/core/src/ImageTest.cpp: create / stride alignment / from / to / view / clone / ref
+    lib = A.lib()
+    img = _cimage(lib, 5, 3, 3, 1)
+    assert lib.ac_image_create(img) == 0
+    assert img.contents.stride == 16 and img.contents.ptr      # 15-byte line rounded up to 4
+    data = np.arange(45, dtype=np.uint8).reshape(3, 15)
+    src = _cimage(lib, 5, 3, 3, 1)
+    assert lib.ac_image_from(src, data.ctypes.data_as(C.c_void_p)) == 0
+    back = np.zeros((3, 15), np.uint8)
+    assert lib.ac_image_to(src, back.ctypes.data_as(C.c_void_p), 0) == 0
+    assert np.array_equal(back, data)
+    view = _cimage(lib, 0, 0, 0, 0)
+    assert lib.ac_image_view(src, view, 1, 1, 100, 100) == 0           # clipped to the image
+    assert (view.contents.width, view.contents.height, view.contents.stride) == (4, 2, src.contents.stride)
+    assert view.contents.ptr == src.contents.ptr + src.contents.stride + 3
+    clone = _cimage(lib, 0, 0, 0, 0)
+    assert lib.ac_image_clone(view, clone) == 0
+    assert (clone.contents.width, clone.contents.height) == (4, 2) and clone.contents.ptr != view.contents.ptr
+    mapped = _cimage(lib, 15, 3, 1, 1)
+    mapped.contents.ptr = data.ctypes.data
+    assert lib.ac_image_map(mapped) == 0 and mapped.contents.ptr == data.ctypes.data and mapped.contents.stride == 15
+    assert lib.ac_image_ref(None, img) == -22 and lib.ac_image_to(img, None, 0) == -22        # -AC_EINVAL
+    for im in (img, src, view, clone, mapped):
+        lib.ac_image_free(C.byref(im))
+        assert not im
+
+
+def test_c_binding_processor_without_compute():
+    lib = A.lib()
+    lib.ac_processor_alloc.restype = C.POINTER(ACProcessor)
+    lib.ac_processor_error.restype = C.c_char_p
+    lib.ac_processor_type_name.restype = C.c_char_p
+    lib.ac_processor_list_info.restype = C.c_char_p
+    lib.ac_processor_info.restype = C.c_char_p
+    assert lib.ac_processor_ok(None) == -22
+    assert b"CUDA:" in lib.ac_processor_list_info() and lib.ac_processor_info(2).startswith(b"CUDA:")
+    p = lib.ac_processor_alloc()
+    p.contents.type, p.contents.model, p.contents.device = b"cpu", b"acnet-legacy-hdn0", 0
+    assert lib.ac_processor_create(p) == -256        # -AC_EPROCESSOR: no CPU backend, reported not thrown
+    assert b"no CPU backend" in lib.ac_processor_error(p)
+    lib.ac_processor_free(C.byref(p))
+    p = lib.ac_processor_alloc()
+    p.contents.type, p.contents.model, p.contents.device = b"cuda", b"acnet-legacy-hdn0", 0
+    rc = lib.ac_processor_create(p)
+    if A.device_count() == 0:
+        assert rc == -256 and lib.ac_processor_error(p) == b"no CUDA device"      # fails loudly, no fallback
+    else:
+        assert rc == 0 and lib.ac_processor_type_name(p) == b"CUDA" and lib.ac_processor_type(p) == 2
+    lib.ac_processor_free(C.byref(p))
+
+
+def test_pyac_surface():
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "anime4kcpp_b200"))
+    import pyac
+    assert pyac.core.Processor.CUDA == 2 and pyac.core.Processor.CPU == 0 and pyac.core.Processor.OpenCL == 1
+    assert int(pyac.core.RESIZE_CATMULL_ROM) == 1 and int(pyac.core.RESIZE_BILINEAR) == 16 and int(pyac.core.IMREAD_RGBA) == 4
+    names = [m["name"] for m in pyac.specs.ModelList]
+    assert "acnet-legacy-hdn0" in names and "arnet-f8b64" in names and len(names) == 33
+    p = pyac.core.Processor("cpu", 0, "acnet-legacy-hdn0")
+    assert not p.ok() and "CPU" in p.error()
+    with pytest.raises(RuntimeError):
+        p(np.zeros((4, 4), np.uint8))
+    if A.device_count() == 0:
+        q = pyac.core.Processor()            # defaults: auto, 0, acnet-f8b8-hdn
+        assert not q.ok() and q.error() == "no CUDA device"
+
+
+def test_session_without_device_fails_loudly():
+    if A.device_count() == 0:
+        with pytest.raises(A.Acb200Error):
+            A.Session(0)

@@ -1,0 +1,110 @@
+"""CPU suite, part 1: the oracle (oracle/ac_oracle.c) against the golden vectors minted from the compiled
+reference, and -- when oracle/_ref has been built in this container -- against the compiled reference itself."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.npz"))
+GRAY_2X = sorted(k.split("/", 1)[1] for k in GOLD.files if k.startswith("gray_noise_2x/"))
+
+
+@pytest.mark.parametrize("name", GRAY_2X)
+def test_oracle_matches_golden_gray(name):
+    out = O.oracle_process(name, GOLD["in_gray_noise"], 2.0)
+    assert np.array_equal(out, GOLD["gray_noise_2x/" + name])      # bit-exact: same arithmetic, same order
+
+
+@pytest.mark.parametrize("key", sorted(k for k in GOLD.files if "/" in k and not k.startswith("gray_noise_2x/")))
+def test_oracle_matches_golden_other(key):
+    kind, name = key.split("/", 1)
+    src = {"gray_smooth_2x": GOLD["in_gray_smooth"], "rgb_2x": GOLD["in_rgb"], "rgb_4x": GOLD["in_rgb"], "rgba_2x": GOLD["in_rgba"],
+           "gray_4x": GOLD["in_gray_noise"][:20, :24],
+           "gray_f32_2x": GOLD["in_gray_noise"].astype(np.float32) / np.float32(255),
+           "gray_u16_2x": GOLD["in_gray_noise"].astype(np.uint16) * 257}[kind]
+    out = O.oracle_process(name, src, 4.0 if kind.endswith("4x") else 2.0)
+    assert np.array_equal(out, GOLD[key])
+
+
+def test_oracle_colour_conversion_golden():
+    rgb = GOLD["in_rgb"]
+    h, w, _ = rgb.shape
+    y = np.empty((h, w), np.uint8)
+    uv = np.empty((h, w, 2), np.uint8)
+    O.oracle().orc_rgb2yuv(rgb.ctypes.data, w, h, 3, rgb.strides[0], O.U8, y.ctypes.data, y.strides[0], uv.ctypes.data, uv.strides[0])
+    assert np.array_equal(y, GOLD["rgb2yuv_y"]) and np.array_equal(uv, GOLD["rgb2yuv_uv"])
+    back = np.empty_like(rgb)
+    O.oracle().orc_yuv2rgb(y.ctypes.data, y.strides[0], uv.ctypes.data, uv.strides[0], w, h, 3, O.U8, back.ctypes.data, back.strides[0])
+    assert np.array_equal(back, GOLD["yuv2rgb_back"])
+
+
+def test_gray_roundtrip_within_one():
+    # reference tests/core/src/ImageProcessTest.cpp:52-137: gray(100) RGB -> YUV -> RGB stays within +-1
+    rgb = np.full((8, 8, 3), 100, np.uint8)
+    y = np.empty((8, 8), np.uint8)
+    uv = np.empty((8, 8, 2), np.uint8)
+    O.oracle().orc_rgb2yuv(rgb.ctypes.data, 8, 8, 3, rgb.strides[0], O.U8, y.ctypes.data, y.strides[0], uv.ctypes.data, uv.strides[0])
+    back = np.empty_like(rgb)
+    O.oracle().orc_yuv2rgb(y.ctypes.data, y.strides[0], uv.ctypes.data, uv.strides[0], 8, 8, 3, O.U8, back.ctypes.data, back.strides[0])
+    assert np.abs(back.astype(int) - 100).max() <= 1
+
+
+def test_catmull_rom_2x_is_exact_dyadic_kernel():
+    # For an exact 2x upscale the four taps are {-3, 29, 111, -9}/128 and mirror; on a float ramp the
+    # interior must reproduce the closed form exactly, and a constant image must stay constant at the borders (clamp).
+    src = np.arange(16, dtype=np.float32).reshape(1, 16).repeat(4, 0) / np.float32(16)
+    out = np.empty((8, 32), np.float32)
+    assert O.oracle().orc_resize_catmull_rom(src.ctypes.data, 16, 4, 1, src.strides[0], O.F32, out.ctypes.data, 32, 8, out.strides[0]) == 0
+    k = np.array([-3, 29, 111, -9], np.float32) / np.float32(128)
+    for n in range(4, 28):
+        j = n // 2
+        taps = src[0, j - 2:j + 2] if n % 2 == 0 else src[0, j - 1:j + 3]
+        kk = k if n % 2 == 0 else k[::-1]
+        assert abs(out[3, n] - float((taps * kk).sum())) < 1e-6
+    const = np.full((5, 7, 2), 77, np.uint8)
+    o2 = np.empty((20, 28, 2), np.uint8)
+    assert O.oracle().orc_resize_catmull_rom(const.ctypes.data, 7, 5, 2, const.strides[0], O.U8, o2.ctypes.data, 28, 20, o2.strides[0]) == 0
+    assert (o2 == 77).all()
+
+
+def test_model_table_shapes():
+    # reference tests/core/src/ModelTest.cpp:5-34: lengths are self-consistent with the layer structure
+    for name, (fam, blocks, k, b, a) in O.models().items():
+        if fam == O.FAMILY_LEGACY:
+            assert (k.size, b.size, a.size) == (72 + 576 * blocks + 32, 8 * (blocks + 1), 0)
+        else:
+            assert (k.size, b.size, a.size) == (72 + 576 * blocks + 288, 8 * (blocks + 1) + 4, 8 * (blocks + 1))
+    fam, blocks, k, b, a = O.model("arnet-f8b64")
+    assert (k.size, b.size, a.size) == (74152, 8 * 130 + 4, 8 * 65)
+
+
+def test_canonical_model_strings():
+    # core/src/processor/Processor.cpp:26-187
+    assert O.canonical("acnet-hdn") == "acnet-f8b8-hdn"           # hdn without legacy is ACNet<8> B8_HDN
+    assert O.canonical("ACNet-Legacy-HDN2") == "acnet-legacy-hdn2"
+    assert O.canonical("something-else") == "acnet-legacy-gan"    # unknown strings fall back to legacy GAN
+    assert O.canonical("arnet") == "arnet-f8b8"
+    assert O.canonical("acnet-f8b18-box") == "acnet-f8b18-box"
+
+
+@pytest.mark.skipif(O.ref() is None, reason="compiled reference (oracle/_ref) only exists in the build container")
+@pytest.mark.parametrize("name", ["acnet-legacy-hdn0", "acnet-f8b4-hdn", "acnet-f8b18-box", "arnet-f8b16"])
+@pytest.mark.parametrize("shape", [(3, 3, 1), (17, 31, 1), (33, 47, 3), (21, 19, 4)])
+def test_oracle_matches_compiled_reference(name, shape):
+    h, w, c = shape
+    img = O.noise_u8(h, w, c, seed=h * 100 + w)
+    for factor in (2.0, 4.0):
+        assert np.array_equal(O.oracle_process(name, img, factor), O.ref_process(name, img, factor, arch=1))
+    f = img.astype(np.float32) / np.float32(255)
+    assert np.array_equal(O.oracle_process(name, f, 2.0), O.ref_process(name, f, 2.0, arch=1))
+
+
+@pytest.mark.skipif(O.ref() is None, reason="compiled reference (oracle/_ref) only exists in the build container")
+def test_reference_isa_noise_floor():
+    # the reference's own auto-ISA backend vs its Generic backend: <= 1 LSB, >= 99.9 % exact (SURVEY finding 3)
+    img = O.noise_u8(128, 160, 1, seed=5)
+    a, b = O.ref_process("acnet-legacy-hdn0", img, 2.0, arch=0), O.ref_process("acnet-legacy-hdn0", img, 2.0, arch=1)
+    mx, exact = O.compare_u8(a, b)
+    assert mx <= 1 and exact >= 0.999

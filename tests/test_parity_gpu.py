@@ -1,0 +1,191 @@
+"""GPU suite: the CUDA path through the C-ABI against the CPU oracle (same seeded inputs) and against the golden
+vectors minted from the compiled reference.  Bars (BASELINE.json north_star): 8/16-bit output <= 1 LSB per channel and
+>= 99.9 % of samples bit-exact; float32 max abs error <= 1e-3."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import anime4kcpp_b200 as A
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.npz"))
+ALL_REAL = sorted(O.models().keys())
+ARNETS = ["arnet-f8b8", "arnet-f8b16-hdn", "arnet-f8b32-box", "arnet-f8b64-box-hdn"]
+ENGINES = [0]
+
+LSB_MAX = 1
+EXACT_MIN = 0.999
+F32_TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def session():
+    assert A.device_count() > 0, "GPU tests need a CUDA device (no CPU fallback exists)"
+    return A.Session(0)
+
+
+_models = {}
+
+
+def gpu_model(name):
+    if name not in _models:
+        _models[name] = A.Model(name)
+    return _models[name]
+
+
+def check_int(out, want):
+    mx, exact = O.compare_u8(out, want)
+    assert mx <= LSB_MAX and exact >= EXACT_MIN, "max diff %d LSB, %.4f %% exact" % (mx, 100 * exact)
+    return mx, exact
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name", ALL_REAL + ARNETS)
+def test_golden_gray_2x(session, name, engine):
+    session.set_engine(engine)
+    out = session.process_host(gpu_model(name), GOLD["in_gray_noise"], 2.0)
+    check_int(out, GOLD["gray_noise_2x/" + name])
+
+
+@pytest.mark.parametrize("key", sorted(k for k in GOLD.files if "/" in k and not k.startswith("gray_noise_2x/")))
+def test_golden_other(session, key):
+    kind, name = key.split("/", 1)
+    src = {"gray_smooth_2x": GOLD["in_gray_smooth"], "rgb_2x": GOLD["in_rgb"], "rgb_4x": GOLD["in_rgb"], "rgba_2x": GOLD["in_rgba"],
+           "gray_4x": GOLD["in_gray_noise"][:20, :24],
+           "gray_f32_2x": GOLD["in_gray_noise"].astype(np.float32) / np.float32(255),
+           "gray_u16_2x": GOLD["in_gray_noise"].astype(np.uint16) * 257}[kind]
+    out = session.process_host(gpu_model(name), src, 4.0 if kind.endswith("4x") else 2.0)
+    if out.dtype == np.float32:
+        assert float(np.abs(out - GOLD[key]).max()) <= F32_TOL
+    else:
+        check_int(out, GOLD[key])
+
+
+@pytest.mark.parametrize("name", ["acnet-legacy-hdn0", "acnet-legacy-gan", "acnet-f8b4", "acnet-f8b8-hdn", "acnet-f8b18-box-hdn", "arnet-f8b8", "arnet-f8b16"])
+@pytest.mark.parametrize("shape", [(3, 3), (1, 7), (9, 1), (17, 31), (40, 40), (41, 39), (64, 64), (97, 131), (255, 257)])
+def test_odd_sizes_gray_vs_oracle(session, name, shape):
+    img = O.noise_u8(shape[0], shape[1], 1, seed=shape[0] * 1000 + shape[1])
+    check_int(session.process_host(gpu_model(name), img, 2.0), O.oracle_process(name, img, 2.0))
+
+
+@pytest.mark.parametrize("name", ["acnet-legacy-hdn1", "acnet-f8b8", "arnet-f8b8-box"])
+@pytest.mark.parametrize("c", [3, 4])
+@pytest.mark.parametrize("factor", [2.0, 4.0])
+def test_colour_vs_oracle(session, name, c, factor):
+    img = O.noise_u8(45, 61, c, seed=c * 10 + int(factor))
+    check_int(session.process_host(gpu_model(name), img, factor), O.oracle_process(name, img, factor))
+    f = img.astype(np.float32) / np.float32(255)
+    assert float(np.abs(session.process_host(gpu_model(name), f, factor) - O.oracle_process(name, f, factor)).max()) <= F32_TOL
+    u = img.astype(np.uint16) * 257
+    check_int(session.process_host(gpu_model(name), u, factor), O.oracle_process(name, u, factor))
+
+
+@pytest.mark.parametrize("value", [0, 128, 255])
+def test_constant_and_checkerboard(session, value):
+    # saturation and clamp-to-edge checks (SURVEY 8d iii)
+    img = np.full((50, 70), value, np.uint8)
+    for name in ("acnet-legacy-hdn0", "acnet-f8b8-hdn"):
+        check_int(session.process_host(gpu_model(name), img, 2.0), O.oracle_process(name, img, 2.0))
+    yy, xx = np.mgrid[0:50, 0:70]
+    cb = (((yy + xx) & 1) * 255).astype(np.uint8)
+    check_int(session.process_host(gpu_model("acnet-legacy-hdn0"), cb, 2.0), O.oracle_process("acnet-legacy-hdn0", cb, 2.0))
+
+
+def test_strided_view_input_and_preallocated_dst(session):
+    # filter frontends hand mapped, padded planes (filter/vapoursynth/src/Filter.cpp:32-42); a non-empty dst is written in place
+    big = O.noise_u8(80, 128, 1, seed=3)
+    view = big[7:60, 13:90]
+    assert not view.flags["C_CONTIGUOUS"]
+    out_big = np.zeros((130, 256), np.uint8)
+    out = out_big[5:5 + 106, 11:11 + 154]
+    rc = A.lib().acb200_process_host(session.handle, gpu_model("acnet-legacy-hdn0").handle, view.ctypes.data, 77, 53, 1, view.strides[0], A.UINT8, 2.0,
+                                     out.ctypes.data, out.strides[0])
+    assert rc == 0
+    check_int(out, O.oracle_process("acnet-legacy-hdn0", np.ascontiguousarray(view), 2.0))
+    assert out_big[:5].sum() == 0 and out_big[:, :11].sum() == 0 and out_big[:, 11 + 154:].sum() == 0     # nothing outside the view was touched
+
+
+def test_colour_conversion_bit_exact(session):
+    rgb = GOLD["in_rgb"]
+    y, uv = session.rgb2yuv(rgb)
+    assert np.array_equal(y, GOLD["rgb2yuv_y"]) and np.array_equal(uv, GOLD["rgb2yuv_uv"])
+    assert np.array_equal(session.yuv2rgb(y, uv), GOLD["yuv2rgb_back"])
+    rgba = O.noise_u8(31, 37, 4, seed=8)
+    yo = np.empty((31, 37), np.uint8)
+    uvo = np.empty((31, 37, 3), np.uint8)
+    O.oracle().orc_rgb2yuv(rgba.ctypes.data, 37, 31, 4, rgba.strides[0], O.U8, yo.ctypes.data, yo.strides[0], uvo.ctypes.data, uvo.strides[0])
+    y, uva = session.rgb2yuv(rgba)
+    assert np.array_equal(y, yo) and np.array_equal(uva, uvo)
+    back = np.empty_like(rgba)
+    O.oracle().orc_yuv2rgb(yo.ctypes.data, yo.strides[0], uvo.ctypes.data, uvo.strides[0], 37, 31, 4, O.U8, back.ctypes.data, back.strides[0])
+    assert np.array_equal(session.yuv2rgb(y, uva), back)
+
+
+@pytest.mark.parametrize("scale", [2, 4])
+@pytest.mark.parametrize("c", [1, 2, 3])
+def test_catmull_rom_resize_bit_exact_vs_oracle(session, scale, c):
+    img = O.noise_u8(23, 29, c, seed=scale * 7 + c)
+    want = np.empty((23 * scale, 29 * scale) + (() if c == 1 else (c,)), np.uint8)
+    assert O.oracle().orc_resize_catmull_rom(img.ctypes.data, 29, 23, c, img.strides[0], O.U8, want.ctypes.data, 29 * scale, 23 * scale, want.strides[0]) == 0
+    assert np.array_equal(session.resize_catmull_rom(img, 29 * scale, 23 * scale), want)
+
+
+def test_full_size_1080p_properties(session):
+    # BASELINE config size: the oracle is too slow for every model here, so check one model against the oracle on the
+    # full frame and use size-independent properties for the rest: tile seams (a crop with full halo reproduces the
+    # whole-frame result bit for bit) and determinism.
+    img = O.smooth_u8(1080, 1920, 1, seed=11)
+    m = gpu_model("acnet-legacy-hdn0")
+    full = session.process_host(m, img, 2.0)
+    assert full.shape == (2160, 3840)
+    check_int(full, O.oracle_process("acnet-legacy-hdn0", img, 2.0))
+    assert np.array_equal(full, session.process_host(m, img, 2.0))
+    halo = 9
+    y0, y1, x0, x1 = 300, 420, 700, 860
+    crop = img[y0 - halo:y1 + halo, x0 - halo:x1 + halo]
+    sub = session.process_host(m, np.ascontiguousarray(crop), 2.0)
+    assert np.array_equal(sub[2 * halo:-2 * halo, 2 * halo:-2 * halo], full[2 * y0:2 * y1, 2 * x0:2 * x1])
+
+
+def test_device_resident_path_matches_host_path(session):
+    import torch
+    img = O.noise_u8(120, 200, 3, seed=21)
+    m = gpu_model("acnet-f8b8-hdn")
+    want = session.process_host(m, img, 2.0)
+    d = torch.from_numpy(img).cuda()
+    out = session.process_device(m, d, 2.0)
+    session.sync()
+    assert np.array_equal(out.cpu().numpy(), want)
+
+
+def test_processor_api_threads_and_errors():
+    # one processor shared by concurrent callers (tools/benchmark/src/Benchmark.cpp:58-62): per-thread sessions
+    import threading
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "anime4kcpp_b200"))
+    import pyac
+    p = pyac.core.Processor("cuda", 0, "acnet-legacy-hdn0")
+    assert p.ok() and p.error() == "NO ERROR" and "NVIDIA" in p.name()
+    imgs = [O.noise_u8(64, 80, 1, seed=s) for s in range(6)]
+    outs = [None] * 6
+
+    def work(i):
+        outs[i] = p(imgs[i], 2.0)
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(6)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    for i in range(6):
+        check_int(outs[i], O.oracle_process("acnet-legacy-hdn0", imgs[i], 2.0))
+    p.process(imgs[0], 3.0)                     # non power-of-two factors are outside the accelerated path
+    assert not p.ok() and "power of two" in p.error()
+    out4 = p.process(np.ascontiguousarray(imgs[0][:16, :16]), 4.0)      # reference ProcessorTest.cpp:93-104: 4x dims
+    assert out4.shape == (64, 64)
+    auto = pyac.core.Processor("auto", -1, "acnet-hdn")
+    assert auto.ok()
+    rgb = O.noise_u8(32, 32, 3, seed=2)
+    check_int(auto(rgb), O.oracle_process("acnet-f8b8-hdn", rgb, 2.0))
+    assert pyac.core.Processor.InfoList[1].startswith("CUDA:\n  [0] ")
