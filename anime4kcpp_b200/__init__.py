@@ -172,6 +172,8 @@ class Session:
         tcode = {torch.uint8: UINT8, torch.int16: UINT16, torch.float16: FLOAT16, torch.float32: FLOAT32}[src.dtype]
         if out is None:
             out = torch.empty((int(h * factor), int(w * factor)) + (() if src.dim() == 2 else (c,)), dtype=src.dtype, device=src.device)
+        if stream == 0:
+            stream = 1      # cudaStreamLegacy: NULL means "the session's own stream" in the C-ABI
         rc = lib().acb200_process_device(self.handle, model.handle, src.data_ptr(), w, h, c, src.stride(0) * src.element_size(), tcode,
                                          float(factor), out.data_ptr(), out.stride(0) * out.element_size(), stream)
         _check(rc, self.handle)

@@ -1,4 +1,4 @@
-// fp32 CUDA-core (FFMA) engine of the fused luma network.
+// fp32 CUDA-core (FFMA) engine of the fused luma network -- the EXACT engine.
 //
 // One CTA computes a T x T tile of the input-resolution luma through a *segment* of the network
 // with every intermediate 8-channel feature map held in shared memory:
@@ -10,19 +10,24 @@
 //
 // What it replaces in the reference: core/src/processor/cuda/Kernel.cu:246-514 (five per-layer kernel
 // templates, one launch + one fp16 HBM round trip per layer) and the layer sequencing of
-// core/src/processor/cuda/CUDAProcessor.cpp:383-422, :451-490, :520-566.  Arithmetic follows the CPU
-// processor (the parity oracle): fp32 activations everywhere (core/internal/.../CPU/Common.hpp:116-393),
-// clamp-to-edge borders at every layer (Common.hpp:121-141), weights `[cout][tap][cin]`
-// (CPU/Generic.hpp:42-46).
+// core/src/processor/cuda/CUDAProcessor.cpp:383-422, :451-490, :520-566.
+//
+// Arithmetic: bit-identical to the reference CPU processor's auto-ISA backend on FMA-capable x86
+// (OpImplX86SIMD256<true>, core/internal/AC/Core/Internal/Processor/CPU/X86/AVX.hpp:24-146, which the AVX512
+// backend also executes for these 8-channel layers, X86/AVX512.hpp:116).  Per output channel: eight FMA chains
+// (one per input channel) over the nine taps in tap order, reduced by the hsum tree
+// ((s0+s4)+(s2+s6))+((s1+s5)+(s3+s7)), added onto the bias; `v*scale + id` and `sat*max + 0.5f` are single FMAs
+// exactly where g++ contracts them in that backend's translation unit.  fp32 activations everywhere
+// (CPU/Common.hpp:116-393), clamp-to-edge borders at every layer (Common.hpp:121-141), weights `[cout][tap][cin]`.
 //
 // Design notes
 //  * Weights ride in the kernel parameter block (__grid_constant__, constant bank 0).  All layers of a
-//    segment are unrolled at compile time, so every weight is a compile-time constant-bank offset and
-//    each MAC is a single `FFMA Rd, Ra, c[0x0][imm], Rd` -- no weight loads, no weight registers.
+//    segment are unrolled at compile time, so every weight sits at a compile-time constant-bank offset and
+//    reaches the FFMA through a uniform register (ULDC) or an LDC -- no shared-memory traffic for weights.
 //  * Feature maps are stored as two float4 planes (channels 0-3 / 4-7) of a fixed 56x56 frame, so a
 //    warp reading 32 consecutive pixels issues conflict-free LDS.128.
-//  * Each thread produces 2 vertically adjacent pixels x 8 output channels (16 accumulators) and
-//    re-uses each loaded input row for both output rows: 24 LDS.128 per 1152 FFMA.
+//  * Each thread produces FFMA_P vertically adjacent pixels x 8 output channels with its (P+2) x 3 x 8 input
+//    window held in registers, so every weight fetched feeds P FFMAs and every input is loaded once per layer.
 //  * Layer l's output region is the frame shrunk by l; positions outside the image are never
 //    computed -- reads clamp their coordinates to the image instead (replicate padding).
 #pragma once
@@ -92,6 +97,42 @@ namespace acb
         int ix0, ix1, iy0, iy1; // image bounds in frame coordinates (inclusive)
     };
 
+#ifndef ACB_FFMA_P
+#define ACB_FFMA_P 4
+#endif
+    constexpr int FFMA_P = ACB_FFMA_P;   // vertically adjacent pixels per thread
+
+    // ((s0+s4)+(s2+s6))+((s1+s5)+(s3+s7)): OpImplX86SIMD256::hsum, X86/AVX.hpp:24-30
+    __device__ __forceinline__ float hsum8(const float (&s)[8])
+    {
+        return __fadd_rn(__fadd_rn(__fadd_rn(s[0], s[4]), __fadd_rn(s[2], s[6])), __fadd_rn(__fadd_rn(s[1], s[5]), __fadd_rn(s[3], s[7])));
+    }
+    __device__ __forceinline__ float prelu(float v, float alpha) { return fmaf(alpha, fminf(v, 0.0f), fmaxf(v, 0.0f)); }
+
+    // fromFloat as the network tails round it in the FMA backend: one FMA for `sat*max + 0.5f`
+    __device__ __forceinline__ void net_store2(void* row, int x, int type, float v0, float v1, bool aligned)
+    {
+        switch (type)
+        {
+        case ACB200_UINT8:
+        {
+            const uint8_t q0 = static_cast<uint8_t>(fmaf(sat01(v0), 255.0f, 0.5f)), q1 = static_cast<uint8_t>(fmaf(sat01(v1), 255.0f, 0.5f));
+            if (aligned) *reinterpret_cast<uchar2*>(static_cast<uint8_t*>(row) + x) = make_uchar2(q0, q1);
+            else { static_cast<uint8_t*>(row)[x] = q0; static_cast<uint8_t*>(row)[x + 1] = q1; }
+            return;
+        }
+        case ACB200_UINT16:
+        {
+            const uint16_t q0 = static_cast<uint16_t>(fmaf(sat01(v0), 65535.0f, 0.5f)), q1 = static_cast<uint16_t>(fmaf(sat01(v1), 65535.0f, 0.5f));
+            if (aligned) *reinterpret_cast<ushort2*>(static_cast<uint16_t*>(row) + x) = make_ushort2(q0, q1);
+            else { static_cast<uint16_t*>(row)[x] = q0; static_cast<uint16_t*>(row)[x + 1] = q1; }
+            return;
+        }
+        default:
+            store_elem2(row, x, type, v0, v1, aligned);
+        }
+    }
+
     // ---- 1->8 head conv from the luma tile: Common.hpp:166-197 ------------------------------------
     template<int ACT, int KOFF, int BOFF, int AOFF, class P>
     __device__ __forceinline__ void head_layer(const P& prm, const float* __restrict__ luma, float4* __restrict__ out, const TileGeom& g)
@@ -110,9 +151,11 @@ namespace acb
 #pragma unroll
             for (int co = 0; co < 8; co++)
             {
-                float s = prm.b[BOFF + co];
+                // conv_cin1<8,9>, X86/AVX.hpp:95-124: taps 0-7 as products through the hsum tree, tap 8 as a scalar FMA, bias last
+                float q[8];
 #pragma unroll
-                for (int p = 0; p < 9; p++) s = fmaf(r[p], prm.k[KOFF + co * 9 + p], s);
+                for (int p = 0; p < 8; p++) q[p] = __fmul_rn(r[p], prm.k[KOFF + co * 9 + p]);
+                float s = __fadd_rn(fmaf(r[8], prm.k[KOFF + co * 9 + 8], hsum8(q)), prm.b[BOFF + co]);
                 if (ACT == ACT_RELU) s = fmaxf(s, 0.0f);
                 else if (ACT == ACT_PRELU) s = fmaf(prm.a[AOFF + co], fminf(s, 0.0f), fmaxf(s, 0.0f));
                 v[co] = s;
@@ -122,183 +165,161 @@ namespace acb
         }
     }
 
-    // 2 vertically adjacent pixels x COUT channels of a 3x3 conv over an 8-ch map, accumulators only
-    template<int COUT, int KOFF, int BOFF, class P>
-    __device__ __forceinline__ void conv_pair(const P& prm, const float4* __restrict__ in, const TileGeom& g, int x, int y, float (&acc)[2][COUT])
+    // FFMA_P vertically adjacent pixels x COUT channels of a 3x3 conv over an 8-ch map,
+    // OpImplX86SIMD256<true>::conv<8,COUT,9>, X86/AVX.hpp:32-58,126-146.  The output-channel loop stays rolled
+    // (runtime `co`) so ptxas cannot hoist a whole layer's worth of constant loads into the 63 uniform registers
+    // and spill them.  `emit(co, v)` receives the FFMA_P finished sums (bias included) of output channel `co`.
+    template<int COUT, int KOFF, int BOFF, class P, class Emit>
+    __device__ __forceinline__ void conv_cols_rolled(const P& prm, const float4* __restrict__ in, const TileGeom& g, int x, int y, Emit&& emit)
     {
-#pragma unroll
-        for (int p = 0; p < 2; p++)
-#pragma unroll
-            for (int co = 0; co < COUT; co++) acc[p][co] = prm.b[BOFF + co];
+        float r[FFMA_P + 2][3][8];
         const int cx[3] = { clampi(x - 1, g.ix0, g.ix1), x, clampi(x + 1, g.ix0, g.ix1) };
 #pragma unroll
-        for (int iy = 0; iy < 4; iy++)
+        for (int iy = 0; iy < FFMA_P + 2; iy++)
         {
             const int ry = clampi(y - 1 + iy, g.iy0, g.iy1) * FT;
 #pragma unroll
             for (int dx = 0; dx < 3; dx++)
             {
                 const float4 v0 = in[ry + cx[dx]], v1 = in[FT * FT + ry + cx[dx]];
-                const float a[8] = { v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w };
-#pragma unroll
-                for (int p = 0; p < 2; p++)
-                {
-                    const int dy = iy - p;
-                    if (dy < 0 || dy > 2) continue;
-#pragma unroll
-                    for (int co = 0; co < COUT; co++)
-#pragma unroll
-                        for (int ci = 0; ci < 8; ci++)
-                            acc[p][co] = fmaf(a[ci], prm.k[KOFF + co * 72 + (dy * 3 + dx) * 8 + ci], acc[p][co]);
-                }
+                r[iy][dx][0] = v0.x; r[iy][dx][1] = v0.y; r[iy][dx][2] = v0.z; r[iy][dx][3] = v0.w;
+                r[iy][dx][4] = v1.x; r[iy][dx][5] = v1.y; r[iy][dx][6] = v1.z; r[iy][dx][7] = v1.w;
             }
+        }
+#pragma unroll 1
+        for (int co = 0; co < COUT; co++)
+        {
+            const float* __restrict__ wk = prm.k + KOFF + co * 72;
+            float s[FFMA_P][8];
+#pragma unroll
+            for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+                for (int dx = 0; dx < 3; dx++)
+#pragma unroll
+                    for (int ci = 0; ci < 8; ci++)
+                    {
+                        const float wgt = wk[(dy * 3 + dx) * 8 + ci];
+#pragma unroll
+                        for (int p = 0; p < FFMA_P; p++)
+                            s[p][ci] = fmaf(r[p + dy][dx][ci], wgt, (dy == 0 && dx == 0) ? 0.0f : s[p][ci]);
+                    }
+            float v[FFMA_P];
+            const float bias = prm.b[BOFF + co];
+#pragma unroll
+            for (int p = 0; p < FFMA_P; p++) v[p] = __fadd_rn(bias, hsum8(s[p]));
+            emit(co, v);
         }
     }
 
     // ---- 8->8 body conv: Common.hpp:116-164 ---------------------------------------------------------
-    // RES: `v*0.2 + out_old` in place (ARNet residual, CPUProcessor.cpp:1479,1483), rounded as mul then add.
-    template<int L, int ACT, bool RES, int KOFF, int BOFF, int AOFF, class P>
+    // RES: `v*0.2 + out_old` in place (ARNet residual, CPUProcessor.cpp:1479,1483), one FMA as in the FMA backend.
+    template<int L, int ACT, bool RES, int KOFF, int BOFF, int AOFF, int COUT = 8, class P>
     __device__ __forceinline__ void conv_layer(const P& prm, const float4* __restrict__ in, float4* __restrict__ out, const TileGeom& g)
     {
         const int xa = max(L, g.ix0), xb = min(FT - L, g.ix1 + 1), ya = max(L, g.iy0), yb = min(FT - L, g.iy1 + 1);
-        const int ncols = xb - xa, n = ncols * ((yb - ya + 1) >> 1);
+        const int ncols = xb - xa, n = ncols * ((yb - ya + FFMA_P - 1) / FFMA_P);
+        float* __restrict__ outf = reinterpret_cast<float*>(out);
         for (int i = threadIdx.x; i < n; i += FFMA_THREADS)
         {
-            const int x = xa + i % ncols, y = ya + 2 * (i / ncols);
-            float acc[2][8];
-            conv_pair<8, KOFF, BOFF>(prm, in, g, x, y, acc);
+            const int x = xa + i % ncols, y = ya + FFMA_P * (i / ncols);
+            conv_cols_rolled<COUT, KOFF, BOFF>(prm, in, g, x, y, [&](const int co, const float (&v)[FFMA_P]) {
+                // channel co lives in plane co/4, component co%4 of the float4 at the pixel
+                float* dst = outf + ((co >> 2) * FT * FT + y * FT + x) * 4 + (co & 3);
+                float alpha = 0.0f;
+                if (ACT == ACT_PRELU) alpha = prm.a[AOFF + co];
 #pragma unroll
-            for (int p = 0; p < 2; p++)
-            {
-                if (y + p >= yb) break;
-                const int o = (y + p) * FT + x;
-                float v[8];
-#pragma unroll
-                for (int co = 0; co < 8; co++)
+                for (int p = 0; p < FFMA_P; p++)
                 {
-                    float s = acc[p][co];
+                    if (y + p >= yb) break;
+                    float s = v[p];
                     if (ACT == ACT_RELU) s = fmaxf(s, 0.0f);
-                    else if (ACT == ACT_PRELU) s = fmaf(prm.a[AOFF + co], fminf(s, 0.0f), fmaxf(s, 0.0f));
-                    v[co] = s;
+                    else if (ACT == ACT_PRELU) s = prelu(s, alpha);
+                    if (RES) s = fmaf(s, 0.2f, dst[p * FT * 4]);
+                    dst[p * FT * 4] = s;
                 }
-                if (RES)
-                {
-                    const float4 r0 = out[o], r1 = out[FT * FT + o];
-                    const float id[8] = { r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w };
-#pragma unroll
-                    for (int co = 0; co < 8; co++) v[co] = __fadd_rn(__fmul_rn(v[co], 0.2f), id[co]);
-                }
-                out[o] = make_float4(v[0], v[1], v[2], v[3]);
-                out[FT * FT + o] = make_float4(v[4], v[5], v[6], v[7]);
-            }
+            });
         }
     }
 
-    // ---- ARNet end of body: conv3x3 *0.2 + x, then 1x1 + bias, PReLU, + feat: Common.hpp:223-288 -----
-    template<int L, int KOFF, int BOFF, int AOFF, class P>
-    __device__ __forceinline__ void arnet_end_layer(const P& prm, const float4* __restrict__ in, float4* __restrict__ out, const TileGeom& g)
+    // ---- ARNet end of body: conv3x3 *0.2 + x (done by conv_layer<IDENTITY, RES>), then this pointwise pass:
+    //      1x1 + bias, PReLU, + feat: Common.hpp:223-288, conv<8,8,1> in X86/AVX.hpp order --------------------------
+    template<int L, int KOFF1, int BOFF1, int AOFF, class P>
+    __device__ __forceinline__ void arnet_fuse_pass(const P& prm, float4* __restrict__ buf, const TileGeom& g)
     {
         const int xa = max(L, g.ix0), xb = min(FT - L, g.ix1 + 1), ya = max(L, g.iy0), yb = min(FT - L, g.iy1 + 1);
-        const int ncols = xb - xa, n = ncols * ((yb - ya + 1) >> 1);
+        const int ncols = xb - xa, n = ncols * (yb - ya);
         for (int i = threadIdx.x; i < n; i += FFMA_THREADS)
         {
-            const int x = xa + i % ncols, y = ya + 2 * (i / ncols);
-            float acc[2][8];
-            conv_pair<8, KOFF, BOFF>(prm, in, g, x, y, acc);
+            const int x = xa + i % ncols, y = ya + i / ncols, o = y * FT + x;
+            const float4 t0 = buf[o], t1 = buf[FT * FT + o];
+            const float t[8] = { t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w };
+            const float* f = prm.feat_in + (static_cast<size_t>(g.oy + y) * prm.w + (g.ox + x)) * 8;
+            const float4 f0 = *reinterpret_cast<const float4*>(f), f1 = *reinterpret_cast<const float4*>(f + 4);
+            const float ft[8] = { f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w };
+            float v[8];
 #pragma unroll
-            for (int p = 0; p < 2; p++)
+            for (int co = 0; co < 8; co++)
             {
-                if (y + p >= yb) break;
-                const int o = (y + p) * FT + x;
-                const float4 r0 = out[o], r1 = out[FT * FT + o];
-                const float id[8] = { r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w };
-                float t[8], v[8];
+                float q[8];
 #pragma unroll
-                for (int c = 0; c < 8; c++) t[c] = __fadd_rn(__fmul_rn(acc[p][c], 0.2f), id[c]);
-                const float* f = prm.feat_in + (static_cast<size_t>(g.oy + y + p) * prm.w + (g.ox + x)) * 8;
-                const float4 f0 = *reinterpret_cast<const float4*>(f), f1 = *reinterpret_cast<const float4*>(f + 4);
-                const float ft[8] = { f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w };
-#pragma unroll
-                for (int co = 0; co < 8; co++)
-                {
-                    float s = prm.b[BOFF + 8 + co];
-#pragma unroll
-                    for (int ci = 0; ci < 8; ci++) s = fmaf(t[ci], prm.k[KOFF + 576 + co * 8 + ci], s);
-                    s = fmaf(prm.a[AOFF + co], fminf(s, 0.0f), fmaxf(s, 0.0f));
-                    v[co] = __fadd_rn(s, ft[co]);
-                }
-                out[o] = make_float4(v[0], v[1], v[2], v[3]);
-                out[FT * FT + o] = make_float4(v[4], v[5], v[6], v[7]);
+                for (int ci = 0; ci < 8; ci++) q[ci] = __fmul_rn(t[ci], prm.k[KOFF1 + co * 8 + ci]);
+                v[co] = __fadd_rn(prelu(__fadd_rn(prm.b[BOFF1 + co], hsum8(q)), prm.a[AOFF + co]), ft[co]);
             }
+            buf[o] = make_float4(v[0], v[1], v[2], v[3]);
+            buf[FT * FT + o] = make_float4(v[4], v[5], v[6], v[7]);
         }
     }
 
-    // ---- ACNetLegacy tail: conv3x3 8->8 + ReLU, 2x2 stride-2 deconv 8->1: Common.hpp:344-393 ---------
-    template<int L, int KOFF, int BOFF, class P>
-    __device__ __forceinline__ void tail_deconv_layer(const P& prm, const float4* __restrict__ in, const TileGeom& g)
+    // ---- ACNetLegacy tail after its conv3x3 + ReLU: 2x2 stride-2 deconv 8->1, Common.hpp:344-393; dot<8> in
+    //      X86/AVX.hpp:61-90 order (products through the hsum tree) --------------------------------------------------
+    template<int L, int KOFF2, class P>
+    __device__ __forceinline__ void deconv_pass(const P& prm, const float4* __restrict__ in, const TileGeom& g)
     {
         const int xa = max(L, g.ix0), xb = min(FT - L, g.ix1 + 1), ya = max(L, g.iy0), yb = min(FT - L, g.iy1 + 1);
-        const int ncols = xb - xa, n = ncols * ((yb - ya + 1) >> 1);
+        const int ncols = xb - xa, n = ncols * (yb - ya);
         const int es = prm.type & 0xff;
         const bool aligned = ((reinterpret_cast<uintptr_t>(prm.dst) | static_cast<uintptr_t>(prm.dst_pitch)) & (2 * es - 1)) == 0;
         for (int i = threadIdx.x; i < n; i += FFMA_THREADS)
         {
-            const int x = xa + i % ncols, y = ya + 2 * (i / ncols);
-            float acc[2][8];
-            conv_pair<8, KOFF, BOFF>(prm, in, g, x, y, acc);
+            const int x = xa + i % ncols, y = ya + i / ncols, o = y * FT + x;
+            const float4 t0 = in[o], t1 = in[FT * FT + o];
+            const float t[8] = { t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w };
+            const int gx = g.ox + x, gy = g.oy + y;
 #pragma unroll
-            for (int p = 0; p < 2; p++)
+            for (int dy = 0; dy < 2; dy++)
             {
-                if (y + p >= yb) break;
-                float t[8];
+                float ov[2];
 #pragma unroll
-                for (int c = 0; c < 8; c++) t[c] = fmaxf(acc[p][c], 0.0f);
-                const int gx = g.ox + x, gy = g.oy + y + p;
-#pragma unroll
-                for (int dy = 0; dy < 2; dy++)
+                for (int dx = 0; dx < 2; dx++)
                 {
-                    float o[2];
+                    float q[8];
 #pragma unroll
-                    for (int dx = 0; dx < 2; dx++)
-                    {
-                        float s = 0.0f;
-#pragma unroll
-                        for (int c = 0; c < 8; c++) s = fmaf(t[c], prm.k[KOFF + 576 + (dy * 2 + dx) * 8 + c], s);
-                        o[dx] = s;
-                    }
-                    void* row = static_cast<uint8_t*>(prm.dst) + static_cast<size_t>(2 * gy + dy) * prm.dst_pitch;
-                    store_elem2(row, 2 * gx, prm.type, o[0], o[1], aligned);
+                    for (int c = 0; c < 8; c++) q[c] = __fmul_rn(t[c], prm.k[KOFF2 + (dy * 2 + dx) * 8 + c]);
+                    ov[dx] = hsum8(q);
                 }
+                void* row = static_cast<uint8_t*>(prm.dst) + static_cast<size_t>(2 * gy + dy) * prm.dst_pitch;
+                net_store2(row, 2 * gx, prm.type, ov[0], ov[1], aligned);
             }
         }
     }
 
-    // ---- ACNet / ARNet tail: conv3x3 8->4, + nearest-upsampled input luma, pixel shuffle: Common.hpp:290-342
-    template<int L, int KOFF, int BOFF, class P>
-    __device__ __forceinline__ void tail_shuffle_layer(const P& prm, const float4* __restrict__ in, const float* __restrict__ luma, const TileGeom& g)
+    // ---- ACNet / ARNet tail after its conv3x3 8->4: + nearest-upsampled input luma, pixel shuffle: Common.hpp:290-342
+    template<int L, class P>
+    __device__ __forceinline__ void shuffle_pass(const P& prm, const float4* __restrict__ in, const float* __restrict__ luma, const TileGeom& g)
     {
         const int xa = max(L, g.ix0), xb = min(FT - L, g.ix1 + 1), ya = max(L, g.iy0), yb = min(FT - L, g.iy1 + 1);
-        const int ncols = xb - xa, n = ncols * ((yb - ya + 1) >> 1);
+        const int ncols = xb - xa, n = ncols * (yb - ya);
         const int es = prm.type & 0xff;
         const bool aligned = ((reinterpret_cast<uintptr_t>(prm.dst) | static_cast<uintptr_t>(prm.dst_pitch)) & (2 * es - 1)) == 0;
         for (int i = threadIdx.x; i < n; i += FFMA_THREADS)
         {
-            const int x = xa + i % ncols, y = ya + 2 * (i / ncols);
-            float acc[2][4];
-            conv_pair<4, KOFF, BOFF>(prm, in, g, x, y, acc);
-#pragma unroll
-            for (int p = 0; p < 2; p++)
-            {
-                if (y + p >= yb) break;
-                const float id = luma[(y + p + 1) * LT + x + 1];
-                const int gx = g.ox + x, gy = g.oy + y + p;
-#pragma unroll
-                for (int dy = 0; dy < 2; dy++)
-                {
-                    void* row = static_cast<uint8_t*>(prm.dst) + static_cast<size_t>(2 * gy + dy) * prm.dst_pitch;
-                    store_elem2(row, 2 * gx, prm.type, __fadd_rn(acc[p][dy * 2], id), __fadd_rn(acc[p][dy * 2 + 1], id), aligned);
-                }
-            }
+            const int x = xa + i % ncols, y = ya + i / ncols;
+            const float4 v = in[y * FT + x];
+            const float id = luma[(y + 1) * LT + x + 1];
+            const int gx = g.ox + x, gy = g.oy + y;
+            uint8_t* row = static_cast<uint8_t*>(prm.dst) + static_cast<size_t>(2 * gy) * prm.dst_pitch;
+            net_store2(row, 2 * gx, prm.type, __fadd_rn(v.x, id), __fadd_rn(v.y, id), aligned);
+            net_store2(row + prm.dst_pitch, 2 * gx, prm.type, __fadd_rn(v.z, id), __fadd_rn(v.w, id), aligned);
         }
     }
 
@@ -398,18 +419,30 @@ namespace acb
             }
         }
         else if constexpr (S::FAM == ACB200_FAMILY_ACNET_LEGACY)
-            tail_deconv_layer<S::NCONV + 1, KT, BT>(prm, cur, g);
+        {
+            conv_layer<S::NCONV + 1, ACT_RELU, false, KT, BT, 0>(prm, cur, oth, g);
+            __syncthreads();
+            deconv_pass<S::NCONV + 1, KT + 576>(prm, oth, g);
+        }
         else if constexpr (S::FAM == ACB200_FAMILY_ACNET)
-            tail_shuffle_layer<S::NCONV + 1, KT, BT>(prm, cur, luma, g);
+        {
+            conv_layer<S::NCONV + 1, ACT_IDENTITY, false, KT, BT, 0, 4>(prm, cur, oth, g);
+            __syncthreads();
+            shuffle_pass<S::NCONV + 1>(prm, oth, luma, g);
+        }
         else
         {
             // ARNet: NCONV is even, so `cur` == bufA holds x
             constexpr int AT = (S::NCONV / 2) * 8;
             conv_layer<S::NCONV + 1, ACT_PRELU, false, KT, BT, AT>(prm, cur, oth, g);
             __syncthreads();
-            arnet_end_layer<S::NCONV + 2, KT + 576, BT + 8, AT + 8>(prm, oth, cur, g);
+            conv_layer<S::NCONV + 2, ACT_IDENTITY, true, KT + 576, BT + 8, 0>(prm, oth, cur, g);
             __syncthreads();
-            tail_shuffle_layer<S::NCONV + 3, KT + 576 + 576 + 64, BT + 8 + 8 + 8>(prm, cur, luma, g);
+            arnet_fuse_pass<S::NCONV + 2, KT + 576 + 576, BT + 8 + 8, AT + 8>(prm, cur, g);
+            __syncthreads();
+            conv_layer<S::NCONV + 3, ACT_IDENTITY, false, KT + 576 + 576 + 64, BT + 8 + 8 + 8, 0, 4>(prm, cur, oth, g);
+            __syncthreads();
+            shuffle_pass<S::NCONV + 3>(prm, oth, luma, g);
         }
     }
 

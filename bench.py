@@ -193,7 +193,9 @@ def run_ours(args):
     host_frames = rs.randint(0, 256, size=(B, H, W, CH), dtype=np.uint8)
     d_in = torch.from_numpy(host_frames).cuda()
     d_out = torch.empty((B, 2 * H, 2 * W, CH), dtype=torch.uint8, device="cuda")
-    stream = torch.cuda.current_stream().cuda_stream
+    work_stream = torch.cuda.Stream()
+    torch.cuda.set_stream(work_stream)          # kernels and torch.cuda.Event timing share this stream
+    stream = work_stream.cuda_stream
 
     def step():
         for i in range(B):

@@ -40,12 +40,36 @@
 #define ORC_ACT_RELU 1
 #define ORC_ACT_PRELU 2
 
+/*
+ * Summation order.  The reference's CPU processor picks one of several per-ISA backends at run time
+ * (core/src/processor/cpu/CPUProcessor.cpp:761-813) and they do not round identically:
+ *   ORC_ORDER_GENERIC (0): OpImplGeneric, CPU/Generic.hpp:55-81 -- per input channel a left fold over the taps,
+ *       products and sums rounded separately; `create("cpu", 1, ...)`, the ground truth of the reference's own tests.
+ *   ORC_ORDER_FMA (1): OpImplX86SIMD256<true>, CPU/X86/AVX.hpp:24-146 -- what the auto-ISA choice executes for the
+ *       8-channel layers on every FMA-capable x86 (the AVX512 backend defers to it for cin < 16,
+ *       X86/AVX512.hpp:116): per input channel an FMA chain over the taps, the 8 chains reduced by the hsum tree
+ *       ((s0+s4)+(s2+s6))+((s1+s5)+(s3+s7)), added onto the bias; scalar epilogue expressions (`v*scale + id`,
+ *       `sat*max + 0.5f`) are contracted into FMAs by g++ in those translation units (-mfma, -ffp-contract=fast).
+ */
+#define ORC_ORDER_GENERIC 0
+#define ORC_ORDER_FMA 1
+static int g_order = ORC_ORDER_GENERIC;
+void orc_set_order(int order) { g_order = order == ORC_ORDER_FMA ? ORC_ORDER_FMA : ORC_ORDER_GENERIC; }
+int orc_get_order(void) { return g_order; }
+
+static inline float hsum8(const float *s) { return ((s[0] + s[4]) + (s[2] + s[6])) + ((s[1] + s[5]) + (s[3] + s[7])); }
+/* `a*b + c` as the backend's translation unit rounds it */
+static inline float muladd(float a, float b, float c) { return g_order == ORC_ORDER_FMA ? fmaf(a, b, c) : a * b + c; }
+
 /* ---- core/internal/AC/Core/Internal/Util.hpp:50-78 ------------------------------------ */
 static inline float to_float_u8(uint8_t v) { return (float)v / 255.0f; }
 static inline float to_float_u16(uint16_t v) { return (float)v / 65535.0f; }
 static inline float saturate(float v) { return v < 0.0f ? 0.0f : (v < 1.0f ? v : 1.0f); }
+/* net_* variants: fromFloat as instantiated inside a backend translation unit (layer tails) */
 static inline uint8_t from_float_u8(float v) { return (uint8_t)(saturate(v) * 255.0f + 0.5f); }
 static inline uint16_t from_float_u16(float v) { return (uint16_t)(saturate(v) * 65535.0f + 0.5f); }
+static inline uint8_t net_from_float_u8(float v) { return (uint8_t)muladd(saturate(v), 255.0f, 0.5f); }
+static inline uint16_t net_from_float_u16(float v) { return (uint16_t)muladd(saturate(v), 65535.0f, 0.5f); }
 
 static inline float load_elem(const uint8_t *row, int x, int type)
 {
@@ -66,6 +90,16 @@ static inline void store_elem(uint8_t *row, int x, int type, float v)
     }
 }
 
+static inline void net_store_elem(uint8_t *row, int x, int type, float v)
+{
+    switch (type)
+    {
+    case ORC_U8: row[x] = net_from_float_u8(v); break;
+    case ORC_U16: ((uint16_t *)row)[x] = net_from_float_u16(v); break;
+    default: ((float *)row)[x] = saturate(v); break;
+    }
+}
+
 /* ---- activations, core/internal/AC/Core/Internal/Processor/CPU/Common.hpp:21-50 -------- */
 static inline float activate(float v, int act, const float *alphas, int c)
 {
@@ -81,6 +115,17 @@ static inline void conv9_c8(const float *const rptr[9], float *out, int cout, co
     for (int n = 0; n < cout; n++)
     {
         const float *k = kernels + n * 8 * 9;
+        if (g_order == ORC_ORDER_FMA)
+        {
+            float s[8];
+            for (int c = 0; c < 8; c++)
+            {
+                s[c] = 0.0f;
+                for (int p = 0; p < 9; p++) s[c] = fmaf(rptr[p][c], k[p * 8 + c], s[c]);
+            }
+            out[n] = biases[n] + hsum8(s);
+            continue;
+        }
         float sum = 0.0f;
         for (int c = 0; c < 8; c++)
         {
@@ -96,6 +141,13 @@ static inline void conv1_c8(const float *in, float *out, const float *kernels, c
 {
     for (int n = 0; n < 8; n++)
     {
+        if (g_order == ORC_ORDER_FMA)
+        {
+            float s[8];
+            for (int c = 0; c < 8; c++) s[c] = in[c] * kernels[n * 8 + c];
+            out[n] = biases[n] + hsum8(s);
+            continue;
+        }
         float sum = 0.0f;
         for (int c = 0; c < 8; c++) sum += in[c] * kernels[n * 8 + c];
         out[n] = sum + biases[n];
@@ -104,6 +156,12 @@ static inline void conv1_c8(const float *in, float *out, const float *kernels, c
 /* OpImplGeneric::dot<8>, CPU/Generic.hpp:55-59 */
 static inline float dot8(const float *a, const float *b)
 {
+    if (g_order == ORC_ORDER_FMA)
+    {
+        float t[8];
+        for (int i = 0; i < 8; i++) t[i] = a[i] * b[i];
+        return hsum8(t);
+    }
     float s = a[0] * b[0];
     for (int i = 1; i < 8; i++) s = s + a[i] * b[i];
     return s;
@@ -138,8 +196,19 @@ static void layer_cin1(const uint8_t *src, int w, int h, int stride, int type, f
             for (int n = 0; n < 8; n++)
             {
                 const float *k = kernels + n * 9;
-                float s = r[0] * k[0];
-                for (int p = 1; p < 9; p++) s = s + r[p] * k[p];
+                float s;
+                if (g_order == ORC_ORDER_FMA)
+                {
+                    /* conv_cin1<8,9>, X86/AVX.hpp:95-124: 8 products through the hsum tree, 9th tap added as a scalar */
+                    float t[8];
+                    for (int p = 0; p < 8; p++) t[p] = r[p] * k[p];
+                    s = muladd(r[8], k[8], hsum8(t));
+                }
+                else
+                {
+                    s = r[0] * k[0];
+                    for (int p = 1; p < 9; p++) s = s + r[p] * k[p];
+                }
                 out[n] = activate(s + biases[n], act, alphas, n);
             }
         }
@@ -163,7 +232,7 @@ static void layer_8to8(const float *src, int w, int h, float *dst, const float *
             for (int n = 0; n < 8; n++)
             {
                 float v = activate(sum[n], act, alphas, n);
-                if (id) v = v * scale + id[n];
+                if (id) v = muladd(v, scale, id[n]);
                 out[n] = v;
             }
         }
@@ -183,7 +252,7 @@ static void layer_8to8_res_1x1(const float *src, int w, int h, float *dst,
             gather9(src, w, h, i, j, rptr);
             conv9_c8(rptr, buf, 8, k3, b3);
             size_t o = ((size_t)i * w + j) * 8;
-            for (int n = 0; n < 8; n++) buf[n] = buf[n] * scale3 + id3[o + n];
+            for (int n = 0; n < 8; n++) buf[n] = muladd(buf[n], scale3, id3[o + n]);
             conv1_c8(buf, sum, k1, b1);
             for (int n = 0; n < 8; n++)
             {
@@ -208,7 +277,7 @@ static void tail_deconv(const float *src, int w, int h, uint8_t *dst, int dst_st
             for (int n = 0; n < 8; n++) sum[n] = sum[n] > 0.0f ? sum[n] : 0.0f;
             for (int dy = 0; dy < 2; dy++)
                 for (int dx = 0; dx < 2; dx++)
-                    store_elem(dst + (size_t)(2 * i + dy) * dst_stride, 2 * j + dx, type, dot8(sum, k2 + 8 * (dy * 2 + dx)));
+                    net_store_elem(dst + (size_t)(2 * i + dy) * dst_stride, 2 * j + dx, type, dot8(sum, k2 + 8 * (dy * 2 + dx)));
         }
 }
 
@@ -226,7 +295,7 @@ static void tail_pixelshuffle(const float *src, int w, int h, uint8_t *dst, int 
             conv9_c8(rptr, sum, 4, kernels, biases);
             float id = load_elem(luma + (size_t)i * luma_stride, j, type);
             for (int n = 0; n < 4; n++)
-                store_elem(dst + (size_t)(2 * i + (n >> 1)) * dst_stride, 2 * j + (n & 1), type, sum[n] * 1.0f + id);
+                net_store_elem(dst + (size_t)(2 * i + (n >> 1)) * dst_stride, 2 * j + (n & 1), type, sum[n] * 1.0f + id);
         }
 }
 

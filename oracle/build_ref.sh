@@ -49,7 +49,7 @@ $CXX -mavx "$GEN/src/AVX.cpp" -o "$O/bAVX.o" & pids+=($!)
 $CXX -mavx -mfma "$GEN/src/FMA.cpp" -o "$O/bFMA.o" & pids+=($!)
 $CXX -mavx512f -mfma "$GEN/src/AVX512.cpp" -o "$O/bAVX512.o" & pids+=($!)
 $CXX "$HERE/ref_shim.cpp" -o "$O/ref_shim.o" & pids+=($!)
-gcc -std=c11 -O2 -fPIC -fopenmp -ffp-contract=off -c "$HERE/ac_oracle.c" -o "$O/ac_oracle.o" & pids+=($!)
+gcc -std=c11 -O2 -fPIC -fopenmp -mfma -ffp-contract=off -c "$HERE/ac_oracle.c" -o "$O/ac_oracle.o" & pids+=($!)
 for p in "${pids[@]}"; do wait "$p"; done
 g++ -shared -fopenmp -o "$OUT/libac_ref.so" "$O"/*.o -lm
 rm -f "$OUT/gen_arnet_standin"

@@ -52,6 +52,17 @@ def main():
     back = np.empty_like(rgb)
     O.ref().ref_yuv2rgb(y.ctypes.data, y.strides[0], uv.ctypes.data, uv.strides[0], 32, 24, 3, O.U8, back.ctypes.data, back.strides[0])
     out["rgb2yuv_y"], out["rgb2yuv_uv"], out["yuv2rgb_back"] = y, uv, back
+    # the same cases on the reference's FMA backend (arch 4 = OpImplX86SIMD256<true>; bit-identical to what the auto-ISA
+    # choice, AVX512, executes for these 8-channel models) -- the order the GPU's exact engine reproduces bit for bit
+    fma = {}
+    for key in list(out.keys()):
+        if "/" not in key:
+            continue
+        kind, name = key.split("/", 1)
+        src = {"gray_noise_2x": gray, "gray_smooth_2x": smooth, "rgb_2x": rgb, "rgb_4x": rgb, "rgba_2x": rgba, "gray_4x": gray[:20, :24],
+               "gray_f32_2x": gray.astype(np.float32) / np.float32(255), "gray_u16_2x": gray.astype(np.uint16) * 257}[kind]
+        fma["fma:" + key] = O.ref_process(name, src, 4.0 if kind.endswith("4x") else 2.0, arch=4)
+    out.update(fma)
     np.savez_compressed(os.path.join(HERE, "reference_vectors.npz"), **out)
     print("wrote", len(out), "arrays,", os.path.getsize(os.path.join(HERE, "reference_vectors.npz")), "bytes")
 

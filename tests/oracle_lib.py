@@ -241,3 +241,12 @@ def compare_u8(a, b):
     """(max abs diff, fraction of elements bit-exact)."""
     d = np.abs(a.astype(np.int32) - b.astype(np.int32))
     return int(d.max()), float((d == 0).mean())
+
+
+ORDER_GENERIC, ORDER_FMA = 0, 1
+
+
+def set_order(order):
+    """Summation order of the oracle's network layers: ORDER_GENERIC (reference `create("cpu", 1, ...)`) or
+    ORDER_FMA (what the reference's auto-ISA backend executes on FMA-capable x86)."""
+    oracle().orc_set_order(order)

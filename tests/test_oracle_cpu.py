@@ -8,7 +8,7 @@ import pytest
 import oracle_lib as O
 
 GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.npz"))
-GRAY_2X = sorted(k.split("/", 1)[1] for k in GOLD.files if k.startswith("gray_noise_2x/"))
+GRAY_2X = sorted(k.split("/", 1)[1] for k in GOLD.files if k.startswith("gray_noise_2x/"))   # Generic-order vectors
 
 
 @pytest.mark.parametrize("name", GRAY_2X)
@@ -17,11 +17,23 @@ def test_oracle_matches_golden_gray(name):
     assert np.array_equal(out, GOLD["gray_noise_2x/" + name])      # bit-exact: same arithmetic, same order
 
 
+@pytest.fixture(autouse=True)
+def _generic_order():
+    O.set_order(O.ORDER_GENERIC)
+    yield
+    O.set_order(O.ORDER_GENERIC)
+
+
 @pytest.mark.parametrize("key", sorted(k for k in GOLD.files if "/" in k and not k.startswith("gray_noise_2x/")))
 def test_oracle_matches_golden_other(key):
-    kind, name = key.split("/", 1)
-    src = {"gray_smooth_2x": GOLD["in_gray_smooth"], "rgb_2x": GOLD["in_rgb"], "rgb_4x": GOLD["in_rgb"], "rgba_2x": GOLD["in_rgba"],
-           "gray_4x": GOLD["in_gray_noise"][:20, :24],
+    if key.startswith("fma:"):
+        O.set_order(O.ORDER_FMA)        # vectors from the reference's FMA backend need the FMA summation order
+        key_kind = key[4:]
+    else:
+        key_kind = key
+    kind, name = key_kind.split("/", 1)
+    src = {"gray_noise_2x": GOLD["in_gray_noise"], "gray_smooth_2x": GOLD["in_gray_smooth"], "rgb_2x": GOLD["in_rgb"], "rgb_4x": GOLD["in_rgb"],
+           "rgba_2x": GOLD["in_rgba"], "gray_4x": GOLD["in_gray_noise"][:20, :24],
            "gray_f32_2x": GOLD["in_gray_noise"].astype(np.float32) / np.float32(255),
            "gray_u16_2x": GOLD["in_gray_noise"].astype(np.uint16) * 257}[kind]
     out = O.oracle_process(name, src, 4.0 if kind.endswith("4x") else 2.0)
@@ -99,6 +111,30 @@ def test_oracle_matches_compiled_reference(name, shape):
         assert np.array_equal(O.oracle_process(name, img, factor), O.ref_process(name, img, factor, arch=1))
     f = img.astype(np.float32) / np.float32(255)
     assert np.array_equal(O.oracle_process(name, f, 2.0), O.ref_process(name, f, 2.0, arch=1))
+
+
+@pytest.mark.skipif(O.ref() is None, reason="compiled reference (oracle/_ref) only exists in the build container")
+@pytest.mark.parametrize("name", ["acnet-legacy-hdn0", "acnet-f8b8-hdn", "arnet-f8b8"])
+def test_fma_order_oracle_matches_reference_fma_and_avx512_backends(name):
+    # arch 4 = FMA, arch 5 = AVX512 (core/src/processor/cpu/CPUProcessor.cpp:17-61): both run OpImplX86SIMD256<true> here
+    O.set_order(O.ORDER_FMA)
+    for c, shape in ((1, (37, 53)), (3, (24, 40))):
+        img = O.noise_u8(shape[0], shape[1], c, seed=77)
+        for factor in (2.0, 4.0):
+            want = O.ref_process(name, img, factor, arch=4)
+            assert np.array_equal(O.oracle_process(name, img, factor), want)
+            if O.ref().ref_processor_name(name.encode(), 0) == b"AVX512":
+                assert np.array_equal(O.ref_process(name, img, factor, arch=5), want)
+
+
+@pytest.mark.skipif(O.ref() is None, reason="compiled reference (oracle/_ref) only exists in the build container")
+def test_reference_isa_spread_4x():
+    # the reference's own backends at 4x (two passes compound): more than 1 LSB apart in places -- the reason 4x results
+    # are pinned bit-for-bit against the FMA order and only loosely against Generic
+    img = O.noise_u8(64, 96, 1, seed=5)
+    a, b = O.ref_process("acnet-f8b4", img, 4.0, arch=4), O.ref_process("acnet-f8b4", img, 4.0, arch=1)
+    mx, exact = O.compare_u8(a, b)
+    assert mx <= 4 and exact >= 0.995
 
 
 @pytest.mark.skipif(O.ref() is None, reason="compiled reference (oracle/_ref) only exists in the build container")

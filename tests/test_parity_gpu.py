@@ -16,17 +16,33 @@ pytestmark = pytest.mark.gpu
 GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.npz"))
 ALL_REAL = sorted(O.models().keys())
 ARNETS = ["arnet-f8b8", "arnet-f8b16-hdn", "arnet-f8b32-box", "arnet-f8b64-box-hdn"]
-ENGINES = [0]
 
+# Bars (BASELINE.json north_star): 8-bit output <= 1 LSB per channel and >= 99.9 % bit-exact; float32 max abs <= 1e-3.
 LSB_MAX = 1
 EXACT_MIN = 0.999
 F32_TOL = 1e-3
+# 16-bit output is 256x finer than the 8-bit bar: hold it to 4 LSB16 (1/64 of an 8-bit LSB)
+U16_LSB_MAX = 4
+# Two 2x passes compound: the reference's OWN backends (FMA vs Generic) differ by up to 4 LSB / ~0.2 % of samples at 4x
+# (measured in this repo: tests/test_oracle_cpu.py::test_reference_isa_spread_4x), so against Generic-order vectors a 4x
+# result is held to that spread; against FMA-order vectors the exact engine must still be bit-identical.
+X4_LSB_MAX, X4_EXACT_MIN = 4, 0.995
+ENGINE_EXACT, ENGINE_TENSOR = 0, 1
+ENGINES = [ENGINE_EXACT]
 
 
 @pytest.fixture(scope="module")
 def session():
     assert A.device_count() > 0, "GPU tests need a CUDA device (no CPU fallback exists)"
     return A.Session(0)
+
+
+@pytest.fixture(autouse=True)
+def _orders(session):
+    O.set_order(O.ORDER_GENERIC)
+    session.set_engine(ENGINE_EXACT)
+    yield
+    O.set_order(O.ORDER_GENERIC)
 
 
 _models = {}
@@ -38,39 +54,58 @@ def gpu_model(name):
     return _models[name]
 
 
-def check_int(out, want):
-    mx, exact = O.compare_u8(out, want)
-    assert mx <= LSB_MAX and exact >= EXACT_MIN, "max diff %d LSB, %.4f %% exact" % (mx, 100 * exact)
-    return mx, exact
-
-
-@pytest.mark.parametrize("engine", ENGINES)
-@pytest.mark.parametrize("name", ALL_REAL + ARNETS)
-def test_golden_gray_2x(session, name, engine):
-    session.set_engine(engine)
-    out = session.process_host(gpu_model(name), GOLD["in_gray_noise"], 2.0)
-    check_int(out, GOLD["gray_noise_2x/" + name])
-
-
-@pytest.mark.parametrize("key", sorted(k for k in GOLD.files if "/" in k and not k.startswith("gray_noise_2x/")))
-def test_golden_other(session, key):
-    kind, name = key.split("/", 1)
-    src = {"gray_smooth_2x": GOLD["in_gray_smooth"], "rgb_2x": GOLD["in_rgb"], "rgb_4x": GOLD["in_rgb"], "rgba_2x": GOLD["in_rgba"],
-           "gray_4x": GOLD["in_gray_noise"][:20, :24],
-           "gray_f32_2x": GOLD["in_gray_noise"].astype(np.float32) / np.float32(255),
-           "gray_u16_2x": GOLD["in_gray_noise"].astype(np.uint16) * 257}[kind]
-    out = session.process_host(gpu_model(name), src, 4.0 if kind.endswith("4x") else 2.0)
+def check_close(out, want, x4=False):
+    """The north_star tolerance against a Generic-order (or any differently rounded) reference result."""
     if out.dtype == np.float32:
-        assert float(np.abs(out - GOLD[key]).max()) <= F32_TOL
-    else:
-        check_int(out, GOLD[key])
+        assert float(np.abs(out - want).max()) <= F32_TOL
+        return
+    mx, exact = O.compare_u8(out, want)
+    if out.dtype == np.uint16:
+        assert mx <= U16_LSB_MAX * (4 if x4 else 1), "max diff %d LSB16" % mx
+        return
+    lim, frac = (X4_LSB_MAX, X4_EXACT_MIN) if x4 else (LSB_MAX, EXACT_MIN)
+    assert mx <= lim and exact >= frac, "max diff %d LSB, %.4f %% exact" % (mx, 100 * exact)
+
+
+def check_int(out, want):
+    check_close(out, want)
+
+
+def src_for(kind):
+    return {"gray_noise_2x": GOLD["in_gray_noise"], "gray_smooth_2x": GOLD["in_gray_smooth"], "rgb_2x": GOLD["in_rgb"], "rgb_4x": GOLD["in_rgb"],
+            "rgba_2x": GOLD["in_rgba"], "gray_4x": GOLD["in_gray_noise"][:20, :24],
+            "gray_f32_2x": GOLD["in_gray_noise"].astype(np.float32) / np.float32(255),
+            "gray_u16_2x": GOLD["in_gray_noise"].astype(np.uint16) * 257}[kind]
+
+
+GOLD_KEYS = sorted(k for k in GOLD.files if "/" in k and not k.startswith("fma:"))
+
+
+@pytest.mark.parametrize("key", GOLD_KEYS)
+def test_exact_engine_is_bit_identical_to_reference_fma_backend(session, key):
+    """Vectors minted from the compiled reference's FMA backend (what its auto-ISA processor executes on x86):
+    the exact engine reproduces them bit for bit -- u8, u16 and f32, gray / RGB / RGBA, 2x and 4x, every model."""
+    kind, name = key.split("/", 1)
+    out = session.process_host(gpu_model(name), src_for(kind), 4.0 if kind.endswith("4x") else 2.0)
+    assert np.array_equal(out, GOLD["fma:" + key])
+
+
+@pytest.mark.parametrize("key", GOLD_KEYS)
+def test_golden_generic_backend_within_tolerance(session, key):
+    """Vectors minted from the reference's Generic backend (`create("cpu", 1, ...)`, ground truth of its own tests)."""
+    kind, name = key.split("/", 1)
+    out = session.process_host(gpu_model(name), src_for(kind), 4.0 if kind.endswith("4x") else 2.0)
+    check_close(out, GOLD[key], x4=kind.endswith("4x"))
 
 
 @pytest.mark.parametrize("name", ["acnet-legacy-hdn0", "acnet-legacy-gan", "acnet-f8b4", "acnet-f8b8-hdn", "acnet-f8b18-box-hdn", "arnet-f8b8", "arnet-f8b16"])
 @pytest.mark.parametrize("shape", [(3, 3), (1, 7), (9, 1), (17, 31), (40, 40), (41, 39), (64, 64), (97, 131), (255, 257)])
 def test_odd_sizes_gray_vs_oracle(session, name, shape):
     img = O.noise_u8(shape[0], shape[1], 1, seed=shape[0] * 1000 + shape[1])
-    check_int(session.process_host(gpu_model(name), img, 2.0), O.oracle_process(name, img, 2.0))
+    out = session.process_host(gpu_model(name), img, 2.0)
+    check_close(out, O.oracle_process(name, img, 2.0))
+    O.set_order(O.ORDER_FMA)
+    assert np.array_equal(out, O.oracle_process(name, img, 2.0))
 
 
 @pytest.mark.parametrize("name", ["acnet-legacy-hdn1", "acnet-f8b8", "arnet-f8b8-box"])
@@ -78,11 +113,14 @@ def test_odd_sizes_gray_vs_oracle(session, name, shape):
 @pytest.mark.parametrize("factor", [2.0, 4.0])
 def test_colour_vs_oracle(session, name, c, factor):
     img = O.noise_u8(45, 61, c, seed=c * 10 + int(factor))
-    check_int(session.process_host(gpu_model(name), img, factor), O.oracle_process(name, img, factor))
     f = img.astype(np.float32) / np.float32(255)
-    assert float(np.abs(session.process_host(gpu_model(name), f, factor) - O.oracle_process(name, f, factor)).max()) <= F32_TOL
     u = img.astype(np.uint16) * 257
-    check_int(session.process_host(gpu_model(name), u, factor), O.oracle_process(name, u, factor))
+    outs = [session.process_host(gpu_model(name), x, factor) for x in (img, f, u)]
+    for x, out in zip((img, f, u), outs):
+        check_close(out, O.oracle_process(name, x, factor), x4=factor == 4.0)
+    O.set_order(O.ORDER_FMA)
+    for x, out in zip((img, f, u), outs):
+        assert np.array_equal(out, O.oracle_process(name, x, factor))
 
 
 @pytest.mark.parametrize("value", [0, 128, 255])
@@ -144,6 +182,9 @@ def test_full_size_1080p_properties(session):
     full = session.process_host(m, img, 2.0)
     assert full.shape == (2160, 3840)
     check_int(full, O.oracle_process("acnet-legacy-hdn0", img, 2.0))
+    O.set_order(O.ORDER_FMA)
+    assert np.array_equal(full, O.oracle_process("acnet-legacy-hdn0", img, 2.0))       # 8.3 M samples, bit for bit
+    O.set_order(O.ORDER_GENERIC)
     assert np.array_equal(full, session.process_host(m, img, 2.0))
     halo = 9
     y0, y1, x0, x1 = 300, 420, 700, 860
