@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libac_b200.so")
+LIB_PATH = os.environ.get("ACB200_LIB") or os.path.join(_HERE, "lib", "libac_b200.so")
 
 UINT8, UINT16, FLOAT16, FLOAT32 = 0x001, 0x002, 0x202, 0x204
 FAMILY_ACNET_LEGACY, FAMILY_ACNET, FAMILY_ARNET = 0, 1, 2

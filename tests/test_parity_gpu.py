@@ -117,7 +117,14 @@ def test_colour_vs_oracle(session, name, c, factor):
     u = img.astype(np.uint16) * 257
     outs = [session.process_host(gpu_model(name), x, factor) for x in (img, f, u)]
     for x, out in zip((img, f, u), outs):
-        check_close(out, O.oracle_process(name, x, factor), x4=factor == 4.0)
+        want = O.oracle_process(name, x, factor)
+        if c == 4:
+            # yuva2rgba divides by alpha (ImageProcess.cpp:289-295): a rounding-order difference in the luma is amplified
+            # by 1/alpha, between the reference's own backends too -- hold the tolerance where alpha >= 1/2 only
+            opaque = want[..., 3].astype(np.float64) >= 0.5 * (1.0 if x.dtype == np.float32 else float(np.iinfo(x.dtype).max))
+            check_close(out[opaque], want[opaque], x4=True)
+        else:
+            check_close(out, want, x4=factor == 4.0)
     O.set_order(O.ORDER_FMA)
     for x, out in zip((img, f, u), outs):
         assert np.array_equal(out, O.oracle_process(name, x, factor))
