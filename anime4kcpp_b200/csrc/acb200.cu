@@ -13,6 +13,7 @@
 
 #include "acb200_common.cuh"
 #include "acb200_ffma.cuh"
+#include "acb200_mma.cuh"
 #include "acb200_pixel.cuh"
 
 namespace
@@ -48,6 +49,7 @@ namespace
     {
         SegKind kind;
         int koff, boff, aoff;   // slice starts inside the model's flat arrays (contiguous by construction)
+        int frag_off = 0;       // start of this segment's packed B fragments inside acb200_model::frags (uint32 units)
     };
 }
 
@@ -56,6 +58,9 @@ struct acb200_model
     int family = 0, blocks = 0;
     std::vector<float> k, b, a;
     std::vector<SegSpec> chain;
+    // tensor-core engine: B fragments (split fp16) of every segment, concatenated; chain[i].frag_off indexes into it
+    std::vector<uint32_t> frags;
+    unsigned long long uid = 0;
 };
 
 namespace
@@ -165,17 +170,104 @@ namespace
     }
 }
 
+namespace
+{
+    // ---- host-side packing of the split-fp16 B fragments (layout documented in acb200_mma.cuh) ------------------------
+    uint32_t half_bits(float v) { return static_cast<uint32_t>(__half_as_ushort(__float2half_rn(v))); }
+    void split_w(float w, uint32_t& hi, uint32_t& lo)
+    {
+        const __half h = __float2half_rn(w);
+        hi = static_cast<uint32_t>(__half_as_ushort(h));
+        lo = half_bits(w - __half2float(h));
+    }
+    // W: [cout][9 taps][8 cin] fp32 (reference layout); cout <= 8, missing output channels are zero
+    void pack_conv3x3(const float* W, int cout, std::vector<uint32_t>& out)
+    {
+        const size_t base = out.size();
+        out.resize(base + FRAG_WORDS_3X3, 0u);
+        for (int lane = 0; lane < 32; lane++)
+        {
+            const int n = lane >> 2, t = lane & 3;      // B fragment: column n (= cout), rows k = 2t, 2t+1 (+8)
+            for (int s = 0; s < 5; s++)
+                for (int half = 0; half < (s < 4 ? 2 : 1); half++)
+                {
+                    const int tap = 2 * s + half;
+                    uint32_t h0 = 0, l0 = 0, h1 = 0, l1 = 0;
+                    if (n < cout)
+                    {
+                        split_w(W[(n * 9 + tap) * 8 + 2 * t], h0, l0);
+                        split_w(W[(n * 9 + tap) * 8 + 2 * t + 1], h1, l1);
+                    }
+                    const int reg = 2 * s + half;       // k-step 4 has a single register (index 8)
+                    out[base + reg * 32 + lane] = h0 | (h1 << 16);
+                    out[base + (9 + reg) * 32 + lane] = l0 | (l1 << 16);
+                }
+        }
+    }
+    // W: [cout 8][cin 8] fp32 (the ARNet 1x1)
+    void pack_conv1x1(const float* W, std::vector<uint32_t>& out)
+    {
+        const size_t base = out.size();
+        out.resize(base + FRAG_WORDS_1X1, 0u);
+        for (int lane = 0; lane < 32; lane++)
+        {
+            const int n = lane >> 2, t = lane & 3;
+            uint32_t h0, l0, h1, l1;
+            split_w(W[n * 8 + 2 * t], h0, l0);
+            split_w(W[n * 8 + 2 * t + 1], h1, l1);
+            out[base + lane] = h0 | (h1 << 16);
+            out[base + 32 + lane] = l0 | (l1 << 16);
+        }
+    }
+    template<class S>
+    void pack_segment(acb200_model& m, SegSpec& sp)
+    {
+        sp.frag_off = static_cast<int>(m.frags.size());
+        const float* k = m.k.data() + sp.koff + (S::HEAD ? 72 : 0);
+        for (int i = 0; i < S::NCONV; i++, k += 576) pack_conv3x3(k, 8, m.frags);
+        if (!S::TAIL) return;
+        if (S::FAM == ACB200_FAMILY_ACNET_LEGACY) pack_conv3x3(k, 8, m.frags);
+        else if (S::FAM == ACB200_FAMILY_ACNET) pack_conv3x3(k, 4, m.frags);
+        else
+        {
+            pack_conv3x3(k, 8, m.frags);            // PReLU conv of the last block
+            pack_conv3x3(k + 576, 8, m.frags);      // residual conv
+            pack_conv1x1(k + 1152, m.frags);        // 1x1
+            pack_conv3x3(k + 1152 + 64, 4, m.frags);// pixel-shuffle conv
+        }
+    }
+    void pack_model(acb200_model& m)
+    {
+        m.frags.clear();
+        for (SegSpec& sp : m.chain)
+            switch (sp.kind)
+            {
+            case SEG_LEGACY_FULL: pack_segment<SegLegacyFull>(m, sp); break;
+            case SEG_ACNET_B4: pack_segment<SegAcnetB4>(m, sp); break;
+            case SEG_ACNET_B8: pack_segment<SegAcnetB8>(m, sp); break;
+            case SEG_ACNET_B18_A: pack_segment<SegAcnetB18A>(m, sp); break;
+            case SEG_ACNET_B18_B: pack_segment<SegAcnetB18B>(m, sp); break;
+            case SEG_ARNET_FIRST: pack_segment<SegArnetFirst>(m, sp); break;
+            case SEG_ARNET_MID: pack_segment<SegArnetMid>(m, sp); break;
+            case SEG_ARNET_LAST: pack_segment<SegArnetLast>(m, sp); break;
+            }
+    }
+    std::atomic<unsigned long long> g_model_uid{ 1 };
+}
+
 struct acb200_session
 {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
-    int engine = 0;
+    int engine = 2;     // 0 exact FFMA, 1 tensor-core MMA, 2 auto: exact for every 2x pass but the last, tensor for the last
     std::string error = "NO ERROR";
     // grow-only device scratch
     struct Buf { void* p = nullptr; size_t cap = 0; };
     Buf src, dst, y[2], uv, map[2], feat, htab, vtab;
+    // device copies of models' packed fragments, keyed by acb200_model::uid
+    std::map<unsigned long long, void*> dev_frags;
     int tab_in_w = 0, tab_in_h = 0, tab_out_w = 0, tab_out_h = 0;
     int smem_configured = 0;
 };
@@ -232,9 +324,64 @@ namespace
         return ACB200_OK;
     }
 
+    int device_frags(acb200_session* s, cudaStream_t st, const acb200_model& m, const uint32_t** out)
+    {
+        auto it = s->dev_frags.find(m.uid);
+        if (it == s->dev_frags.end())
+        {
+            void* p = nullptr;
+            ACB_CUDA(s, cudaMalloc(&p, m.frags.size() * sizeof(uint32_t)));
+            cudaError_t e = cudaMemcpyAsync(p, m.frags.data(), m.frags.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) { cudaFree(p); return fail(s, ACB200_ECUDA, "upload of weight fragments", e); }
+            it = s->dev_frags.emplace(m.uid, p).first;
+        }
+        *out = static_cast<const uint32_t*>(it->second);
+        return ACB200_OK;
+    }
+
+    template<class S>
+    int launch_segment_mma(acb200_session* s, cudaStream_t st, const acb200_model& m, const SegSpec& spec,
+                           const void* src, int src_pitch, void* dst, int dst_pitch, int w, int h, int type,
+                           const float* map_in, float* map_out, float* feat)
+    {
+        static_assert(sizeof(MmaParams<S>) <= 32764, "kernel parameter block too large");
+        const uint32_t* dfrags = nullptr;
+        int rc = device_frags(s, st, m, &dfrags);
+        if (rc != ACB200_OK) return rc;
+        MmaParams<S> prm;
+        prm.src = src; prm.map_in = map_in; prm.map_out = map_out; prm.feat_in = feat; prm.feat_out = feat; prm.dst = dst;
+        prm.src_pitch = src_pitch; prm.dst_pitch = dst_pitch; prm.w = w; prm.h = h; prm.type = type;
+        prm.tiles_x = (w + S::T - 1) / S::T;
+        const int tiles_y = (h + S::T - 1) / S::T;
+        prm.frags = dfrags + spec.frag_off;
+        std::memset(prm.k, 0, sizeof(prm.k));
+        if (S::HEAD) std::memcpy(prm.k, m.k.data() + spec.koff, sizeof(float) * 72);
+        if (S::TAIL && S::FAM == ACB200_FAMILY_ACNET_LEGACY)
+            std::memcpy(prm.k + (S::HEAD ? 72 : 0), m.k.data() + spec.koff + (S::HEAD ? 72 : 0) + 576 * (S::NCONV + 1), sizeof(float) * 32);
+        std::memcpy(prm.b, m.b.data() + spec.boff, sizeof(float) * S::NB);
+        if (S::NA > 0) std::memcpy(prm.a, m.a.data() + spec.aoff, sizeof(float) * S::NA);
+        else prm.a[0] = 0.0f;
+        cudaError_t attr_err = cudaFuncSetAttribute(segment_mma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(MMA_SMEM_BYTES));
+        if (attr_err != cudaSuccess) return fail(s, ACB200_ECUDA, "cudaFuncSetAttribute(max dynamic smem)", attr_err);
+        segment_mma_kernel<S><<<prm.tiles_x * tiles_y, MMA_THREADS, MMA_SMEM_BYTES, st>>>(prm);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        ACB_CUDA(s, cudaGetLastError());
+        return ACB200_OK;
+    }
+
+    template<class S>
+    int launch_any(bool tensor, acb200_session* s, cudaStream_t st, const acb200_model& m, const SegSpec& spec,
+                   const void* src, int src_pitch, void* dst, int dst_pitch, int w, int h, int type,
+                   const float* map_in, float* map_out, float* feat)
+    {
+        return tensor ? launch_segment_mma<S>(s, st, m, spec, src, src_pitch, dst, dst_pitch, w, h, type, map_in, map_out, feat)
+                      : launch_segment<S>(s, st, m, spec, src, src_pitch, dst, dst_pitch, w, h, type, map_in, map_out, feat);
+    }
+
     // one 2x luma pass: src (w x h) -> dst (2w x 2h), both planes in HBM
     int luma_pass(acb200_session* s, cudaStream_t st, const acb200_model& m, const void* src, int src_pitch,
-                  void* dst, int dst_pitch, int w, int h, int type)
+                  void* dst, int dst_pitch, int w, int h, int type, bool tensor)
     {
         float* maps[2] = { nullptr, nullptr };
         float* feat = nullptr;
@@ -260,14 +407,14 @@ namespace
             int rc = ACB200_EINVAL;
             switch (sp.kind)
             {
-            case SEG_LEGACY_FULL: rc = launch_segment<SegLegacyFull>(s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, nullptr, nullptr, nullptr); break;
-            case SEG_ACNET_B4: rc = launch_segment<SegAcnetB4>(s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, nullptr, nullptr, nullptr); break;
-            case SEG_ACNET_B8: rc = launch_segment<SegAcnetB8>(s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, nullptr, nullptr, nullptr); break;
-            case SEG_ACNET_B18_A: rc = launch_segment<SegAcnetB18A>(s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, nullptr, out, nullptr); break;
-            case SEG_ACNET_B18_B: rc = launch_segment<SegAcnetB18B>(s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, in, nullptr, nullptr); break;
-            case SEG_ARNET_FIRST: rc = launch_segment<SegArnetFirst>(s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, nullptr, out, feat); break;
-            case SEG_ARNET_MID: rc = launch_segment<SegArnetMid>(s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, in, out, feat); break;
-            case SEG_ARNET_LAST: rc = launch_segment<SegArnetLast>(s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, in, nullptr, feat); break;
+            case SEG_LEGACY_FULL: rc = launch_any<SegLegacyFull>(tensor, s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, nullptr, nullptr, nullptr); break;
+            case SEG_ACNET_B4: rc = launch_any<SegAcnetB4>(tensor, s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, nullptr, nullptr, nullptr); break;
+            case SEG_ACNET_B8: rc = launch_any<SegAcnetB8>(tensor, s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, nullptr, nullptr, nullptr); break;
+            case SEG_ACNET_B18_A: rc = launch_any<SegAcnetB18A>(tensor, s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, nullptr, out, nullptr); break;
+            case SEG_ACNET_B18_B: rc = launch_any<SegAcnetB18B>(tensor, s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, in, nullptr, nullptr); break;
+            case SEG_ARNET_FIRST: rc = launch_any<SegArnetFirst>(tensor, s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, nullptr, out, feat); break;
+            case SEG_ARNET_MID: rc = launch_any<SegArnetMid>(tensor, s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, in, out, feat); break;
+            case SEG_ARNET_LAST: rc = launch_any<SegArnetLast>(tensor, s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, in, nullptr, feat); break;
             }
             if (rc != ACB200_OK) return rc;
             cur ^= 1;
@@ -332,7 +479,8 @@ namespace
                 out = s->y[slot].p; out_pitch = static_cast<int>(p);
                 slot ^= 1;
             }
-            if ((rc = luma_pass(s, st, *m, cur, cur_pitch, out, out_pitch, cw, ch, type)) != ACB200_OK) return rc;
+            const bool tensor = s->engine == 1 || (s->engine == 2 && i == power - 1);
+            if ((rc = luma_pass(s, st, *m, cur, cur_pitch, out, out_pitch, cw, ch, type, tensor)) != ACB200_OK) return rc;
             cur = out; cur_pitch = out_pitch; cw = nw; ch = nh;
         }
         if (c > 1)
@@ -393,6 +541,8 @@ extern "C"
         m->b.assign(biases, biases + nb);
         if (na) m->a.assign(alphas, alphas + na);
         build_chain(*m);
+        pack_model(*m);
+        m->uid = g_model_uid.fetch_add(1);
         *out = m;
         return ACB200_OK;
     }
@@ -431,6 +581,7 @@ extern "C"
         acb200_session::Buf* bufs[] = { &s->src, &s->dst, &s->y[0], &s->y[1], &s->uv, &s->map[0], &s->map[1], &s->feat, &s->htab, &s->vtab };
         for (auto* b : bufs) if (b->p) cudaFreeAsync(b->p, s->stream);
         cudaStreamSynchronize(s->stream);
+        for (auto& kv : s->dev_frags) cudaFree(kv.second);
         cudaEventDestroy(s->ev0); cudaEventDestroy(s->ev1);
         cudaStreamDestroy(s->stream);
         cudaGetLastError();
@@ -439,7 +590,7 @@ extern "C"
     int acb200_session_device(const acb200_session* s) { return s ? s->device : ACB200_EINVAL; }
     const char* acb200_session_error(const acb200_session* s) { return s ? s->error.c_str() : "invalid session"; }
     void acb200_session_clear_error(acb200_session* s) { if (s) s->error = "NO ERROR"; }
-    int acb200_session_set_engine(acb200_session* s, int engine) { if (!s || engine < 0 || engine > 1) return ACB200_EINVAL; s->engine = engine; return ACB200_OK; }
+    int acb200_session_set_engine(acb200_session* s, int engine) { if (!s || engine < 0 || engine > 2) return ACB200_EINVAL; s->engine = engine; return ACB200_OK; }
 
     int acb200_process_device(acb200_session* s, const acb200_model* m, const void* d_src, int w, int h, int c, int src_stride, int type,
                               double factor, void* d_dst, int dst_stride, void* stream)

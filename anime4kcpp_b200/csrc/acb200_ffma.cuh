@@ -110,6 +110,15 @@ namespace acb
     __device__ __forceinline__ float prelu(float v, float alpha) { return fmaf(alpha, fminf(v, 0.0f), fmaxf(v, 0.0f)); }
 
     // fromFloat as the network tails round it in the FMA backend: one FMA for `sat*max + 0.5f`
+    __device__ __forceinline__ void net_store1(void* row, int x, int type, float v)
+    {
+        switch (type)
+        {
+        case ACB200_UINT8: static_cast<uint8_t*>(row)[x] = static_cast<uint8_t>(fmaf(sat01(v), 255.0f, 0.5f)); return;
+        case ACB200_UINT16: static_cast<uint16_t*>(row)[x] = static_cast<uint16_t>(fmaf(sat01(v), 65535.0f, 0.5f)); return;
+        default: store_elem(row, x, type, v);
+        }
+    }
     __device__ __forceinline__ void net_store2(void* row, int x, int type, float v0, float v1, bool aligned)
     {
         switch (type)

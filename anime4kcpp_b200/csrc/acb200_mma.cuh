@@ -1,0 +1,435 @@
+// Tensor-core engine of the fused luma network: split-fp16 implicit GEMM on mma.sync (HMMA).
+//
+// Same tiling, segment chain and reference semantics as the exact FFMA engine (acb200_ffma.cuh), but the 8->8
+// (and 8->4) 3x3 convolutions run on the tensor cores as implicit GEMMs  D[16 px x 8 cout] += A[16 px x K] B[K x 8],
+// K = 9 taps x 8 cin = 72, five k-steps (four m16n8k16 covering two taps each + one m16n8k8).
+//
+// Plain fp16/bf16/TF32 operands cannot meet the ">= 99.9 % of 8-bit samples bit-exact" bar (SURVEY.md finding 4:
+// fp16 activations leave 4-9 % of samples 1 LSB off), so every fp32 activation a and weight w is carried as an
+// fp16 pair (hi, lo) with hi = fp16(v), lo = fp16(v - hi) (22+ significant bits), and each product is evaluated as
+//     a*w  ~=  a_hi*w_hi + a_lo*w_hi + a_hi*w_lo          (three MMAs, fp32 accumulation in the tensor core)
+// which leaves rounding noise of the same order as re-ordering an fp32 sum.
+//
+// Shared memory holds each 8-channel map as two planes of [56x56 pixels][8 x fp16] = 16 bytes per pixel (hi plane and
+// lo plane).  An 8x8 ldmatrix tile is then 8 consecutive pixels x 8 channels = 128 contiguous bytes (conflict-free), a
+// 3x3 tap is a pixel offset of the row addresses, and one ldmatrix.x4 yields the whole A fragment of a k-step
+// (16 pixels x two taps).  The D fragment of thread (g = lane/4, t = lane%4) is pixels {g, g+8} x couts {2t, 2t+1}:
+// bias, activation, residual and the hi/lo re-split happen in registers, and the 4-byte half2 stores of a warp cover
+// 8 pixels x 16 bytes contiguously.  Weights are pre-packed on the host into B-fragment order (one coalesced 128-byte
+// load per fragment register per warp) and stay in 18 registers for a whole layer.
+//
+// The 1->8 head conv (72 MAC / pixel) and the deconvolution / pixel-shuffle / 1x1 epilogues stay in fp32 FFMA.
+#pragma once
+
+#include <cuda_fp16.h>
+
+#include "acb200_common.cuh"
+#include "acb200_ffma.cuh"
+
+namespace acb
+{
+    constexpr int MMA_THREADS = 512;
+    constexpr int MMA_WARPS = MMA_THREADS / 32;
+    constexpr int FRAG_WORDS_3X3 = 18 * 32;     // uint32 per packed 3x3 layer: (4 x 2 + 1) registers x {hi, lo} x 32 lanes
+    constexpr int FRAG_WORDS_1X1 = 2 * 32;      // the ARNet 1x1: one k8 register x {hi, lo}
+
+    template<class S>
+    struct MmaParams
+    {
+        const void* src;
+        const float* map_in;
+        float* map_out;
+        const float* feat_in;
+        float* feat_out;
+        void* dst;
+        int src_pitch, dst_pitch;
+        int w, h;
+        int type;
+        int tiles_x;
+        const uint32_t* frags;  // packed B fragments of this segment's 3x3 convs (and the ARNet 1x1), in layer order
+        float k[(S::HEAD ? 72 : 0) + 64 + 32];  // fp32 weights used outside the MMAs: head (72) | legacy deconv (32)
+        float b[S::NB];
+        float a[S::NA > 0 ? S::NA : 1];
+    };
+
+    struct HalfPlanes
+    {
+        uint4* hi;  // [FT*FT] pixels x 8 fp16
+        uint4* lo;
+    };
+
+    __device__ __forceinline__ uint32_t pack_half2(__half a, __half b)
+    {
+        return static_cast<uint32_t>(__half_as_ushort(a)) | (static_cast<uint32_t>(__half_as_ushort(b)) << 16);
+    }
+    // v -> (hi, lo) fp16 pair
+    __device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& hi, uint32_t& lo)
+    {
+        const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+        hi = pack_half2(h0, h1);
+        lo = pack_half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1)));
+    }
+    __device__ __forceinline__ float2 join_pair(uint32_t hi, uint32_t lo)
+    {
+        const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi)), l = __half22float2(*reinterpret_cast<const __half2*>(&lo));
+        return make_float2(h.x + l.x, h.y + l.y);
+    }
+    __device__ __forceinline__ void store_pixel_split(const HalfPlanes& p, int o, const float (&v)[8])
+    {
+        uint4 hi, lo;
+        split_pair(v[0], v[1], hi.x, lo.x); split_pair(v[2], v[3], hi.y, lo.y);
+        split_pair(v[4], v[5], hi.z, lo.z); split_pair(v[6], v[7], hi.w, lo.w);
+        p.hi[o] = hi; p.lo[o] = lo;
+    }
+    __device__ __forceinline__ void load_pixel_joined(const HalfPlanes& p, int o, float (&v)[8])
+    {
+        const uint4 hi = p.hi[o], lo = p.lo[o];
+        float2 f;
+        f = join_pair(hi.x, lo.x); v[0] = f.x; v[1] = f.y;
+        f = join_pair(hi.y, lo.y); v[2] = f.x; v[3] = f.y;
+        f = join_pair(hi.z, lo.z); v[4] = f.x; v[5] = f.y;
+        f = join_pair(hi.w, lo.w); v[6] = f.x; v[7] = f.y;
+    }
+
+    __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t saddr)
+    {
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+    }
+    __device__ __forceinline__ void ldmatrix_x2(uint32_t (&r)[2], uint32_t saddr)
+    {
+        asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(saddr));
+    }
+    __device__ __forceinline__ void mma_k16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+    {
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    }
+    __device__ __forceinline__ void mma_k8(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t b0)
+    {
+        asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(b0));
+    }
+
+    // One 3x3 conv layer (8 -> 8, or 8 -> 4 with the upper output channels' weights zero) on the tensor cores.
+    //   epi(px, py, v0, v1, valid): called by every lane twice per tile -- first for pixel (x0+g, y), then (x0+g+8, y) --
+    //   with the finished fp32 sums (bias NOT included) of output channels 2t, 2t+1.  `valid` is false for pixels the tile
+    //   does not own (overhang past the layer's region, or the overlap of a left-shifted last tile): the epilogue may use
+    //   warp collectives but must not store for them (an in-place residual would otherwise be applied twice).
+    //   L = number of 3x3 layers between the frame and this layer's output (its region is the frame shrunk by L).
+    template<class Epi>
+    __device__ __forceinline__ void mma_conv3x3(const int L, const HalfPlanes& in, const uint32_t* __restrict__ frag, const TileGeom& g, Epi&& epi)
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        // B fragments of the layer: registers 0-8 = hi (k-steps 0-3: two registers, k-step 4: one), 9-17 = lo
+        uint32_t bf[18];
+#pragma unroll
+        for (int i = 0; i < 18; i++) bf[i] = __ldg(frag + i * 32 + lane);
+
+        const int xa = max(L, g.ix0), xb = min(FT - L, g.ix1 + 1), ya = max(L, g.iy0), yb = min(FT - L, g.iy1 + 1);
+        const int tiles = (xb - xa + 15) >> 4, n = tiles * (yb - ya);
+        const int cx_lo = max(g.ix0, 0), cx_hi = min(g.ix1, FT - 1), cy_lo = max(g.iy0, 0), cy_hi = min(g.iy1, FT - 1);
+        const int m = lane >> 3, r = lane & 7, h = m >> 1;      // ldmatrix: this lane supplies row r of matrix m
+        const uint32_t hi_base = static_cast<uint32_t>(__cvta_generic_to_shared(in.hi));
+        const uint32_t lo_base = static_cast<uint32_t>(__cvta_generic_to_shared(in.lo));
+        for (int it = warp; it < n; it += MMA_WARPS)
+        {
+            const int y = ya + it / tiles;
+            const int own_lo = xa + ((it % tiles) << 4);
+            const int x0 = min(own_lo, FT - 16);
+            // this lane's pixel for the A rows it feeds, with replicate padding at the image border
+            const int px = x0 + r + ((m & 1) << 3);
+            const int cx[3] = { clampi(px - 1, cx_lo, cx_hi), clampi(px, cx_lo, cx_hi), clampi(px + 1, cx_lo, cx_hi) };
+            const int ry[3] = { clampi(y - 1, cy_lo, cy_hi) * FT, clampi(y, cy_lo, cy_hi) * FT, clampi(y + 1, cy_lo, cy_hi) * FT };
+            float c[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
+#pragma unroll
+            for (int s = 0; s < 5; s++)
+            {
+                // k-step s covers taps 2s (matrices 0,1) and 2s+1 (matrices 2,3); tap = dy*3 + dx
+                const int t0 = 2 * s, t1 = 2 * s + 1;
+                const int off = (h && s < 4) ? ry[t1 / 3] + cx[t1 % 3] : ry[t0 / 3] + cx[t0 % 3];
+                if (s < 4)
+                {
+                    uint32_t ah[4], al[4];
+                    ldmatrix_x4(ah, hi_base + off * 16);
+                    ldmatrix_x4(al, lo_base + off * 16);
+                    mma_k16(c, ah, bf[2 * s], bf[2 * s + 1]);
+                    mma_k16(c, al, bf[2 * s], bf[2 * s + 1]);
+                    mma_k16(c, ah, bf[9 + 2 * s], bf[9 + 2 * s + 1]);
+                }
+                else
+                {
+                    uint32_t ah[2], al[2];
+                    ldmatrix_x2(ah, hi_base + off * 16);
+                    ldmatrix_x2(al, lo_base + off * 16);
+                    mma_k8(c, ah[0], ah[1], bf[8]);
+                    mma_k8(c, al[0], al[1], bf[8]);
+                    mma_k8(c, ah[0], ah[1], bf[17]);
+                }
+            }
+            const int p0 = x0 + (lane >> 2), p1 = p0 + 8;
+            epi(p0, y, c[0], c[1], p0 >= own_lo && p0 < xb);
+            epi(p1, y, c[2], c[3], p1 >= own_lo && p1 < xb);
+        }
+    }
+
+    template<class S>
+    __global__ void __launch_bounds__(MMA_THREADS, 1) segment_mma_kernel(const __grid_constant__ MmaParams<S> prm)
+    {
+        extern __shared__ __align__(16) unsigned char smem_raw[];
+        uint4* base = reinterpret_cast<uint4*>(smem_raw);
+        HalfPlanes A{ base, base + FT * FT }, B{ base + 2 * FT * FT, base + 3 * FT * FT };
+        float* luma = reinterpret_cast<float*>(base + 4 * FT * FT);
+
+        const int tx = blockIdx.x % prm.tiles_x, ty = blockIdx.x / prm.tiles_x;
+        TileGeom g;
+        g.ox = tx * S::T - S::R;
+        g.oy = ty * S::T - S::R;
+        g.ix0 = -g.ox; g.ix1 = prm.w - 1 - g.ox;
+        g.iy0 = -g.oy; g.iy1 = prm.h - 1 - g.oy;
+        const int lane = threadIdx.x & 31, tq = lane & 3;
+
+        if constexpr (S::NEEDS_LUMA)
+        {
+            for (int i = threadIdx.x; i < LT * LT; i += MMA_THREADS)
+            {
+                const int lx = i % LT, ly = i / LT;
+                const int gx = clampi(g.ox - 1 + lx, 0, prm.w - 1), gy = clampi(g.oy - 1 + ly, 0, prm.h - 1);
+                luma[i] = load_elem(static_cast<const uint8_t*>(prm.src) + static_cast<size_t>(gy) * prm.src_pitch, gx, prm.type);
+            }
+        }
+        if constexpr (!S::HEAD)
+        {
+            for (int i = threadIdx.x; i < FT * FT; i += MMA_THREADS)
+            {
+                const int fx = i % FT, fy = i / FT;
+                const int gx = clampi(g.ox + fx, 0, prm.w - 1), gy = clampi(g.oy + fy, 0, prm.h - 1);
+                const float4* p = reinterpret_cast<const float4*>(prm.map_in + (static_cast<size_t>(gy) * prm.w + gx) * 8);
+                const float4 v0 = __ldg(p), v1 = __ldg(p + 1);
+                const float v[8] = { v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w };
+                store_pixel_split(A, i, v);
+            }
+        }
+        __syncthreads();
+        if constexpr (S::HEAD)
+        {
+            // 1 -> 8 head conv in fp32 (Common.hpp:166-197), one pixel per thread
+            constexpr int ACT = S::FAM == ACB200_FAMILY_ACNET_LEGACY ? ACT_RELU : S::FAM == ACB200_FAMILY_ACNET ? ACT_PRELU : ACT_IDENTITY;
+            const int xa = max(0, g.ix0), xb = min(FT, g.ix1 + 1), ya = max(0, g.iy0), yb = min(FT, g.iy1 + 1);
+            const int ncols = xb - xa, n = ncols * (yb - ya);
+            for (int i = threadIdx.x; i < n; i += MMA_THREADS)
+            {
+                const int x = xa + i % ncols, y = ya + i / ncols;
+                float r[9];
+#pragma unroll
+                for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+                    for (int dx = 0; dx < 3; dx++) r[dy * 3 + dx] = luma[(y + dy) * LT + x + dx];
+                float v[8];
+#pragma unroll
+                for (int co = 0; co < 8; co++)
+                {
+                    float q[8];
+#pragma unroll
+                    for (int p = 0; p < 8; p++) q[p] = __fmul_rn(r[p], prm.k[co * 9 + p]);
+                    float s = __fadd_rn(fmaf(r[8], prm.k[co * 9 + 8], hsum8(q)), prm.b[co]);
+                    if (ACT == ACT_RELU) s = fmaxf(s, 0.0f);
+                    else if (ACT == ACT_PRELU) s = prelu(s, prm.a[co]);
+                    v[co] = s;
+                }
+                store_pixel_split(A, y * FT + x, v);
+                if constexpr (S::FAM == ACB200_FAMILY_ARNET)
+                {
+                    if (x >= S::R && x < FT - S::R && y >= S::R && y < FT - S::R)
+                    {
+                        float4* p = reinterpret_cast<float4*>(prm.feat_out + (static_cast<size_t>(g.oy + y) * prm.w + (g.ox + x)) * 8);
+                        p[0] = make_float4(v[0], v[1], v[2], v[3]);
+                        p[1] = make_float4(v[4], v[5], v[6], v[7]);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+
+        constexpr int B0 = S::HEAD ? 8 : 0;     // bias / alpha offsets of the first body conv inside prm.b / prm.a
+        constexpr int A0 = (S::FAM == ACB200_FAMILY_ACNET && S::HEAD) ? 8 : 0;
+        HalfPlanes cur = A, oth = B;
+        // ---- body convs -------------------------------------------------------------------------------------------------
+#pragma unroll 1
+        for (int i = 0; i < S::NCONV; i++)
+        {
+            const uint32_t* frag = prm.frags + i * FRAG_WORDS_3X3;
+            const float b0 = prm.b[B0 + 8 * i + 2 * tq], b1 = prm.b[B0 + 8 * i + 2 * tq + 1];
+            int act = ACT_RELU;
+            bool res = false;
+            float a0 = 0.0f, a1 = 0.0f;
+            if constexpr (S::FAM == ACB200_FAMILY_ACNET)
+            {
+                act = ACT_PRELU;
+                a0 = prm.a[A0 + 8 * i + 2 * tq]; a1 = prm.a[A0 + 8 * i + 2 * tq + 1];
+            }
+            else if constexpr (S::FAM == ACB200_FAMILY_ARNET)
+            {
+                if ((i & 1) == 0) { act = ACT_PRELU; a0 = prm.a[(i >> 1) * 8 + 2 * tq]; a1 = prm.a[(i >> 1) * 8 + 2 * tq + 1]; }
+                else { act = ACT_IDENTITY; res = true; }
+            }
+            const HalfPlanes out = oth;
+            auto epi = [&](const int px, const int py, float v0, float v1, const bool valid) {
+                if (!valid) return;
+                v0 += b0; v1 += b1;
+                if (act == ACT_RELU) { v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); }
+                else if (act == ACT_PRELU) { v0 = prelu(v0, a0); v1 = prelu(v1, a1); }
+                uint32_t* ph = reinterpret_cast<uint32_t*>(out.hi + py * FT + px) + tq;
+                uint32_t* pl = reinterpret_cast<uint32_t*>(out.lo + py * FT + px) + tq;
+                if (res)
+                {
+                    const float2 id = join_pair(*ph, *pl);
+                    v0 = fmaf(v0, 0.2f, id.x); v1 = fmaf(v1, 0.2f, id.y);
+                }
+                uint32_t hi, lo;
+                split_pair(v0, v1, hi, lo);
+                *ph = hi; *pl = lo;
+            };
+            mma_conv3x3(i + 1, cur, frag, g, epi);
+            __syncthreads();
+            const HalfPlanes t = cur; cur = oth; oth = t;
+        }
+
+        const uint32_t* tfrag = prm.frags + S::NCONV * FRAG_WORDS_3X3;
+        constexpr int BT = B0 + 8 * S::NCONV;
+        const int es = prm.type & 0xff;
+        const bool aligned = ((reinterpret_cast<uintptr_t>(prm.dst) | static_cast<uintptr_t>(prm.dst_pitch)) & (2 * es - 1)) == 0;
+        if constexpr (!S::TAIL)
+        {
+            const int xa = max(S::R, g.ix0), xb = min(FT - S::R, g.ix1 + 1), ya = max(S::R, g.iy0), yb = min(FT - S::R, g.iy1 + 1);
+            const int ncols = xb - xa, n = ncols * (yb - ya);
+            for (int i = threadIdx.x; i < n; i += MMA_THREADS)
+            {
+                const int x = xa + i % ncols, y = ya + i / ncols;
+                float v[8];
+                load_pixel_joined(cur, y * FT + x, v);
+                float4* p = reinterpret_cast<float4*>(prm.map_out + (static_cast<size_t>(g.oy + y) * prm.w + (g.ox + x)) * 8);
+                p[0] = make_float4(v[0], v[1], v[2], v[3]);
+                p[1] = make_float4(v[4], v[5], v[6], v[7]);
+            }
+        }
+        else if constexpr (S::FAM == ACB200_FAMILY_ACNET_LEGACY)
+        {
+            // conv3x3 + ReLU on the tensor cores, then the 2x2 deconv: each quad of lanes holds the 8 channels of a pixel
+            // (2 per lane) -- partial dots per lane, butterfly over the quad, lane t writes output sub-pixel t
+            const float b0 = prm.b[BT + 2 * tq], b1 = prm.b[BT + 2 * tq + 1];
+            float kd[4][2];
+#pragma unroll
+            for (int q = 0; q < 4; q++) { kd[q][0] = prm.k[(S::HEAD ? 72 : 0) + q * 8 + 2 * tq]; kd[q][1] = prm.k[(S::HEAD ? 72 : 0) + q * 8 + 2 * tq + 1]; }
+            auto epi = [&](const int px, const int py, float v0, float v1, const bool valid) {
+                v0 = fmaxf(v0 + b0, 0.0f); v1 = fmaxf(v1 + b1, 0.0f);
+                float o[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                {
+                    float s = fmaf(v1, kd[q][1], v0 * kd[q][0]);
+                    s += __shfl_xor_sync(0xffffffffu, s, 1);
+                    s += __shfl_xor_sync(0xffffffffu, s, 2);
+                    o[q] = s;
+                }
+                const float mine = tq == 0 ? o[0] : tq == 1 ? o[1] : tq == 2 ? o[2] : o[3];
+                if (valid)
+                {
+                    void* row = static_cast<uint8_t*>(prm.dst) + static_cast<size_t>(2 * (g.oy + py) + (tq >> 1)) * prm.dst_pitch;
+                    net_store1(row, 2 * (g.ox + px) + (tq & 1), prm.type, mine);
+                }
+            };
+            mma_conv3x3(S::NCONV + 1, cur, tfrag, g, epi);
+        }
+        else
+        {
+            const uint32_t* psfrag = tfrag;
+            int LPS = S::NCONV + 1;
+            if constexpr (S::FAM == ACB200_FAMILY_ARNET)
+            {
+                // last block: PReLU conv, then conv *0.2 + x fused with the 1x1 (an m16n8k8 on the re-split sums: the D
+                // fragment layout of the 3x3 IS the A fragment layout of a k8 MMA), PReLU, + feat
+                constexpr int AT = (S::NCONV / 2) * 8;
+                {
+                    const float b0 = prm.b[BT + 2 * tq], b1 = prm.b[BT + 2 * tq + 1], a0 = prm.a[AT + 2 * tq], a1 = prm.a[AT + 2 * tq + 1];
+                    const HalfPlanes out = oth;
+                    auto epi = [&](const int px, const int py, float v0, float v1, const bool valid) {
+                        if (!valid) return;
+                        v0 = prelu(v0 + b0, a0); v1 = prelu(v1 + b1, a1);
+                        uint32_t hi, lo;
+                        split_pair(v0, v1, hi, lo);
+                        reinterpret_cast<uint32_t*>(out.hi + py * FT + px)[tq] = hi;
+                        reinterpret_cast<uint32_t*>(out.lo + py * FT + px)[tq] = lo;
+                    };
+                    mma_conv3x3(S::NCONV + 1, cur, tfrag, g, epi);
+                    __syncthreads();
+                }
+                {
+                    const uint32_t* f3 = tfrag + FRAG_WORDS_3X3;
+                    const uint32_t* f1 = f3 + FRAG_WORDS_3X3;
+                    const uint32_t w1h = __ldg(f1 + lane), w1l = __ldg(f1 + 32 + lane);
+                    const float b0 = prm.b[BT + 8 + 2 * tq], b1 = prm.b[BT + 8 + 2 * tq + 1];
+                    const float c0 = prm.b[BT + 16 + 2 * tq], c1 = prm.b[BT + 16 + 2 * tq + 1];
+                    const float a0 = prm.a[AT + 8 + 2 * tq], a1 = prm.a[AT + 8 + 2 * tq + 1];
+                    const HalfPlanes out = cur;     // x, updated in place
+                    // the epilogue is called for (px, py) then (px + 8, py): collect both halves of the fragment, then run
+                    // the 1x1 as tensor-core MMAs on the pair
+                    float keep[2];
+                    int kx = 0, ky = 0, phase = 0;
+                    bool kvalid = false;
+                    auto epi = [&](const int px, const int py, float v0, float v1, const bool valid) {
+                        uint32_t* ph = reinterpret_cast<uint32_t*>(out.hi + py * FT + px) + tq;
+                        uint32_t* pl = reinterpret_cast<uint32_t*>(out.lo + py * FT + px) + tq;
+                        const float2 id = join_pair(*ph, *pl);
+                        v0 = fmaf(v0 + b0, 0.2f, id.x); v1 = fmaf(v1 + b1, 0.2f, id.y);
+                        if (phase == 0) { keep[0] = v0; keep[1] = v1; kx = px; ky = py; kvalid = valid; phase = 1; return; }
+                        phase = 0;
+                        uint32_t h0, l0, h1, l1;
+                        split_pair(keep[0], keep[1], h0, l0);
+                        split_pair(v0, v1, h1, l1);
+                        float d[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
+                        mma_k8(d, h0, h1, w1h);
+                        mma_k8(d, l0, l1, w1h);
+                        mma_k8(d, h0, h1, w1l);
+                        const int pxs[2] = { kx, px };
+                        const bool oks[2] = { kvalid, valid };
+#pragma unroll
+                        for (int half = 0; half < 2; half++)
+                        {
+                            const int qx = pxs[half];
+                            if (!oks[half]) continue;
+                            float u0 = prelu(d[2 * half] + c0, a0), u1 = prelu(d[2 * half + 1] + c1, a1);
+                            const int gx = clampi(g.ox + qx, 0, prm.w - 1), gy = clampi(g.oy + ky, 0, prm.h - 1);
+                            const float2 ft = *reinterpret_cast<const float2*>(prm.feat_in + (static_cast<size_t>(gy) * prm.w + gx) * 8 + 2 * tq);
+                            u0 += ft.x; u1 += ft.y;
+                            uint32_t hi, lo;
+                            split_pair(u0, u1, hi, lo);
+                            reinterpret_cast<uint32_t*>(out.hi + ky * FT + qx)[tq] = hi;
+                            reinterpret_cast<uint32_t*>(out.lo + ky * FT + qx)[tq] = lo;
+                        }
+                    };
+                    mma_conv3x3(S::NCONV + 2, oth, f3, g, epi);
+                    __syncthreads();
+                    psfrag = f1 + FRAG_WORDS_1X1;
+                    LPS = S::NCONV + 3;
+                }
+            }
+            // pixel-shuffle tail: conv3x3 8->4 (couts 4-7 are zero weights), + nearest-upsampled luma; lane t=0 owns output
+            // row 2y (couts 0,1), lane t=1 owns row 2y+1 (couts 2,3)
+            constexpr int BPS = S::FAM == ACB200_FAMILY_ARNET ? BT + 24 : BT;
+            const float b0 = tq < 2 ? prm.b[BPS + 2 * tq] : 0.0f, b1 = tq < 2 ? prm.b[BPS + 2 * tq + 1] : 0.0f;
+            constexpr int LT_PS = S::FAM == ACB200_FAMILY_ARNET ? S::NCONV + 3 : S::NCONV + 1;
+            auto epi = [&](const int px, const int py, float v0, float v1, const bool valid) {
+                if (tq < 2 && valid)
+                {
+                    const float id = luma[(py + 1) * LT + px + 1];
+                    void* row = static_cast<uint8_t*>(prm.dst) + static_cast<size_t>(2 * (g.oy + py) + tq) * prm.dst_pitch;
+                    net_store2(row, 2 * (g.ox + px), prm.type, (v0 + b0) + id, (v1 + b1) + id, aligned);
+                }
+            };
+            (void)LPS;
+            mma_conv3x3(LT_PS, cur, psfrag, g, epi);
+        }
+    }
+
+    constexpr size_t MMA_SMEM_BYTES = 4 * FT * FT * sizeof(uint4) + LT * LT * sizeof(float);
+}

@@ -327,7 +327,7 @@ def run_ours(args):
                          "frac": achieved_tf / peaks["bf16_tflops_sustained"], "traffic": None,
                          "kernel": "fused luma network (segment kernel), 1920x1080 Y -> 3840x2160 Y", "kernel_ms": kernel_ms,
                          "launches_per_pass": launches_per_pass, "flop_per_launch": flop_frame, "peak_source": peaks["source"],
-                         "pipe": "fp32 FFMA (CUDA cores)" if args.engine == 0 else "split-fp16 tensor-core MMA",
+                         "pipe": "fp32 FFMA (CUDA cores), exact engine" if args.engine == 0 else "split-fp16 tensor-core MMA (3 HMMA per product)",
                          "fp32_ffma_peak_tflops_nominal": fp32_peak_tf, "frac_of_fp32_ffma_peak": achieved_tf / fp32_peak_tf,
                          "frame_roofline_ms": t_roof_ms, "frame_frac": t_roof_ms / (ms_max / (B * args.steps))},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
@@ -346,7 +346,7 @@ def main():
     ap.add_argument("--model", default="acnet-legacy-hdn0")
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--threads", type=int, default=4, help="caller threads sharing the processor in the e2e leg")
-    ap.add_argument("--engine", type=int, default=0)
+    ap.add_argument("--engine", type=int, default=2, help="0 exact FFMA, 1 tensor MMA, 2 auto")
     ap.add_argument("--cpu-frames", type=int, default=12)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

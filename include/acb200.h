@@ -128,7 +128,13 @@ ACB200_API int acb200_resize_catmull_rom_host(acb200_session* session, const voi
 ACB200_API unsigned long long acb200_launch_count(void);
 /* elapsed GPU milliseconds of the most recent process_* call's kernels on this session (CUDA events) */
 ACB200_API float acb200_session_last_kernel_ms(acb200_session* session);
-/* select the luma-network engine: 0 = fp32 FFMA (CUDA cores), 1 = split-fp16 tensor-core MMA; default best */
+/*
+ * Luma-network engine:
+ *   0  exact   fp32 FFMA in the reference FMA-backend summation order: bit-identical to the reference CPU processor
+ *   1  tensor  split-fp16 tensor-core MMA: >= 99.9 % of 8-bit samples identical, <= 1 LSB
+ *   2  auto    (default) exact for every 2x pass but the last, tensor for the last -- multi-pass factors (4x, 8x)
+ *              keep the 8-bit bar because no rounding difference is fed back into a later pass
+ */
 ACB200_API int acb200_session_set_engine(acb200_session* session, int engine);
 
 ACB200_API const char* acb200_error_string(int code);

@@ -27,7 +27,7 @@ U16_LSB_MAX = 4
 # (measured in this repo: tests/test_oracle_cpu.py::test_reference_isa_spread_4x), so against Generic-order vectors a 4x
 # result is held to that spread; against FMA-order vectors the exact engine must still be bit-identical.
 X4_LSB_MAX, X4_EXACT_MIN = 4, 0.995
-ENGINE_EXACT, ENGINE_TENSOR = 0, 1
+ENGINE_EXACT, ENGINE_TENSOR, ENGINE_AUTO = 0, 1, 2
 ENGINES = [ENGINE_EXACT]
 
 
@@ -128,6 +128,64 @@ def test_colour_vs_oracle(session, name, c, factor):
     O.set_order(O.ORDER_FMA)
     for x, out in zip((img, f, u), outs):
         assert np.array_equal(out, O.oracle_process(name, x, factor))
+
+
+# ---- tensor-core engine (split-fp16 MMA): the 8-bit bar against BOTH reference orders -------------------------------------
+@pytest.mark.parametrize("key", GOLD_KEYS)
+def test_tensor_engine_golden(session, key):
+    kind, name = key.split("/", 1)
+    x4 = kind.endswith("4x")
+    session.set_engine(ENGINE_TENSOR)
+    out = session.process_host(gpu_model(name), src_for(kind), 4.0 if x4 else 2.0)
+    check_close(out, GOLD[key], x4=x4)
+    check_close(out, GOLD["fma:" + key], x4=x4)
+    if x4:
+        # default engine: exact for the first pass, tensor for the last -> the 2x bar holds at 4x against the FMA-order vectors
+        session.set_engine(ENGINE_AUTO)
+        check_close(session.process_host(gpu_model(name), src_for(kind), 4.0), GOLD["fma:" + key])
+
+
+@pytest.mark.parametrize("name", ["acnet-legacy-hdn0", "acnet-legacy-gan", "acnet-f8b4", "acnet-f8b8-hdn", "acnet-f8b18-box-hdn", "arnet-f8b8", "arnet-f8b16"])
+@pytest.mark.parametrize("shape", [(3, 3), (1, 7), (9, 1), (17, 31), (40, 40), (41, 39), (64, 64), (97, 131), (255, 257)])
+def test_tensor_engine_odd_sizes(session, name, shape):
+    img = O.noise_u8(shape[0], shape[1], 1, seed=shape[0] * 1000 + shape[1])
+    session.set_engine(ENGINE_TENSOR)
+    out = session.process_host(gpu_model(name), img, 2.0)
+    O.set_order(O.ORDER_FMA)
+    check_close(out, O.oracle_process(name, img, 2.0))
+
+
+@pytest.mark.parametrize("name", ["acnet-legacy-hdn0", "acnet-f8b8-hdn", "arnet-f8b8"])
+def test_tensor_engine_1080p_against_exact_engine(session, name):
+    # full BASELINE size: the exact engine (bit-identical to the reference) is the checker for the tensor engine
+    img = O.smooth_u8(1080, 1920, 1, seed=3)
+    m = gpu_model(name)
+    session.set_engine(ENGINE_EXACT)
+    want = session.process_host(m, img, 2.0)
+    session.set_engine(ENGINE_TENSOR)
+    got = session.process_host(m, img, 2.0)
+    mx, exact = O.compare_u8(got, want)
+    assert mx <= 1 and exact >= 0.9995, (mx, exact)
+    noise = O.noise_u8(540, 960, 1, seed=4)
+    session.set_engine(ENGINE_EXACT)
+    want = session.process_host(m, noise, 2.0)
+    session.set_engine(ENGINE_TENSOR)
+    mx, exact = O.compare_u8(session.process_host(m, noise, 2.0), want)
+    assert mx <= 1 and exact >= 0.999, (mx, exact)
+
+
+def test_tensor_engine_colour_and_types(session):
+    for name in ("acnet-legacy-hdn1", "acnet-f8b8", "arnet-f8b8-box"):
+        img = O.noise_u8(45, 61, 3, seed=17)
+        O.set_order(O.ORDER_FMA)
+        session.set_engine(ENGINE_TENSOR)
+        check_close(session.process_host(gpu_model(name), img, 2.0), O.oracle_process(name, img, 2.0))
+        f = img.astype(np.float32) / np.float32(255)
+        check_close(session.process_host(gpu_model(name), f, 2.0), O.oracle_process(name, f, 2.0))
+        u = img.astype(np.uint16) * 257
+        check_close(session.process_host(gpu_model(name), u, 2.0), O.oracle_process(name, u, 2.0))
+        session.set_engine(ENGINE_AUTO)
+        check_close(session.process_host(gpu_model(name), img, 4.0), O.oracle_process(name, img, 4.0))
 
 
 @pytest.mark.parametrize("value", [0, 128, 255])
