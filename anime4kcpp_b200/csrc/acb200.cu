@@ -486,8 +486,18 @@ namespace
         if (c > 1)
         {
             if ((rc = ensure_tables(s, st, w, h, cw, ch)) != ACB200_OK) return rc;
-            chroma_merge_kernel<<<dim3((cw + 31) / 32, (ch + 7) / 8), blk, 0, st>>>(cur, cur_pitch, s->uv.p, static_cast<int>(pitch_of(w, c - 1, es)),
-                static_cast<const Contrib*>(s->htab.p), static_cast<const Contrib*>(s->vtab.p), cw, ch, c, type, d_dst, dst_pitch);
+            const int uv_pitch = static_cast<int>(pitch_of(w, c - 1, es));
+            const Contrib* ht = static_cast<const Contrib*>(s->htab.p);
+            const Contrib* vt = static_cast<const Contrib*>(s->vtab.p);
+            const dim3 cgrid((cw + CM_OW - 1) / CM_OW, (ch + CM_OH - 1) / CM_OH);
+            if (type == ACB200_UINT8 && c == 3)
+                chroma_merge_u8_kernel<3><<<cgrid, CM_THREADS, 0, st>>>(static_cast<const uint8_t*>(cur), cur_pitch, static_cast<const uint8_t*>(s->uv.p), uv_pitch,
+                                                                         ht, vt, cw, ch, static_cast<uint8_t*>(d_dst), dst_pitch);
+            else if (type == ACB200_UINT8 && c == 4)
+                chroma_merge_u8_kernel<4><<<cgrid, CM_THREADS, 0, st>>>(static_cast<const uint8_t*>(cur), cur_pitch, static_cast<const uint8_t*>(s->uv.p), uv_pitch,
+                                                                         ht, vt, cw, ch, static_cast<uint8_t*>(d_dst), dst_pitch);
+            else
+                chroma_merge_kernel<<<dim3((cw + 31) / 32, (ch + 7) / 8), blk, 0, st>>>(cur, cur_pitch, s->uv.p, uv_pitch, ht, vt, cw, ch, c, type, d_dst, dst_pitch);
             g_launches.fetch_add(1, std::memory_order_relaxed);
             ACB_CUDA(s, cudaGetLastError());
         }

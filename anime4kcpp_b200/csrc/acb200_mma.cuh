@@ -110,14 +110,30 @@ namespace acb
                      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(b0));
     }
 
+    __device__ __forceinline__ void ldmatrix_x4_off(uint32_t (&r)[4], uint32_t saddr, int imm_plane)
+    {
+        // second plane (lo) sits at a fixed byte distance from the first: fold it into the address immediate
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4+%5];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr), "n"(FT * FT * 16));
+        (void)imm_plane;
+    }
+    __device__ __forceinline__ void ldmatrix_x2_off(uint32_t (&r)[2], uint32_t saddr)
+    {
+        asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2+%3];" : "=r"(r[0]), "=r"(r[1]) : "r"(saddr), "n"(FT * FT * 16));
+    }
+
     // One 3x3 conv layer (8 -> 8, or 8 -> 4 with the upper output channels' weights zero) on the tensor cores.
-    //   epi(px, py, v0, v1, valid): called by every lane twice per tile -- first for pixel (x0+g, y), then (x0+g+8, y) --
-    //   with the finished fp32 sums (bias NOT included) of output channels 2t, 2t+1.  `valid` is false for pixels the tile
-    //   does not own (overhang past the layer's region, or the overlap of a left-shifted last tile): the epilogue may use
-    //   warp collectives but must not store for them (an in-place residual would otherwise be applied twice).
+    //
+    // The layer's output region (image-clipped, Wr x Hr pixels) is tiled FLAT: M-tile j is the 16 row-major-consecutive
+    // region pixels 16j .. 16j+15, wrapping across region rows.  ldmatrix takes one row address per lane, so a wrap costs
+    // nothing but an occasional 2-way bank conflict, and no MMA row is spent on padding a region width up to a multiple of 16.
+    //
+    //   epi(px, py, v0, v1, valid): called by every lane twice per tile -- for the D-fragment rows g and g+8 -- with the
+    //   finished fp32 sums (bias NOT included) of output channels 2t, 2t+1 at frame pixel (px, py).  `valid` is false only in
+    //   the overhang of the last tile: the epilogue may use warp collectives but must not store for those.
     //   L = number of 3x3 layers between the frame and this layer's output (its region is the frame shrunk by L).
-    template<class Epi>
-    __device__ __forceinline__ void mma_conv3x3(const int L, const HalfPlanes& in, const uint32_t* __restrict__ frag, const TileGeom& g, Epi&& epi)
+    //   The hi plane and the lo plane of `in` must be FT*FT*16 bytes apart (they are: see the kernel's smem carve-up).
+    template<bool BORDER, class Epi>
+    __device__ __forceinline__ void mma_conv3x3_impl(const int L, const HalfPlanes& in, const uint32_t* __restrict__ frag, const TileGeom& g, Epi&& epi)
     {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         // B fragments of the layer: registers 0-8 = hi (k-steps 0-3: two registers, k-step 4: one), 9-17 = lo
@@ -126,50 +142,78 @@ namespace acb
         for (int i = 0; i < 18; i++) bf[i] = __ldg(frag + i * 32 + lane);
 
         const int xa = max(L, g.ix0), xb = min(FT - L, g.ix1 + 1), ya = max(L, g.iy0), yb = min(FT - L, g.iy1 + 1);
-        const int tiles = (xb - xa + 15) >> 4, n = tiles * (yb - ya);
+        const int wr = xb - xa, npix = wr * (yb - ya), tiles = (npix + 15) >> 4;
+        const uint32_t rcp = (1u << 20) / static_cast<uint32_t>(max(wr, 1)) + 1u;     // q / wr == (q * rcp) >> 20 for q < 3300, wr <= 56
         const int cx_lo = max(g.ix0, 0), cx_hi = min(g.ix1, FT - 1), cy_lo = max(g.iy0, 0), cy_hi = min(g.iy1, FT - 1);
         const int m = lane >> 3, r = lane & 7, h = m >> 1;      // ldmatrix: this lane supplies row r of matrix m
         const uint32_t hi_base = static_cast<uint32_t>(__cvta_generic_to_shared(in.hi));
-        const uint32_t lo_base = static_cast<uint32_t>(__cvta_generic_to_shared(in.lo));
-        for (int it = warp; it < n; it += MMA_WARPS)
-        {
-            const int y = ya + it / tiles;
-            const int own_lo = xa + ((it % tiles) << 4);
-            const int x0 = min(own_lo, FT - 16);
-            // this lane's pixel for the A rows it feeds, with replicate padding at the image border
-            const int px = x0 + r + ((m & 1) << 3);
-            const int cx[3] = { clampi(px - 1, cx_lo, cx_hi), clampi(px, cx_lo, cx_hi), clampi(px + 1, cx_lo, cx_hi) };
-            const int ry[3] = { clampi(y - 1, cy_lo, cy_hi) * FT, clampi(y, cy_lo, cy_hi) * FT, clampi(y + 1, cy_lo, cy_hi) * FT };
-            float c[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
+        // byte offset of this lane's tap for k-step s relative to its pixel (interior tiles: no clamping needed, every
+        // read stays inside the frame because the region is the frame shrunk by L >= 1)
+        int toff[5];
 #pragma unroll
-            for (int s = 0; s < 5; s++)
+        for (int s = 0; s < 5; s++)
+        {
+            const int tap = (h && s < 4) ? 2 * s + 1 : 2 * s;
+            toff[s] = ((tap / 3 - 1) * FT + (tap % 3 - 1)) * 16;
+        }
+        const int arow = r + ((m & 1) << 3), drow = lane >> 2;
+        for (int it = warp; it < tiles; it += MMA_WARPS)
+        {
+            const int q = min(it * 16 + arow, npix - 1);
+            const int qy = static_cast<int>((static_cast<uint32_t>(q) * rcp) >> 20), qx = q - qy * wr;
+            const int px = xa + qx, py = ya + qy;
+            float c0[4] = { 0.0f, 0.0f, 0.0f, 0.0f }, c1[4] = { 0.0f, 0.0f, 0.0f, 0.0f }, c2[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
+            uint32_t addr[5];
+            if (BORDER)
             {
-                // k-step s covers taps 2s (matrices 0,1) and 2s+1 (matrices 2,3); tap = dy*3 + dx
-                const int t0 = 2 * s, t1 = 2 * s + 1;
-                const int off = (h && s < 4) ? ry[t1 / 3] + cx[t1 % 3] : ry[t0 / 3] + cx[t0 % 3];
-                if (s < 4)
+                const int cx[3] = { clampi(px - 1, cx_lo, cx_hi), px, clampi(px + 1, cx_lo, cx_hi) };
+                const int ry[3] = { clampi(py - 1, cy_lo, cy_hi) * FT, py * FT, clampi(py + 1, cy_lo, cy_hi) * FT };
+#pragma unroll
+                for (int s = 0; s < 5; s++)
                 {
-                    uint32_t ah[4], al[4];
-                    ldmatrix_x4(ah, hi_base + off * 16);
-                    ldmatrix_x4(al, lo_base + off * 16);
-                    mma_k16(c, ah, bf[2 * s], bf[2 * s + 1]);
-                    mma_k16(c, al, bf[2 * s], bf[2 * s + 1]);
-                    mma_k16(c, ah, bf[9 + 2 * s], bf[9 + 2 * s + 1]);
-                }
-                else
-                {
-                    uint32_t ah[2], al[2];
-                    ldmatrix_x2(ah, hi_base + off * 16);
-                    ldmatrix_x2(al, lo_base + off * 16);
-                    mma_k8(c, ah[0], ah[1], bf[8]);
-                    mma_k8(c, al[0], al[1], bf[8]);
-                    mma_k8(c, ah[0], ah[1], bf[17]);
+                    const int t0 = 2 * s, t1 = 2 * s + 1;
+                    addr[s] = hi_base + (((h && s < 4) ? ry[t1 / 3] + cx[t1 % 3] : ry[t0 / 3] + cx[t0 % 3]) << 4);
                 }
             }
-            const int p0 = x0 + (lane >> 2), p1 = p0 + 8;
-            epi(p0, y, c[0], c[1], p0 >= own_lo && p0 < xb);
-            epi(p1, y, c[2], c[3], p1 >= own_lo && p1 < xb);
+            else
+            {
+                const uint32_t pix = hi_base + ((py * FT + px) << 4);
+#pragma unroll
+                for (int s = 0; s < 5; s++) addr[s] = pix + toff[s];
+            }
+            // three independent accumulator chains (hi*hi, lo*hi, hi*lo) so consecutive MMAs never wait on each other
+#pragma unroll
+            for (int s = 0; s < 4; s++)
+            {
+                uint32_t ah[4], al[4];
+                ldmatrix_x4(ah, addr[s]);
+                ldmatrix_x4_off(al, addr[s], 0);
+                mma_k16(c0, ah, bf[2 * s], bf[2 * s + 1]);
+                mma_k16(c1, al, bf[2 * s], bf[2 * s + 1]);
+                mma_k16(c2, ah, bf[9 + 2 * s], bf[9 + 2 * s + 1]);
+            }
+            {
+                uint32_t ah[2], al[2];
+                ldmatrix_x2(ah, addr[4]);
+                ldmatrix_x2_off(al, addr[4]);
+                mma_k8(c0, ah[0], ah[1], bf[8]);
+                mma_k8(c1, al[0], al[1], bf[8]);
+                mma_k8(c2, ah[0], ah[1], bf[17]);
+            }
+            // D fragment rows: region pixels 16*it + g and + 8
+            const int q0 = it * 16 + drow, q1 = q0 + 8;
+            const int y0 = static_cast<int>((static_cast<uint32_t>(min(q0, npix - 1)) * rcp) >> 20), x0 = min(q0, npix - 1) - y0 * wr;
+            const int y1 = static_cast<int>((static_cast<uint32_t>(min(q1, npix - 1)) * rcp) >> 20), x1 = min(q1, npix - 1) - y1 * wr;
+            epi(xa + x0, ya + y0, (c0[0] + c1[0]) + c2[0], (c0[1] + c1[1]) + c2[1], q0 < npix);
+            epi(xa + x1, ya + y1, (c0[2] + c1[2]) + c2[2], (c0[3] + c1[3]) + c2[3], q1 < npix);
         }
+    }
+    template<class Epi>
+    __device__ __forceinline__ void mma_conv3x3(const int L, const HalfPlanes& in, const uint32_t* __restrict__ frag, const TileGeom& g, Epi&& epi)
+    {
+        // interior CTA: the image covers the whole frame, no replicate padding anywhere in this tile (uniform branch)
+        if (g.ix0 <= 0 && g.iy0 <= 0 && g.ix1 >= FT - 1 && g.iy1 >= FT - 1) mma_conv3x3_impl<false>(L, in, frag, g, epi);
+        else mma_conv3x3_impl<true>(L, in, frag, g, epi);
     }
 
     template<class S>
@@ -390,21 +434,21 @@ namespace acb
                         mma_k8(d, h0, h1, w1h);
                         mma_k8(d, l0, l1, w1h);
                         mma_k8(d, h0, h1, w1l);
-                        const int pxs[2] = { kx, px };
+                        const int pxs[2] = { kx, px }, pys[2] = { ky, py };
                         const bool oks[2] = { kvalid, valid };
 #pragma unroll
                         for (int half = 0; half < 2; half++)
                         {
-                            const int qx = pxs[half];
+                            const int qx = pxs[half], qy = pys[half];
                             if (!oks[half]) continue;
                             float u0 = prelu(d[2 * half] + c0, a0), u1 = prelu(d[2 * half + 1] + c1, a1);
-                            const int gx = clampi(g.ox + qx, 0, prm.w - 1), gy = clampi(g.oy + ky, 0, prm.h - 1);
+                            const int gx = clampi(g.ox + qx, 0, prm.w - 1), gy = clampi(g.oy + qy, 0, prm.h - 1);
                             const float2 ft = *reinterpret_cast<const float2*>(prm.feat_in + (static_cast<size_t>(gy) * prm.w + gx) * 8 + 2 * tq);
                             u0 += ft.x; u1 += ft.y;
                             uint32_t hi, lo;
                             split_pair(u0, u1, hi, lo);
-                            reinterpret_cast<uint32_t*>(out.hi + ky * FT + qx)[tq] = hi;
-                            reinterpret_cast<uint32_t*>(out.lo + ky * FT + qx)[tq] = lo;
+                            reinterpret_cast<uint32_t*>(out.hi + qy * FT + qx)[tq] = hi;
+                            reinterpret_cast<uint32_t*>(out.lo + qy * FT + qx)[tq] = lo;
                         }
                     };
                     mma_conv3x3(S::NCONV + 2, oth, f3, g, epi);
