@@ -268,7 +268,7 @@ struct acb200_session
     Buf src, dst, y[2], uv, map[2], feat, htab, vtab;
     // device copies of models' packed fragments, keyed by acb200_model::uid
     std::map<unsigned long long, void*> dev_frags;
-    int tab_in_w = 0, tab_in_h = 0, tab_out_w = 0, tab_out_h = 0;
+    int tab_in_w = 0, tab_in_h = 0, tab_out_w = 0, tab_out_h = 0, tab_max_cnt = 0;
     int smem_configured = 0;
 };
 
@@ -435,6 +435,9 @@ namespace
         ACB_CUDA(s, cudaMemcpyAsync(s->vtab.p, vt.data(), vt.size() * sizeof(Contrib), cudaMemcpyHostToDevice, st));
         ACB_CUDA(s, cudaStreamSynchronize(st));
         s->tab_in_w = w; s->tab_in_h = h; s->tab_out_w = ow; s->tab_out_h = oh;
+        s->tab_max_cnt = 0;
+        for (const Contrib& k : ht) s->tab_max_cnt = std::max(s->tab_max_cnt, k.cnt);
+        for (const Contrib& k : vt) s->tab_max_cnt = std::max(s->tab_max_cnt, k.cnt);
         return ACB200_OK;
     }
 
@@ -490,12 +493,12 @@ namespace
             const Contrib* ht = static_cast<const Contrib*>(s->htab.p);
             const Contrib* vt = static_cast<const Contrib*>(s->vtab.p);
             const dim3 cgrid((cw + CM_OW - 1) / CM_OW, (ch + CM_OH - 1) / CM_OH);
-            if (type == ACB200_UINT8 && c == 3)
+            if (type == ACB200_UINT8 && c == 3 && s->tab_max_cnt <= 4)
                 chroma_merge_u8_kernel<3><<<cgrid, CM_THREADS, 0, st>>>(static_cast<const uint8_t*>(cur), cur_pitch, static_cast<const uint8_t*>(s->uv.p), uv_pitch,
-                                                                         ht, vt, cw, ch, static_cast<uint8_t*>(d_dst), dst_pitch);
-            else if (type == ACB200_UINT8 && c == 4)
+                                                                         w, h, ht, vt, cw, ch, static_cast<uint8_t*>(d_dst), dst_pitch);
+            else if (type == ACB200_UINT8 && c == 4 && s->tab_max_cnt <= 4)
                 chroma_merge_u8_kernel<4><<<cgrid, CM_THREADS, 0, st>>>(static_cast<const uint8_t*>(cur), cur_pitch, static_cast<const uint8_t*>(s->uv.p), uv_pitch,
-                                                                         ht, vt, cw, ch, static_cast<uint8_t*>(d_dst), dst_pitch);
+                                                                         w, h, ht, vt, cw, ch, static_cast<uint8_t*>(d_dst), dst_pitch);
             else
                 chroma_merge_kernel<<<dim3((cw + 31) / 32, (ch + 7) / 8), blk, 0, st>>>(cur, cur_pitch, s->uv.p, uv_pitch, ht, vt, cw, ch, c, type, d_dst, dst_pitch);
             g_launches.fetch_add(1, std::memory_order_relaxed);

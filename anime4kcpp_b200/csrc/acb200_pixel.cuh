@@ -180,99 +180,125 @@ namespace acb
     }
 
     // ---- 8-bit fast path of the fused chroma resize + merge ------------------------------------------------------------
-    // One CTA produces a CM_OW x CM_OH tile of the output: it stages the contributor tables and the decoded source (u,v[,a])
-    // tile in shared memory, runs the horizontal pass ONCE per source row (not once per output row), then each thread does
-    // the vertical pass, the re-quantisation and the YUV->RGB merge for 4 adjacent output pixels and writes them as 32-bit
-    // words.  Same arithmetic, same rounding points and same summation order as chroma_merge_kernel (the general path).
+    // One CTA produces a CM_OW x CM_OH tile of the output: it stages the decoded source (u,v[,a]) tile in shared memory, runs
+    // the horizontal pass ONCE per source row (not once per output row), then each thread does the vertical pass, the
+    // re-quantisation and the YUV->RGB merge for 4 adjacent output pixels and writes them as 32-bit words.
+    // Same arithmetic, rounding points and summation order as chroma_merge_kernel (the general path); taps beyond a
+    // contributor's count carry a zero coefficient, which leaves every partial sum unchanged.  Requires cnt <= 4 (true for
+    // every upscale: the Catmull-Rom support spans 4 source pixels).
     constexpr int CM_OW = 64, CM_OH = 16, CM_THREADS = 256;
-    constexpr int CM_SRC_W = CM_OW + 6, CM_SRC_H = CM_OH + 6;      // worst case (scale -> 1): tile + Catmull-Rom support
+    constexpr int CM_SRC_W = CM_OW + 8, CM_SRC_H = CM_OH + 8;      // worst case (scale -> 1): tile + support + unrolled-tap slack
 
     template<int C>
     __global__ void __launch_bounds__(CM_THREADS) chroma_merge_u8_kernel(const uint8_t* __restrict__ yp, int y_pitch, const uint8_t* __restrict__ uvp, int uv_pitch,
+                                                                      int sw_img, int sh_img,
                                                                       const Contrib* __restrict__ htab, const Contrib* __restrict__ vtab,
                                                                       int ow, int oh, uint8_t* __restrict__ dst, int dst_pitch)
     {
         constexpr int UVC = C - 1;
-        __shared__ Contrib sh_h[CM_OW], sh_v[CM_OH];
         __shared__ float lut[256];
         __shared__ float s_src[CM_SRC_H][CM_SRC_W * UVC];
         __shared__ float s_hp[CM_SRC_H][CM_OW * UVC];
-        const int tid = threadIdx.x;
+        const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
         const int ox0 = blockIdx.x * CM_OW, oy0 = blockIdx.y * CM_OH;
         const int ncols = min(CM_OW, ow - ox0), nrows = min(CM_OH, oh - oy0);
         lut[tid] = __fdiv_rn(static_cast<float>(tid), 255.0f);       // toFloat<u8>: a true division (Util.hpp:53-54)
-        if (tid < ncols) sh_h[tid] = htab[ox0 + tid];
-        else if (tid >= 128 && tid - 128 < nrows) sh_v[tid - 128] = vtab[oy0 + tid - 128];
-        __syncthreads();
-        const int sx0 = sh_h[0].n0, sx1 = sh_h[ncols - 1].n0 + sh_h[ncols - 1].cnt - 1;
-        const int sy0 = sh_v[0].n0, sy1 = sh_v[nrows - 1].n0 + sh_v[nrows - 1].cnt - 1;
-        const int sw = sx1 - sx0 + 1, shh = sy1 - sy0 + 1;
-        // decoded source tile (stb decode: q * (1/255), a multiply)
-        for (int i = tid; i < shh * sw * UVC; i += CM_THREADS)
-        {
-            const int row = i / (sw * UVC), e = i - row * (sw * UVC);
-            s_src[row][e] = __fmul_rn(static_cast<float>(uvp[static_cast<size_t>(sy0 + row) * uv_pitch + sx0 * UVC + e]), 1.0f / 255.0f);
-        }
-        __syncthreads();
-        // horizontal pass
-        for (int i = tid; i < shh * ncols * UVC; i += CM_THREADS)
-        {
-            const int row = i / (ncols * UVC), e = i - row * (ncols * UVC);
-            const int col = e / UVC, ch = e - col * UVC;
-            const Contrib& k = sh_h[col];
-            const float* srow = &s_src[row][(k.n0 - sx0) * UVC + ch];
-            float hsum = __fmul_rn(k.c[0], srow[0]);
-            for (int j = 1; j < k.cnt; j++) hsum = __fadd_rn(hsum, __fmul_rn(k.c[j], srow[j * UVC]));
-            s_hp[row][e] = hsum;
-        }
-        __syncthreads();
-        // vertical pass + re-quantise + merge: 4 adjacent output pixels per thread
-        for (int i = tid; i < nrows * (CM_OW / 4); i += CM_THREADS)
-        {
-            const int orow = i / (CM_OW / 4), c4 = (i - orow * (CM_OW / 4)) * 4;
-            if (c4 >= ncols) continue;
-            const Contrib& k = sh_v[orow];
-            const int oy = oy0 + orow;
-            const uint8_t* yrow = yp + static_cast<size_t>(oy) * y_pitch + ox0 + c4;
-            uint8_t outb[4 * C];
-#pragma unroll
-            for (int p = 0; p < 4; p++)
+        // source window of the tile (tables are monotonic in n0)
+        const Contrib hfirst = htab[ox0], hlast = htab[ox0 + ncols - 1], vfirst = vtab[oy0], vlast = vtab[oy0 + nrows - 1];
+        const int sx0 = hfirst.n0, sy0 = vfirst.n0;
+        const int sw = min(hlast.n0 + 4, sw_img) - sx0 + 0, shh = min(vlast.n0 + 4, sh_img) - sy0;
+        // decoded source tile (stb decode: q * (1/255), a multiply); columns / rows past the image stay zero-weighted
+        const int drows = min(vlast.n0 + 4 - sy0, CM_SRC_H), dcols = min(hlast.n0 + 4 - sx0, CM_SRC_W) * UVC;
+        for (int row = warp; row < drows; row += CM_THREADS / 32)
+            for (int e = lane; e < dcols; e += 32)
             {
-                const int col = min(c4 + p, ncols - 1);
-                float q[3] = { 0.0f, 0.0f, 1.0f };
+                float v = 0.0f;
+                if (row < shh && e < sw * UVC) v = __fmul_rn(static_cast<float>(uvp[static_cast<size_t>(sy0 + row) * uv_pitch + sx0 * UVC + e]), 1.0f / 255.0f);
+                s_src[row][e] = v;
+            }
+        // this lane's two output columns of the horizontal pass
+        Contrib hk[2];
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+        {
+            const int col = min(lane + 32 * j, ncols - 1);
+            hk[j] = htab[ox0 + col];
+            hk[j].n0 -= sx0;
+        }
+        __syncthreads();
+        // rows / columns past the image are zero in s_src and carry zero coefficients: run the pass over them too so the
+        // vertical pass never multiplies 0 by uninitialised shared memory
+        const int hrows = min(vlast.n0 + 4 - sy0, CM_SRC_H);
+        for (int row = warp; row < hrows; row += CM_THREADS / 32)
+#pragma unroll
+            for (int j = 0; j < 2; j++)
+            {
+                const float* srow = &s_src[row][hk[j].n0 * UVC];
 #pragma unroll
                 for (int ch = 0; ch < UVC; ch++)
                 {
-                    const float* hcol = &s_hp[k.n0 - sy0][col * UVC + ch];
-                    float sum = __fmul_rn(k.c[0], hcol[0]);
-                    for (int j = 1; j < k.cnt; j++) sum = __fadd_rn(sum, __fmul_rn(k.c[j], hcol[j * CM_OW * UVC]));
-                    float f = __fadd_rn(__fmul_rn(sum, 255.0f), 0.5f);      // stb encode, then toFloat of the stored byte
-                    f = f < 0.0f ? 0.0f : (f > 255.0f ? 255.0f : f);
-                    q[ch] = lut[static_cast<int>(f)];
+                    float hsum = __fmul_rn(hk[j].c[0], srow[ch]);
+                    hsum = __fadd_rn(hsum, __fmul_rn(hk[j].c[1], srow[UVC + ch]));
+                    hsum = __fadd_rn(hsum, __fmul_rn(hk[j].c[2], srow[2 * UVC + ch]));
+                    hsum = __fadd_rn(hsum, __fmul_rn(hk[j].c[3], srow[3 * UVC + ch]));
+                    s_hp[row][(lane + 32 * j) * UVC + ch] = hsum;
                 }
-                const float yv = lut[yrow[min(p, ncols - 1 - c4)]];
-                const float u = __fsub_rn(q[0], 0.5f), v = __fsub_rn(q[1], 0.5f);
-                float r = __fadd_rn(yv, __fmul_rn(1.403f, v));
-                float gch = __fsub_rn(__fsub_rn(yv, __fmul_rn(0.344f, u)), __fmul_rn(0.714f, v));
-                float b = __fadd_rn(yv, __fmul_rn(1.773f, u));
-                if (C == 4)
-                {
-                    if (q[2] > 1e-6f) { r = __fdiv_rn(r, q[2]); gch = __fdiv_rn(gch, q[2]); b = __fdiv_rn(b, q[2]); }
-                    else r = gch = b = 0.0f;
-                    outb[p * C + 3] = quant_u8(q[2]);
-                }
-                outb[p * C + 0] = quant_u8(r); outb[p * C + 1] = quant_u8(gch); outb[p * C + 2] = quant_u8(b);
             }
-            uint8_t* orow_ptr = dst + static_cast<size_t>(oy) * dst_pitch + static_cast<size_t>(ox0 + c4) * C;
-            if (c4 + 4 <= ncols && ((reinterpret_cast<uintptr_t>(orow_ptr) & 3) == 0))
-            {
+        __syncthreads();
+        // vertical pass + re-quantise + merge: consecutive lanes take consecutive output columns (conflict-free reads of the
+        // horizontal-pass rows); the finished bytes are staged in shared memory and leave as 16-byte vectors
+        __shared__ __align__(16) uint8_t s_out[CM_OH][CM_OW * C];
+        for (int idx = tid; idx < CM_OW * CM_OH; idx += CM_THREADS)
+        {
+            const int orow = idx / CM_OW, col = idx % CM_OW;
+            if (orow >= nrows || col >= ncols) continue;
+            const Contrib k = vtab[oy0 + orow];
+            const int r0 = k.n0 - sy0;
+            float q[3] = { 0.0f, 0.0f, 1.0f };
 #pragma unroll
-                for (int wd = 0; wd < C; wd++)
-                    reinterpret_cast<uint32_t*>(orow_ptr)[wd] = static_cast<uint32_t>(outb[4 * wd]) | (static_cast<uint32_t>(outb[4 * wd + 1]) << 8) |
-                                                                 (static_cast<uint32_t>(outb[4 * wd + 2]) << 16) | (static_cast<uint32_t>(outb[4 * wd + 3]) << 24);
+            for (int ch = 0; ch < UVC; ch++)
+            {
+                const float* hcol = &s_hp[r0][col * UVC + ch];
+                float sum = __fmul_rn(k.c[0], hcol[0]);
+                sum = __fadd_rn(sum, __fmul_rn(k.c[1], hcol[CM_OW * UVC]));
+                sum = __fadd_rn(sum, __fmul_rn(k.c[2], hcol[2 * CM_OW * UVC]));
+                sum = __fadd_rn(sum, __fmul_rn(k.c[3], hcol[3 * CM_OW * UVC]));
+                float f = __fadd_rn(__fmul_rn(sum, 255.0f), 0.5f);      // stb encode, then toFloat of the stored byte
+                f = f < 0.0f ? 0.0f : (f > 255.0f ? 255.0f : f);
+                q[ch] = lut[static_cast<int>(f)];
             }
-            else
-                for (int e = 0; e < (ncols - c4 < 4 ? ncols - c4 : 4) * C; e++) orow_ptr[e] = outb[e];
+            const float yv = lut[yp[static_cast<size_t>(oy0 + orow) * y_pitch + ox0 + col]];
+            const float u = __fsub_rn(q[0], 0.5f), v = __fsub_rn(q[1], 0.5f);
+            float r = __fadd_rn(yv, __fmul_rn(1.403f, v));
+            float gch = __fsub_rn(__fsub_rn(yv, __fmul_rn(0.344f, u)), __fmul_rn(0.714f, v));
+            float b = __fadd_rn(yv, __fmul_rn(1.773f, u));
+            uint8_t* o = &s_out[orow][col * C];
+            if (C == 4)
+            {
+                if (q[2] > 1e-6f) { r = __fdiv_rn(r, q[2]); gch = __fdiv_rn(gch, q[2]); b = __fdiv_rn(b, q[2]); }
+                else r = gch = b = 0.0f;
+                o[3] = quant_u8(q[2]);
+            }
+            o[0] = quant_u8(r); o[1] = quant_u8(gch); o[2] = quant_u8(b);
+        }
+        __syncthreads();
+        uint8_t* tile_dst = dst + static_cast<size_t>(oy0) * dst_pitch + static_cast<size_t>(ox0) * C;
+        if (ncols == CM_OW && ((reinterpret_cast<uintptr_t>(tile_dst) | static_cast<uintptr_t>(dst_pitch)) & 15) == 0)
+        {
+            constexpr int VEC_PER_ROW = CM_OW * C / 16;
+            for (int i = tid; i < nrows * VEC_PER_ROW; i += CM_THREADS)
+            {
+                const int row = i / VEC_PER_ROW, v = i % VEC_PER_ROW;
+                reinterpret_cast<uint4*>(tile_dst + static_cast<size_t>(row) * dst_pitch)[v] = reinterpret_cast<const uint4*>(s_out[row])[v];
+            }
+        }
+        else
+        {
+            for (int i = tid; i < nrows * ncols * C; i += CM_THREADS)
+            {
+                const int row = i / (ncols * C), e = i % (ncols * C);
+                tile_dst[static_cast<size_t>(row) * dst_pitch + e] = s_out[row][e];
+            }
         }
     }
 }
