@@ -28,7 +28,10 @@
 
 namespace acb
 {
-    constexpr int MMA_THREADS = 512;
+#ifndef ACB_MMA_THREADS
+#define ACB_MMA_THREADS 512
+#endif
+    constexpr int MMA_THREADS = ACB_MMA_THREADS;
     constexpr int MMA_WARPS = MMA_THREADS / 32;
     constexpr int FRAG_WORDS_3X3 = 18 * 32;     // uint32 per packed 3x3 layer: (4 x 2 + 1) registers x {hi, lo} x 32 lanes
     constexpr int FRAG_WORDS_1X1 = 2 * 32;      // the ARNet 1x1: one k8 register x {hi, lo}
@@ -65,9 +68,11 @@ namespace acb
     // v -> (hi, lo) fp16 pair
     __device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& hi, uint32_t& lo)
     {
-        const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
-        hi = pack_half2(h0, h1);
-        lo = pack_half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1)));
+        const __half2 h = __floats2half2_rn(v0, v1);        // one packed conversion
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+        hi = *reinterpret_cast<const uint32_t*>(&h);
+        lo = *reinterpret_cast<const uint32_t*>(&l);
     }
     __device__ __forceinline__ float2 join_pair(uint32_t hi, uint32_t lo)
     {
@@ -162,7 +167,7 @@ namespace acb
             const int q = min(it * 16 + arow, npix - 1);
             const int qy = static_cast<int>((static_cast<uint32_t>(q) * rcp) >> 20), qx = q - qy * wr;
             const int px = xa + qx, py = ya + qy;
-            float c0[4] = { 0.0f, 0.0f, 0.0f, 0.0f }, c1[4] = { 0.0f, 0.0f, 0.0f, 0.0f }, c2[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
+            float c0[4] = { 0.0f, 0.0f, 0.0f, 0.0f }, c2[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
             uint32_t addr[5];
             if (BORDER)
             {
@@ -181,7 +186,7 @@ namespace acb
 #pragma unroll
                 for (int s = 0; s < 5; s++) addr[s] = pix + toff[s];
             }
-            // three independent accumulator chains (hi*hi, lo*hi, hi*lo) so consecutive MMAs never wait on each other
+            // two independent accumulator chains (a*w_hi and a_hi*w_lo) so back-to-back MMAs rarely wait on each other
 #pragma unroll
             for (int s = 0; s < 4; s++)
             {
@@ -189,23 +194,23 @@ namespace acb
                 ldmatrix_x4(ah, addr[s]);
                 ldmatrix_x4_off(al, addr[s], 0);
                 mma_k16(c0, ah, bf[2 * s], bf[2 * s + 1]);
-                mma_k16(c1, al, bf[2 * s], bf[2 * s + 1]);
                 mma_k16(c2, ah, bf[9 + 2 * s], bf[9 + 2 * s + 1]);
+                mma_k16(c0, al, bf[2 * s], bf[2 * s + 1]);
             }
             {
                 uint32_t ah[2], al[2];
                 ldmatrix_x2(ah, addr[4]);
                 ldmatrix_x2_off(al, addr[4]);
                 mma_k8(c0, ah[0], ah[1], bf[8]);
-                mma_k8(c1, al[0], al[1], bf[8]);
                 mma_k8(c2, ah[0], ah[1], bf[17]);
+                mma_k8(c0, al[0], al[1], bf[8]);
             }
-            // D fragment rows: region pixels 16*it + g and + 8
-            const int q0 = it * 16 + drow, q1 = q0 + 8;
-            const int y0 = static_cast<int>((static_cast<uint32_t>(min(q0, npix - 1)) * rcp) >> 20), x0 = min(q0, npix - 1) - y0 * wr;
-            const int y1 = static_cast<int>((static_cast<uint32_t>(min(q1, npix - 1)) * rcp) >> 20), x1 = min(q1, npix - 1) - y1 * wr;
-            epi(xa + x0, ya + y0, (c0[0] + c1[0]) + c2[0], (c0[1] + c1[1]) + c2[1], q0 < npix);
-            epi(xa + x1, ya + y1, (c0[2] + c1[2]) + c2[2], (c0[3] + c1[3]) + c2[3], q1 < npix);
+            // D fragment rows are region pixels 16*it + g and + 8: exactly the pixels lanes g and g + 8 addressed above
+            const int packed = (py << 8) | px;
+            const int d0 = __shfl_sync(0xffffffffu, packed, drow), d1 = __shfl_sync(0xffffffffu, packed, drow + 8);
+            const int q0 = it * 16 + drow;
+            epi(d0 & 0xff, d0 >> 8, c0[0] + c2[0], c0[1] + c2[1], q0 < npix);
+            epi(d1 & 0xff, d1 >> 8, c0[2] + c2[2], c0[3] + c2[3], q0 + 8 < npix);
         }
     }
     template<class Epi>
