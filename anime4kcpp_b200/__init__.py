@@ -58,6 +58,15 @@ def lib():
         L.acb200_rgb2yuv_packed_host.argtypes = [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i]
         L.acb200_yuv2rgb_packed_host.argtypes = [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i]
         L.acb200_resize_catmull_rom_host.argtypes = [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i]
+        L.acb200_model_halo.argtypes = [_vp]
+        L.acb200_band_plan.argtypes = [_i, _d, _i, _i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]
+        L.acb200_process_host_band.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _i, _d, _i, _i, _vp, _i]
+        L.acb200_frame_owner.argtypes = [C.c_longlong, _i]
+        L.acb200_stream_create.argtypes = [_vp, C.POINTER(_i), _i, _i, _i, C.POINTER(_vp)]
+        L.acb200_stream_submit.argtypes = [_vp, _vp, _i, _i, _i, _i, _i, _d, _vp, _i, C.POINTER(C.c_longlong)]
+        L.acb200_stream_next.argtypes = [_vp, C.POINTER(C.c_longlong), C.POINTER(_i)]
+        L.acb200_stream_destroy.argtypes = [_vp]
+        L.acb200_stream_destroy.restype = None
         L.acb200_launch_count.restype = C.c_ulonglong
         L.acb200_error_string.argtypes = [_i]
         L.acb200_error_string.restype = _cp
@@ -118,6 +127,9 @@ class Model:
                                        alphas.ctypes.data_as(_fp) if alphas.size else C.cast(None, _fp), alphas.size, h)
         _check(rc)
         self.handle = h
+
+    def halo(self):
+        return lib().acb200_model_halo(self.handle)
 
     def __del__(self):
         h, self.handle = getattr(self, "handle", None), None
@@ -205,6 +217,60 @@ class Session:
         _check(lib().acb200_resize_catmull_rom_host(self.handle, img.ctypes.data, w, h, c, img.strides[0], _NP_TYPES[img.dtype], out.ctypes.data,
                                                     ow, oh, out.strides[0]), self.handle)
         return out
+
+
+def band_plan(h, factor, halo, n_bands, band):
+    """(src_y0, src_y1, out_y0, out_y1) of one row band (acb200_band_plan)."""
+    a, b, c, d = _i(), _i(), _i(), _i()
+    _check(lib().acb200_band_plan(h, float(factor), halo, n_bands, band, a, b, c, d))
+    return a.value, b.value, c.value, d.value
+
+
+def frame_owner(seq, n_devices):
+    return lib().acb200_frame_owner(seq, n_devices)
+
+
+def process_band(session, model, img, factor, n_bands, band, out):
+    """Upscale row band `band` of `n_bands` of a host image on `session`'s GPU, writing only that band's rows of `out`."""
+    h, w = img.shape[:2]
+    c = 1 if img.ndim == 2 else img.shape[2]
+    _check(lib().acb200_process_host_band(session.handle, model.handle, img.ctypes.data, w, h, c, img.strides[0], _NP_TYPES[img.dtype], float(factor),
+                                          n_bands, band, out.ctypes.data, out.strides[0]), session.handle)
+
+
+class FrameStream:
+    """acb200_stream: frames dealt round-robin over `devices`, results delivered in submission order."""
+
+    def __init__(self, model, devices, workers_per_device=2, queue_depth=2):
+        arr = (_i * len(devices))(*devices)
+        h = _vp()
+        _check(lib().acb200_stream_create(model.handle, arr, len(devices), workers_per_device, queue_depth, h))
+        self.handle, self.model = h, model
+        self._keep = {}
+
+    def submit(self, img, factor, out):
+        h, w = img.shape[:2]
+        c = 1 if img.ndim == 2 else img.shape[2]
+        seq = C.c_longlong()
+        _check(lib().acb200_stream_submit(self.handle, img.ctypes.data, w, h, c, img.strides[0], _NP_TYPES[img.dtype], float(factor),
+                                          out.ctypes.data, out.strides[0], seq))
+        self._keep[seq.value] = (img, out)
+        return seq.value
+
+    def next(self):
+        seq, status = C.c_longlong(), _i()
+        _check(lib().acb200_stream_next(self.handle, seq, status))
+        _check(status.value)
+        return seq.value, self._keep.pop(seq.value)[1]
+
+    def close(self):
+        h, self.handle = self.handle, None
+        if h:
+            lib().acb200_stream_destroy(h)
+
+    def __del__(self):
+        if getattr(self, "handle", None) and _lib is not None:
+            self.close()
 
 
 def device_count():

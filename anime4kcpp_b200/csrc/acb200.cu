@@ -618,13 +618,15 @@ extern "C"
         return process_on_device(s, m, st, d_src, w, h, c, src_stride, type, power, d_dst, dst_stride);
     }
 
-    int acb200_process_host(acb200_session* s, const acb200_model* m, const void* src, int w, int h, int c, int src_stride, int type,
-                            double factor, void* dst, int dst_stride)
+    // rows [out_y0, out_y1) of the result only; `dst` points at output row out_y0
+    static int process_host_rows(acb200_session* s, const acb200_model* m, const void* src, int w, int h, int c, int src_stride, int type,
+                                 double factor, int out_y0, int out_y1, void* dst, int dst_stride)
     {
         int power, rc;
         if ((rc = check_args(s, m, src, w, h, c, type, factor, dst, power)) != ACB200_OK) return rc;
         ACB_CUDA(s, cudaSetDevice(s->device));
         const int es = type & 0xff, ow = w << power, oh = h << power;
+        if (out_y0 < 0 || out_y1 > oh || out_y0 >= out_y1) return fail(s, ACB200_EINVAL, "row range outside the result");
         const size_t line_in = static_cast<size_t>(w) * c * es, line_out = static_cast<size_t>(ow) * c * es;
         if (src_stride < static_cast<int>(line_in)) src_stride = static_cast<int>(line_in);
         if (dst_stride < static_cast<int>(line_out)) dst_stride = static_cast<int>(line_out);
@@ -636,9 +638,55 @@ extern "C"
         if ((rc = process_on_device(s, m, s->stream, s->src.p, w, h, c, static_cast<int>(sp), type, power, s->dst.p, static_cast<int>(dp))) != ACB200_OK) return rc;
         ACB_CUDA(s, cudaEventRecord(s->ev1, s->stream));
         s->timed = true;
-        ACB_CUDA(s, cudaMemcpy2DAsync(dst, dst_stride, s->dst.p, dp, line_out, oh, cudaMemcpyDeviceToHost, s->stream));
+        ACB_CUDA(s, cudaMemcpy2DAsync(dst, dst_stride, static_cast<const uint8_t*>(s->dst.p) + static_cast<size_t>(out_y0) * dp, dp, line_out, out_y1 - out_y0,
+                                      cudaMemcpyDeviceToHost, s->stream));
         ACB_CUDA(s, cudaStreamSynchronize(s->stream));
         return ACB200_OK;
+    }
+    int acb200_process_host(acb200_session* s, const acb200_model* m, const void* src, int w, int h, int c, int src_stride, int type,
+                            double factor, void* dst, int dst_stride)
+    {
+        int power = passes_for(factor);
+        return process_host_rows(s, m, src, w, h, c, src_stride, type, factor, 0, power ? (h << power) : 1, dst, dst_stride);
+    }
+
+    // ---- row bands (one very large image over several GPUs) --------------------------------------------------------------
+    int acb200_model_halo(const acb200_model* m)
+    {
+        if (!m) return ACB200_EINVAL;
+        // 3x3 layers on the path of one 2x pass = rows of input context each output row depends on
+        return m->family == ACB200_FAMILY_ACNET_LEGACY ? m->blocks + 1 : m->family == ACB200_FAMILY_ACNET ? m->blocks + 2 : 2 * m->blocks + 2;
+    }
+    int acb200_band_plan(int h, double factor, int halo, int n_bands, int band, int* src_y0, int* src_y1, int* out_y0, int* out_y1)
+    {
+        const int power = passes_for(factor);
+        if (!power || h <= 0 || n_bands <= 0 || band < 0 || band >= n_bands || halo < 0 || !src_y0 || !src_y1 || !out_y0 || !out_y1) return ACB200_EINVAL;
+        // contiguous bands of source rows, as even as possible; every band but possibly the last few is non-empty
+        const int base = h / n_bands, extra = h % n_bands;
+        const int y0 = band * base + std::min(band, extra), y1 = y0 + base + (band < extra ? 1 : 0);
+        *out_y0 = y0 << power; *out_y1 = y1 << power;
+        // Context per 2x pass is `halo` rows at that pass's input resolution: halo * (1 + 1/2 + 1/4 ...) < 2 * halo source rows
+        // over all passes, plus 2 rows of Catmull-Rom support for the chroma plane and 1 for rounding.  At the true image
+        // border the band simply ends there and the network's own replicate padding applies -- that is what makes the bands
+        // reproduce the whole-image result bit for bit.
+        const int ctx = power == 1 ? halo + 3 : 2 * halo + 3;
+        *src_y0 = std::max(0, y0 - ctx); *src_y1 = std::min(h, y1 + ctx);
+        return ACB200_OK;
+    }
+    int acb200_process_host_band(acb200_session* s, const acb200_model* m, const void* src, int w, int h, int c, int src_stride, int type,
+                                 double factor, int n_bands, int band, void* dst, int dst_stride)
+    {
+        if (!s) return ACB200_EINVAL;
+        if (!m || !src || !dst) return fail(s, ACB200_EINVAL, "null argument");
+        int sy0, sy1, oy0, oy1;
+        if (acb200_band_plan(h, factor, acb200_model_halo(m), n_bands, band, &sy0, &sy1, &oy0, &oy1) != ACB200_OK) return fail(s, ACB200_EINVAL, "bad band request");
+        if (oy0 == oy1) return ACB200_OK;   // more bands than rows
+        const int power = passes_for(factor), es = type & 0xff;
+        if (src_stride < w * c * es) src_stride = w * c * es;
+        if (dst_stride < (w << power) * c * es) dst_stride = (w << power) * c * es;
+        const uint8_t* sub = static_cast<const uint8_t*>(src) + static_cast<size_t>(sy0) * src_stride;
+        uint8_t* out = static_cast<uint8_t*>(dst) + static_cast<size_t>(oy0) * dst_stride;
+        return process_host_rows(s, m, sub, w, sy1 - sy0, c, src_stride, type, factor, oy0 - (sy0 << power), oy1 - (sy0 << power), out, dst_stride);
     }
     int acb200_session_sync(acb200_session* s)
     {

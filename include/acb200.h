@@ -109,6 +109,20 @@ ACB200_API int acb200_process_device(acb200_session* session, const acb200_model
 ACB200_API int acb200_session_sync(acb200_session* session);
 
 /*
+ * Multi-GPU sharding of ONE very large image into halo-overlapped row bands (no collective: every band is independent,
+ * the host already holds the whole source).  Band `band` of `n_bands` covers a contiguous range of source rows; the
+ * session's GPU receives those rows plus the network's context rows, and only the band's own output rows are copied
+ * back into `dst` (the full destination image).  Bands reproduce the whole-image result bit for bit.
+ *   acb200_model_halo  rows of input context per 2x pass (= 3x3 layers on the path)
+ *   acb200_band_plan   the source rows [src_y0, src_y1) a band reads and the output rows [out_y0, out_y1) it owns
+ */
+ACB200_API int acb200_model_halo(const acb200_model* model);
+ACB200_API int acb200_band_plan(int h, double factor, int halo, int n_bands, int band, int* src_y0, int* src_y1, int* out_y0, int* out_y1);
+ACB200_API int acb200_process_host_band(acb200_session* session, const acb200_model* model,
+                                        const void* src, int w, int h, int c, int src_stride, int elem_type,
+                                        double factor, int n_bands, int band, void* dst, int dst_stride);
+
+/*
  * Stand-alone image ops of the hot path on HOST images (reference: core/src/ImageProcess.cpp:38-61,
  * 113-138,191-215,275-308 and the Catmull-Rom upscale of core/src/ImageResize.cpp:136-272).
  */
@@ -123,6 +137,21 @@ ACB200_API int acb200_yuv2rgb_packed_host(acb200_session* session, const void* y
                                           void* dst, int dst_stride);
 ACB200_API int acb200_resize_catmull_rom_host(acb200_session* session, const void* src, int w, int h, int c, int src_stride,
                                               int elem_type, void* dst, int ow, int oh, int dst_stride);
+
+/*
+ * Multi-GPU frame stream (video frames / filter frontends): frame n is dealt to devices[n mod n_devices]; each device runs
+ * `workers_per_device` worker threads with their own session; submit() blocks while that device's bounded queue
+ * (`queue_depth` frames) is full; next() hands back finished frames strictly in submission order.  Replaces the worker /
+ * ordering core of the reference's video/src/Filter.cpp:33-121; no collective is involved.
+ */
+typedef struct acb200_stream acb200_stream;
+ACB200_API int acb200_frame_owner(long long seq, int n_devices);
+ACB200_API int acb200_stream_create(const acb200_model* model, const int* devices, int n_devices, int workers_per_device, int queue_depth,
+                                    acb200_stream** out);
+ACB200_API int acb200_stream_submit(acb200_stream* stream, const void* src, int w, int h, int c, int src_stride, int elem_type, double factor,
+                                    void* dst, int dst_stride, long long* seq_out);
+ACB200_API int acb200_stream_next(acb200_stream* stream, long long* seq_out, int* status_out);
+ACB200_API void acb200_stream_destroy(acb200_stream* stream);
 
 /* number of kernels this library has launched since load (all sessions); for bench.py's gpu_launches */
 ACB200_API unsigned long long acb200_launch_count(void);

@@ -295,3 +295,37 @@ def test_processor_api_threads_and_errors():
     rgb = O.noise_u8(32, 32, 3, seed=2)
     check_int(auto(rgb), O.oracle_process("acnet-f8b8-hdn", rgb, 2.0))
     assert pyac.core.Processor.InfoList[1].startswith("CUDA:\n  [0] ")
+
+
+# ---- multi-GPU sharding primitives on one device: bands and the ordered frame stream -----------------------------------------
+@pytest.mark.parametrize("name,factor,c", [("acnet-legacy-hdn0", 2.0, 1), ("acnet-legacy-hdn0", 4.0, 3), ("acnet-f8b8-hdn", 2.0, 3), ("arnet-f8b8", 2.0, 1)])
+def test_row_bands_reproduce_the_whole_image_bit_for_bit(session, name, factor, c):
+    img = O.noise_u8(150, 96, c, seed=31)
+    m = gpu_model(name)
+    for engine in (ENGINE_EXACT, ENGINE_AUTO):
+        session.set_engine(engine)
+        whole = session.process_host(m, img, factor)
+        for n_bands in (2, 3, 8):
+            out = np.zeros_like(whole)
+            for b in range(n_bands):
+                A.process_band(session, m, img, factor, n_bands, b, out)
+            assert np.array_equal(out, whole), (engine, n_bands)
+
+
+def test_frame_stream_delivers_in_order_and_matches_single_calls(session):
+    m = gpu_model("acnet-legacy-hdn0")
+    frames = [O.noise_u8(72, 120, 3, seed=100 + i) for i in range(12)]
+    outs = [np.zeros((144, 240, 3), np.uint8) for _ in frames]
+    stream = A.FrameStream(m, [0, 0], workers_per_device=2, queue_depth=2)      # two lanes on the one device of the test box
+    got = []
+    for i, (f, o) in enumerate(zip(frames, outs)):
+        stream.submit(f, 2.0, o)
+        if i >= 4:
+            got.append(stream.next()[0])
+    while len(got) < len(frames):
+        got.append(stream.next()[0])
+    stream.close()
+    assert got == list(range(len(frames)))
+    session.set_engine(ENGINE_AUTO)
+    for f, o in zip(frames, outs):
+        assert np.array_equal(o, session.process_host(m, f, 2.0))
