@@ -101,10 +101,26 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------------
 # CPU arms: the reference's own CPU processor (oracle/_ref) when it travelled with the repo, else the oracle port
 # ------------------------------------------------------------------------------------------------------------------
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arms must use every host thread the box has (and say how many)."""
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        pass
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    try:
+        C.CDLL("libgomp.so.1").omp_set_num_threads(n)
+    except OSError:
+        pass
+    return n
+
+
 def cpu_time_frames(model, frames, threads_in_flight=1):
     """Seconds for `frames` 1080p RGB u8 frames through Processor::process(img, 2.0) on the host cores."""
     import numpy as np
     import oracle_lib as O
+    use_all_host_threads()
     ref = O.ref()
     if ref is not None:
         t = ref.ref_benchmark(model.encode(), 0, W, H, CH, frames, threads_in_flight, 1234)
@@ -121,7 +137,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = use_all_host_threads()
     frames_per_step = 1
     for _ in range(max(args.warmup, 0)):
         cpu_time_frames(args.model, frames_per_step)
@@ -311,7 +327,7 @@ def run_ours(args):
     if rank == 0 and not args.no_cpu:
         frames = args.cpu_frames
         tc, kind, backend = cpu_time_frames(args.model, frames)
-        cpu = {"value": OUT_MP * frames / tc, "unit": "MP/s", "cores": os.cpu_count() or 1, "kind": kind,
+        cpu = {"value": OUT_MP * frames / tc, "unit": "MP/s", "cores": use_all_host_threads(), "kind": kind,
                "sample": "%d 1080p RGB frames, backend %s, one frame at a time with OpenMP over all host threads" % (frames, backend),
                "fps": frames / tc}
 
