@@ -49,6 +49,7 @@ def lib():
         L.acb200_session_error.restype = _cp
         L.acb200_session_sync.argtypes = [_vp]
         L.acb200_session_set_engine.argtypes = [_vp, _i]
+        L.acb200_session_set_tensor_impl.argtypes = [_vp, _i]
         L.acb200_session_last_kernel_ms.argtypes = [_vp]
         L.acb200_session_last_kernel_ms.restype = C.c_float
         L.acb200_process_host.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _i, _d, _vp, _i]
@@ -153,6 +154,9 @@ class Session:
 
     def set_engine(self, engine):
         _check(lib().acb200_session_set_engine(self.handle, engine), self.handle)
+
+    def set_tensor_impl(self, impl):
+        _check(lib().acb200_session_set_tensor_impl(self.handle, impl), self.handle)
 
     def sync(self):
         _check(lib().acb200_session_sync(self.handle), self.handle)

@@ -14,6 +14,7 @@
 #include "acb200_common.cuh"
 #include "acb200_ffma.cuh"
 #include "acb200_mma.cuh"
+#include "acb200_tc5.cuh"
 #include "acb200_pixel.cuh"
 
 namespace
@@ -50,6 +51,7 @@ namespace
         SegKind kind;
         int koff, boff, aoff;   // slice starts inside the model's flat arrays (contiguous by construction)
         int frag_off = 0;       // start of this segment's packed B fragments inside acb200_model::frags (uint32 units)
+        int bop_off = 0;        // start of this segment's tcgen05 B operands inside acb200_model::bops (uint32 units)
     };
 }
 
@@ -60,6 +62,8 @@ struct acb200_model
     std::vector<SegSpec> chain;
     // tensor-core engine: B fragments (split fp16) of every segment, concatenated; chain[i].frag_off indexes into it
     std::vector<uint32_t> frags;
+    // tcgen05 engine: B operands (split fp16, no-swizzle K-major canonical layout), TC_B_WORDS_LAYER words per 3x3 conv
+    std::vector<uint32_t> bops;
     unsigned long long uid = 0;
 };
 
@@ -219,9 +223,42 @@ namespace
             out[base + 32 + lane] = l0 | (l1 << 16);
         }
     }
+    // tcgen05 B operand of one 3x3 conv: for dy in 0..2 a [N = 48][K = 16] fp16 matrix, K-major canonical layout
+    // (element (n, k) at byte (k/8)*768 + n*16 + (k%8)*2).  Row n = dx*16 + j: j < 8 -> cout j, K chunk 0 (times a_hi) and chunk 1
+    // (times a_lo) both carry w_hi; j >= 8 -> cout j-8, chunk 0 carries w_lo, chunk 1 is zero.
+    void pack_bop3x3(const float* W, int cout, std::vector<uint32_t>& out)
+    {
+        const size_t base = out.size();
+        out.resize(base + TC_B_WORDS_LAYER, 0u);
+        uint16_t* h = reinterpret_cast<uint16_t*>(out.data() + base);
+        for (int dy = 0; dy < 3; dy++)
+            for (int dx = 0; dx < 3; dx++)
+                for (int co = 0; co < cout; co++)
+                    for (int ci = 0; ci < 8; ci++)
+                    {
+                        uint32_t hi, lo;
+                        split_w(W[(co * 9 + dy * 3 + dx) * 8 + ci], hi, lo);
+                        uint16_t* m = h + dy * (TC_B_BYTES_DY / 2);
+                        const int n_hi = dx * 16 + co, n_lo = dx * 16 + 8 + co;
+                        m[0 * (TC_N * 8) + n_hi * 8 + ci] = static_cast<uint16_t>(hi);     // chunk 0 (a_hi) x w_hi
+                        m[1 * (TC_N * 8) + n_hi * 8 + ci] = static_cast<uint16_t>(hi);     // chunk 1 (a_lo) x w_hi
+                        m[0 * (TC_N * 8) + n_lo * 8 + ci] = static_cast<uint16_t>(lo);     // chunk 0 (a_hi) x w_lo
+                    }
+    }
     template<class S>
     void pack_segment(acb200_model& m, SegSpec& sp)
     {
+        {
+            sp.bop_off = static_cast<int>(m.bops.size());
+            const float* kk = m.k.data() + sp.koff + (S::HEAD ? 72 : 0);
+            for (int i = 0; i < S::NCONV; i++, kk += 576) pack_bop3x3(kk, 8, m.bops);
+            if (S::TAIL)
+            {
+                if (S::FAM == ACB200_FAMILY_ACNET_LEGACY) pack_bop3x3(kk, 8, m.bops);
+                else if (S::FAM == ACB200_FAMILY_ACNET) pack_bop3x3(kk, 4, m.bops);
+                else { pack_bop3x3(kk, 8, m.bops); pack_bop3x3(kk + 576, 8, m.bops); pack_bop3x3(kk + 1152 + 64, 4, m.bops); }
+            }
+        }
         sp.frag_off = static_cast<int>(m.frags.size());
         const float* k = m.k.data() + sp.koff + (S::HEAD ? 72 : 0);
         for (int i = 0; i < S::NCONV; i++, k += 576) pack_conv3x3(k, 8, m.frags);
@@ -239,6 +276,7 @@ namespace
     void pack_model(acb200_model& m)
     {
         m.frags.clear();
+        m.bops.clear();
         for (SegSpec& sp : m.chain)
             switch (sp.kind)
             {
@@ -261,6 +299,7 @@ struct acb200_session
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
+    int tensor_impl = 0;    // tensor engine implementation: 0 mma.sync (HMMA), 1 tcgen05 (UTCHMMA + TMEM)
     int engine = 2;     // 0 exact FFMA, 1 tensor-core MMA, 2 auto: exact for every 2x pass but the last, tensor for the last
     std::string error = "NO ERROR";
     // grow-only device scratch
@@ -268,6 +307,7 @@ struct acb200_session
     Buf src, dst, y[2], uv, map[2], feat, htab, vtab;
     // device copies of models' packed fragments, keyed by acb200_model::uid
     std::map<unsigned long long, void*> dev_frags;
+    std::map<unsigned long long, void*> dev_bops;
     int tab_in_w = 0, tab_in_h = 0, tab_out_w = 0, tab_out_h = 0, tab_max_cnt = 0;
     int smem_configured = 0;
 };
@@ -370,11 +410,61 @@ namespace
         return ACB200_OK;
     }
 
+    int device_bops(acb200_session* s, cudaStream_t st, const acb200_model& m, const uint32_t** out)
+    {
+        auto it = s->dev_bops.find(m.uid);
+        if (it == s->dev_bops.end())
+        {
+            void* p = nullptr;
+            ACB_CUDA(s, cudaMalloc(&p, m.bops.size() * sizeof(uint32_t)));
+            cudaError_t e = cudaMemcpyAsync(p, m.bops.data(), m.bops.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) { cudaFree(p); return fail(s, ACB200_ECUDA, "upload of tcgen05 B operands", e); }
+            it = s->dev_bops.emplace(m.uid, p).first;
+        }
+        *out = static_cast<const uint32_t*>(it->second);
+        return ACB200_OK;
+    }
+
+    template<class S>
+    int launch_segment_tc5(acb200_session* s, cudaStream_t st, const acb200_model& m, const SegSpec& spec,
+                           const void* src, int src_pitch, void* dst, int dst_pitch, int w, int h, int type,
+                           const float* map_in, float* map_out, float* feat)
+    {
+        static_assert(sizeof(Tc5Params<S>) <= 32764, "kernel parameter block too large");
+        const uint32_t* dbops = nullptr;
+        int rc = device_bops(s, st, m, &dbops);
+        if (rc != ACB200_OK) return rc;
+        Tc5Params<S> prm;
+        prm.src = src; prm.map_in = map_in; prm.map_out = map_out; prm.feat_in = feat; prm.feat_out = feat; prm.dst = dst;
+        prm.src_pitch = src_pitch; prm.dst_pitch = dst_pitch; prm.w = w; prm.h = h; prm.type = type;
+        prm.tiles_x = (w + S::T - 1) / S::T;
+        const int tiles_y = (h + S::T - 1) / S::T;
+        prm.bops = dbops + spec.bop_off;
+        std::memset(prm.k, 0, sizeof(prm.k));
+        constexpr int K0 = S::HEAD ? 72 : 0;
+        if (S::HEAD) std::memcpy(prm.k, m.k.data() + spec.koff, sizeof(float) * 72);
+        if (S::TAIL && S::FAM == ACB200_FAMILY_ACNET_LEGACY)
+            std::memcpy(prm.k + K0 + 64, m.k.data() + spec.koff + K0 + 576 * (S::NCONV + 1), sizeof(float) * 32);
+        if (S::TAIL && S::FAM == ACB200_FAMILY_ARNET)
+            std::memcpy(prm.k + K0, m.k.data() + spec.koff + K0 + 576 * (S::NCONV + 2), sizeof(float) * 64);
+        std::memcpy(prm.b, m.b.data() + spec.boff, sizeof(float) * S::NB);
+        if (S::NA > 0) std::memcpy(prm.a, m.a.data() + spec.aoff, sizeof(float) * S::NA);
+        else prm.a[0] = 0.0f;
+        cudaError_t attr_err = cudaFuncSetAttribute(segment_tc5_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(TC_SMEM_BYTES));
+        if (attr_err != cudaSuccess) return fail(s, ACB200_ECUDA, "cudaFuncSetAttribute(max dynamic smem)", attr_err);
+        segment_tc5_kernel<S><<<prm.tiles_x * tiles_y, TC_THREADS, TC_SMEM_BYTES, st>>>(prm);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        ACB_CUDA(s, cudaGetLastError());
+        return ACB200_OK;
+    }
+
     template<class S>
     int launch_any(bool tensor, acb200_session* s, cudaStream_t st, const acb200_model& m, const SegSpec& spec,
                    const void* src, int src_pitch, void* dst, int dst_pitch, int w, int h, int type,
                    const float* map_in, float* map_out, float* feat)
     {
+        if (tensor && s->tensor_impl == 1) return launch_segment_tc5<S>(s, st, m, spec, src, src_pitch, dst, dst_pitch, w, h, type, map_in, map_out, feat);
         return tensor ? launch_segment_mma<S>(s, st, m, spec, src, src_pitch, dst, dst_pitch, w, h, type, map_in, map_out, feat)
                       : launch_segment<S>(s, st, m, spec, src, src_pitch, dst, dst_pitch, w, h, type, map_in, map_out, feat);
     }
@@ -595,6 +685,7 @@ extern "C"
         for (auto* b : bufs) if (b->p) cudaFreeAsync(b->p, s->stream);
         cudaStreamSynchronize(s->stream);
         for (auto& kv : s->dev_frags) cudaFree(kv.second);
+        for (auto& kv : s->dev_bops) cudaFree(kv.second);
         cudaEventDestroy(s->ev0); cudaEventDestroy(s->ev1);
         cudaStreamDestroy(s->stream);
         cudaGetLastError();
@@ -603,6 +694,7 @@ extern "C"
     int acb200_session_device(const acb200_session* s) { return s ? s->device : ACB200_EINVAL; }
     const char* acb200_session_error(const acb200_session* s) { return s ? s->error.c_str() : "invalid session"; }
     void acb200_session_clear_error(acb200_session* s) { if (s) s->error = "NO ERROR"; }
+    int acb200_session_set_tensor_impl(acb200_session* s, int impl) { if (!s || impl < 0 || impl > 1) return ACB200_EINVAL; s->tensor_impl = impl; return ACB200_OK; }
     int acb200_session_set_engine(acb200_session* s, int engine) { if (!s || engine < 0 || engine > 2) return ACB200_EINVAL; s->engine = engine; return ACB200_OK; }
 
     int acb200_process_device(acb200_session* s, const acb200_model* m, const void* d_src, int w, int h, int c, int src_stride, int type,

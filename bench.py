@@ -205,6 +205,8 @@ def run_ours(args):
     model = A.Model(args.model)
     sess = A.Session(local)
     sess.set_engine(args.engine)
+    if args.tensor_impl is not None:
+        sess.set_tensor_impl(args.tensor_impl)
     rs = np.random.RandomState(1234 + rank)
     host_frames = rs.randint(0, 256, size=(B, H, W, CH), dtype=np.uint8)
     d_in = torch.from_numpy(host_frames).cuda()
@@ -364,6 +366,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--threads", type=int, default=4, help="caller threads sharing the processor in the e2e leg")
     ap.add_argument("--engine", type=int, default=2, help="0 exact FFMA, 1 tensor MMA, 2 auto")
+    ap.add_argument("--tensor-impl", type=int, default=None, help="0 mma.sync, 1 tcgen05 (default: library default)")
     ap.add_argument("--cpu-frames", type=int, default=12)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -165,6 +165,8 @@ ACB200_API float acb200_session_last_kernel_ms(acb200_session* session);
  *              keep the 8-bit bar because no rounding difference is fed back into a later pass
  */
 ACB200_API int acb200_session_set_engine(acb200_session* session, int engine);
+/* implementation of the tensor engine: 0 = mma.sync (HMMA, operands via ldmatrix), 1 = tcgen05 (UTCHMMA, accumulators in TMEM) */
+ACB200_API int acb200_session_set_tensor_impl(acb200_session* session, int impl);
 
 ACB200_API const char* acb200_error_string(int code);
 ACB200_API const char* acb200_version(void);

@@ -29,6 +29,8 @@ U16_LSB_MAX = 4
 X4_LSB_MAX, X4_EXACT_MIN = 4, 0.995
 ENGINE_EXACT, ENGINE_TENSOR, ENGINE_AUTO = 0, 1, 2
 ENGINES = [ENGINE_EXACT]
+# tensor engine implementation under test: 0 = mma.sync, 1 = tcgen05 (ACB_TEST_TENSOR_IMPL selects; default = library default path)
+TENSOR_IMPL = int(os.environ.get("ACB_TEST_TENSOR_IMPL", "1"))
 
 
 @pytest.fixture(scope="module")
@@ -41,6 +43,7 @@ def session():
 def _orders(session):
     O.set_order(O.ORDER_GENERIC)
     session.set_engine(ENGINE_EXACT)
+    session.set_tensor_impl(TENSOR_IMPL)
     yield
     O.set_order(O.ORDER_GENERIC)
 
@@ -316,6 +319,7 @@ def test_frame_stream_delivers_in_order_and_matches_single_calls(session):
     m = gpu_model("acnet-legacy-hdn0")
     frames = [O.noise_u8(72, 120, 3, seed=100 + i) for i in range(12)]
     outs = [np.zeros((144, 240, 3), np.uint8) for _ in frames]
+    session.set_tensor_impl(0)           # the stream's own sessions run the library default implementation
     stream = A.FrameStream(m, [0, 0], workers_per_device=2, queue_depth=2)      # two lanes on the one device of the test box
     got = []
     for i, (f, o) in enumerate(zip(frames, outs)):

@@ -118,6 +118,66 @@ __global__ void __launch_bounds__(128, 1) probe(const __half* __restrict__ a_ini
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u));
 }
 
+// Pipeline probe: per "tile" 3 accumulating MMAs into one of 8 TMEM slots + one tcgen05.commit to that slot's mbarrier,
+// optionally waiting (try_wait) on the barrier of the tile issued 8 tiles earlier.  LBO selects the K-chunk distance.
+__global__ void __launch_bounds__(128, 1) pipe_probe(long long* __restrict__ cycles, int tiles, uint32_t lbo_bytes, int do_wait, int mmas_per_tile)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 200 * 1024);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 200 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    if (tid == 0)
+    {
+        for (int i = 0; i < 8; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(bars + i)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0)
+    {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(48 >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+    const uint32_t a_base = smem_u32(smem), b_base = smem_u32(smem + 150 * 1024);
+    if (tid == 0)
+    {
+        const long long t0 = clock64();
+        for (int t = 0; t < tiles; t++)
+        {
+            const uint32_t slot = t & 7, use = t >> 3;
+            if (do_wait && use > 0) mbar_wait(smem_u32(bars + slot), (use - 1) & 1);
+            if (do_wait) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t base = a_base + ((t * 126) % 2000) * 16 + 57 * 16;
+            for (int dy = 0; dy < mmas_per_tile; dy++)
+                mma_f16_ss(tmem + slot * 64, make_desc(base + (dy - 1) * 56 * 16, lbo_bytes, 128), make_desc(b_base + dy * 1536, 768, 128), idesc, dy > 0);
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bars + slot)) : "memory");
+        }
+        mbar_wait(smem_u32(bars + ((tiles - 1) & 7)), ((tiles - 1) >> 3) & 1);
+        cycles[blockIdx.x] = clock64() - t0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u));
+}
+void run_pipe(uint32_t lbo, int do_wait, int mmas)
+{
+    long long* dc; cudaMalloc(&dc, 148 * 8);
+    const size_t smem = 200 * 1024 + 128;
+    cudaFuncSetAttribute(pipe_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int tiles = 4000;
+    pipe_probe<<<148, 128, smem>>>(dc, tiles, lbo, do_wait, mmas);
+    cudaError_t err = cudaDeviceSynchronize();
+    std::vector<long long> hc(148); cudaMemcpy(hc.data(), dc, 148 * 8, cudaMemcpyDeviceToHost);
+    double avg = 0; for (auto c : hc) avg += double(c); avg /= 148;
+    printf("pipe: LBO %6u B, %d MMA/tile, wait %d: %s, %.1f cycles per tile\n", lbo, mmas, do_wait, cudaGetErrorString(err), avg / tiles);
+    cudaFree(dc);
+}
+
 template<int N, int ACCS>
 void run(const std::vector<__half>& ha, int reps)
 {
@@ -159,6 +219,7 @@ int main()
 {
     std::vector<__half> ha(A_PIXELS * 8);
     for (int p = 0; p < A_PIXELS; p++) for (int c = 0; c < 8; c++) ha[p * 8 + c] = __float2half(float((p * 3 + c) % 7));
+    run_pipe(912, 0, 3); run_pipe(50176, 0, 3); run_pipe(50176 + 16, 0, 3); run_pipe(50176 + 64, 0, 3); run_pipe(50176, 1, 3); run_pipe(50176, 0, 1); run_pipe(50176, 0, 6);
     run<16, 1>(ha, 2000);
     run<16, 2>(ha, 2000);
     run<16, 5>(ha, 2000);
