@@ -20,9 +20,10 @@
 //  * Replicate padding: the MMA cannot clamp coordinates, so CTAs that touch the image border copy the edge values one pixel
 //    outwards after every layer (border CTAs only, uniform branch).
 //
-// Warp roles (384 threads): warp 0 lane 0 issues the MMAs; warps 1-3 prefetch the next layer's B operand into shared memory;
-// warps 4-11 are two epilogue groups (one warp per TMEM lane quadrant each) that take alternate tiles.  Up to 8 tiles are in
-// flight in TMEM (8 x 64 columns); full/empty mbarriers per slot; tcgen05.commit signals completion.
+// Warp roles (640 threads): lane 0 of warps 0 and 1 issue the MMAs (one thread per TMEM buffer); warps 2-3 prefetch the next
+// layer's B operand into shared memory; warps 4-19 are four epilogue groups (one warp per TMEM lane quadrant each), group g
+// taking tile g of every batch.  Two batches of four tiles are in flight in TMEM (2 x 4 x 64 columns) with full/empty mbarriers
+// per batch buffer; ONE tcgen05.commit per batch signals completion (a commit drains the tensor pipe, so it is amortised).
 #pragma once
 
 #include <cuda_fp16.h>
@@ -158,8 +159,10 @@ namespace acb
         // (2 x 4 TMEM slots of 64 columns) are in flight: full[buf] / empty[buf] mbarriers.
         const int batches = (tiles + TC_GROUPS - 1) / TC_GROUPS;
         const uint32_t b0 = ctx.tile_counter;       // batches issued so far in this kernel
-        if (warp == 0)
+        if (warp < 2)
         {
+            // two issuing threads (lane 0 of warps 0 and 1), one per TMEM buffer: while one thread sits in its mbarrier wait or
+            // its commit drain, the other thread's MMAs keep the tensor pipe busy
             if (lane == 0)
             {
                 const uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(TC_N >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
@@ -167,6 +170,7 @@ namespace acb
                 for (int bi = 0; bi < batches; bi++)
                 {
                     const uint32_t bt = b0 + bi, buf = bt & 1, use = bt >> 1;
+                    if (static_cast<int>(buf) != warp) continue;
                     if (use > 0) tc_mbar_wait(bars + (2 + buf) * 8, (use - 1) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     for (int k = 0; k < TC_GROUPS; k++)
@@ -382,8 +386,8 @@ namespace acb
         {
             const uint32_t bop_smem = tc_smem_u32(bop) + (li & 1) * TC_B_BYTES_LAYER;
             // helper warps: next layer's B operand into the other half of the double buffer
-            if (warp >= 1 && warp < 4 && li + 1 < NLAYERS)
-                for (int i = threadIdx.x - 32; i < TC_B_WORDS_LAYER; i += 96)
+            if (warp >= 2 && warp < 4 && li + 1 < NLAYERS)
+                for (int i = threadIdx.x - 64; i < TC_B_WORDS_LAYER; i += 64)
                     bop[((li + 1) & 1) * TC_B_WORDS_LAYER + i] = __ldg(prm.bops + (li + 1) * TC_B_WORDS_LAYER + i);
 
             const bool is_body = li < S::NCONV;
