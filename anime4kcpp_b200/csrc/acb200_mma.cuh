@@ -239,12 +239,26 @@ namespace acb
 
         if constexpr (S::NEEDS_LUMA)
         {
-            for (int i = threadIdx.x; i < LT * LT; i += MMA_THREADS)
+            if (prm.type == ACB200_UINT8)
             {
-                const int lx = i % LT, ly = i / LT;
-                const int gx = clampi(g.ox - 1 + lx, 0, prm.w - 1), gy = clampi(g.oy - 1 + ly, 0, prm.h - 1);
-                luma[i] = load_elem(static_cast<const uint8_t*>(prm.src) + static_cast<size_t>(gy) * prm.src_pitch, gx, prm.type);
+                // toFloat<u8> is a true division; do the 256 possible divisions once per CTA and look the pixels up
+                float* lut = reinterpret_cast<float*>(B.hi);      // buffer B is free until the first conv layer writes it
+                if (threadIdx.x < 256) lut[threadIdx.x] = __fdiv_rn(static_cast<float>(threadIdx.x), 255.0f);
+                __syncthreads();
+                for (int i = threadIdx.x; i < LT * LT; i += MMA_THREADS)
+                {
+                    const int lx = i % LT, ly = i / LT;
+                    const int gx = clampi(g.ox - 1 + lx, 0, prm.w - 1), gy = clampi(g.oy - 1 + ly, 0, prm.h - 1);
+                    luma[i] = lut[static_cast<const uint8_t*>(prm.src)[static_cast<size_t>(gy) * prm.src_pitch + gx]];
+                }
             }
+            else
+                for (int i = threadIdx.x; i < LT * LT; i += MMA_THREADS)
+                {
+                    const int lx = i % LT, ly = i / LT;
+                    const int gx = clampi(g.ox - 1 + lx, 0, prm.w - 1), gy = clampi(g.oy - 1 + ly, 0, prm.h - 1);
+                    luma[i] = load_elem(static_cast<const uint8_t*>(prm.src) + static_cast<size_t>(gy) * prm.src_pitch, gx, prm.type);
+                }
         }
         if constexpr (!S::HEAD)
         {
@@ -277,10 +291,10 @@ namespace acb
 #pragma unroll
                 for (int co = 0; co < 8; co++)
                 {
-                    float q[8];
+                    // plain FMA chain: this engine is held to the 8-bit tolerance, not to the reference's summation order
+                    float s = prm.b[co];
 #pragma unroll
-                    for (int p = 0; p < 8; p++) q[p] = __fmul_rn(r[p], prm.k[co * 9 + p]);
-                    float s = __fadd_rn(fmaf(r[8], prm.k[co * 9 + 8], hsum8(q)), prm.b[co]);
+                    for (int p = 0; p < 9; p++) s = fmaf(r[p], prm.k[co * 9 + p], s);
                     if (ACT == ACT_RELU) s = fmaxf(s, 0.0f);
                     else if (ACT == ACT_PRELU) s = prelu(s, prm.a[co]);
                     v[co] = s;
@@ -369,6 +383,12 @@ namespace acb
             float kd[4][2];
 #pragma unroll
             for (int q = 0; q < 4; q++) { kd[q][0] = prm.k[(S::HEAD ? 72 : 0) + q * 8 + 2 * tq]; kd[q][1] = prm.k[(S::HEAD ? 72 : 0) + q * 8 + 2 * tq + 1]; }
+            // 8-bit output: the 2T x 2T result tile is staged in shared memory (the luma tile is dead after the head) and leaves
+            // as 16-byte vectors; other element types are stored directly
+            constexpr int OT = 2 * S::T, OPITCH = ((OT + 15) / 16) * 16;
+            static_assert(OPITCH * OT <= LT * LT * 4, "output staging does not fit the luma tile");
+            uint8_t* s_out = reinterpret_cast<uint8_t*>(luma);
+            const bool staged = prm.type == ACB200_UINT8 && S::HEAD;
             auto epi = [&](const int px, const int py, float v0, float v1, const bool valid) {
                 v0 = fmaxf(v0 + b0, 0.0f); v1 = fmaxf(v1 + b1, 0.0f);
                 float o[4];
@@ -383,11 +403,36 @@ namespace acb
                 const float mine = tq == 0 ? o[0] : tq == 1 ? o[1] : tq == 2 ? o[2] : o[3];
                 if (valid)
                 {
-                    void* row = static_cast<uint8_t*>(prm.dst) + static_cast<size_t>(2 * (g.oy + py) + (tq >> 1)) * prm.dst_pitch;
-                    net_store1(row, 2 * (g.ox + px) + (tq & 1), prm.type, mine);
+                    if (staged)
+                        s_out[(2 * (py - S::R) + (tq >> 1)) * OPITCH + 2 * (px - S::R) + (tq & 1)] = static_cast<uint8_t>(fmaf(sat01(mine), 255.0f, 0.5f));
+                    else
+                    {
+                        void* row = static_cast<uint8_t*>(prm.dst) + static_cast<size_t>(2 * (g.oy + py) + (tq >> 1)) * prm.dst_pitch;
+                        net_store1(row, 2 * (g.ox + px) + (tq & 1), prm.type, mine);
+                    }
                 }
             };
             mma_conv3x3(S::NCONV + 1, cur, tfrag, g, epi);
+            if (staged)
+            {
+                __syncthreads();
+                const int vw = min(OT, 2 * (prm.w - (g.ox + S::R))), vh = min(OT, 2 * (prm.h - (g.oy + S::R)));     // valid part of the output tile
+                uint8_t* tile_dst = static_cast<uint8_t*>(prm.dst) + static_cast<size_t>(2 * (g.oy + S::R)) * prm.dst_pitch + 2 * (g.ox + S::R);
+                if (((reinterpret_cast<uintptr_t>(tile_dst) | static_cast<uintptr_t>(prm.dst_pitch)) & 15) == 0)
+                {
+                    const int vecs = vw >> 4;
+                    for (int i = threadIdx.x; i < vh * (OPITCH / 16); i += MMA_THREADS)
+                    {
+                        const int row = i / (OPITCH / 16), v = i % (OPITCH / 16);
+                        if (v < vecs) reinterpret_cast<uint4*>(tile_dst + static_cast<size_t>(row) * prm.dst_pitch)[v] = reinterpret_cast<const uint4*>(s_out + row * OPITCH)[v];
+                        else
+                            for (int e = v * 16; e < min(vw, v * 16 + 16); e++) tile_dst[static_cast<size_t>(row) * prm.dst_pitch + e] = s_out[row * OPITCH + e];
+                    }
+                }
+                else
+                    for (int i = threadIdx.x; i < vh * vw; i += MMA_THREADS)
+                        tile_dst[static_cast<size_t>(i / vw) * prm.dst_pitch + (i % vw)] = s_out[(i / vw) * OPITCH + (i % vw)];
+            }
         }
         else
         {
