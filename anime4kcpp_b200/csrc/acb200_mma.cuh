@@ -473,7 +473,8 @@ namespace acb
                     auto epi = [&](const int px, const int py, float v0, float v1, const bool valid) {
                         uint32_t* ph = reinterpret_cast<uint32_t*>(out.hi + py * FT + px) + tq;
                         uint32_t* pl = reinterpret_cast<uint32_t*>(out.lo + py * FT + px) + tq;
-                        const float2 id = join_pair(*ph, *pl);
+                        // overhang lanes of the last tile alias its last valid pixel: they must not touch it
+                        const float2 id = valid ? join_pair(*ph, *pl) : make_float2(0.0f, 0.0f);
                         v0 = fmaf(v0 + b0, 0.2f, id.x); v1 = fmaf(v1 + b1, 0.2f, id.y);
                         if (phase == 0) { keep[0] = v0; keep[1] = v1; kx = px; ky = py; kvalid = valid; phase = 1; return; }
                         phase = 0;
