@@ -197,12 +197,14 @@ namespace acb
     {
         constexpr int UVC = C - 1;
         __shared__ float lut[256];
+        __shared__ Contrib sh_v[CM_OH];
         __shared__ float s_src[CM_SRC_H][CM_SRC_W * UVC];
         __shared__ float s_hp[CM_SRC_H][CM_OW * UVC];
         const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
         const int ox0 = blockIdx.x * CM_OW, oy0 = blockIdx.y * CM_OH;
         const int ncols = min(CM_OW, ow - ox0), nrows = min(CM_OH, oh - oy0);
         lut[tid] = __fdiv_rn(static_cast<float>(tid), 255.0f);       // toFloat<u8>: a true division (Util.hpp:53-54)
+        if (tid < nrows * 8) reinterpret_cast<uint32_t*>(sh_v)[tid] = reinterpret_cast<const uint32_t*>(vtab + oy0)[tid];    // the tile's vertical taps, once
         // source window of the tile (tables are monotonic in n0)
         const Contrib hfirst = htab[ox0], hlast = htab[ox0 + ncols - 1], vfirst = vtab[oy0], vlast = vtab[oy0 + nrows - 1];
         const int sx0 = hfirst.n0, sy0 = vfirst.n0;
@@ -252,7 +254,7 @@ namespace acb
         {
             const int orow = idx / CM_OW, col = idx % CM_OW;
             if (orow >= nrows || col >= ncols) continue;
-            const Contrib k = vtab[oy0 + orow];
+            const Contrib& k = sh_v[orow];
             const int r0 = k.n0 - sy0;
             float q[3] = { 0.0f, 0.0f, 1.0f };
 #pragma unroll

@@ -340,10 +340,14 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "%s 2x on a batch of %d synthetic 1920x1080 RGB u8 frames per GPU (BASELINE configs[1])" % (args.model, B),
                        "frames_per_step_per_gpu": B, "fps": frames_total / (ms_max / 1e3), "engine": args.engine,
+                       "tensor_impl": "mma.sync" if args.tensor_impl in (None, 0) else "tcgen05",
                        "cache": "inputs larger than L2: %d MB in + %d MB out per step" % (B * W * H * CH >> 20, B * 4 * W * H * CH >> 20),
                        "parity_spot_check": parity},
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                         "frac": achieved_tf / peaks["bf16_tflops_sustained"], "traffic": None,
+                         "frac": achieved_tf / peaks["bf16_tflops_sustained"],
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full, profiles/r01_mma_flat_ncu_summary.json):
+                         # the 2.07 MB input plane is read once; the 8.3 MB result is still in the 126 MB L2 when the kernel retires
+                         "traffic": 2119168, "algorithmic_bytes": W * H + 4 * W * H,
                          "kernel": "fused luma network (segment kernel), 1920x1080 Y -> 3840x2160 Y", "kernel_ms": kernel_ms,
                          "launches_per_pass": launches_per_pass, "flop_per_launch": flop_frame, "peak_source": peaks["source"],
                          "pipe": "fp32 FFMA (CUDA cores), exact engine" if args.engine == 0 else "split-fp16 tensor-core MMA (3 HMMA per product)",
