@@ -29,8 +29,9 @@ U16_LSB_MAX = 4
 X4_LSB_MAX, X4_EXACT_MIN = 4, 0.995
 ENGINE_EXACT, ENGINE_TENSOR, ENGINE_AUTO = 0, 1, 2
 ENGINES = [ENGINE_EXACT]
-# tensor engine implementation under test: 0 = mma.sync, 1 = tcgen05 (ACB_TEST_TENSOR_IMPL selects; default = library default path)
-TENSOR_IMPL = int(os.environ.get("ACB_TEST_TENSOR_IMPL", "1"))
+# tensor engine implementations: 0 = mma.sync (library default), 1 = tcgen05; the tensor-engine tests run both
+TENSOR_IMPL = 0
+TENSOR_IMPLS = [0, 1]
 
 
 @pytest.fixture(scope="module")
@@ -135,7 +136,9 @@ def test_colour_vs_oracle(session, name, c, factor):
 
 # ---- tensor-core engine (split-fp16 MMA): the 8-bit bar against BOTH reference orders -------------------------------------
 @pytest.mark.parametrize("key", GOLD_KEYS)
-def test_tensor_engine_golden(session, key):
+@pytest.mark.parametrize("impl", TENSOR_IMPLS)
+def test_tensor_engine_golden(session, key, impl):
+    session.set_tensor_impl(impl)
     kind, name = key.split("/", 1)
     x4 = kind.endswith("4x")
     session.set_engine(ENGINE_TENSOR)
@@ -150,7 +153,9 @@ def test_tensor_engine_golden(session, key):
 
 @pytest.mark.parametrize("name", ["acnet-legacy-hdn0", "acnet-legacy-gan", "acnet-f8b4", "acnet-f8b8-hdn", "acnet-f8b18-box-hdn", "arnet-f8b8", "arnet-f8b16"])
 @pytest.mark.parametrize("shape", [(3, 3), (1, 7), (9, 1), (17, 31), (40, 40), (41, 39), (64, 64), (97, 131), (255, 257)])
-def test_tensor_engine_odd_sizes(session, name, shape):
+@pytest.mark.parametrize("impl", TENSOR_IMPLS)
+def test_tensor_engine_odd_sizes(session, name, shape, impl):
+    session.set_tensor_impl(impl)
     img = O.noise_u8(shape[0], shape[1], 1, seed=shape[0] * 1000 + shape[1])
     session.set_engine(ENGINE_TENSOR)
     out = session.process_host(gpu_model(name), img, 2.0)
@@ -159,7 +164,9 @@ def test_tensor_engine_odd_sizes(session, name, shape):
 
 
 @pytest.mark.parametrize("name", ["acnet-legacy-hdn0", "acnet-f8b8-hdn", "arnet-f8b8"])
-def test_tensor_engine_1080p_against_exact_engine(session, name):
+@pytest.mark.parametrize("impl", TENSOR_IMPLS)
+def test_tensor_engine_1080p_against_exact_engine(session, name, impl):
+    session.set_tensor_impl(impl)
     # full BASELINE size: the exact engine (bit-identical to the reference) is the checker for the tensor engine
     img = O.smooth_u8(1080, 1920, 1, seed=3)
     m = gpu_model(name)
@@ -177,7 +184,9 @@ def test_tensor_engine_1080p_against_exact_engine(session, name):
     assert mx <= 1 and exact >= 0.999, (mx, exact)
 
 
-def test_tensor_engine_colour_and_types(session):
+@pytest.mark.parametrize("impl", TENSOR_IMPLS)
+def test_tensor_engine_colour_and_types(session, impl):
+    session.set_tensor_impl(impl)
     for name in ("acnet-legacy-hdn1", "acnet-f8b8", "arnet-f8b8-box"):
         img = O.noise_u8(45, 61, 3, seed=17)
         O.set_order(O.ORDER_FMA)
