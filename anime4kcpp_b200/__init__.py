@@ -25,6 +25,27 @@ _fp = C.POINTER(C.c_float)
 _lib = None
 
 
+class Plane(C.Structure):
+    """acb200_plane == one entry of ac::video::Frame::plane (video/include/AC/Video/Pipeline.hpp:18-24)."""
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("channel", C.c_int), ("stride", C.c_int), ("data", C.c_void_p)]
+
+
+def _planes_of(arrays):
+    """numpy planes (H,W) / (H,W,2) -> ctypes array of acb200_plane (the arrays must stay alive during the call)."""
+    out = (Plane * len(arrays))()
+    for i, a in enumerate(arrays):
+        if a.strides[-1] != a.itemsize or (a.ndim == 3 and a.strides[1] != a.itemsize * a.shape[2]):
+            raise ValueError("planes must be contiguous along a row")
+        out[i] = Plane(a.shape[1], a.shape[0], 1 if a.ndim == 2 else a.shape[2], a.strides[0], a.ctypes.data)
+    return out
+
+
+def frame_result_planes(planes, factor):
+    """Destination planes of one video frame: every plane `factor` x its source (what Pipeline::request allocates)."""
+    f = int(factor)
+    return [np.empty((p.shape[0] * f, p.shape[1] * f) + p.shape[2:], p.dtype) for p in planes]
+
+
 class NativeLibraryMissing(RuntimeError):
     pass
 
@@ -59,6 +80,9 @@ def lib():
         L.acb200_rgb2yuv_packed_host.argtypes = [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i]
         L.acb200_yuv2rgb_packed_host.argtypes = [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i]
         L.acb200_resize_catmull_rom_host.argtypes = [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i]
+        L.acb200_process_frame_host.argtypes = [_vp, _vp, C.POINTER(Plane), C.POINTER(Plane), _i, _i, _i, _d]
+        L.acb200_process_frame_device.argtypes = [_vp, _vp, C.POINTER(Plane), C.POINTER(Plane), _i, _i, _i, _d, _vp]
+        L.acb200_stream_submit_frame.argtypes = [_vp, C.POINTER(Plane), C.POINTER(Plane), _i, _i, _i, _d, C.POINTER(C.c_longlong)]
         L.acb200_model_halo.argtypes = [_vp]
         L.acb200_band_plan.argtypes = [_i, _d, _i, _i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]
         L.acb200_process_host_band.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _i, _d, _i, _i, _vp, _i]
@@ -195,6 +219,16 @@ class Session:
         _check(rc, self.handle)
         return out
 
+    def process_frame(self, model, planes, factor=2.0, shift=0, out=None):
+        """One planar / semi-planar YUV frame (acb200_process_frame_host): planes[0] = luma (H,W) through the network,
+        the others = chroma (h,w) or (h,w,2) through the Catmull-Rom resize; returns the list of result planes."""
+        if out is None:
+            out = frame_result_planes(planes, factor)
+        src, dst = _planes_of(planes), _planes_of(out)
+        _check(lib().acb200_process_frame_host(self.handle, model.handle, src, dst, len(planes), _NP_TYPES[planes[0].dtype], int(shift), float(factor)),
+               self.handle)
+        return out
+
     def rgb2yuv(self, img):
         img = np.ascontiguousarray(img)
         h, w, c = img.shape
@@ -259,6 +293,14 @@ class FrameStream:
         _check(lib().acb200_stream_submit(self.handle, img.ctypes.data, w, h, c, img.strides[0], _NP_TYPES[img.dtype], float(factor),
                                           out.ctypes.data, out.strides[0], seq))
         self._keep[seq.value] = (img, out)
+        return seq.value
+
+    def submit_frame(self, planes, factor, out, shift=0):
+        """planar-frame form of submit (acb200_stream_submit_frame)."""
+        seq = C.c_longlong()
+        _check(lib().acb200_stream_submit_frame(self.handle, _planes_of(planes), _planes_of(out), len(planes), _NP_TYPES[planes[0].dtype], int(shift),
+                                                float(factor), seq))
+        self._keep[seq.value] = (planes, out)
         return seq.value
 
     def next(self):

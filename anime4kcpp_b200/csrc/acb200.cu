@@ -305,6 +305,7 @@ struct acb200_session
     // grow-only device scratch
     struct Buf { void* p = nullptr; size_t cap = 0; };
     Buf src, dst, y[2], uv, map[2], feat, htab, vtab;
+    Buf pin[3], pout[3];    // planar video frames: staged source / result planes (host entry)
     // device copies of models' packed fragments, keyed by acb200_model::uid
     std::map<unsigned long long, void*> dev_frags;
     std::map<unsigned long long, void*> dev_bops;
@@ -597,6 +598,96 @@ namespace
         return ACB200_OK;
     }
 
+    int frame_stride(const acb200_plane& p, int es) { const int line = p.width * p.channel * es; return p.stride < line ? line : p.stride; }
+
+    // cli/src/Main.cpp:183-206 on device-resident planes: plane 0 -> [shl] network [shr]; planes 1.. -> Catmull-Rom resize.
+    int process_frame_on_device(acb200_session* s, const acb200_model* m, cudaStream_t st, const acb200_plane* src, const acb200_plane* dst,
+                                int planes, int type, int shift, int power)
+    {
+        const int es = type & 0xff;
+        const dim3 blk(32, 8);
+        const bool integer = type == ACB200_UINT8 || type == ACB200_UINT16;
+        const int sh = integer ? shift : 0;
+        int rc;
+        // ---- luma ----------------------------------------------------------------------------------------------------------
+        const void* cur = src[0].data;
+        int cur_pitch = frame_stride(src[0], es), cw = src[0].width, ch = src[0].height;
+        int slot = 0;
+        if (sh)
+        {
+            const size_t p = pitch_of(cw, 1, es);
+            if ((rc = ensure(s, s->y[slot], p * ch)) != ACB200_OK) return rc;
+            shift_kernel<<<dim3((cw + 31) / 32, (ch + 7) / 8), blk, 0, st>>>(cur, cur_pitch, s->y[slot].p, static_cast<int>(p), cw, ch, es, sh, 1);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            ACB_CUDA(s, cudaGetLastError());
+            cur = s->y[slot].p; cur_pitch = static_cast<int>(p);
+            slot ^= 1;
+        }
+        for (int i = 0; i < power; i++)
+        {
+            const int nw = cw * 2, nh = ch * 2;
+            void* out; int out_pitch;
+            if (i == power - 1) { out = dst[0].data; out_pitch = frame_stride(dst[0], es); }
+            else
+            {
+                const size_t p = pitch_of(nw, 1, es);
+                if ((rc = ensure(s, s->y[slot], p * nh)) != ACB200_OK) return rc;
+                out = s->y[slot].p; out_pitch = static_cast<int>(p);
+                slot ^= 1;
+            }
+            const bool tensor = s->engine == 1 || (s->engine == 2 && i == power - 1);
+            if ((rc = luma_pass(s, st, *m, cur, cur_pitch, out, out_pitch, cw, ch, type, tensor)) != ACB200_OK) return rc;
+            cur = out; cur_pitch = out_pitch; cw = nw; ch = nh;
+        }
+        if (sh)
+        {
+            shift_kernel<<<dim3((cw + 31) / 32, (ch + 7) / 8), blk, 0, st>>>(dst[0].data, cur_pitch, dst[0].data, cur_pitch, cw, ch, es, sh, 0);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            ACB_CUDA(s, cudaGetLastError());
+        }
+        // ---- chroma --------------------------------------------------------------------------------------------------------
+        for (int i = 1; i < planes; i++)
+        {
+            const acb200_plane& a = src[i];
+            const acb200_plane& b = dst[i];
+            if ((rc = ensure_tables(s, st, a.width, a.height, b.width, b.height)) != ACB200_OK) return rc;
+            resize_catmull_kernel<<<dim3((b.width + 31) / 32, (b.height + 7) / 8), blk, 0, st>>>(a.data, frame_stride(a, es), a.channel, type,
+                static_cast<const Contrib*>(s->htab.p), static_cast<const Contrib*>(s->vtab.p), b.data, b.width, b.height, frame_stride(b, es));
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            ACB_CUDA(s, cudaGetLastError());
+        }
+        return ACB200_OK;
+    }
+
+    int check_frame_args(acb200_session* s, const acb200_model* m, const acb200_plane* src, const acb200_plane* dst, int planes, int type, int shift,
+                         double factor, int& power)
+    {
+        if (!s) return ACB200_EINVAL;
+        if (!m || !src || !dst) return fail(s, ACB200_EINVAL, "null argument");
+        if (planes < 1 || planes > 3 || !valid_type(type)) return fail(s, ACB200_EINVAL, "frame: 1 to 3 planes of a supported element type");
+        if (shift < 0 || shift >= 8 * (type & 0xff)) return fail(s, ACB200_EINVAL, "frame: shift outside the element width");
+        power = passes_for(factor);
+        if (!power) return fail(s, ACB200_EINVAL, "factor must be a power of two >= 2");
+        for (int i = 0; i < planes; i++)
+        {
+            const acb200_plane& a = src[i];
+            const acb200_plane& b = dst[i];
+            if (!a.data || !b.data || a.width <= 0 || a.height <= 0) return fail(s, ACB200_EINVAL, "frame: empty plane");
+            if (i == 0)
+            {
+                if (a.channel != 1 || b.channel != 1) return fail(s, ACB200_EINVAL, "frame: plane 0 must be the 1-channel luma plane");
+                if (b.width != (a.width << power) || b.height != (a.height << power)) return fail(s, ACB200_EINVAL, "frame: destination luma plane must be factor x the source");
+                if ((static_cast<long long>(a.width) << power) > 0x7fffffffLL / 16 || (static_cast<long long>(a.height) << power) > 0x7fffffffLL / 16) return fail(s, ACB200_EINVAL, "image too large");
+            }
+            else
+            {
+                if (a.channel < 1 || a.channel > 2 || b.channel != a.channel) return fail(s, ACB200_EINVAL, "frame: chroma planes have 1 or 2 channels");
+                if (b.width < a.width || b.height < a.height) return fail(s, ACB200_EINVAL, "frame: chroma resize is upscale only");
+            }
+        }
+        return ACB200_OK;
+    }
+
     int check_args(acb200_session* s, const acb200_model* m, const void* src, int w, int h, int c, int type, double factor, void* dst, int& power)
     {
         if (!s) return ACB200_EINVAL;
@@ -681,7 +772,8 @@ extern "C"
         if (!s) return;
         cudaSetDevice(s->device);
         cudaStreamSynchronize(s->stream);
-        acb200_session::Buf* bufs[] = { &s->src, &s->dst, &s->y[0], &s->y[1], &s->uv, &s->map[0], &s->map[1], &s->feat, &s->htab, &s->vtab };
+        acb200_session::Buf* bufs[] = { &s->src, &s->dst, &s->y[0], &s->y[1], &s->uv, &s->map[0], &s->map[1], &s->feat, &s->htab, &s->vtab,
+                                        &s->pin[0], &s->pin[1], &s->pin[2], &s->pout[0], &s->pout[1], &s->pout[2] };
         for (auto* b : bufs) if (b->p) cudaFreeAsync(b->p, s->stream);
         cudaStreamSynchronize(s->stream);
         for (auto& kv : s->dev_frags) cudaFree(kv.second);
@@ -740,6 +832,44 @@ extern "C"
     {
         int power = passes_for(factor);
         return process_host_rows(s, m, src, w, h, c, src_stride, type, factor, 0, power ? (h << power) : 1, dst, dst_stride);
+    }
+
+    // ---- planar / semi-planar video frames ---------------------------------------------------------------------------------
+    int acb200_process_frame_device(acb200_session* s, const acb200_model* m, const acb200_plane* d_src, const acb200_plane* d_dst, int planes,
+                                    int type, int shift, double factor, void* stream)
+    {
+        int power, rc;
+        if ((rc = check_frame_args(s, m, d_src, d_dst, planes, type, shift, factor, power)) != ACB200_OK) return rc;
+        ACB_CUDA(s, cudaSetDevice(s->device));
+        return process_frame_on_device(s, m, stream ? static_cast<cudaStream_t>(stream) : s->stream, d_src, d_dst, planes, type, shift, power);
+    }
+    int acb200_process_frame_host(acb200_session* s, const acb200_model* m, const acb200_plane* src, const acb200_plane* dst, int planes,
+                                  int type, int shift, double factor)
+    {
+        int power, rc;
+        if ((rc = check_frame_args(s, m, src, dst, planes, type, shift, factor, power)) != ACB200_OK) return rc;
+        ACB_CUDA(s, cudaSetDevice(s->device));
+        const int es = type & 0xff;
+        acb200_plane din[3], dout[3];
+        for (int i = 0; i < planes; i++)
+        {
+            const size_t ip = pitch_of(src[i].width, src[i].channel, es), op = pitch_of(dst[i].width, dst[i].channel, es);
+            if ((rc = ensure(s, s->pin[i], ip * src[i].height)) != ACB200_OK) return rc;
+            if ((rc = ensure(s, s->pout[i], op * dst[i].height)) != ACB200_OK) return rc;
+            din[i] = src[i]; din[i].data = static_cast<unsigned char*>(s->pin[i].p); din[i].stride = static_cast<int>(ip);
+            dout[i] = dst[i]; dout[i].data = static_cast<unsigned char*>(s->pout[i].p); dout[i].stride = static_cast<int>(op);
+            ACB_CUDA(s, cudaMemcpy2DAsync(din[i].data, ip, src[i].data, frame_stride(src[i], es), static_cast<size_t>(src[i].width) * src[i].channel * es, src[i].height,
+                                          cudaMemcpyHostToDevice, s->stream));
+        }
+        ACB_CUDA(s, cudaEventRecord(s->ev0, s->stream));
+        if ((rc = process_frame_on_device(s, m, s->stream, din, dout, planes, type, shift, power)) != ACB200_OK) return rc;
+        ACB_CUDA(s, cudaEventRecord(s->ev1, s->stream));
+        s->timed = true;
+        for (int i = 0; i < planes; i++)
+            ACB_CUDA(s, cudaMemcpy2DAsync(dst[i].data, frame_stride(dst[i], es), dout[i].data, dout[i].stride, static_cast<size_t>(dst[i].width) * dst[i].channel * es, dst[i].height,
+                                          cudaMemcpyDeviceToHost, s->stream));
+        ACB_CUDA(s, cudaStreamSynchronize(s->stream));
+        return ACB200_OK;
     }
 
     // ---- row bands (one very large image over several GPUs) --------------------------------------------------------------

@@ -161,6 +161,26 @@ namespace acb
             resize_encode_store(row, x * c + ch, type, catmull_sample(src, src_pitch, c, ch, type, hc, vc), true);
     }
 
+    // ac::core::shl / shr on an integer plane (core/src/ImageProcess.cpp:601-616): `a << n` / `a >> n` evaluated in int and
+    // truncated to the element type on store.  left != 0: shl from src into dst; left == 0: shr (src may equal dst).
+    __global__ void shift_kernel(const void* __restrict__ src, int src_pitch, void* __restrict__ dst, int dst_pitch, int n_elems, int h, int es, int n, int left)
+    {
+        const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+        if (x >= n_elems || y >= h) return;
+        const uint8_t* in = static_cast<const uint8_t*>(src) + static_cast<size_t>(y) * src_pitch;
+        uint8_t* out = static_cast<uint8_t*>(dst) + static_cast<size_t>(y) * dst_pitch;
+        if (es == 1)
+        {
+            const int a = in[x];
+            out[x] = static_cast<uint8_t>(left ? a << n : a >> n);
+        }
+        else
+        {
+            const int a = reinterpret_cast<const uint16_t*>(in)[x];
+            reinterpret_cast<uint16_t*>(out)[x] = static_cast<uint16_t>(left ? a << n : a >> n);
+        }
+    }
+
     // Processor.cpp:251-253 fused: Catmull-Rom upscale of the (u,v[,a]) plane by the full factor, re-quantised to
     // the element type exactly where the reference materialises the resized plane, then YUV->RGB merge with the
     // network's luma.

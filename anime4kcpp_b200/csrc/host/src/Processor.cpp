@@ -300,9 +300,12 @@ extern "C" AC_CORE_EXPORT int ac_b200_model_arrays(const char* model, int* block
     const ModelChoice c = parseModel(model);
     auto fill = [&](const auto& m) {
         if (blocks) *blocks = m.blocks();
-        if (k) *k = m.kernel(); if (nk) *nk = m.kernelLength();
-        if (b) *b = m.bias(); if (nb) *nb = m.biasLength();
-        if (a) *a = m.alphaLength() ? m.alpha() : nullptr; if (na) *na = m.alphaLength();
+        if (k) *k = m.kernel();
+        if (nk) *nk = m.kernelLength();
+        if (b) *b = m.bias();
+        if (nb) *nb = m.biasLength();
+        if (a) *a = m.alphaLength() ? m.alpha() : nullptr;
+        if (na) *na = m.alphaLength();
     };
     switch (c.family)
     {

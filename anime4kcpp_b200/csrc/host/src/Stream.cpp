@@ -23,6 +23,9 @@ namespace
         const void* src = nullptr; int w = 0, h = 0, c = 0, src_stride = 0, type = 0;
         double factor = 2.0;
         void* dst = nullptr; int dst_stride = 0;
+        // planar video frame (planes > 0): cli/src/Main.cpp:183-206 per frame
+        int planes = 0, shift = 0;
+        acb200_plane fsrc[3] = {}, fdst[3] = {};
     };
     struct Done
     {
@@ -66,7 +69,9 @@ struct acb200_stream
                 lane.q.pop_front();
             }
             lane.not_full.notify_one();
-            const int rc = acb200_process_host(s, model, job.src, job.w, job.h, job.c, job.src_stride, job.type, job.factor, job.dst, job.dst_stride);
+            const int rc = job.planes > 0
+                ? acb200_process_frame_host(s, model, job.fsrc, job.fdst, job.planes, job.type, job.shift, job.factor)
+                : acb200_process_host(s, model, job.src, job.w, job.h, job.c, job.src_stride, job.type, job.factor, job.dst, job.dst_stride);
             {
                 std::lock_guard<std::mutex> lock(dm);
                 finished.push({ job.seq, rc });
@@ -112,12 +117,29 @@ extern "C"
         return ACB200_OK;
     }
 
+    static int enqueue(acb200_stream* st, Job& job, long long* seq_out);
+
     int acb200_stream_submit(acb200_stream* st, const void* src, int w, int h, int c, int src_stride, int elem_type, double factor,
                              void* dst, int dst_stride, long long* seq_out)
     {
         if (!st || !src || !dst) return ACB200_EINVAL;
         Job job;
         job.src = src; job.w = w; job.h = h; job.c = c; job.src_stride = src_stride; job.type = elem_type; job.factor = factor; job.dst = dst; job.dst_stride = dst_stride;
+        return enqueue(st, job, seq_out);
+    }
+
+    int acb200_stream_submit_frame(acb200_stream* st, const acb200_plane* src, const acb200_plane* dst, int planes, int elem_type, int shift, double factor,
+                                   long long* seq_out)
+    {
+        if (!st || !src || !dst || planes < 1 || planes > 3) return ACB200_EINVAL;
+        Job job;
+        job.planes = planes; job.shift = shift; job.type = elem_type; job.factor = factor;
+        for (int i = 0; i < planes; i++) { job.fsrc[i] = src[i]; job.fdst[i] = dst[i]; }
+        return enqueue(st, job, seq_out);
+    }
+
+    static int enqueue(acb200_stream* st, Job& job, long long* seq_out)
+    {
         {
             std::lock_guard<std::mutex> lock(st->dm);
             job.seq = st->submitted++;

@@ -109,6 +109,33 @@ ACB200_API int acb200_process_device(acb200_session* session, const acb200_model
 ACB200_API int acb200_session_sync(acb200_session* session);
 
 /*
+ * One planar / semi-planar YUV video frame -- what every video caller of the reference does per frame
+ * (cli/src/Main.cpp:183-206, filter/vapoursynth/src/Filter.cpp:31-42): plane 0 is the 1-channel luma plane and goes through
+ * the network (Processor::process), every further plane is chroma (1 channel each: I420/I422/I444, or one interleaved
+ * 2-channel plane: NV12/P010...) and goes through the Catmull-Rom resize (ac::core::resize(srcp, dstp, 0.0, 0.0)) to the
+ * size of its destination plane.  Here all of it is ONE submission on the session stream.
+ *   acb200_plane   same members, in the same order, as one entry of ac::video::Frame::plane
+ *                  (video/include/AC/Video/Pipeline.hpp:18-24): a caller can pass `frame.plane` directly
+ *   elem_type      ACB200_UINT8 / ACB200_UINT16 (also the float types; `shift` is ignored for them, like ac::core::shl)
+ *   shift          for 10/12-bit samples stored LSB-aligned in 16-bit words (cli/src/Main.cpp:175): luma is shifted left by
+ *                  `shift` bits before the network and the result shifted right again (ac::core::shl / shr,
+ *                  core/src/ImageProcess.cpp:601-616); the source plane itself is not modified; chroma is not shifted
+ *   dst planes     caller-allocated; plane 0 must be factor x the source luma, chroma planes at least the source size
+ */
+typedef struct acb200_plane
+{
+    int width, height, channel, stride;     /* stride in bytes; 0 = tightly packed */
+    unsigned char* data;
+} acb200_plane;
+ACB200_API int acb200_process_frame_host(acb200_session* session, const acb200_model* model,
+                                         const acb200_plane* src, const acb200_plane* dst, int planes,
+                                         int elem_type, int shift, double factor);
+/* the same on device-resident planes (NVDEC / NVENC surfaces); enqueued on `stream` (NULL: the session stream), no sync */
+ACB200_API int acb200_process_frame_device(acb200_session* session, const acb200_model* model,
+                                           const acb200_plane* d_src, const acb200_plane* d_dst, int planes,
+                                           int elem_type, int shift, double factor, void* stream);
+
+/*
  * Multi-GPU sharding of ONE very large image into halo-overlapped row bands (no collective: every band is independent,
  * the host already holds the whole source).  Band `band` of `n_bands` covers a contiguous range of source rows; the
  * session's GPU receives those rows plus the network's context rows, and only the band's own output rows are copied
@@ -150,6 +177,9 @@ ACB200_API int acb200_stream_create(const acb200_model* model, const int* device
                                     acb200_stream** out);
 ACB200_API int acb200_stream_submit(acb200_stream* stream, const void* src, int w, int h, int c, int src_stride, int elem_type, double factor,
                                     void* dst, int dst_stride, long long* seq_out);
+/* planar-frame form of submit (acb200_process_frame_host per frame); the plane arrays are copied, the pixel data is not */
+ACB200_API int acb200_stream_submit_frame(acb200_stream* stream, const acb200_plane* src, const acb200_plane* dst, int planes,
+                                          int elem_type, int shift, double factor, long long* seq_out);
 ACB200_API int acb200_stream_next(acb200_stream* stream, long long* seq_out, int* status_out);
 ACB200_API void acb200_stream_destroy(acb200_stream* stream);
 

@@ -209,6 +209,31 @@ def ref_process(name, img, factor=2.0, arch=1):
     return out
 
 
+def oracle_resize(img, ow, oh):
+    """ac::core::resize(src, dst, 0, 0) (Catmull-Rom) on the CPU oracle; img (H,W) or (H,W,C)."""
+    img = np.ascontiguousarray(img)
+    h, w = img.shape[:2]
+    c = 1 if img.ndim == 2 else img.shape[2]
+    out = np.empty((oh, ow) + (() if img.ndim == 2 else (c,)), img.dtype)
+    assert oracle().orc_resize_catmull_rom(img.ctypes.data, w, h, c, img.strides[0], _type_of(img), out.ctypes.data, ow, oh, out.strides[0]) == 0
+    return out
+
+
+def oracle_frame(name, planes, factor=2.0, shift=0):
+    """The reference's per-frame video callback (cli/src/Main.cpp:183-206) composed from oracle pieces:
+    luma: shl(shift) -> Processor::process -> shr(shift) (core/src/ImageProcess.cpp:601-616: integer types only);
+    every other plane: ac::core::resize(srcp, dstp, 0.0, 0.0) to factor x its size."""
+    y = planes[0]
+    integer = y.dtype in (np.uint8, np.uint16)
+    if shift and integer:
+        y = np.left_shift(y.astype(np.int64), shift).astype(y.dtype)        # `a << n` truncated to the element type
+    oy = oracle_process(name, y, factor)
+    if shift and integer:
+        oy = np.right_shift(oy, shift).astype(oy.dtype)
+    f = int(factor)
+    return [oy] + [oracle_resize(p, p.shape[1] * f, p.shape[0] * f) for p in planes[1:]]
+
+
 # ---------------------------------------------------------------------------------------------
 # synthetic inputs (SURVEY.md 8d)
 # ---------------------------------------------------------------------------------------------

@@ -144,3 +144,27 @@ def test_reference_isa_noise_floor():
     a, b = O.ref_process("acnet-legacy-hdn0", img, 2.0, arch=0), O.ref_process("acnet-legacy-hdn0", img, 2.0, arch=1)
     mx, exact = O.compare_u8(a, b)
     assert mx <= 1 and exact >= 0.999
+
+
+def test_video_frame_composition_matches_reference_callback_semantics():
+    """cli/src/Main.cpp:183-206: luma = shr(process(shl(y))), chroma = Catmull-Rom resize, source untouched."""
+    rs = np.random.RandomState(3)
+    y = rs.randint(0, 1024, (12, 20)).astype(np.uint16)          # 10-bit samples, LSB aligned
+    u = rs.randint(0, 1024, (6, 10)).astype(np.uint16)
+    v = rs.randint(0, 1024, (6, 10)).astype(np.uint16)
+    y0 = y.copy()
+    oy, ou, ov = O.oracle_frame("acnet-legacy-hdn0", [y, u, v], 2.0, shift=6)
+    assert np.array_equal(y, y0)
+    assert oy.shape == (24, 40) and ou.shape == (12, 20) and ov.shape == (12, 20)
+    assert int(oy.max()) < 1024                                  # back in the 10-bit range
+    # the shifted pass is the plain 16-bit pass on MSB-aligned samples
+    full = O.oracle_process("acnet-legacy-hdn0", (y.astype(np.uint32) << 6).astype(np.uint16), 2.0)
+    assert np.array_equal(oy, full >> 6)
+    # chroma is not shifted: identical to the stand-alone resize
+    assert np.array_equal(ou, O.oracle_resize(u, 20, 12))
+    # `a << n` wraps in the element type, like the reference's elementwise op
+    wrap = O.oracle_frame("acnet-legacy-hdn0", [np.full((4, 4), 0xFFFF, np.uint16)], 2.0, shift=4)[0]
+    assert np.array_equal(wrap, O.oracle_process("acnet-legacy-hdn0", np.full((4, 4), 0xFFF0, np.uint16), 2.0) >> 4)
+    # float planes: shl/shr are no-ops (ImageProcess.cpp:412,422)
+    yf = rs.rand(6, 6).astype(np.float32)
+    assert np.array_equal(O.oracle_frame("acnet-legacy-hdn0", [yf], 2.0, shift=3)[0], O.oracle_process("acnet-legacy-hdn0", yf, 2.0))

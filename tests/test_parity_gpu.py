@@ -342,3 +342,128 @@ def test_frame_stream_delivers_in_order_and_matches_single_calls(session):
     session.set_engine(ENGINE_AUTO)
     for f, o in zip(frames, outs):
         assert np.array_equal(o, session.process_host(m, f, 2.0))
+
+
+# ---- planar / semi-planar video frames (cli/src/Main.cpp:183-206) -----------------------------
+def _yuv_frame(h, w, layout, dtype, bits, seed):
+    """Synthetic frame: luma (h,w) + chroma planes for I420 / I444 / NV12, samples LSB-aligned in `bits` bits."""
+    rs = np.random.RandomState(seed)
+    top = 1 << bits
+    y = (O.smooth_u8(h, w, 1, seed).astype(np.uint32) * top // 256 + rs.randint(0, max(top // 64, 2), (h, w))).clip(0, top - 1).astype(dtype)
+    ch, cw = (h, w) if layout == "i444" else (h // 2, w // 2)
+    u = rs.randint(0, top, (ch, cw)).astype(dtype)
+    v = (O.smooth_u8(ch, cw, 1, seed + 1).astype(np.uint32) * top // 256).astype(dtype)
+    if layout == "nv12":
+        return [y, np.ascontiguousarray(np.stack([u, v], axis=-1))]
+    if layout == "gray":
+        return [y]
+    return [y, u, v]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("layout", ["i420", "i444", "nv12", "gray"])
+@pytest.mark.parametrize("name", ["acnet-legacy-hdn0", "acnet-f8b8-hdn", "arnet-f8b8"])
+def test_video_frame_u8_bit_identical_to_oracle(session, layout, name):
+    planes = _yuv_frame(54, 98, layout, np.uint8, 8, seed=5)
+    O.set_order(O.ORDER_FMA)
+    want = O.oracle_frame(name, planes, 2.0)
+    got = session.process_frame(gpu_model(name), planes, 2.0)
+    assert len(got) == len(want)
+    for g, w_ in zip(got, want):
+        assert g.shape == w_.shape and np.array_equal(g, w_)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bits,shift", [(10, 6), (12, 4), (16, 0)])
+@pytest.mark.parametrize("layout", ["i420", "nv12"])
+def test_video_frame_high_bit_depth_shift_normalisation(session, bits, shift, layout):
+    """10/12-bit samples LSB-aligned in 16-bit words: shl before the network, shr after (cli/src/Main.cpp:175,188,195)."""
+    planes = _yuv_frame(40, 66, layout, np.uint16, bits, seed=9)
+    O.set_order(O.ORDER_FMA)
+    want = O.oracle_frame("acnet-legacy-hdn0", planes, 2.0, shift)
+    src_copy = [p.copy() for p in planes]
+    got = session.process_frame(gpu_model("acnet-legacy-hdn0"), planes, 2.0, shift)
+    for g, w_ in zip(got, want):
+        assert np.array_equal(g, w_)
+    assert int(got[0].max()) < (1 << bits)
+    for p, q in zip(planes, src_copy):
+        assert np.array_equal(p, q)          # the decoded source frame is not modified
+
+
+@pytest.mark.gpu
+def test_video_frame_4x_tensor_engine_and_strided_planes(session):
+    planes = _yuv_frame(46, 70, "i420", np.uint8, 8, seed=21)
+    O.set_order(O.ORDER_FMA)
+    want = O.oracle_frame("acnet-legacy-hdn1", planes, 4.0)
+    m = gpu_model("acnet-legacy-hdn1")
+    # padded source rows (a decoder's linesize) and a padded destination luma plane
+    padded = [np.zeros((p.shape[0], p.shape[1] + 13), p.dtype) for p in planes]
+    views = []
+    for p, q in zip(planes, padded):
+        q[:, :p.shape[1]] = p
+        views.append(q[:, :p.shape[1]])
+    out = A.frame_result_planes(planes, 4.0)
+    big = np.zeros((out[0].shape[0], out[0].shape[1] + 32), np.uint8)
+    out[0] = big[:, :out[0].shape[1]]
+    got = session.process_frame(m, views, 4.0, out=out)
+    for g, w_ in zip(got, want):
+        assert np.array_equal(g, w_)
+    assert not big[:, out[0].shape[1]:].any()
+    for impl in TENSOR_IMPLS:
+        session.set_engine(ENGINE_AUTO)
+        session.set_tensor_impl(impl)
+        got = session.process_frame(m, planes, 4.0)
+        mx, same = O.compare_u8(got[0], want[0])
+        assert mx <= 1 and same >= 0.999, (impl, mx, same)
+        assert np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
+
+
+@pytest.mark.gpu
+def test_video_frame_1080p_i420_properties(session):
+    """Full-size frame: luma equals the gray-image path bit for bit; chroma equals the stand-alone resize."""
+    planes = _yuv_frame(1080, 1920, "i420", np.uint8, 8, seed=33)
+    m = gpu_model("acnet-legacy-hdn0")
+    session.set_engine(ENGINE_AUTO)
+    got = session.process_frame(m, planes, 2.0)
+    assert np.array_equal(got[0], session.process_host(m, planes[0], 2.0))
+    for i in (1, 2):
+        assert np.array_equal(got[i], session.resize_catmull_rom(planes[i], 1920, 1080))
+
+
+@pytest.mark.gpu
+def test_video_frame_errors(session):
+    m = gpu_model("acnet-legacy-hdn0")
+    planes = _yuv_frame(16, 16, "i420", np.uint8, 8, seed=1)
+    with pytest.raises(A.Acb200Error):
+        session.process_frame(m, planes, 3.0)                                   # not a power of two
+    with pytest.raises(A.Acb200Error):
+        session.process_frame(m, [planes[0]] * 4, 2.0)                          # too many planes
+    bad = A.frame_result_planes(planes, 2.0)
+    bad[0] = np.zeros((31, 32), np.uint8)
+    with pytest.raises(A.Acb200Error):
+        session.process_frame(m, planes, 2.0, out=bad)                          # luma destination of the wrong size
+    with pytest.raises(A.Acb200Error):
+        session.process_frame(m, planes, 2.0, shift=8)                          # shift outside the element width
+    # the session still works after the errors
+    assert session.process_frame(m, planes, 2.0)[0].shape == (32, 32)
+
+
+@pytest.mark.gpu
+def test_frame_stream_planar_frames_in_order(session):
+    m = gpu_model("acnet-legacy-hdn0")
+    frames = [_yuv_frame(36, 64, "i420" if i % 2 else "nv12", np.uint8, 8, seed=200 + i) for i in range(10)]
+    outs = [A.frame_result_planes(f, 2.0) for f in frames]
+    stream = A.FrameStream(m, [0, 0], workers_per_device=2, queue_depth=2)
+    got = []
+    for i, (f, o) in enumerate(zip(frames, outs)):
+        stream.submit_frame(f, 2.0, o)
+        if i >= 3:
+            got.append(stream.next()[0])
+    while len(got) < len(frames):
+        got.append(stream.next()[0])
+    stream.close()
+    assert got == list(range(len(frames)))
+    session.set_engine(ENGINE_AUTO)
+    for f, o in zip(frames, outs):
+        for a, b in zip(o, session.process_frame(m, f, 2.0)):
+            assert np.array_equal(a, b)
