@@ -165,6 +165,18 @@ int ac_processor_process(ACProcessor* const processor, const ACImage* const src,
     publish(dst->hptr->image, dst);
     return ac_processor_ok(processor);
 }
+extern "C" int ac_b200_process_frame(ac::core::Processor* processor, const struct acb200_plane* src, const struct acb200_plane* dst, int planes,
+                                     int elementType, int shift, double factor);
+int ac_processor_process_frame(ACProcessor* const processor, const ACPlane* const src, const ACPlane* const dst, const int planes, const int element_type,
+                               const int shift, const double factor)
+{
+    if (!processor || !processor->hptr || !processor->hptr->processor || !src || !dst) return AC_ERROR(AC_EINVAL);
+    // ACPlane and acb200_plane are the same POD (both mirror ac::video::Frame::plane)
+    if (ac_b200_process_frame(processor->hptr->processor.get(), reinterpret_cast<const acb200_plane*>(src), reinterpret_cast<const acb200_plane*>(dst), planes,
+                              element_type, shift, factor) != 0 && processor->hptr->processor->ok())
+        return AC_ERROR(AC_EPROCESSOR);     // not a B200 processor: nothing ran
+    return ac_processor_ok(processor);
+}
 int ac_processor_ok(const ACProcessor* const processor)
 {
     if (!processor || !processor->hptr || !processor->hptr->processor) return AC_ERROR(AC_EINVAL);

@@ -9,6 +9,7 @@
 // processor whose ok() is false.
 #include <algorithm>
 #include <cctype>
+#include <cstddef>
 #include <map>
 #include <mutex>
 #include <shared_mutex>
@@ -18,6 +19,7 @@
 
 #include "AC/Core/Model.hpp"
 #include "AC/Core/Processor.hpp"
+#include "AC/Video/Frame.hpp"
 
 #include "../../../../include/acb200.h"
 #include "Internal.hpp"
@@ -144,6 +146,18 @@ namespace
         const char* name() const noexcept override { return deviceName.c_str(); }
         int type() const noexcept override { return Processor::CUDA; }
         const char* typeName() const noexcept override { return "CUDA"; }
+
+        // one planar / semi-planar video frame as one submission (acb200_process_frame_host)
+        bool processFrame(const acb200_plane* src, const acb200_plane* dst, const int planes, const int elementType, const int shift, const double factor)
+        {
+            if (!createError.empty()) return false;
+            State& st = local();
+            if (!st.session) return false;
+            const int rc = acb200_process_frame_host(st.session, model, src, dst, planes, elementType, shift, factor);
+            st.good = rc == ACB200_OK;
+            if (!st.good) st.error = acb200_session_error(st.session);
+            return st.good;
+        }
 
     protected:
         void processImage(const Image& src, Image& dst, const double factor) override
@@ -281,6 +295,29 @@ const char* ac::core::Processor::listInfo()
 }
 
 // exported for bindings / tests: the canonical name a model string resolves to (empty = out of scope)
+// planes == one ac::video::Frame::plane array; 0 on success.  Processors without the B200 backend report failure (there is
+// no CPU path in this library).
+extern "C" AC_CORE_EXPORT int ac_b200_process_frame(ac::core::Processor* processor, const acb200_plane* src, const acb200_plane* dst, int planes,
+                                                    int elementType, int shift, double factor)
+{
+    auto* p = dynamic_cast<B200Processor*>(processor);
+    if (!p || !src || !dst) return -1;
+    return p->processFrame(src, dst, planes, elementType, shift, factor) ? 0 : -1;
+}
+
+bool ac::video::upscale(core::Processor& processor, const Frame& src, Frame& dst, const double factor, const int shift) noexcept
+{
+    static_assert(sizeof(acb200_plane) == sizeof(src.plane[0]) && offsetof(acb200_plane, data) == 16, "acb200_plane must mirror Frame::plane");
+    if (src.planes < 1 || src.planes > 3 || dst.planes != src.planes) return false;
+    acb200_plane a[3], b[3];
+    for (int i = 0; i < src.planes; i++)
+    {
+        a[i] = { src.plane[i].width, src.plane[i].height, src.plane[i].channel, src.plane[i].stride, src.plane[i].data };
+        b[i] = { dst.plane[i].width, dst.plane[i].height, dst.plane[i].channel, dst.plane[i].stride, dst.plane[i].data };
+    }
+    return ac_b200_process_frame(&processor, a, b, src.planes, src.elementType, shift, factor) == 0;
+}
+
 extern "C" AC_CORE_EXPORT const char* ac_b200_resolve_model(const char* model)
 {
     const ModelChoice c = parseModel(model);

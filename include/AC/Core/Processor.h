@@ -27,6 +27,18 @@ AC_C_API void ac_processor_unref(ACProcessor* processor);
 AC_C_API int ac_processor_create(ACProcessor* processor);
 /* src and dst both need a handle; dst's plain fields are refreshed afterwards; returns ac_processor_ok() */
 AC_C_API int ac_processor_process(ACProcessor* processor, const ACImage* src, ACImage* dst, double factor);
+/*
+ * Extension (not in the reference's libac_c): one planar / semi-planar YUV video frame -- plane 0 (luma) through the network
+ * with the shl / shr bit-depth normalisation, the other planes through the Catmull-Rom resize -- as ONE GPU submission;
+ * the body of the reference's per-frame video callback (cli/src/Main.cpp:183-206).  ACPlane mirrors one entry of
+ * ac::video::Frame::plane.  dst planes are caller-allocated.  Returns ac_processor_ok().
+ */
+typedef struct ACPlane
+{
+    int width, height, channel, stride;
+    uint8_t* data;
+} ACPlane;
+AC_C_API int ac_processor_process_frame(ACProcessor* processor, const ACPlane* src, const ACPlane* dst, int planes, int element_type, int shift, double factor);
 AC_C_API int ac_processor_ok(const ACProcessor* processor);
 AC_C_API const char* ac_processor_error(const ACProcessor* processor);
 AC_C_API const char* ac_processor_name(const ACProcessor* processor);

@@ -467,3 +467,32 @@ def test_frame_stream_planar_frames_in_order(session):
     for f, o in zip(frames, outs):
         for a, b in zip(o, session.process_frame(m, f, 2.0)):
             assert np.array_equal(a, b)
+
+
+@pytest.mark.gpu
+def test_c_binding_process_frame_extension(session):
+    """ac_processor_process_frame (include/AC/Core/Processor.h): the reference's per-frame video callback as one C call."""
+    import ctypes as C
+    L = A.lib()
+
+    class ACProcessor(C.Structure):
+        _fields_ = [("device", C.c_int), ("type", C.c_char_p), ("model", C.c_char_p), ("hptr", C.c_void_p)]
+    L.ac_processor_alloc.restype = C.POINTER(ACProcessor)
+    L.ac_processor_error.restype = C.c_char_p
+    L.ac_processor_process_frame.argtypes = [C.POINTER(ACProcessor), C.POINTER(A.Plane), C.POINTER(A.Plane), C.c_int, C.c_int, C.c_int, C.c_double]
+    p = L.ac_processor_alloc()
+    p.contents.type, p.contents.model, p.contents.device = b"cuda", b"acnet-legacy-hdn0", 0
+    assert L.ac_processor_create(p) == 0
+    planes = _yuv_frame(30, 44, "i420", np.uint16, 10, seed=77)
+    out = A.frame_result_planes(planes, 2.0)
+    src, dst = A._planes_of(planes), A._planes_of(out)
+    assert L.ac_processor_process_frame(p, src, dst, 3, 0x002, 6, 2.0) == 0
+    session.set_engine(ENGINE_AUTO)
+    for a, b in zip(out, session.process_frame(gpu_model("acnet-legacy-hdn0"), planes, 2.0, 6)):
+        assert np.array_equal(a, b)
+    # failure is reported through the processor's sticky status, like ac_processor_process
+    assert L.ac_processor_process_frame(p, src, dst, 3, 0x002, 6, 3.0) == -256
+    assert b"power of two" in L.ac_processor_error(p)
+    assert L.ac_processor_process_frame(p, src, dst, 3, 0x002, 6, 2.0) == 0
+    assert L.ac_processor_process_frame(None, src, dst, 3, 0x002, 6, 2.0) == -22
+    L.ac_processor_free(C.byref(p))
