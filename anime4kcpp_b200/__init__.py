@@ -219,6 +219,23 @@ class Session:
         _check(rc, self.handle)
         return out
 
+    def process_frame_device(self, model, planes, out, factor=2.0, shift=0, stream=None):
+        """acb200_process_frame_device on torch CUDA tensors (planes and `out`: lists of (H,W) / (H,W,2) tensors in HBM)."""
+        import torch
+        tcode = {torch.uint8: UINT8, torch.int16: UINT16, torch.float16: FLOAT16, torch.float32: FLOAT32}[planes[0].dtype]
+
+        def pack(ts):
+            arr = (Plane * len(ts))()
+            for i, t in enumerate(ts):
+                assert t.is_cuda and t.stride(-1) == 1
+                arr[i] = Plane(t.shape[1], t.shape[0], 1 if t.dim() == 2 else t.shape[2], t.stride(0) * t.element_size(), t.data_ptr())
+            return arr
+        if stream == 0:
+            stream = 1
+        _check(lib().acb200_process_frame_device(self.handle, model.handle, pack(planes), pack(out), len(planes), tcode, int(shift), float(factor), stream),
+               self.handle)
+        return out
+
     def process_frame(self, model, planes, factor=2.0, shift=0, out=None):
         """One planar / semi-planar YUV frame (acb200_process_frame_host): planes[0] = luma (H,W) through the network,
         the others = chroma (h,w) or (h,w,2) through the Catmull-Rom resize; returns the list of result planes."""

@@ -651,6 +651,30 @@ namespace
             const acb200_plane& a = src[i];
             const acb200_plane& b = dst[i];
             if ((rc = ensure_tables(s, st, a.width, a.height, b.width, b.height)) != ACB200_OK) return rc;
+            if (integer && s->tab_max_cnt <= 4)
+            {
+                // tiled integer kernel; two equally shaped planes (the U and V of a planar frame) share one launch
+                const bool pair = i + 1 < planes && src[i + 1].width == a.width && src[i + 1].height == a.height && src[i + 1].channel == a.channel &&
+                                  dst[i + 1].width == b.width && dst[i + 1].height == b.height;
+                ResizePlanes pl;
+                for (int k = 0; k < 2; k++)
+                {
+                    const int j = (k == 1 && pair) ? i + 1 : i;
+                    pl.src[k] = src[j].data; pl.dst[k] = dst[j].data;
+                    pl.src_pitch[k] = frame_stride(src[j], es); pl.dst_pitch[k] = frame_stride(dst[j], es);
+                }
+                const dim3 grid((b.width + CM_OW - 1) / CM_OW, (b.height + CM_OH - 1) / CM_OH, pair ? 2 : 1);
+                const Contrib* ht = static_cast<const Contrib*>(s->htab.p);
+                const Contrib* vt = static_cast<const Contrib*>(s->vtab.p);
+                if (es == 1 && a.channel == 1) resize_tile_kernel<uint8_t, 1><<<grid, CM_THREADS, 0, st>>>(pl, a.width, a.height, ht, vt, b.width, b.height);
+                else if (es == 1) resize_tile_kernel<uint8_t, 2><<<grid, CM_THREADS, 0, st>>>(pl, a.width, a.height, ht, vt, b.width, b.height);
+                else if (a.channel == 1) resize_tile_kernel<uint16_t, 1><<<grid, CM_THREADS, 0, st>>>(pl, a.width, a.height, ht, vt, b.width, b.height);
+                else resize_tile_kernel<uint16_t, 2><<<grid, CM_THREADS, 0, st>>>(pl, a.width, a.height, ht, vt, b.width, b.height);
+                g_launches.fetch_add(1, std::memory_order_relaxed);
+                ACB_CUDA(s, cudaGetLastError());
+                if (pair) i++;
+                continue;
+            }
             resize_catmull_kernel<<<dim3((b.width + 31) / 32, (b.height + 7) / 8), blk, 0, st>>>(a.data, frame_stride(a, es), a.channel, type,
                 static_cast<const Contrib*>(s->htab.p), static_cast<const Contrib*>(s->vtab.p), b.data, b.width, b.height, frame_stride(b, es));
             g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -323,4 +323,106 @@ namespace acb
             }
         }
     }
+    // ---- integer fast path of the stand-alone Catmull-Rom upscale (video chroma planes) -------------------------------------
+    // Same tiling and arithmetic as chroma_merge_u8_kernel without the merge: T = uint8_t / uint16_t samples, NC = 1 (planar
+    // U or V) or 2 (interleaved UV) channels; blockIdx.z selects one of up to two equally sized planes, so the U and V
+    // planes of an I420 / I444 frame are ONE launch.  Bit-identical to resize_catmull_kernel (same products, sums and rounding
+    // points; the extra taps of a short contributor carry zero coefficients).
+    struct ResizePlanes
+    {
+        const void* src[2];
+        void* dst[2];
+        int src_pitch[2], dst_pitch[2];
+    };
+
+    template<typename T, int NC>
+    __global__ void __launch_bounds__(CM_THREADS) resize_tile_kernel(const ResizePlanes pl, int sw_img, int sh_img,
+                                                                  const Contrib* __restrict__ htab, const Contrib* __restrict__ vtab, int ow, int oh)
+    {
+        constexpr float MAXV = sizeof(T) == 1 ? 255.0f : 65535.0f;
+        constexpr float RCP = 1.0f / MAXV;
+        __shared__ Contrib sh_v[CM_OH];
+        __shared__ float s_src[CM_SRC_H][CM_SRC_W * NC];
+        __shared__ float s_hp[CM_SRC_H][CM_OW * NC];
+        __shared__ __align__(16) T s_out[CM_OH][CM_OW * NC];
+        const T* __restrict__ src = static_cast<const T*>(pl.src[blockIdx.z]);
+        T* __restrict__ dst = static_cast<T*>(pl.dst[blockIdx.z]);
+        const int src_pitch = pl.src_pitch[blockIdx.z], dst_pitch = pl.dst_pitch[blockIdx.z];
+        const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+        const int ox0 = blockIdx.x * CM_OW, oy0 = blockIdx.y * CM_OH;
+        const int ncols = min(CM_OW, ow - ox0), nrows = min(CM_OH, oh - oy0);
+        if (tid < nrows * 8) reinterpret_cast<uint32_t*>(sh_v)[tid] = reinterpret_cast<const uint32_t*>(vtab + oy0)[tid];
+        const Contrib hfirst = htab[ox0], hlast = htab[ox0 + ncols - 1], vfirst = vtab[oy0], vlast = vtab[oy0 + nrows - 1];
+        const int sx0 = hfirst.n0, sy0 = vfirst.n0;
+        const int sw = min(hlast.n0 + 4, sw_img) - sx0, shh = min(vlast.n0 + 4, sh_img) - sy0;
+        const int drows = min(vlast.n0 + 4 - sy0, CM_SRC_H), dcols = min(hlast.n0 + 4 - sx0, CM_SRC_W) * NC;
+        for (int row = warp; row < drows; row += CM_THREADS / 32)
+        {
+            const T* srow = reinterpret_cast<const T*>(reinterpret_cast<const uint8_t*>(src) + static_cast<size_t>(sy0 + row) * src_pitch) + sx0 * NC;
+            for (int e = lane; e < dcols; e += 32)
+                s_src[row][e] = (row < shh && e < sw * NC) ? __fmul_rn(static_cast<float>(srow[e]), RCP) : 0.0f;
+        }
+        Contrib hk[2];
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+        {
+            hk[j] = htab[ox0 + min(lane + 32 * j, ncols - 1)];
+            hk[j].n0 -= sx0;
+        }
+        __syncthreads();
+        for (int row = warp; row < drows; row += CM_THREADS / 32)
+#pragma unroll
+            for (int j = 0; j < 2; j++)
+            {
+                const float* srow = &s_src[row][hk[j].n0 * NC];
+#pragma unroll
+                for (int ch = 0; ch < NC; ch++)
+                {
+                    float hsum = __fmul_rn(hk[j].c[0], srow[ch]);
+                    hsum = __fadd_rn(hsum, __fmul_rn(hk[j].c[1], srow[NC + ch]));
+                    hsum = __fadd_rn(hsum, __fmul_rn(hk[j].c[2], srow[2 * NC + ch]));
+                    hsum = __fadd_rn(hsum, __fmul_rn(hk[j].c[3], srow[3 * NC + ch]));
+                    s_hp[row][(lane + 32 * j) * NC + ch] = hsum;
+                }
+            }
+        __syncthreads();
+        for (int idx = tid; idx < CM_OW * CM_OH; idx += CM_THREADS)
+        {
+            const int orow = idx / CM_OW, col = idx % CM_OW;
+            if (orow >= nrows || col >= ncols) continue;
+            const Contrib& k = sh_v[orow];
+            const int r0 = k.n0 - sy0;
+#pragma unroll
+            for (int ch = 0; ch < NC; ch++)
+            {
+                const float* hcol = &s_hp[r0][col * NC + ch];
+                float sum = __fmul_rn(k.c[0], hcol[0]);
+                sum = __fadd_rn(sum, __fmul_rn(k.c[1], hcol[CM_OW * NC]));
+                sum = __fadd_rn(sum, __fmul_rn(k.c[2], hcol[2 * CM_OW * NC]));
+                sum = __fadd_rn(sum, __fmul_rn(k.c[3], hcol[3 * CM_OW * NC]));
+                float f = __fadd_rn(__fmul_rn(sum, MAXV), 0.5f);
+                f = f < 0.0f ? 0.0f : (f > MAXV ? MAXV : f);
+                s_out[orow][col * NC + ch] = static_cast<T>(f);
+            }
+        }
+        __syncthreads();
+        uint8_t* tile_dst = reinterpret_cast<uint8_t*>(dst) + static_cast<size_t>(oy0) * dst_pitch + static_cast<size_t>(ox0) * NC * sizeof(T);
+        if (ncols == CM_OW && ((reinterpret_cast<uintptr_t>(tile_dst) | static_cast<uintptr_t>(dst_pitch)) & 15) == 0)
+        {
+            constexpr int VEC_PER_ROW = CM_OW * NC * static_cast<int>(sizeof(T)) / 16;
+            for (int i = tid; i < nrows * VEC_PER_ROW; i += CM_THREADS)
+            {
+                const int row = i / VEC_PER_ROW, v = i % VEC_PER_ROW;
+                reinterpret_cast<uint4*>(tile_dst + static_cast<size_t>(row) * dst_pitch)[v] = reinterpret_cast<const uint4*>(s_out[row])[v];
+            }
+        }
+        else
+        {
+            for (int i = tid; i < nrows * ncols * NC; i += CM_THREADS)
+            {
+                const int row = i / (ncols * NC), e = i % (ncols * NC);
+                reinterpret_cast<T*>(tile_dst + static_cast<size_t>(row) * dst_pitch)[e] = s_out[row][e];
+            }
+        }
+    }
 }

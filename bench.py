@@ -325,6 +325,74 @@ def run_ours(args):
     e2e = {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": B * W * H * CH, "d2h_bytes_per_step": B * 4 * W * H * CH,
            "fps": frames_total / float(te.item()), "caller_threads": n_threads, "api": "ac_processor_process (libac_c binding), pinned host images"}
 
+    # ---- the video callers' format: planar YUV420 u8 frames, Y through the network, U and V
+    #      through the Catmull-Rom resize, one submission per frame; same metric, counted on the luma plane ----------------
+    yuv = None
+    if not args.no_yuv:
+        f_y = [d_in[i, :, :, 0].contiguous() for i in range(B)]
+        f_u = [d_in[i, ::2, ::2, 1].contiguous() for i in range(B)]
+        f_v = [d_in[i, ::2, ::2, 2].contiguous() for i in range(B)]
+        o_y = [torch.empty((2 * H, 2 * W), dtype=torch.uint8, device="cuda") for _ in range(B)]
+        o_u = [torch.empty((H, W), dtype=torch.uint8, device="cuda") for _ in range(B)]
+        o_v = [torch.empty((H, W), dtype=torch.uint8, device="cuda") for _ in range(B)]
+
+        def yuv_step():
+            for i in range(B):
+                sess.process_frame_device(model, [f_y[i], f_u[i], f_v[i]], [o_y[i], o_u[i], o_v[i]], FACTOR, 0, stream)
+        for _ in range(3):
+            yuv_step()
+        barrier()
+        y0, y1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        y0.record()
+        for _ in range(args.steps):
+            yuv_step()
+        y1.record()
+        barrier()
+        ty = torch.tensor([y0.elapsed_time(y1)], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(ty, op=dist.ReduceOp.MAX)
+        yuv_ms = float(ty.item())
+        # end to end: pinned host planes through the C binding's frame call, caller threads sharing the processor
+        hp_in = [[t.cpu().pin_memory() for t in (f_y[i], f_u[i], f_v[i])] for i in range(B)]
+        hp_out = [[torch.empty(t.shape, dtype=torch.uint8).pin_memory() for t in (o_y[i], o_u[i], o_v[i])] for i in range(B)]
+        lib.ac_processor_process_frame.argtypes = [C.POINTER(ACProcessor), C.POINTER(A.Plane), C.POINTER(A.Plane), C.c_int, C.c_int, C.c_int, C.c_double]
+        pl_in = [A._planes_of([t.numpy() for t in f]) for f in hp_in]
+        pl_out = [A._planes_of([t.numpy() for t in f]) for f in hp_out]
+
+        def yuv_e2e_step():
+            nxt = [0]
+            lock = threading.Lock()
+
+            def worker():
+                while True:
+                    with lock:
+                        i = nxt[0]
+                        nxt[0] += 1
+                    if i >= B:
+                        return
+                    rc = lib.ac_processor_process_frame(proc, pl_in[i], pl_out[i], 3, 1, 0, FACTOR)
+                    assert rc == 0, lib.ac_processor_error(proc)
+            ts = [threading.Thread(target=worker) for _ in range(n_threads)]
+            [x.start() for x in ts]
+            [x.join() for x in ts]
+        for _ in range(2):
+            yuv_e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            yuv_e2e_step()
+        barrier()
+        tye = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(tye, op=dist.ReduceOp.MAX)
+        if rank == 0 and args.engine == 2:
+            assert all(np.array_equal(a.numpy(), b.cpu().numpy()) for a, b in zip(hp_out[0], (o_y[0], o_u[0], o_v[0]))), "yuv host and device paths disagree"
+        yuv = {"workload": "planar YUV420 u8 1080p frames: Y through the network, U/V 960x540 -> 1920x1080 Catmull-Rom, one submission per frame",
+               "value": OUT_MP * frames_total / (yuv_ms / 1e3), "unit": "MP/s", "fps": frames_total / (yuv_ms / 1e3),
+               "e2e": {"value": OUT_MP * frames_total / float(tye.item()), "unit": "MP/s", "fps": frames_total / float(tye.item()),
+                       "h2d_bytes_per_step": B * W * H * 3 // 2, "d2h_bytes_per_step": B * 4 * W * H * 3 // 2,
+                       "api": "ac_processor_process_frame (C binding extension), pinned host planes", "caller_threads": n_threads}}
+
     cpu = None
     if rank == 0 and not args.no_cpu:
         frames = args.cpu_frames
@@ -353,7 +421,7 @@ def run_ours(args):
                          "pipe": "fp32 FFMA (CUDA cores), exact engine" if args.engine == 0 else "split-fp16 tensor-core MMA (3 HMMA per product)",
                          "fp32_ffma_peak_tflops_nominal": fp32_peak_tf, "frac_of_fp32_ffma_peak": achieved_tf / fp32_peak_tf,
                          "frame_roofline_ms": t_roof_ms, "frame_frac": t_roof_ms / (ms_max / (B * args.steps))},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "yuv420": yuv,
         }
         print(json.dumps(line))
     if dist is not None:
@@ -373,6 +441,7 @@ def main():
     ap.add_argument("--tensor-impl", type=int, default=None, help="0 mma.sync, 1 tcgen05 (default: library default)")
     ap.add_argument("--cpu-frames", type=int, default=12)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-yuv", action="store_true", help="skip the planar-YUV420 (video caller) section")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
