@@ -137,14 +137,19 @@ namespace acb
     //   the overhang of the last tile: the epilogue may use warp collectives but must not store for those.
     //   L = number of 3x3 layers between the frame and this layer's output (its region is the frame shrunk by L).
     //   The hi plane and the lo plane of `in` must be FT*FT*16 bytes apart (they are: see the kernel's smem carve-up).
-    template<bool BORDER, class Epi>
-    __device__ __forceinline__ void mma_conv3x3_impl(const int L, const HalfPlanes& in, const uint32_t* __restrict__ frag, const TileGeom& g, Epi&& epi)
+    // B fragments of one 3x3 layer, one register per tap: 0-8 = w_hi, 9-17 = w_lo.  The kernel loads them one layer AHEAD (while
+    // the previous layer's MMAs run), so no layer starts by waiting ~700 cycles for 18 L2 loads.
+    __device__ __forceinline__ void mma_load_bfrag(uint32_t (&bf)[18], const uint32_t* __restrict__ frag)
     {
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        // B fragments of the layer: registers 0-8 = hi (k-steps 0-3: two registers, k-step 4: one), 9-17 = lo
-        uint32_t bf[18];
+        const int lane = threadIdx.x & 31;
 #pragma unroll
         for (int i = 0; i < 18; i++) bf[i] = __ldg(frag + i * 32 + lane);
+    }
+
+    template<bool BORDER, class Epi>
+    __device__ __forceinline__ void mma_conv3x3_impl(const int L, const HalfPlanes& in, const uint32_t (&bf)[18], const TileGeom& g, Epi&& epi)
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
         const int xa = max(L, g.ix0), xb = min(FT - L, g.ix1 + 1), ya = max(L, g.iy0), yb = min(FT - L, g.iy1 + 1);
         const int wr = xb - xa, npix = wr * (yb - ya), tiles = (npix + 15) >> 4;
@@ -167,7 +172,7 @@ namespace acb
             const int q = min(it * 16 + arow, npix - 1);
             const int qy = static_cast<int>((static_cast<uint32_t>(q) * rcp) >> 20), qx = q - qy * wr;
             const int px = xa + qx, py = ya + qy;
-            float c0[4] = { 0.0f, 0.0f, 0.0f, 0.0f }, c2[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
+            float c0[4] = { 0.0f, 0.0f, 0.0f, 0.0f }, c1[4] = { 0.0f, 0.0f, 0.0f, 0.0f }, c2[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
             uint32_t addr[5];
             if (BORDER)
             {
@@ -186,7 +191,9 @@ namespace acb
 #pragma unroll
                 for (int s = 0; s < 5; s++) addr[s] = pix + toff[s];
             }
-            // two independent accumulator chains (a*w_hi and a_hi*w_lo) so back-to-back MMAs rarely wait on each other
+            // Three independent accumulator chains (a_hi*w_hi, a_lo*w_hi, a_hi*w_lo).  An m16n8k8 occupies the tensor pipe exactly
+            // as long as an m16n8k16 (8 cycles per SM partition, tools/microbench_hmma_latency.cu), so the odd ninth tap is loaded as
+            // ONE fragment {hi | lo} and multiplied by [w_hi ; w_hi] in a single k16: 14 MMA slots per tile instead of 15.
 #pragma unroll
             for (int s = 0; s < 4; s++)
             {
@@ -195,16 +202,16 @@ namespace acb
                 ldmatrix_x4_off(al, addr[s], 0);
                 mma_k16(c0, ah, bf[2 * s], bf[2 * s + 1]);
                 mma_k16(c2, ah, bf[9 + 2 * s], bf[9 + 2 * s + 1]);
-                mma_k16(c0, al, bf[2 * s], bf[2 * s + 1]);
+                mma_k16(c1, al, bf[2 * s], bf[2 * s + 1]);
             }
             {
-                uint32_t ah[2], al[2];
-                ldmatrix_x2(ah, addr[4]);
-                ldmatrix_x2_off(al, addr[4]);
-                mma_k8(c0, ah[0], ah[1], bf[8]);
-                mma_k8(c2, ah[0], ah[1], bf[17]);
-                mma_k8(c0, al[0], al[1], bf[8]);
+                uint32_t f8[4];
+                ldmatrix_x4(f8, addr[4] + (h ? static_cast<uint32_t>(FT * FT * 16) : 0u));     // matrices 0,1: hi plane; 2,3: lo plane
+                mma_k16(c1, f8, bf[8], bf[8]);
+                mma_k8(c2, f8[0], f8[1], bf[17]);
             }
+#pragma unroll
+            for (int e = 0; e < 4; e++) c0[e] += c1[e];
             // D fragment rows are region pixels 16*it + g and + 8: exactly the pixels lanes g and g + 8 addressed above
             const int packed = (py << 8) | px;
             const int d0 = __shfl_sync(0xffffffffu, packed, drow), d1 = __shfl_sync(0xffffffffu, packed, drow + 8);
@@ -214,11 +221,11 @@ namespace acb
         }
     }
     template<class Epi>
-    __device__ __forceinline__ void mma_conv3x3(const int L, const HalfPlanes& in, const uint32_t* __restrict__ frag, const TileGeom& g, Epi&& epi)
+    __device__ __forceinline__ void mma_conv3x3(const int L, const HalfPlanes& in, const uint32_t (&bf)[18], const TileGeom& g, Epi&& epi)
     {
         // interior CTA: the image covers the whole frame, no replicate padding anywhere in this tile (uniform branch)
-        if (g.ix0 <= 0 && g.iy0 <= 0 && g.ix1 >= FT - 1 && g.iy1 >= FT - 1) mma_conv3x3_impl<false>(L, in, frag, g, epi);
-        else mma_conv3x3_impl<true>(L, in, frag, g, epi);
+        if (g.ix0 <= 0 && g.iy0 <= 0 && g.ix1 >= FT - 1 && g.iy1 >= FT - 1) mma_conv3x3_impl<false>(L, in, bf, g, epi);
+        else mma_conv3x3_impl<true>(L, in, bf, g, epi);
     }
 
     template<class S>
@@ -236,6 +243,8 @@ namespace acb
         g.ix0 = -g.ox; g.ix1 = prm.w - 1 - g.ox;
         g.iy0 = -g.oy; g.iy1 = prm.h - 1 - g.oy;
         const int lane = threadIdx.x & 31, tq = lane & 3;
+        uint32_t bf[18], nb[18];        // B fragments of the current / the next 3x3 layer
+        mma_load_bfrag(bf, prm.frags);  // consumed after the input load (and the head): the latency is hidden
 
         if constexpr (S::NEEDS_LUMA)
         {
@@ -243,13 +252,25 @@ namespace acb
             {
                 // toFloat<u8> is a true division; do the 256 possible divisions once per CTA and look the pixels up
                 float* lut = reinterpret_cast<float*>(B.hi);      // buffer B is free until the first conv layer writes it
-                if (threadIdx.x < 256) lut[threadIdx.x] = __fdiv_rn(static_cast<float>(threadIdx.x), 255.0f);
-                __syncthreads();
-                for (int i = threadIdx.x; i < LT * LT; i += MMA_THREADS)
+                // all of this thread's pixel loads are issued before the first one is consumed (one exposed HBM/L2 latency
+                // instead of one per loop iteration)
+                constexpr int PER = (LT * LT + MMA_THREADS - 1) / MMA_THREADS;
+                uint8_t px[PER];
+#pragma unroll
+                for (int k = 0; k < PER; k++)
                 {
+                    const int i = min(threadIdx.x + k * MMA_THREADS, LT * LT - 1);
                     const int lx = i % LT, ly = i / LT;
                     const int gx = clampi(g.ox - 1 + lx, 0, prm.w - 1), gy = clampi(g.oy - 1 + ly, 0, prm.h - 1);
-                    luma[i] = lut[static_cast<const uint8_t*>(prm.src)[static_cast<size_t>(gy) * prm.src_pitch + gx]];
+                    px[k] = __ldg(static_cast<const uint8_t*>(prm.src) + static_cast<size_t>(gy) * prm.src_pitch + gx);
+                }
+                if (threadIdx.x < 256) lut[threadIdx.x] = __fdiv_rn(static_cast<float>(threadIdx.x), 255.0f);
+                __syncthreads();
+#pragma unroll
+                for (int k = 0; k < PER; k++)
+                {
+                    const int i = threadIdx.x + k * MMA_THREADS;
+                    if (i < LT * LT) luma[i] = lut[px[k]];
                 }
             }
             else
@@ -320,7 +341,8 @@ namespace acb
 #pragma unroll 1
         for (int i = 0; i < S::NCONV; i++)
         {
-            const uint32_t* frag = prm.frags + i * FRAG_WORDS_3X3;
+            const bool more = i + 1 < S::NCONV || S::TAIL;      // a further 3x3 layer follows in this segment
+            if (more) mma_load_bfrag(nb, prm.frags + (i + 1) * FRAG_WORDS_3X3);
             const float b0 = prm.b[B0 + 8 * i + 2 * tq], b1 = prm.b[B0 + 8 * i + 2 * tq + 1];
             int act = ACT_RELU;
             bool res = false;
@@ -352,8 +374,13 @@ namespace acb
                 split_pair(v0, v1, hi, lo);
                 *ph = hi; *pl = lo;
             };
-            mma_conv3x3(i + 1, cur, frag, g, epi);
+            mma_conv3x3(i + 1, cur, bf, g, epi);
             __syncthreads();
+            if (more)
+            {
+#pragma unroll
+                for (int e = 0; e < 18; e++) bf[e] = nb[e];
+            }
             const HalfPlanes t = cur; cur = oth; oth = t;
         }
 
@@ -412,7 +439,7 @@ namespace acb
                     }
                 }
             };
-            mma_conv3x3(S::NCONV + 1, cur, tfrag, g, epi);
+            mma_conv3x3(S::NCONV + 1, cur, bf, g, epi);
             if (staged)
             {
                 __syncthreads();
@@ -436,7 +463,6 @@ namespace acb
         }
         else
         {
-            const uint32_t* psfrag = tfrag;
             int LPS = S::NCONV + 1;
             if constexpr (S::FAM == ACB200_FAMILY_ARNET)
             {
@@ -454,8 +480,11 @@ namespace acb
                         reinterpret_cast<uint32_t*>(out.hi + py * FT + px)[tq] = hi;
                         reinterpret_cast<uint32_t*>(out.lo + py * FT + px)[tq] = lo;
                     };
-                    mma_conv3x3(S::NCONV + 1, cur, tfrag, g, epi);
+                    mma_load_bfrag(nb, tfrag + FRAG_WORDS_3X3);
+                    mma_conv3x3(S::NCONV + 1, cur, bf, g, epi);
                     __syncthreads();
+#pragma unroll
+                    for (int e = 0; e < 18; e++) bf[e] = nb[e];
                 }
                 {
                     const uint32_t* f3 = tfrag + FRAG_WORDS_3X3;
@@ -502,9 +531,11 @@ namespace acb
                             reinterpret_cast<uint32_t*>(out.lo + qy * FT + qx)[tq] = lo;
                         }
                     };
-                    mma_conv3x3(S::NCONV + 2, oth, f3, g, epi);
+                    mma_load_bfrag(nb, f1 + FRAG_WORDS_1X1);
+                    mma_conv3x3(S::NCONV + 2, oth, bf, g, epi);
                     __syncthreads();
-                    psfrag = f1 + FRAG_WORDS_1X1;
+#pragma unroll
+                    for (int e = 0; e < 18; e++) bf[e] = nb[e];
                     LPS = S::NCONV + 3;
                 }
             }
@@ -522,7 +553,7 @@ namespace acb
                 }
             };
             (void)LPS;
-            mma_conv3x3(LT_PS, cur, psfrag, g, epi);
+            mma_conv3x3(LT_PS, cur, bf, g, epi);
         }
     }
 

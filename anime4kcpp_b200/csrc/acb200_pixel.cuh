@@ -218,8 +218,8 @@ namespace acb
         constexpr int UVC = C - 1;
         __shared__ float lut[256];
         __shared__ Contrib sh_v[CM_OH];
-        __shared__ float s_src[CM_SRC_H][CM_SRC_W * UVC];
-        __shared__ float s_hp[CM_SRC_H][CM_OW * UVC];
+        __shared__ __align__(16) float s_src[CM_SRC_H][CM_SRC_W * UVC];
+        __shared__ __align__(16) float s_hp[CM_SRC_H][CM_OW * UVC];
         const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
         const int ox0 = blockIdx.x * CM_OW, oy0 = blockIdx.y * CM_OH;
         const int ncols = min(CM_OW, ow - ox0), nrows = min(CM_OH, oh - oy0);
@@ -256,14 +256,27 @@ namespace acb
             for (int j = 0; j < 2; j++)
             {
                 const float* srow = &s_src[row][hk[j].n0 * UVC];
-#pragma unroll
-                for (int ch = 0; ch < UVC; ch++)
+                if constexpr (UVC == 2)
                 {
-                    float hsum = __fmul_rn(hk[j].c[0], srow[ch]);
-                    hsum = __fadd_rn(hsum, __fmul_rn(hk[j].c[1], srow[UVC + ch]));
-                    hsum = __fadd_rn(hsum, __fmul_rn(hk[j].c[2], srow[2 * UVC + ch]));
-                    hsum = __fadd_rn(hsum, __fmul_rn(hk[j].c[3], srow[3 * UVC + ch]));
-                    s_hp[row][(lane + 32 * j) * UVC + ch] = hsum;
+                    // both channels of a tap in one 8-byte access (half the shared-memory wavefronts of two scalar ones)
+                    const float2 t0 = *reinterpret_cast<const float2*>(srow), t1 = *reinterpret_cast<const float2*>(srow + 2);
+                    const float2 t2 = *reinterpret_cast<const float2*>(srow + 4), t3 = *reinterpret_cast<const float2*>(srow + 6);
+                    float2 hs;
+                    hs.x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(hk[j].c[0], t0.x), __fmul_rn(hk[j].c[1], t1.x)), __fmul_rn(hk[j].c[2], t2.x)), __fmul_rn(hk[j].c[3], t3.x));
+                    hs.y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(hk[j].c[0], t0.y), __fmul_rn(hk[j].c[1], t1.y)), __fmul_rn(hk[j].c[2], t2.y)), __fmul_rn(hk[j].c[3], t3.y));
+                    *reinterpret_cast<float2*>(&s_hp[row][(lane + 32 * j) * 2]) = hs;
+                }
+                else
+                {
+#pragma unroll
+                    for (int ch = 0; ch < UVC; ch++)
+                    {
+                        float hsum = __fmul_rn(hk[j].c[0], srow[ch]);
+                        hsum = __fadd_rn(hsum, __fmul_rn(hk[j].c[1], srow[UVC + ch]));
+                        hsum = __fadd_rn(hsum, __fmul_rn(hk[j].c[2], srow[2 * UVC + ch]));
+                        hsum = __fadd_rn(hsum, __fmul_rn(hk[j].c[3], srow[3 * UVC + ch]));
+                        s_hp[row][(lane + 32 * j) * UVC + ch] = hsum;
+                    }
                 }
             }
         __syncthreads();
@@ -277,15 +290,32 @@ namespace acb
             const Contrib& k = sh_v[orow];
             const int r0 = k.n0 - sy0;
             float q[3] = { 0.0f, 0.0f, 1.0f };
+            float vs[UVC];
+            if constexpr (UVC == 2)
+            {
+                const float* hcol = &s_hp[r0][col * 2];
+                const float2 t0 = *reinterpret_cast<const float2*>(hcol), t1 = *reinterpret_cast<const float2*>(hcol + CM_OW * 2);
+                const float2 t2 = *reinterpret_cast<const float2*>(hcol + 2 * CM_OW * 2), t3 = *reinterpret_cast<const float2*>(hcol + 3 * CM_OW * 2);
+                vs[0] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(k.c[0], t0.x), __fmul_rn(k.c[1], t1.x)), __fmul_rn(k.c[2], t2.x)), __fmul_rn(k.c[3], t3.x));
+                vs[1] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(k.c[0], t0.y), __fmul_rn(k.c[1], t1.y)), __fmul_rn(k.c[2], t2.y)), __fmul_rn(k.c[3], t3.y));
+            }
+            else
+            {
+#pragma unroll
+                for (int ch = 0; ch < UVC; ch++)
+                {
+                    const float* hcol = &s_hp[r0][col * UVC + ch];
+                    float sum = __fmul_rn(k.c[0], hcol[0]);
+                    sum = __fadd_rn(sum, __fmul_rn(k.c[1], hcol[CM_OW * UVC]));
+                    sum = __fadd_rn(sum, __fmul_rn(k.c[2], hcol[2 * CM_OW * UVC]));
+                    sum = __fadd_rn(sum, __fmul_rn(k.c[3], hcol[3 * CM_OW * UVC]));
+                    vs[ch] = sum;
+                }
+            }
 #pragma unroll
             for (int ch = 0; ch < UVC; ch++)
             {
-                const float* hcol = &s_hp[r0][col * UVC + ch];
-                float sum = __fmul_rn(k.c[0], hcol[0]);
-                sum = __fadd_rn(sum, __fmul_rn(k.c[1], hcol[CM_OW * UVC]));
-                sum = __fadd_rn(sum, __fmul_rn(k.c[2], hcol[2 * CM_OW * UVC]));
-                sum = __fadd_rn(sum, __fmul_rn(k.c[3], hcol[3 * CM_OW * UVC]));
-                float f = __fadd_rn(__fmul_rn(sum, 255.0f), 0.5f);      // stb encode, then toFloat of the stored byte
+                float f = __fadd_rn(__fmul_rn(vs[ch], 255.0f), 0.5f);   // stb encode, then toFloat of the stored byte
                 f = f < 0.0f ? 0.0f : (f > 255.0f ? 255.0f : f);
                 q[ch] = lut[static_cast<int>(f)];
             }
