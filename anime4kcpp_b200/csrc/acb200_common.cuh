@@ -16,12 +16,23 @@ namespace acb
     // reference's translation units are built without FMA contraction).
     __device__ __forceinline__ float sat01(float v) { return v < 0.0f ? 0.0f : (v < 1.0f ? v : 1.0f); }
 
+    // q / MAXV correctly rounded for every integer q in [0, MAXV], MAXV = 255 or 65535, without the division sequence:
+    // one Newton correction of q * (1/MAXV).  Equal to __fdiv_rn(q, MAXV) for all 256 / 65536 inputs (checked exhaustively,
+    // tests/test_oracle_cpu.py::test_division_free_to_float_is_exact restates the check in numpy).
+    template<int MAXV>
+    __device__ __forceinline__ float unit_from_int(float q)
+    {
+        constexpr float RCP = 1.0f / static_cast<float>(MAXV);
+        const float y = __fmul_rn(q, RCP);
+        return __fmaf_rn(__fmaf_rn(-static_cast<float>(MAXV), y, q), RCP, y);
+    }
+
     __device__ __forceinline__ float load_elem(const void* row, int x, int type)
     {
         switch (type)
         {
-        case ACB200_UINT8: return __fdiv_rn(static_cast<float>(static_cast<const uint8_t*>(row)[x]), 255.0f);
-        case ACB200_UINT16: return __fdiv_rn(static_cast<float>(static_cast<const uint16_t*>(row)[x]), 65535.0f);
+        case ACB200_UINT8: return unit_from_int<255>(static_cast<float>(static_cast<const uint8_t*>(row)[x]));
+        case ACB200_UINT16: return unit_from_int<65535>(static_cast<float>(static_cast<const uint16_t*>(row)[x]));
         case ACB200_FLOAT16: return __half2float(static_cast<const __half*>(row)[x]);
         default: return static_cast<const float*>(row)[x];
         }
@@ -43,8 +54,8 @@ namespace acb
     {
         switch (type)
         {
-        case ACB200_UINT8: return __fdiv_rn(static_cast<float>(quant_u8(v)), 255.0f);
-        case ACB200_UINT16: return __fdiv_rn(static_cast<float>(quant_u16(v)), 65535.0f);
+        case ACB200_UINT8: return unit_from_int<255>(static_cast<float>(quant_u8(v)));
+        case ACB200_UINT16: return unit_from_int<65535>(static_cast<float>(quant_u16(v)));
         case ACB200_FLOAT16: return __half2float(__float2half_rn(sat01(v)));
         default: return sat01(v);
         }

@@ -250,8 +250,6 @@ namespace acb
         {
             if (prm.type == ACB200_UINT8)
             {
-                // toFloat<u8> is a true division; do the 256 possible divisions once per CTA and look the pixels up
-                float* lut = reinterpret_cast<float*>(B.hi);      // buffer B is free until the first conv layer writes it
                 // all of this thread's pixel loads are issued before the first one is consumed (one exposed HBM/L2 latency
                 // instead of one per loop iteration)
                 constexpr int PER = (LT * LT + MMA_THREADS - 1) / MMA_THREADS;
@@ -264,13 +262,11 @@ namespace acb
                     const int gx = clampi(g.ox - 1 + lx, 0, prm.w - 1), gy = clampi(g.oy - 1 + ly, 0, prm.h - 1);
                     px[k] = __ldg(static_cast<const uint8_t*>(prm.src) + static_cast<size_t>(gy) * prm.src_pitch + gx);
                 }
-                if (threadIdx.x < 256) lut[threadIdx.x] = __fdiv_rn(static_cast<float>(threadIdx.x), 255.0f);
-                __syncthreads();
 #pragma unroll
                 for (int k = 0; k < PER; k++)
                 {
                     const int i = threadIdx.x + k * MMA_THREADS;
-                    if (i < LT * LT) luma[i] = lut[px[k]];
+                    if (i < LT * LT) luma[i] = unit_from_int<255>(static_cast<float>(px[k]));     // toFloat<u8>, exact, no division
                 }
             }
             else

@@ -106,7 +106,7 @@ namespace acb
             f = f < 0.0f ? 0.0f : (f > 255.0f ? 255.0f : f);
             const uint8_t q = static_cast<uint8_t>(f);
             if (do_store) static_cast<uint8_t*>(row)[x] = q;
-            return __fdiv_rn(static_cast<float>(q), 255.0f);
+            return unit_from_int<255>(static_cast<float>(q));
         }
         case ACB200_UINT16:
         {
@@ -114,7 +114,7 @@ namespace acb
             f = f < 0.0f ? 0.0f : (f > 65535.0f ? 65535.0f : f);
             const uint16_t q = static_cast<uint16_t>(f);
             if (do_store) static_cast<uint16_t*>(row)[x] = q;
-            return __fdiv_rn(static_cast<float>(q), 65535.0f);
+            return unit_from_int<65535>(static_cast<float>(q));
         }
         case ACB200_FLOAT16:
         {
@@ -216,14 +216,12 @@ namespace acb
                                                                       int ow, int oh, uint8_t* __restrict__ dst, int dst_pitch)
     {
         constexpr int UVC = C - 1;
-        __shared__ float lut[256];
         __shared__ Contrib sh_v[CM_OH];
         __shared__ __align__(16) float s_src[CM_SRC_H][CM_SRC_W * UVC];
         __shared__ __align__(16) float s_hp[CM_SRC_H][CM_OW * UVC];
         const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
         const int ox0 = blockIdx.x * CM_OW, oy0 = blockIdx.y * CM_OH;
         const int ncols = min(CM_OW, ow - ox0), nrows = min(CM_OH, oh - oy0);
-        lut[tid] = __fdiv_rn(static_cast<float>(tid), 255.0f);       // toFloat<u8>: a true division (Util.hpp:53-54)
         if (tid < nrows * 8) reinterpret_cast<uint32_t*>(sh_v)[tid] = reinterpret_cast<const uint32_t*>(vtab + oy0)[tid];    // the tile's vertical taps, once
         // source window of the tile (tables are monotonic in n0)
         const Contrib hfirst = htab[ox0], hlast = htab[ox0 + ncols - 1], vfirst = vtab[oy0], vlast = vtab[oy0 + nrows - 1];
@@ -317,9 +315,9 @@ namespace acb
             {
                 float f = __fadd_rn(__fmul_rn(vs[ch], 255.0f), 0.5f);   // stb encode, then toFloat of the stored byte
                 f = f < 0.0f ? 0.0f : (f > 255.0f ? 255.0f : f);
-                q[ch] = lut[static_cast<int>(f)];
+                q[ch] = unit_from_int<255>(truncf(f));                  // toFloat<u8>: a true division (Util.hpp:53-54), computed without one
             }
-            const float yv = lut[yp[static_cast<size_t>(oy0 + orow) * y_pitch + ox0 + col]];
+            const float yv = unit_from_int<255>(static_cast<float>(yp[static_cast<size_t>(oy0 + orow) * y_pitch + ox0 + col]));
             const float u = __fsub_rn(q[0], 0.5f), v = __fsub_rn(q[1], 0.5f);
             float r = __fadd_rn(yv, __fmul_rn(1.403f, v));
             float gch = __fsub_rn(__fsub_rn(yv, __fmul_rn(0.344f, u)), __fmul_rn(0.714f, v));

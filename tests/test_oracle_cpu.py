@@ -168,3 +168,17 @@ def test_video_frame_composition_matches_reference_callback_semantics():
     # float planes: shl/shr are no-ops (ImageProcess.cpp:412,422)
     yf = rs.rand(6, 6).astype(np.float32)
     assert np.array_equal(O.oracle_frame("acnet-legacy-hdn0", [yf], 2.0, shift=3)[0], O.oracle_process("acnet-legacy-hdn0", yf, 2.0))
+
+
+def test_division_free_to_float_is_exact():
+    """acb200_common.cuh unit_from_int: q * (1/M) with one Newton correction equals the correctly rounded q / M
+    (toFloat<u8/u16>, core/internal/AC/Core/Internal/Util.hpp:50-56) for every integer input."""
+    for m in (255, 65535):
+        q = np.arange(m + 1, dtype=np.float32)
+        rcp = np.float32(1.0) / np.float32(m)
+        y = (q * rcp).astype(np.float32)
+        # fmaf(a, b, c): the float32 product is exact in float64; one rounding of the exact sum (|sum| small, float64 exact)
+        r = (np.float64(-m) * y.astype(np.float64) + q.astype(np.float64)).astype(np.float32)
+        y2 = (r.astype(np.float64) * np.float64(rcp) + y.astype(np.float64)).astype(np.float32)
+        want = (q.astype(np.float64) / np.float64(m)).astype(np.float32)
+        assert np.array_equal(y2, want), m
