@@ -23,4 +23,22 @@ for name, shape, c in (("acnet-legacy-hdn0", (70, 90), 3), ("acnet-f8b8-hdn", (5
         got = s.process_host(m, img, 2.0)
         ok = c == 4 or O.compare_u8(got, want)[0] <= 1
         print(name, "engine", engine, "impl", impl, O.compare_u8(got, want), "ok" if ok else "MISMATCH")
+# planar / semi-planar video frames: shift kernels, the tiled chroma-plane kernel (u8 / u16, 1 and 2 channels), 4x
+rs = np.random.RandomState(5)
+m = A.Model("acnet-legacy-hdn0")
+s.set_engine(2)
+s.set_tensor_impl(0)
+for dtype, bits, shift, layout, factor in ((np.uint8, 8, 0, "i420", 2.0), (np.uint16, 10, 6, "nv12", 2.0), (np.uint16, 16, 0, "i444", 4.0), (np.float32, 0, 0, "i420", 2.0)):
+    h, w = 38, 70
+    ch, cw = (h, w) if layout == "i444" else (h // 2, w // 2)
+    if dtype == np.float32:
+        planes = [rs.rand(h, w).astype(dtype), rs.rand(ch, cw).astype(dtype), rs.rand(ch, cw).astype(dtype)]
+    else:
+        planes = [rs.randint(0, 1 << bits, (h, w)).astype(dtype), rs.randint(0, 1 << bits, (ch, cw)).astype(dtype), rs.randint(0, 1 << bits, (ch, cw)).astype(dtype)]
+    if layout == "nv12":
+        planes = [planes[0], np.ascontiguousarray(np.stack(planes[1:], axis=-1))]
+    got = s.process_frame(m, planes, factor, shift)
+    want = O.oracle_frame("acnet-legacy-hdn0", planes, factor, shift)
+    ok = all(np.array_equal(a, b) for a, b in zip(got[1:], want[1:]))
+    print("frame", layout, np.dtype(dtype).name, "shift", shift, "factor", factor, "chroma", "ok" if ok else "MISMATCH")
 print("done")
