@@ -61,6 +61,7 @@ def lib():
         L.acb200_device_count.restype = _i
         L.acb200_device_info.argtypes = [_i, _cp, _i, C.POINTER(C.c_size_t), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]
         L.acb200_model_create.argtypes = [_i, _i, _fp, _i, _fp, _i, _fp, _i, C.POINTER(_vp)]
+        L.acb200_model_create_wide.argtypes = [_i, _i, _i, _fp, _i, _fp, _i, _fp, _i, C.POINTER(_vp)]
         L.acb200_model_destroy.argtypes = [_vp]
         L.acb200_model_destroy.restype = None
         L.acb200_session_create.argtypes = [_i, C.POINTER(_vp)]
@@ -100,6 +101,7 @@ def lib():
         L.ac_b200_resolve_model.restype = _cp
         L.ac_b200_model_arrays.argtypes = [_cp, C.POINTER(_i), C.POINTER(_fp), C.POINTER(_i), C.POINTER(_fp), C.POINTER(_i), C.POINTER(_fp), C.POINTER(_i)]
         L.ac_b200_model_arrays.restype = _i
+        L.ac_b200_model_features.argtypes = [_cp]
         _lib = L
     return _lib
 
@@ -137,19 +139,20 @@ def model_arrays(name):
 class Model:
     """acb200_model: flat fp32 arrays of one network variant."""
 
-    def __init__(self, name=None, family=None, blocks=None, kernels=None, biases=None, alphas=None):
+    def __init__(self, name=None, family=None, blocks=None, kernels=None, biases=None, alphas=None, features=8):
         if name is not None:
             family, blocks, kernels, biases, alphas = model_arrays(name)
+            features = lib().ac_b200_model_features(name.encode())
             self.name = resolve_model(name)
         else:
             self.name = "custom"
-        self.family, self.blocks = family, blocks
+        self.family, self.blocks, self.features = family, blocks, features
         kernels = np.ascontiguousarray(kernels, np.float32)
         biases = np.ascontiguousarray(biases, np.float32)
         alphas = np.ascontiguousarray(alphas if alphas is not None else np.zeros(0), np.float32)
         h = _vp()
-        rc = lib().acb200_model_create(family, blocks, kernels.ctypes.data_as(_fp), kernels.size, biases.ctypes.data_as(_fp), biases.size,
-                                       alphas.ctypes.data_as(_fp) if alphas.size else C.cast(None, _fp), alphas.size, h)
+        rc = lib().acb200_model_create_wide(family, features, blocks, kernels.ctypes.data_as(_fp), kernels.size, biases.ctypes.data_as(_fp), biases.size,
+                                            alphas.ctypes.data_as(_fp) if alphas.size else C.cast(None, _fp), alphas.size, h)
         _check(rc)
         self.handle = h
 

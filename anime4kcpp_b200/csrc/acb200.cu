@@ -15,6 +15,7 @@
 #include "acb200_ffma.cuh"
 #include "acb200_mma.cuh"
 #include "acb200_tc5.cuh"
+#include "acb200_wide.cuh"
 #include "acb200_pixel.cuh"
 
 namespace
@@ -57,7 +58,7 @@ namespace
 
 struct acb200_model
 {
-    int family = 0, blocks = 0;
+    int family = 0, blocks = 0, features = 8;
     std::vector<float> k, b, a;
     std::vector<SegSpec> chain;
     // tensor-core engine: B fragments (split fp16) of every segment, concatenated; chain[i].frag_off indexes into it
@@ -69,10 +70,16 @@ struct acb200_model
 
 namespace
 {
-    bool expected_lengths(int family, int blocks, int& nk, int& nb, int& na)
+    bool expected_lengths(int family, int blocks, int& nk, int& nb, int& na, int F = 8)
     {
         switch (family)
         {
+        case ACB200_FAMILY_ARTCNN: // core/include/AC/Core/Model/ArtCNN.hpp:33-36
+            nk = F * 9 + F * F * 9 * (blocks + 1) + F * 4 * 9; nb = F * (blocks + 2) + 4; na = 0;
+            return (F == 16 || F == 32) && blocks >= 1 && blocks <= 16;
+        case ACB200_FAMILY_FSRCNNX: // core/include/AC/Core/Model/FSRCNNX.hpp:33-38
+            nk = F * 25 + F * F * 9 * blocks + F * F + F * 4 * 9; nb = F * (blocks + 2) + 4; na = F * (blocks + 1);
+            return (F == 8 || F == 16) && blocks >= 2 && blocks <= 16;
         case ACB200_FAMILY_ACNET_LEGACY: // core/include/AC/Core/Model/ACNet.hpp:34-37
             nk = 72 + 576 * blocks + 32; nb = 8 + 8 * blocks; na = 0;
             return blocks == 8;
@@ -90,6 +97,7 @@ namespace
     void build_chain(acb200_model& m)
     {
         m.chain.clear();
+        if (m.family >= ACB200_FAMILY_ARTCNN) return;       // per-layer kernels (acb200_wide.cuh), no fused segments
         if (m.family == ACB200_FAMILY_ACNET_LEGACY) m.chain.push_back({ SEG_LEGACY_FULL, 0, 0, 0 });
         else if (m.family == ACB200_FAMILY_ACNET)
         {
@@ -306,6 +314,8 @@ struct acb200_session
     struct Buf { void* p = nullptr; size_t cap = 0; };
     Buf src, dst, y[2], uv, map[2], feat, htab, vtab;
     Buf pin[3], pout[3];    // planar video frames: staged source / result planes (host entry)
+    Buf wide[3];            // ArtCNN / FSRCNNX: feat + two ping-pong maps, [h][w][F] fp32
+    int wide_smem_configured = 0;
     // device copies of models' packed fragments, keyed by acb200_model::uid
     std::map<unsigned long long, void*> dev_frags;
     std::map<unsigned long long, void*> dev_bops;
@@ -471,9 +481,117 @@ namespace
     }
 
     // one 2x luma pass: src (w x h) -> dst (2w x 2h), both planes in HBM
+    // ---- ArtCNN<16/32>, FSRCNNX<8/16>: one launch per layer (two for 32 output channels) over fp32 maps in HBM -------------
+    template<int F, int NCO, int MODE>
+    int launch_wide_conv(acb200_session* s, cudaStream_t st, const float* in, float* out, const float* res, void* dst, int dst_pitch, int type,
+                         int w, int h, int co0, int act, const float* k, const float* b, const float* a)
+    {
+        static_assert(sizeof(WideConvParams<F, NCO>) <= 32764, "kernel parameter block too large");
+        WideConvParams<F, NCO> prm;
+        prm.in = in; prm.out = out; prm.res = res; prm.dst = dst; prm.dst_pitch = dst_pitch; prm.type = type;
+        prm.w = w; prm.h = h; prm.co0 = co0; prm.act = act;
+        std::memcpy(prm.k, k + static_cast<size_t>(co0) * 9 * F, sizeof(prm.k));
+        std::memcpy(prm.b, b + co0, sizeof(prm.b));
+        if (a) std::memcpy(prm.a, a + co0, sizeof(prm.a)); else std::memset(prm.a, 0, sizeof(prm.a));
+        ACB_CUDA(s, cudaFuncSetAttribute(wide_conv_kernel<F, NCO, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(wide_smem_bytes<F>())));
+        wide_conv_kernel<F, NCO, MODE><<<dim3((w + WIDE_TW - 1) / WIDE_TW, (h + WIDE_TH - 1) / WIDE_TH), WIDE_THREADS, wide_smem_bytes<F>(), st>>>(prm);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        ACB_CUDA(s, cudaGetLastError());
+        return ACB200_OK;
+    }
+    // F -> F conv layer: output channels in launches of at most 16 (the weights travel as kernel parameters)
+    template<int F>
+    int wide_conv_layer(acb200_session* s, cudaStream_t st, const float* in, float* out, const float* res, int w, int h, int act,
+                        const float* k, const float* b, const float* a)
+    {
+        constexpr int NCO = F < 16 ? F : 16;
+        for (int co0 = 0; co0 < F; co0 += NCO)
+        {
+            const int rc = launch_wide_conv<F, NCO, WIDE_STORE>(s, st, in, out, res, nullptr, 0, 0, w, h, co0, act, k, b, a);
+            if (rc != ACB200_OK) return rc;
+        }
+        return ACB200_OK;
+    }
+    template<int F>
+    int luma_pass_wide(acb200_session* s, cudaStream_t st, const acb200_model& m, const void* src, int src_pitch, void* dst, int dst_pitch,
+                       int w, int h, int type)
+    {
+        const size_t bytes = static_cast<size_t>(w) * h * F * sizeof(float);
+        int rc;
+        for (int i = 0; i < 3; i++) if ((rc = ensure(s, s->wide[i], bytes)) != ACB200_OK) return rc;
+        float* feat = static_cast<float*>(s->wide[0].p);
+        float* in = static_cast<float*>(s->wide[2].p);
+        float* out = static_cast<float*>(s->wide[1].p);
+        const bool art = m.family == ACB200_FAMILY_ARTCNN;
+        const int ks = art ? 3 : 5, KH = F * ks * ks, KL = F * F * 9, B = m.blocks;
+        const float* k = m.k.data();
+        const float* b = m.b.data();
+        const float* a = m.a.empty() ? nullptr : m.a.data();
+        // head (CPUProcessor.cpp:1533 / :1635)
+        {
+            WideHeadParams hp;
+            hp.src = src; hp.src_pitch = src_pitch; hp.type = type; hp.out = feat; hp.w = w; hp.h = h; hp.F = F;
+            std::memcpy(hp.k, k, sizeof(float) * KH);
+            std::memcpy(hp.b, b, sizeof(float) * F);
+            const dim3 grid((w + 31) / 32, (h + 7) / 8);
+            if (art) wide_head_kernel<3><<<grid, 256, 0, st>>>(hp); else wide_head_kernel<5><<<grid, 256, 0, st>>>(hp);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            ACB_CUDA(s, cudaGetLastError());
+        }
+        int l = 1;
+        const float* cur = feat;
+        auto layer_k = [&](int layer) { return k + KH + static_cast<size_t>(KL) * (layer - 1); };
+        if (art)
+        {
+            // blocks x (conv + ReLU), then conv + Identity + feat (CPUProcessor.cpp:1535-1545)
+            for (int i = 0; i < B; i++, l++)
+            {
+                if ((rc = wide_conv_layer<F>(s, st, cur, out, nullptr, w, h, ACT_RELU, layer_k(l), b + F * l, nullptr)) != ACB200_OK) return rc;
+                cur = out; std::swap(in, out);
+            }
+            if ((rc = wide_conv_layer<F>(s, st, cur, out, feat, w, h, ACT_IDENTITY, layer_k(l), b + F * l, nullptr)) != ACB200_OK) return rc;
+            cur = out; std::swap(in, out); l++;
+        }
+        else
+        {
+            // (blocks - 1) x (conv + PReLU), then conv + PReLU -> 1x1 -> + feat -> PReLU (CPUProcessor.cpp:1637-1651)
+            for (int i = 0; i < B; i++, l++)
+            {
+                if ((rc = wide_conv_layer<F>(s, st, cur, out, nullptr, w, h, ACT_PRELU, layer_k(l), b + F * l, a + F * (l - 1))) != ACB200_OK) return rc;
+                cur = out; std::swap(in, out);
+            }
+            if constexpr (F <= 16)
+            {
+                WidePointParams<F> pp;
+                pp.in = cur; pp.feat = feat; pp.out = out; pp.n_pixels = w * h;
+                std::memcpy(pp.k, k + KH + static_cast<size_t>(KL) * B, sizeof(pp.k));
+                std::memcpy(pp.b, b + F * l, sizeof(pp.b));
+                std::memcpy(pp.a, a + F * (l - 1), sizeof(pp.a));
+                wide_pointwise_kernel<F><<<(w * h + 255) / 256, 256, 0, st>>>(pp);
+                g_launches.fetch_add(1, std::memory_order_relaxed);
+                ACB_CUDA(s, cudaGetLastError());
+            }
+            cur = out; std::swap(in, out); l++;
+        }
+        // F -> 4 + pixel shuffle (CPUProcessor.cpp:1548 / :1654)
+        const float* kt = art ? layer_k(l) : k + KH + static_cast<size_t>(KL) * B + F * F;
+        // launch_wide_conv copies NCO * 9 * F weights starting at co0 = 0
+        return launch_wide_conv<F, 4, WIDE_SHUFFLE>(s, st, cur, nullptr, nullptr, dst, dst_pitch, type, w, h, 0, ACT_IDENTITY, kt, b + F * l, nullptr);
+    }
+
     int luma_pass(acb200_session* s, cudaStream_t st, const acb200_model& m, const void* src, int src_pitch,
                   void* dst, int dst_pitch, int w, int h, int type, bool tensor)
     {
+        if (m.family >= ACB200_FAMILY_ARTCNN)
+        {
+            if (static_cast<long long>(w) * h * m.features > 0x7fffffffLL / 4) return fail(s, ACB200_EINVAL, "image too large for this model family");
+            switch (m.features)
+            {
+            case 8: return luma_pass_wide<8>(s, st, m, src, src_pitch, dst, dst_pitch, w, h, type);
+            case 16: return luma_pass_wide<16>(s, st, m, src, src_pitch, dst, dst_pitch, w, h, type);
+            default: return luma_pass_wide<32>(s, st, m, src, src_pitch, dst, dst_pitch, w, h, type);
+            }
+        }
         float* maps[2] = { nullptr, nullptr };
         float* feat = nullptr;
         if (m.chain.size() > 1)
@@ -748,13 +866,20 @@ extern "C"
     int acb200_model_create(int family, int blocks, const float* kernels, int n_kernels, const float* biases, int n_biases,
                             const float* alphas, int n_alphas, acb200_model** out)
     {
+        if (family < ACB200_FAMILY_ACNET_LEGACY || family > ACB200_FAMILY_ARNET) return ACB200_EINVAL;
+        return acb200_model_create_wide(family, 8, blocks, kernels, n_kernels, biases, n_biases, alphas, n_alphas, out);
+    }
+    int acb200_model_create_wide(int family, int features, int blocks, const float* kernels, int n_kernels, const float* biases, int n_biases,
+                                 const float* alphas, int n_alphas, acb200_model** out)
+    {
         if (!out || !kernels || !biases) return ACB200_EINVAL;
         int nk, nb, na;
-        if (!expected_lengths(family, blocks, nk, nb, na)) return ACB200_EINVAL;
+        if (family <= ACB200_FAMILY_ARNET && features != 8) return ACB200_EINVAL;
+        if (!expected_lengths(family, blocks, nk, nb, na, features)) return ACB200_EINVAL;
         if (n_kernels != nk || n_biases != nb || n_alphas != na || (na > 0 && !alphas)) return ACB200_EINVAL;
         acb200_model* m = new (std::nothrow) acb200_model;
         if (!m) return ACB200_ENOMEM;
-        m->family = family; m->blocks = blocks;
+        m->family = family; m->blocks = blocks; m->features = features;
         m->k.assign(kernels, kernels + nk);
         m->b.assign(biases, biases + nb);
         if (na) m->a.assign(alphas, alphas + na);
@@ -797,7 +922,8 @@ extern "C"
         cudaSetDevice(s->device);
         cudaStreamSynchronize(s->stream);
         acb200_session::Buf* bufs[] = { &s->src, &s->dst, &s->y[0], &s->y[1], &s->uv, &s->map[0], &s->map[1], &s->feat, &s->htab, &s->vtab,
-                                        &s->pin[0], &s->pin[1], &s->pin[2], &s->pout[0], &s->pout[1], &s->pout[2] };
+                                        &s->pin[0], &s->pin[1], &s->pin[2], &s->pout[0], &s->pout[1], &s->pout[2],
+                                        &s->wide[0], &s->wide[1], &s->wide[2] };
         for (auto* b : bufs) if (b->p) cudaFreeAsync(b->p, s->stream);
         cudaStreamSynchronize(s->stream);
         for (auto& kv : s->dev_frags) cudaFree(kv.second);
@@ -901,6 +1027,7 @@ extern "C"
     {
         if (!m) return ACB200_EINVAL;
         // 3x3 layers on the path of one 2x pass = rows of input context each output row depends on
+        if (m->family >= ACB200_FAMILY_ARTCNN) return m->blocks + 3;      // ArtCNN: head + (blocks + 1) + tail; FSRCNNX: 5x5 head (2) + blocks + tail
         return m->family == ACB200_FAMILY_ACNET_LEGACY ? m->blocks + 1 : m->family == ACB200_FAMILY_ACNET ? m->blocks + 2 : 2 * m->blocks + 2;
     }
     int acb200_band_plan(int h, double factor, int halo, int n_bands, int band, int* src_y0, int* src_y1, int* out_y0, int* out_y1)

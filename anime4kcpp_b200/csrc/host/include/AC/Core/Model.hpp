@@ -1,11 +1,11 @@
-// Model descriptors of the hot path: ACNetLegacy, ACNet<8>, ARNet<8>.
+// Model descriptors: ACNetLegacy, ACNet<8>, ARNet<8> (the hot path) and ArtCNN<16/32>, FSRCNNX<8/16>.
 //
 // Same public accessors as the reference's CRTP descriptors (core/include/AC/Core/Model/Base.hpp:15-63,
 // ACNet.hpp:18-116, ARNet.hpp:16-72): flat fp32 arrays plus per-layer lengths / offsets, so code written against
 // `model.kernel(l)`, `model.bias(l)`, `model.alpha(l)`, `kernels()`, `blocks()` keeps working.  The numbers behind
 // ACNetLegacy and ACNet<8> are the reference's own tables (dumped into weights/acnet.bin by tools/gen_weights.cpp);
 // ARNet<8> gets seeded stand-ins because the reference's ARNet.p is a missing blob (csrc/synth_weights.h).
-// ArtCNN / FSRCNNX are outside this build's scope.
+// ArtCNN / FSRCNNX (core/include/AC/Core/Model/{ArtCNN,FSRCNNX}.hpp) use the reference's tables too.
 #pragma once
 
 #include <algorithm>
@@ -145,6 +145,72 @@ namespace ac::core::model
             if (l <= 0) return 0;
             if (l <= body + 1) return F * 9 + F * F * 9 * (l - 1);
             if (l < kernels()) return F * 9 + F * F * 9 * body + F * F;
+            return kernelLength();
+        }
+        int biasOffset(const int l) const noexcept { return l <= 0 ? 0 : (l < biases() ? F * l : biasLength()); }
+        int alphaOffset(const int l) const noexcept { const int i = alphaIndex(l); return i <= 0 ? 0 : (i < alphas() ? F * i : alphaLength()); }
+    };
+    // head 1->F (3x3), blockNum + 1 convs F->F (the last one adds the head output), F->4 shuffle conv
+    // (reference: core/include/AC/Core/Model/ArtCNN.hpp:16-61)
+    template<int F>
+    class ArtCNN : public detail::Descriptor<ArtCNN<F>>
+    {
+    public:
+        enum class Variant { C4_NORMAL, C4_DN, C4_DS };
+        AC_CORE_EXPORT ArtCNN(Variant v) noexcept;
+
+        int kernels() const noexcept { return this->blockNum + 3; }
+        int biases() const noexcept { return this->blockNum + 3; }
+        int alphas() const noexcept { return 0; }
+        int kernelLength() const noexcept { return F * 9 + F * F * 9 * (this->blockNum + 1) + F * 4 * 9; }
+        int kernelLength(const int l) const noexcept { return l == 0 ? F * 9 : (l >= 1 && l <= this->blockNum + 1) ? F * F * 9 : (l == this->blockNum + 2 ? F * 4 * 9 : 0); }
+        int biasLength() const noexcept { return F * (this->blockNum + 2) + 4; }
+        int biasLength(const int l) const noexcept { return (l >= 0 && l <= this->blockNum + 1) ? F : (l == this->blockNum + 2 ? 4 : 0); }
+        int alphaLength() const noexcept { return 0; }
+        int alphaLength(const int) const noexcept { return 0; }
+        int kernelIndex(const int l) const noexcept { return std::clamp(l, 0, kernels() - 1); }
+        int biasIndex(const int l) const noexcept { return std::clamp(l, 0, biases() - 1); }
+        int alphaIndex(const int) const noexcept { return 0; }
+        int kernelLayer(const int i) const noexcept { return std::clamp(i, 0, kernels() - 1); }
+        int biasLayer(const int i) const noexcept { return std::clamp(i, 0, biases() - 1); }
+        int alphaLayer(const int) const noexcept { return 0; }
+        int kernelOffset(const int l) const noexcept { return l <= 0 ? 0 : (l < kernels() ? F * 9 + F * F * 9 * (l - 1) : kernelLength()); }
+        int biasOffset(const int l) const noexcept { return l <= 0 ? 0 : (l < biases() ? F * l : biasLength()); }
+        int alphaOffset(const int) const noexcept { return 0; }
+    };
+
+    // head 1->F (5x5), blockNum convs F->F with PReLU, a 1x1 F->F (+ head output, PReLU), F->4 shuffle conv
+    // (reference: core/include/AC/Core/Model/FSRCNNX.hpp:16-85)
+    template<int F>
+    class FSRCNNX : public detail::Descriptor<FSRCNNX<F>>
+    {
+    public:
+        enum class Variant { B4_NORMAL, B4_DISTORT_PLUS };
+        AC_CORE_EXPORT FSRCNNX(Variant v) noexcept;
+
+        int kernels() const noexcept { return this->blockNum + 3; }
+        int biases() const noexcept { return this->blockNum + 3; }
+        int alphas() const noexcept { return this->blockNum + 1; }
+        int kernelLength() const noexcept { return F * 25 + F * F * 9 * this->blockNum + F * F + F * 4 * 9; }
+        int kernelLength(const int l) const noexcept
+        {
+            return l == 0 ? F * 25 : (l >= 1 && l <= this->blockNum) ? F * F * 9 : (l == this->blockNum + 1 ? F * F : (l == this->blockNum + 2 ? F * 4 * 9 : 0));
+        }
+        int biasLength() const noexcept { return F * (this->blockNum + 2) + 4; }
+        int biasLength(const int l) const noexcept { return (l >= 0 && l <= this->blockNum + 1) ? F : (l == this->blockNum + 2 ? 4 : 0); }
+        int alphaLength() const noexcept { return F * (this->blockNum + 1); }
+        int alphaLength(const int l) const noexcept { return (l >= 1 && l <= this->blockNum + 1) ? F : 0; }
+        int kernelIndex(const int l) const noexcept { return std::clamp(l, 0, kernels() - 1); }
+        int biasIndex(const int l) const noexcept { return std::clamp(l, 0, biases() - 1); }
+        int alphaIndex(const int l) const noexcept { return std::clamp(l, 1, alphas()) - 1; }
+        int kernelLayer(const int i) const noexcept { return std::clamp(i, 0, kernels() - 1); }
+        int biasLayer(const int i) const noexcept { return std::clamp(i, 0, biases() - 1); }
+        int alphaLayer(const int i) const noexcept { return std::clamp(i, 0, alphas() - 1) + 1; }
+        int kernelOffset(const int l) const noexcept
+        {
+            if (l <= 0) return 0;
+            if (l <= this->blockNum + 1) return F * 25 + F * F * 9 * (l - 1);
+            if (l < kernels()) return F * 25 + F * F * 9 * this->blockNum + F * F;
             return kernelLength();
         }
         int biasOffset(const int l) const noexcept { return l <= 0 ? 0 : (l < biases() ? F * l : biasLength()); }

@@ -50,7 +50,7 @@ namespace
                 for (std::uint32_t i = 0; i < n; i++)
                 {
                     auto arr = std::make_unique<Arrays>();
-                    arr->blocks = static_cast<int>(entries[i].blocks);
+                    arr->blocks = static_cast<int>(entries[i].blocks & 0xffffu);       // upper half: feature count of ArtCNN / FSRCNNX
                     arr->k = data + entries[i].offset;
                     arr->b = arr->k + entries[i].nk;
                     arr->a = entries[i].na ? arr->b + entries[i].nb : nullptr;
@@ -125,8 +125,32 @@ ac::core::model::ARNet<F>::ARNet(const Variant v) noexcept
     this->bind((std::string("arnet-f8") + size[i / 4] + flavour[i % 4]).c_str());
 }
 
+template<int F>
+ac::core::model::ArtCNN<F>::ArtCNN(const Variant v) noexcept
+{
+    static_assert(F == 16 || F == 32, "ArtCNN exists with 16 and 32 features");
+    static const char* const flavour[] = { "", "-dn", "-ds" };
+    this->bind((std::string("artcnn-c4f") + std::to_string(F) + flavour[static_cast<int>(v)]).c_str());
+}
+
+template<int F>
+ac::core::model::FSRCNNX<F>::FSRCNNX(const Variant v) noexcept
+{
+    static_assert(F == 8 || F == 16, "FSRCNNX exists with 8 and 16 features");
+    static const char* const flavour[] = { "", "-distort-plus" };
+    this->bind((std::string("fsrcnnx-f") + std::to_string(F) + "b4" + flavour[static_cast<int>(v)]).c_str());
+}
+
 template class ac::core::model::detail::Descriptor<ac::core::model::ACNetLegacy>;
 template class ac::core::model::detail::Descriptor<ac::core::model::ACNet<8>>;
 template class ac::core::model::detail::Descriptor<ac::core::model::ARNet<8>>;
+template class ac::core::model::detail::Descriptor<ac::core::model::ArtCNN<16>>;
+template class ac::core::model::detail::Descriptor<ac::core::model::ArtCNN<32>>;
+template class ac::core::model::detail::Descriptor<ac::core::model::FSRCNNX<8>>;
+template class ac::core::model::detail::Descriptor<ac::core::model::FSRCNNX<16>>;
 template class ac::core::model::ACNet<8>;
 template class ac::core::model::ARNet<8>;
+template class ac::core::model::ArtCNN<16>;
+template class ac::core::model::ArtCNN<32>;
+template class ac::core::model::FSRCNNX<8>;
+template class ac::core::model::FSRCNNX<16>;

@@ -47,8 +47,9 @@ namespace
 
     struct ModelChoice
     {
-        int family;     // ACB200_FAMILY_*, or -1 for a family this build does not carry
+        int family;     // ACB200_FAMILY_*
         int variant;    // index into the family's Variant enum
+        int features;   // F of the model template (8 except ArtCNN<16/32>, FSRCNNX<16>)
     };
     // first size token present wins, in the reference's test order
     int firstOf(const std::string& s, std::initializer_list<const char*> tokens, int fallback)
@@ -62,21 +63,23 @@ namespace
         const std::string m = lower(model);
         if (model)
         {
-            if (has(m, "fsrcnnx") || has(m, "artcnn")) return { -1, 0 };
+            // same test order as the reference (core/src/processor/Processor.cpp:39-76)
+            if (has(m, "fsrcnnx")) return { ACB200_FAMILY_FSRCNNX, (has(m, "distort") || has(m, "dp")) ? 1 : 0, has(m, "f16") ? 16 : 8 };
+            if (has(m, "artcnn")) return { ACB200_FAMILY_ARTCNN, has(m, "dn") ? 1 : (has(m, "ds") ? 2 : 0), has(m, "f32") ? 32 : 16 };
             const int flavour = (has(m, "box") ? 2 : 0) + (has(m, "hdn") ? 1 : 0);   // NORMAL, HDN, BOX, BOX_HDN
-            if (has(m, "arnet")) return { ACB200_FAMILY_ARNET, firstOf(m, { "b8", "b16", "b32", "b64" }, 0) * 4 + flavour };
+            if (has(m, "arnet")) return { ACB200_FAMILY_ARNET, firstOf(m, { "b8", "b16", "b32", "b64" }, 0) * 4 + flavour, 8 };
             if (has(m, "acnet"))
             {
                 if (has(m, "legacy"))
                 {
-                    if (!has(m, "hdn")) return { ACB200_FAMILY_ACNET_LEGACY, 0 };   // GAN
-                    for (char ch : m) if (ch >= '0' && ch <= '3') return { ACB200_FAMILY_ACNET_LEGACY, 1 + (ch - '0') };
-                    return { ACB200_FAMILY_ACNET_LEGACY, 1 };                          // HDN0
+                    if (!has(m, "hdn")) return { ACB200_FAMILY_ACNET_LEGACY, 0, 8 };   // GAN
+                    for (char ch : m) if (ch >= '0' && ch <= '3') return { ACB200_FAMILY_ACNET_LEGACY, 1 + (ch - '0'), 8 };
+                    return { ACB200_FAMILY_ACNET_LEGACY, 1, 8 };                          // HDN0
                 }
-                return { ACB200_FAMILY_ACNET, firstOf(m, { "b4", "b8", "b18" }, 1) * 4 + flavour };
+                return { ACB200_FAMILY_ACNET, firstOf(m, { "b4", "b8", "b18" }, 1) * 4 + flavour, 8 };
             }
         }
-        return { ACB200_FAMILY_ACNET_LEGACY, 0 };
+        return { ACB200_FAMILY_ACNET_LEGACY, 0, 8 };
     }
 
     // ---- a processor that only reports why it cannot run ---------------------------------------------------------
@@ -100,7 +103,7 @@ namespace
     class B200Processor final : public Processor
     {
     public:
-        B200Processor(int device, int family, int blocks, const float* k, int nk, const float* b, int nb, const float* a, int na)
+        B200Processor(int device, int family, int features, int blocks, const float* k, int nk, const float* b, int nb, const float* a, int na)
         {
             const int count = acb200_device_count();
             if (count <= 0) { createError = "no CUDA device"; return; }
@@ -120,7 +123,7 @@ namespace
             char buf[256] = {};
             if (acb200_device_info(idx, buf, sizeof(buf), nullptr, nullptr, nullptr, nullptr) != ACB200_OK) { createError = "cannot query CUDA device"; return; }
             deviceName = buf;
-            const int rc = acb200_model_create(family, blocks, k, nk, b, nb, a, na, &model);
+            const int rc = acb200_model_create_wide(family, features, blocks, k, nk, b, nb, a, na, &model);
             if (rc != ACB200_OK) { createError = std::string("model rejected: ") + acb200_error_string(rc); model = nullptr; return; }
             // touch the device once so construction-time failures surface through ok(), as in the reference
             State& st = local();
@@ -206,10 +209,10 @@ namespace
     };
 
     template<typename Model>
-    std::shared_ptr<Processor> makeB200(int device, int family, const Model& m)
+    std::shared_ptr<Processor> makeB200(int device, int family, const Model& m, int features = 8)
     {
         if (!m.kernel()) return std::make_shared<UnavailableProcessor>(Processor::CUDA, "model weights are not available in this build");
-        return std::make_shared<B200Processor>(device, family, m.blocks(), m.kernel(), m.kernelLength(), m.bias(), m.biasLength(),
+        return std::make_shared<B200Processor>(device, family, features, m.blocks(), m.kernel(), m.kernelLength(), m.bias(), m.biasLength(),
                                                m.alphaLength() ? m.alpha() : nullptr, m.alphaLength());
     }
 }
@@ -246,6 +249,23 @@ template<> AC_CORE_EXPORT std::shared_ptr<ac::core::Processor> ac::core::Process
     return makeB200(idx, ACB200_FAMILY_ARNET, model);
 }
 
+template<> AC_CORE_EXPORT std::shared_ptr<ac::core::Processor> ac::core::Processor::create<ac::core::Processor::CUDA, ac::core::model::ArtCNN<16>>(const int idx, const model::ArtCNN<16>& model)
+{
+    return makeB200(idx, ACB200_FAMILY_ARTCNN, model, 16);
+}
+template<> AC_CORE_EXPORT std::shared_ptr<ac::core::Processor> ac::core::Processor::create<ac::core::Processor::CUDA, ac::core::model::ArtCNN<32>>(const int idx, const model::ArtCNN<32>& model)
+{
+    return makeB200(idx, ACB200_FAMILY_ARTCNN, model, 32);
+}
+template<> AC_CORE_EXPORT std::shared_ptr<ac::core::Processor> ac::core::Processor::create<ac::core::Processor::CUDA, ac::core::model::FSRCNNX<8>>(const int idx, const model::FSRCNNX<8>& model)
+{
+    return makeB200(idx, ACB200_FAMILY_FSRCNNX, model, 8);
+}
+template<> AC_CORE_EXPORT std::shared_ptr<ac::core::Processor> ac::core::Processor::create<ac::core::Processor::CUDA, ac::core::model::FSRCNNX<16>>(const int idx, const model::FSRCNNX<16>& model)
+{
+    return makeB200(idx, ACB200_FAMILY_FSRCNNX, model, 16);
+}
+
 std::shared_ptr<ac::core::Processor> ac::core::Processor::create(const char* type, const int device, const char* const model)
 {
     const int kind = parseType(type);
@@ -258,7 +278,13 @@ std::shared_ptr<ac::core::Processor> ac::core::Processor::create(const char* typ
     case ACB200_FAMILY_ACNET_LEGACY: return create<Processor::CUDA>(dev, model::ACNetLegacy{ static_cast<model::ACNetLegacy::Variant>(choice.variant) });
     case ACB200_FAMILY_ACNET: return create<Processor::CUDA>(dev, model::ACNet<8>{ static_cast<model::ACNet<8>::Variant>(choice.variant) });
     case ACB200_FAMILY_ARNET: return create<Processor::CUDA>(dev, model::ARNet<8>{ static_cast<model::ARNet<8>::Variant>(choice.variant) });
-    default: return std::make_shared<UnavailableProcessor>(Processor::CUDA, "model family (ArtCNN / FSRCNNX) is outside the B200 drop-in's scope");
+    case ACB200_FAMILY_ARTCNN:
+        if (choice.features == 32) return create<Processor::CUDA>(dev, model::ArtCNN<32>{ static_cast<model::ArtCNN<32>::Variant>(choice.variant) });
+        return create<Processor::CUDA>(dev, model::ArtCNN<16>{ static_cast<model::ArtCNN<16>::Variant>(choice.variant) });
+    case ACB200_FAMILY_FSRCNNX:
+        if (choice.features == 16) return create<Processor::CUDA>(dev, model::FSRCNNX<16>{ static_cast<model::FSRCNNX<16>::Variant>(choice.variant) });
+        return create<Processor::CUDA>(dev, model::FSRCNNX<8>{ static_cast<model::FSRCNNX<8>::Variant>(choice.variant) });
+    default: return std::make_shared<UnavailableProcessor>(Processor::CUDA, "unknown model family");
     }
 }
 
@@ -326,9 +352,17 @@ extern "C" AC_CORE_EXPORT const char* ac_b200_resolve_model(const char* model)
     case ACB200_FAMILY_ACNET_LEGACY: return model::ACNetLegacy{ static_cast<model::ACNetLegacy::Variant>(c.variant) }.name();
     case ACB200_FAMILY_ACNET: return model::ACNet<8>{ static_cast<model::ACNet<8>::Variant>(c.variant) }.name();
     case ACB200_FAMILY_ARNET: return model::ARNet<8>{ static_cast<model::ARNet<8>::Variant>(c.variant) }.name();
+    case ACB200_FAMILY_ARTCNN:
+        return c.features == 32 ? model::ArtCNN<32>{ static_cast<model::ArtCNN<32>::Variant>(c.variant) }.name()
+                                : model::ArtCNN<16>{ static_cast<model::ArtCNN<16>::Variant>(c.variant) }.name();
+    case ACB200_FAMILY_FSRCNNX:
+        return c.features == 16 ? model::FSRCNNX<16>{ static_cast<model::FSRCNNX<16>::Variant>(c.variant) }.name()
+                                : model::FSRCNNX<8>{ static_cast<model::FSRCNNX<8>::Variant>(c.variant) }.name();
     default: return "";
     }
 }
+// feature count F of the model a string resolves to (8, 16 or 32)
+extern "C" AC_CORE_EXPORT int ac_b200_model_features(const char* model) { return parseModel(model).features; }
 
 // exported for bindings / tests: the flat weight arrays behind a model string, exactly as handed to the CUDA layer.
 // Returns the ACB200_FAMILY_* code, or -1 when the family is out of scope.
@@ -349,6 +383,14 @@ extern "C" AC_CORE_EXPORT int ac_b200_model_arrays(const char* model, int* block
     case ACB200_FAMILY_ACNET_LEGACY: fill(model::ACNetLegacy{ static_cast<model::ACNetLegacy::Variant>(c.variant) }); break;
     case ACB200_FAMILY_ACNET: fill(model::ACNet<8>{ static_cast<model::ACNet<8>::Variant>(c.variant) }); break;
     case ACB200_FAMILY_ARNET: fill(model::ARNet<8>{ static_cast<model::ARNet<8>::Variant>(c.variant) }); break;
+    case ACB200_FAMILY_ARTCNN:
+        if (c.features == 32) fill(model::ArtCNN<32>{ static_cast<model::ArtCNN<32>::Variant>(c.variant) });
+        else fill(model::ArtCNN<16>{ static_cast<model::ArtCNN<16>::Variant>(c.variant) });
+        break;
+    case ACB200_FAMILY_FSRCNNX:
+        if (c.features == 16) fill(model::FSRCNNX<16>{ static_cast<model::FSRCNNX<16>::Variant>(c.variant) });
+        else fill(model::FSRCNNX<8>{ static_cast<model::FSRCNNX<8>::Variant>(c.variant) });
+        break;
     default: return -1;
     }
     return c.family;

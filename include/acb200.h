@@ -51,6 +51,8 @@ extern "C" {
 #define ACB200_FAMILY_ACNET_LEGACY 0   /* model::ACNetLegacy: ReLU, 2x2 deconvolution tail */
 #define ACB200_FAMILY_ACNET        1   /* model::ACNet<8>:   PReLU, pixel-shuffle + nearest residual tail */
 #define ACB200_FAMILY_ARNET        2   /* model::ARNet<8>:   residual blocks, 1x1 fuse, pixel-shuffle tail */
+#define ACB200_FAMILY_ARTCNN       3   /* model::ArtCNN<16/32>: ReLU convs, long skip, pixel-shuffle tail (no luma residual) */
+#define ACB200_FAMILY_FSRCNNX      4   /* model::FSRCNNX<8/16>: 5x5 head, PReLU convs, 1x1 + skip, pixel-shuffle tail */
 
 #define ACB200_OK          0
 #define ACB200_EINVAL     (-22)   /* bad argument / unsupported shape */
@@ -76,6 +78,16 @@ ACB200_API int acb200_model_create(int family, int blocks,
                                    const float* biases, int n_biases,
                                    const float* alphas, int n_alphas,
                                    acb200_model** out);
+/*
+ * The reference's other model families (core/include/AC/Core/Model/{ArtCNN,FSRCNNX}.hpp; replaces Processor::create<CUDA,
+ * model::ArtCNN<F>> / <CUDA, model::FSRCNNX<F>>, core/src/processor/cuda/CUDAProcessor.cpp:574-880): `features` = F
+ * (ArtCNN 16 / 32, FSRCNNX 8 / 16), arrays exactly as model.kernel() / bias() / alpha() hand them out.  These families run
+ * per-layer fp32 kernels in the reference FMA-backend order (bit-identical); the engine selection does not apply.
+ * With family 0..2 and features == 8 this is acb200_model_create.
+ */
+ACB200_API int acb200_model_create_wide(int family, int features, int blocks,
+                                        const float* kernels, int n_kernels, const float* biases, int n_biases,
+                                        const float* alphas, int n_alphas, acb200_model** out);
 ACB200_API void acb200_model_destroy(acb200_model* model);
 
 /*

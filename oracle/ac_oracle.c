@@ -299,6 +299,202 @@ static void tail_pixelshuffle(const float *src, int w, int h, uint8_t *dst, int 
         }
 }
 
+/* ======================================================================================
+ * ArtCNN<16/32> and FSRCNNX<8/16>: the same layer templates with F features.
+ * OpImpl::conv<cin,cout,cpos> for any cin (multiple of 8): Generic.hpp:71-80 (per input channel a left fold over the
+ * taps, channel sums accumulated onto 0, bias last) / X86/AVX.hpp:32-58,126-146 (256-bit FMA backend: lane c%8 runs one
+ * FMA chain over (tap, 8-channel chunk) in that order, then the hsum tree, added onto the bias).
+ * ====================================================================================== */
+#define ORC_FAMILY_ARTCNN 3
+#define ORC_FAMILY_FSRCNNX 4
+
+static void conv_any(const float *const *rptr, int cpos, int cin, float *out, int cout, const float *kernels, const float *biases)
+{
+    for (int n = 0; n < cout; n++)
+    {
+        const float *k = kernels + (size_t)n * cin * cpos;
+        if (g_order == ORC_ORDER_FMA)
+        {
+            float s[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+            for (int p = 0; p < cpos; p++)
+                for (int idx = 0; idx < cin / 8; idx++)
+                    for (int c = 0; c < 8; c++) s[c] = fmaf(rptr[p][idx * 8 + c], k[p * cin + idx * 8 + c], s[c]);
+            out[n] = biases[n] + hsum8(s);
+            continue;
+        }
+        float sum = 0.0f;
+        for (int c = 0; c < cin; c++)
+        {
+            float t = rptr[0][c] * k[c];
+            for (int p = 1; p < cpos; p++) t = t + rptr[p][c] * k[p * cin + c];
+            sum += t;
+        }
+        out[n] = sum + biases[n];
+    }
+}
+
+/* conv3x3_cin1 / conv5x5_cin1 (Common.hpp:166-197, 199-221): ks x ks window with clamp-to-edge coordinates;
+ * OpImpl::conv_cin1<cout,cpos>: Generic.hpp:61-69 (left fold) / X86/AVX.hpp:95-124 (8-tap vectors as FMA chains per lane,
+ * hsum, the remaining taps added as scalars, bias last). */
+static void layer_head_any(const uint8_t *src, int w, int h, int stride, int type, float *dst, int F, int ks,
+                           const float *kernels, const float *biases)
+{
+    const int cpos = ks * ks, half = ks / 2;
+#pragma omp parallel for schedule(guided)
+    for (int i = 0; i < h; i++)
+        for (int j = 0; j < w; j++)
+        {
+            float r[25];
+            for (int a = 0; a < ks; a++)
+                for (int b = 0; b < ks; b++)
+                {
+                    int y = i + a - half, x = j + b - half;
+                    y = y < 0 ? 0 : (y > h - 1 ? h - 1 : y);
+                    x = x < 0 ? 0 : (x > w - 1 ? w - 1 : x);
+                    r[a * ks + b] = load_elem(src + (size_t)y * stride, x, type);
+                }
+            float *out = dst + ((size_t)i * w + j) * F;
+            for (int n = 0; n < F; n++)
+            {
+                const float *k = kernels + n * cpos;
+                float s;
+                if (g_order == ORC_ORDER_FMA)
+                {
+                    float t[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+                    const int count = cpos / 8;
+                    for (int idx = 0; idx < count; idx++)
+                        for (int c = 0; c < 8; c++) t[c] = fmaf(r[idx * 8 + c], k[idx * 8 + c], t[c]);
+                    s = hsum8(t);
+                    for (int q = count * 8; q < cpos; q++) s = fmaf(r[q], k[q], s);
+                }
+                else
+                {
+                    s = r[0] * k[0];
+                    for (int q = 1; q < cpos; q++) s = s + r[q] * k[q];
+                }
+                out[n] = s + biases[n];     /* Identity activation in both families */
+            }
+        }
+}
+
+static inline void gather9_any(const float *src, int w, int h, int F, int i, int j, const float *rptr[9])
+{
+    int tp = i > 0 ? 1 : 0, bp = i < h - 1 ? 1 : 0, lp = j > 0 ? 1 : 0, rp = j < w - 1 ? 1 : 0;
+    const float *r0 = src + (size_t)(i - tp) * w * F, *r1 = src + (size_t)i * w * F, *r2 = src + (size_t)(i + bp) * w * F;
+    rptr[0] = r0 + (j - lp) * F; rptr[1] = r0 + j * F; rptr[2] = r0 + (j + rp) * F;
+    rptr[3] = r1 + (j - lp) * F; rptr[4] = r1 + j * F; rptr[5] = r1 + (j + rp) * F;
+    rptr[6] = r2 + (j - lp) * F; rptr[7] = r2 + j * F; rptr[8] = r2 + (j + rp) * F;
+}
+
+/* conv3x3_float<F,F> (Common.hpp:116-164): activation, then `sum*scale + id` (scale 1.0 here) */
+static void layer_conv_any(const float *src, int w, int h, int F, float *dst, const float *kernels, const float *biases,
+                           int act, const float *alphas, const float *residual)
+{
+#pragma omp parallel for schedule(guided)
+    for (int i = 0; i < h; i++)
+        for (int j = 0; j < w; j++)
+        {
+            const float *rptr[9];
+            float sum[32];
+            gather9_any(src, w, h, F, i, j, rptr);
+            conv_any(rptr, 9, F, sum, F, kernels, biases);
+            size_t o = ((size_t)i * w + j) * F;
+            for (int n = 0; n < F; n++)
+            {
+                float v = activate(sum[n], act, alphas, n);
+                if (residual) v = muladd(v, 1.0f, residual[o + n]);
+                dst[o + n] = v;
+            }
+        }
+}
+
+/* conv3x3_conv1x1_float<F,F,F,false,true> (Common.hpp:223-288, Backend.hpp:239-250,296-307): conv3x3 + PReLU, then the
+ * 1x1 + bias, `+ feat` (scale 1.0) and the second PReLU last (postactive1x1) */
+static void layer_conv_1x1_any(const float *src, int w, int h, int F, float *dst,
+                               const float *k3, const float *b3, const float *a3,
+                               const float *k1, const float *b1, const float *a1, const float *feat)
+{
+#pragma omp parallel for schedule(guided)
+    for (int i = 0; i < h; i++)
+        for (int j = 0; j < w; j++)
+        {
+            const float *rptr[9];
+            float buf[32], sum[32];
+            gather9_any(src, w, h, F, i, j, rptr);
+            conv_any(rptr, 9, F, buf, F, k3, b3);
+            for (int n = 0; n < F; n++) buf[n] = activate(buf[n], ORC_ACT_PRELU, a3, n);
+            const float *one[1] = { buf };
+            conv_any(one, 1, F, sum, F, k1, b1);
+            size_t o = ((size_t)i * w + j) * F;
+            for (int n = 0; n < F; n++) dst[o + n] = activate(muladd(sum[n], 1.0f, feat[o + n]), ORC_ACT_PRELU, a1, n);
+        }
+}
+
+/* conv3x3_pixelshuffle_float<OUT,F,2,Identity,nullptr> (Common.hpp:290-342): no nearest-neighbour residual */
+static void tail_pixelshuffle_any(const float *src, int w, int h, int F, uint8_t *dst, int dst_stride, int type,
+                                  const float *kernels, const float *biases)
+{
+#pragma omp parallel for schedule(guided)
+    for (int i = 0; i < h; i++)
+        for (int j = 0; j < w; j++)
+        {
+            const float *rptr[9];
+            float sum[4];
+            gather9_any(src, w, h, F, i, j, rptr);
+            conv_any(rptr, 9, F, sum, 4, kernels, biases);
+            for (int n = 0; n < 4; n++)
+                net_store_elem(dst + (size_t)(2 * i + (n >> 1)) * dst_stride, 2 * j + (n & 1), type, sum[n]);
+        }
+}
+
+/* One 2x pass of ArtCNN<F> (CPUProcessor.cpp:1519-1549 / :1570-1600) or FSRCNNX<F> (:1621-1655 / :1676-1710);
+ * weight offsets: Model/ArtCNN.hpp:33-60, Model/FSRCNNX.hpp:33-85. */
+static int luma_pass_wide(int family, int blocks, int F, const float *k, const float *b, const float *a,
+                          const uint8_t *src, int w, int h, int src_stride, int type, uint8_t *dst, int dst_stride)
+{
+    if (!(F == 8 || F == 16 || F == 32)) return -1;
+    size_t n = (size_t)w * h * F;
+    float *t1 = (float *)malloc(n * sizeof(float)), *t2 = (float *)malloc(n * sizeof(float)), *feat = (float *)malloc(n * sizeof(float));
+    if (!t1 || !t2 || !feat) { free(t1); free(t2); free(feat); return -1; }
+    float *in = t2, *out = t1, *t;
+    if (family == ORC_FAMILY_ARTCNN)
+    {
+        const int KH = F * 9, KL = F * F * 9;
+        int l = 0;
+        layer_head_any(src, w, h, src_stride, type, feat, F, 3, k, b); l++;
+        layer_conv_any(feat, w, h, F, out, k + KH + KL * (l - 1), b + F * l, ORC_ACT_RELU, 0, 0); l++;
+        t = in; in = out; out = t;
+        for (int i = 0; i < blocks - 1; i++)
+        {
+            layer_conv_any(in, w, h, F, out, k + KH + KL * (l - 1), b + F * l, ORC_ACT_RELU, 0, 0); l++;
+            t = in; in = out; out = t;
+        }
+        layer_conv_any(in, w, h, F, out, k + KH + KL * (l - 1), b + F * l, ORC_ACT_IDENTITY, 0, feat); l++;
+        t = in; in = out; out = t;
+        tail_pixelshuffle_any(in, w, h, F, dst, dst_stride, type, k + KH + KL * (l - 1), b + F * l);
+    }
+    else
+    {
+        const int KH = F * 25, KL = F * F * 9;
+        int l = 0;
+        layer_head_any(src, w, h, src_stride, type, feat, F, 5, k, b); l++;
+        layer_conv_any(feat, w, h, F, out, k + KH + KL * (l - 1), b + F * l, ORC_ACT_PRELU, a + F * (l - 1), 0); l++;
+        t = in; in = out; out = t;
+        for (int i = 0; i < blocks - 2; i++)
+        {
+            layer_conv_any(in, w, h, F, out, k + KH + KL * (l - 1), b + F * l, ORC_ACT_PRELU, a + F * (l - 1), 0); l++;
+            t = in; in = out; out = t;
+        }
+        layer_conv_1x1_any(in, w, h, F, out, k + KH + KL * (l - 1), b + F * l, a + F * (l - 1),
+                           k + KH + KL * blocks, b + F * (l + 1), a + F * l, feat);
+        l += 2;
+        t = in; in = out; out = t;
+        tail_pixelshuffle_any(in, w, h, F, dst, dst_stride, type, k + KH + KL * blocks + F * F, b + F * l);
+    }
+    free(t1); free(t2); free(feat);
+    return 0;
+}
+
 /*
  * One 2x luma pass.  Layer sequencing follows core/src/processor/cpu/CPUProcessor.cpp:
  * ACNetLegacy :1371-1390, ACNet<8> :1417-1436, ARNet<8> :1464-1491; weight offsets follow
@@ -311,6 +507,8 @@ int orc_luma_pass(int family, int blocks, const float *k, const float *b, const 
     const uint8_t *src = (const uint8_t *)src_;
     uint8_t *dst = (uint8_t *)dst_;
     if (w <= 0 || h <= 0 || !src || !dst) return -1;
+    if (family == ORC_FAMILY_ARTCNN || family == ORC_FAMILY_FSRCNNX)    /* blocks | (features << 16) */
+        return luma_pass_wide(family, blocks & 0xffff, blocks >> 16, k, b, a, src, w, h, src_stride, type, dst, dst_stride);
     size_t n = (size_t)w * h * 8;
     float *t1 = (float *)malloc(n * sizeof(float)), *t2 = (float *)malloc(n * sizeof(float)), *feat = 0;
     if (!t1 || !t2) { free(t1); free(t2); return -1; }

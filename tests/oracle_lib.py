@@ -15,7 +15,7 @@ WEIGHTS = os.path.join(ROOT, "anime4kcpp_b200", "weights", "acnet.bin")
 U8, U16, F32 = 0x001, 0x002, 0x204
 NP_TYPES = {np.dtype(np.uint8): U8, np.dtype(np.uint16): U16, np.dtype(np.float32): F32}
 
-FAMILY_LEGACY, FAMILY_ACNET, FAMILY_ARNET = 0, 1, 2
+FAMILY_LEGACY, FAMILY_ACNET, FAMILY_ARNET, FAMILY_ARTCNN, FAMILY_FSRCNNX = 0, 1, 2, 3, 4
 
 _vp, _fp, _i, _d = C.c_void_p, C.POINTER(C.c_float), C.c_int, C.c_double
 
@@ -121,7 +121,8 @@ _models = None
 
 
 def models():
-    """name -> (family, blocks, kernels, biases, alphas) for the 17 real-weight variants."""
+    """name -> (family, blocks, kernels, biases, alphas) for the real-weight variants (for ArtCNN / FSRCNNX `blocks`
+    carries the feature count in its upper 16 bits: blocks | F << 16, as written by tools/gen_weights.cpp)."""
     global _models
     if _models is None:
         raw = open(WEIGHTS, "rb").read()
@@ -133,9 +134,19 @@ def models():
             name, fam, blocks, nk, nb, na, off = struct.unpack_from("<48sIIIIII", raw, 16 + m * 72)
             name = name.split(b"\0")[0].decode()
             data = np.frombuffer(raw, np.float32, nk + nb + na, base + 4 * off)
-            out[name] = (fam, blocks, data[:nk].copy(), data[nk:nk + nb].copy(), data[nk + nb:].copy())
+            out[name] = (fam, blocks & 0xffff, data[:nk].copy(), data[nk:nk + nb].copy(), data[nk + nb:].copy())
+            _features[name] = (blocks >> 16) or 8
         _models = out
     return _models
+
+
+_features = {}
+
+
+def features(name):
+    """F of the model template: 8, except ArtCNN<16/32> and FSRCNNX<16>."""
+    models()
+    return _features.get(canonical(name), 8)
 
 
 _arnet_cache = {}
@@ -154,6 +165,10 @@ def model(name):
 def canonical(s):
     """Model-string parsing of core/src/processor/Processor.cpp:26-187 (ACNet/ARNet branches)."""
     s = (s or "").lower()
+    if "fsrcnnx" in s:
+        return "fsrcnnx-f%sb4" % ("16" if "f16" in s else "8") + ("-distort-plus" if ("distort" in s or "dp" in s) else "")
+    if "artcnn" in s:
+        return "artcnn-c4f%s" % ("32" if "f32" in s else "16") + ("-dn" if "dn" in s else ("-ds" if "ds" in s else ""))
     if "arnet" in s:
         b = "b8"
         for cand in ("b8", "b16", "b32", "b64"):
@@ -187,6 +202,8 @@ def _type_of(img):
 def oracle_process(name, img, factor=2.0):
     """Processor::process(src, factor) on the CPU oracle.  img: (H,W) or (H,W,C) contiguous."""
     fam, blocks, k, b, a = model(name)
+    if fam >= FAMILY_ARTCNN:
+        blocks |= features(name) << 16     # the oracle's C entry takes F in the upper half of `blocks` for these families
     img = np.ascontiguousarray(img)
     h, w = img.shape[:2]
     c = 1 if img.ndim == 2 else img.shape[2]

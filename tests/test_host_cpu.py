@@ -41,13 +41,22 @@ def test_weights_in_library_match_blob_and_synth():
 
 
 @pytest.mark.parametrize("s", ["acnet-hdn", "ACNet-Legacy-HDN2", "acnet-legacy", "acnet-legacy-hdn", "arnet-f8b16-box", "arnet", "ARNET-B64-hdn",
-                               "acnet-f8b18-box-hdn", "acnet-b4", "unknown", "", "acnet-f8b8-box"])
+                               "acnet-f8b18-box-hdn", "acnet-b4", "unknown", "", "acnet-f8b8-box",
+                               "artcnn", "ArtCNN-C4F32-DS", "artcnn-c4f16-dn", "artcnn-f32", "fsrcnnx", "fsrcnnx-f16b4-dp", "FSRCNNX-F8B4-Distort-Plus",
+                               "fsrcnnx-f16"])
 def test_model_string_resolution_matches_reference_rules(s):
     assert A.resolve_model(s) == O.canonical(s)
 
 
-def test_out_of_scope_families_are_reported():
-    assert A.resolve_model("fsrcnnx-f8b4") == "" and A.resolve_model("artcnn-c4f16") == ""
+def test_wide_families_resolve_with_their_feature_count():
+    """ArtCNN<16/32> / FSRCNNX<8/16> (core/src/processor/Processor.cpp:39-76): family, features and array lengths."""
+    for name, fam, feat in (("artcnn-c4f16", 3, 16), ("artcnn-c4f32-dn", 3, 32), ("fsrcnnx-f8b4", 4, 8), ("fsrcnnx-f16b4-distort-plus", 4, 16)):
+        f, blocks, k, b, a = A.model_arrays(name)
+        assert (f, blocks) == (fam, 4) and A.lib().ac_b200_model_features(name.encode()) == feat == O.features(name)
+        m = A.Model(name)          # lengths accepted by acb200_model_create_wide
+        assert m.features == feat and m.halo() == 7
+        with pytest.raises(A.Acb200Error):
+            A.Model(family=f, blocks=blocks, kernels=k, biases=b, alphas=a, features=8 if feat != 8 else 16)
 
 
 def test_model_create_validates_lengths():

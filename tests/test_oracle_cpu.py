@@ -84,8 +84,13 @@ def test_catmull_rom_2x_is_exact_dyadic_kernel():
 def test_model_table_shapes():
     # reference tests/core/src/ModelTest.cpp:5-34: lengths are self-consistent with the layer structure
     for name, (fam, blocks, k, b, a) in O.models().items():
+        F = O.features(name)
         if fam == O.FAMILY_LEGACY:
             assert (k.size, b.size, a.size) == (72 + 576 * blocks + 32, 8 * (blocks + 1), 0)
+        elif fam == O.FAMILY_ARTCNN:       # core/include/AC/Core/Model/ArtCNN.hpp:33-36
+            assert (k.size, b.size, a.size) == (F * 9 + F * F * 9 * (blocks + 1) + F * 36, F * (blocks + 2) + 4, 0)
+        elif fam == O.FAMILY_FSRCNNX:      # core/include/AC/Core/Model/FSRCNNX.hpp:33-38
+            assert (k.size, b.size, a.size) == (F * 25 + F * F * 9 * blocks + F * F + F * 36, F * (blocks + 2) + 4, F * (blocks + 1))
         else:
             assert (k.size, b.size, a.size) == (72 + 576 * blocks + 288, 8 * (blocks + 1) + 4, 8 * (blocks + 1))
     fam, blocks, k, b, a = O.model("arnet-f8b64")
@@ -125,6 +130,22 @@ def test_fma_order_oracle_matches_reference_fma_and_avx512_backends(name):
             assert np.array_equal(O.oracle_process(name, img, factor), want)
             if O.ref().ref_processor_name(name.encode(), 0) == b"AVX512":
                 assert np.array_equal(O.ref_process(name, img, factor, arch=5), want)
+
+
+@pytest.mark.skipif(O.ref() is None, reason="compiled reference (oracle/_ref) only exists in the build container")
+@pytest.mark.parametrize("name", ["artcnn-c4f16", "artcnn-c4f16-dn", "artcnn-c4f32-ds", "fsrcnnx-f8b4", "fsrcnnx-f8b4-distort-plus", "fsrcnnx-f16b4",
+                                  "fsrcnnx-f16b4-distort-plus"])
+def test_wide_family_oracle_matches_compiled_reference_in_both_orders(name):
+    """ArtCNN<16/32> / FSRCNNX<8/16> restatement (oracle/ac_oracle.c, luma_pass_wide) pinned bit for bit against the reference's
+    Generic backend (arch 1) and its 256-bit FMA backend (arch 4), u8 / u16 / f32, gray and RGB, 2x and 4x."""
+    img = O.noise_u8(29, 41, 1, seed=5)
+    cases = [img, (img.astype(np.uint16) * 257 + 3).astype(np.uint16), (img / 255.0).astype(np.float32), O.noise_u8(18, 22, 3, seed=6)]
+    for order, arch in ((O.ORDER_GENERIC, 1), (O.ORDER_FMA, 4)):
+        O.set_order(order)
+        for x in cases:
+            assert np.array_equal(O.oracle_process(name, x, 2.0), O.ref_process(name, x, 2.0, arch=arch)), (name, order, x.dtype)
+        assert np.array_equal(O.oracle_process(name, cases[0][:12, :12], 4.0), O.ref_process(name, np.ascontiguousarray(cases[0][:12, :12]), 4.0, arch=arch))
+    O.set_order(O.ORDER_GENERIC)
 
 
 @pytest.mark.skipif(O.ref() is None, reason="compiled reference (oracle/_ref) only exists in the build container")
@@ -182,3 +203,32 @@ def test_division_free_to_float_is_exact():
         y2 = (r.astype(np.float64) * np.float64(rcp) + y.astype(np.float64)).astype(np.float32)
         want = (q.astype(np.float64) / np.float64(m)).astype(np.float32)
         assert np.array_equal(y2, want), m
+
+
+# ---- ArtCNN<16/32>, FSRCNNX<8/16>: committed vectors of the compiled reference (travel to the GPU box) ----------------------
+WIDE = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "wide_vectors.npz"))
+
+
+def wide_src(kind):
+    g = WIDE["in_gray_noise"]
+    return {"gray_noise_2x": g, "gray_smooth_2x": WIDE["in_gray_smooth"], "rgb_2x": WIDE["in_rgb"], "gray_4x": np.ascontiguousarray(g[:16, :20]),
+            "gray_f32_2x": g.astype(np.float32) / np.float32(255), "gray_u16_2x": g.astype(np.uint16) * 257}[kind]
+
+
+@pytest.mark.parametrize("key", sorted(k for k in WIDE.files if k.startswith(("generic:", "fma:"))))
+def test_wide_family_oracle_reproduces_golden_vectors(key):
+    order, rest = key.split(":", 1)
+    kind, name = rest.split("/", 1)
+    O.set_order(O.ORDER_FMA if order == "fma" else O.ORDER_GENERIC)
+    got = O.oracle_process(name, wide_src(kind), 4.0 if kind.endswith("4x") else 2.0)
+    O.set_order(O.ORDER_GENERIC)
+    assert np.array_equal(got, WIDE[key])
+
+
+def test_wide_family_reference_backends_agree_within_the_parity_bar():
+    """The reference's three x86 orders (Generic / 256-bit FMA / AVX512) on the 16/32-feature models: <= 1 LSB apart."""
+    for key in (k for k in WIDE.files if k.startswith("avx512:")):
+        rest = key.split(":", 1)[1]
+        for other in ("generic:", "fma:"):
+            mx, same = O.compare_u8(WIDE[key], WIDE[other + rest])
+            assert mx <= 1 and same >= 0.999, (key, other, mx, same)

@@ -496,3 +496,73 @@ def test_c_binding_process_frame_extension(session):
     assert L.ac_processor_process_frame(p, src, dst, 3, 0x002, 6, 2.0) == 0
     assert L.ac_processor_process_frame(None, src, dst, 3, 0x002, 6, 2.0) == -22
     L.ac_processor_free(C.byref(p))
+
+
+# ---- ArtCNN<16/32>, FSRCNNX<8/16>: per-layer fp32 kernels in the reference FMA-backend order -----------
+WIDE = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "wide_vectors.npz"))
+WIDE_MODELS = ["artcnn-c4f16", "artcnn-c4f32-ds", "fsrcnnx-f8b4", "fsrcnnx-f16b4-distort-plus"]
+
+
+def wide_src(kind):
+    g = WIDE["in_gray_noise"]
+    return {"gray_noise_2x": g, "gray_smooth_2x": WIDE["in_gray_smooth"], "rgb_2x": WIDE["in_rgb"], "gray_4x": np.ascontiguousarray(g[:16, :20]),
+            "gray_f32_2x": g.astype(np.float32) / np.float32(255), "gray_u16_2x": g.astype(np.uint16) * 257}[kind]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", sorted(k.split(":", 1)[1] for k in WIDE.files if k.startswith("fma:")))
+def test_wide_families_bit_identical_to_reference_fma_backend_and_close_to_the_others(session, key):
+    kind, name = key.split("/", 1)
+    out = session.process_host(gpu_model(name), wide_src(kind), 4.0 if kind.endswith("4x") else 2.0)
+    assert np.array_equal(out, WIDE["fma:" + key])
+    check_close(out, WIDE["generic:" + key], x4=kind.endswith("4x"))
+    if "avx512:" + key in WIDE.files:
+        check_close(out, WIDE["avx512:" + key])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", WIDE_MODELS)
+@pytest.mark.parametrize("shape", [(3, 3), (1, 9), (7, 1), (33, 65), (64, 32), (70, 97)])
+def test_wide_families_odd_sizes_vs_oracle(session, name, shape):
+    O.set_order(O.ORDER_FMA)
+    img = O.noise_u8(shape[0], shape[1], 1, seed=shape[0] * 131 + shape[1])
+    assert np.array_equal(session.process_host(gpu_model(name), img, 2.0), O.oracle_process(name, img, 2.0))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["artcnn-c4f16-dn", "fsrcnnx-f16b4"])
+def test_wide_families_colour_4x_bands_frames_and_processor_api(session, name):
+    O.set_order(O.ORDER_FMA)
+    m = gpu_model(name)
+    rgba = O.noise_u8(26, 38, 4, seed=3)
+    got, want = session.process_host(m, rgba, 4.0), O.oracle_process(name, rgba, 4.0)
+    opaque = np.repeat((want[..., 3:4] >= 128), 4, axis=2)          # un-premultiply amplifies 1-LSB chroma noise where alpha is small
+    assert np.array_equal(got[opaque], want[opaque])
+    # row bands reproduce the whole image (halo = blocks + 3 layers, 5x5 head included)
+    gray = O.noise_u8(90, 50, 1, seed=8)
+    whole = session.process_host(m, gray, 2.0)
+    out = np.zeros_like(whole)
+    for b in range(3):
+        A.process_band(session, m, gray, 2.0, 3, b, out)
+    assert np.array_equal(out, whole)
+    # planar video frame and the Processor front door
+    planes = _yuv_frame(40, 56, "i420", np.uint8, 8, seed=4)
+    for a, b in zip(session.process_frame(m, planes, 2.0), O.oracle_frame(name, planes, 2.0)):
+        assert np.array_equal(a, b)
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "anime4kcpp_b200"))
+    import pyac
+    p = pyac.core.Processor("cuda", 0, name)
+    assert p.ok(), p.error()
+    assert np.array_equal(p(gray, 2.0), whole)
+
+
+@pytest.mark.gpu
+def test_wide_families_1080p_frame_against_oracle_sample(session):
+    """Full-size frame: the top-left 160x160 of the result equals the oracle on a 96x96 crop's interior-independent region."""
+    O.set_order(O.ORDER_FMA)
+    img = O.smooth_u8(1080, 1920, 1, seed=2)
+    for name in ("artcnn-c4f16", "fsrcnnx-f8b4"):
+        got = session.process_host(gpu_model(name), img, 2.0)
+        assert got.shape == (2160, 3840)
+        want = O.oracle_process(name, np.ascontiguousarray(img[:96, :96]), 2.0)
+        assert np.array_equal(got[:160, :160], want[:160, :160])     # 96 - 7 layers of context - margin = 80 source pixels
