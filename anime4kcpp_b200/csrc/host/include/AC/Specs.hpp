@@ -53,6 +53,16 @@ namespace ac::specs
         { "arnet-f8b64-hdn", "ARNet f8b64, denoising variant (synthetic weights).", 75716 },
         { "arnet-f8b64-box", "ARNet f8b64, box variant (synthetic weights).", 75716 },
         { "arnet-f8b64-box-hdn", "ARNet f8b64, box + denoising variant (synthetic weights).", 75716 },
+        { "artcnn-c4f16", "ArtCNN C4F16, neutral.", 12340, nullptr, "Artoriuz", "https://github.com/Artoriuz/ArtCNN" },
+        { "artcnn-c4f16-dn", "ArtCNN C4F16, denoise and soften.", 12340, nullptr, "Artoriuz", "https://github.com/Artoriuz/ArtCNN" },
+        { "artcnn-c4f16-ds", "ArtCNN C4F16, denoise and sharpen.", 12340, nullptr, "Artoriuz", "https://github.com/Artoriuz/ArtCNN" },
+        { "artcnn-c4f32", "ArtCNN C4F32, neutral.", 47716, nullptr, "Artoriuz", "https://github.com/Artoriuz/ArtCNN" },
+        { "artcnn-c4f32-dn", "ArtCNN C4F32, denoise and soften.", 47716, nullptr, "Artoriuz", "https://github.com/Artoriuz/ArtCNN" },
+        { "artcnn-c4f32-ds", "ArtCNN C4F32, denoise and sharpen.", 47716, nullptr, "Artoriuz", "https://github.com/Artoriuz/ArtCNN" },
+        { "fsrcnnx-f8b4", "FSRCNNX x2 8-0-4-1, slight denoising.", 2948, nullptr, "igv" },
+        { "fsrcnnx-f8b4-distort-plus", "FSRCNNX x2 8-0-4-1 distort-plus, strong denoising.", 2948, nullptr, "nessotrin" },
+        { "fsrcnnx-f16b4", "FSRCNNX x2 16-0-4-1, slight denoising.", 10628, nullptr, "igv" },
+        { "fsrcnnx-f16b4-distort-plus", "FSRCNNX x2 16-0-4-1 distort-plus, strong denoising.", 10628, nullptr, "nessotrin" },
     };
 
     constexpr Processor ProcessorList[] = {

@@ -35,7 +35,8 @@ W, H, CH = 1920, 1080, 3
 FACTOR = 2.0
 OUT_MP = (W * 2) * (H * 2) / 1e6
 MACS_PER_PIXEL = {"acnet-legacy": 4712, "acnet-f8b4": 2664, "acnet-f8b8": 4968, "acnet-f8b18": 10728,
-                  "arnet-f8b8": 9640, "arnet-f8b16": 18856, "arnet-f8b32": 37288, "arnet-f8b64": 74152}
+                  "arnet-f8b8": 9640, "arnet-f8b16": 18856, "arnet-f8b32": 37288, "arnet-f8b64": 74152,
+                  "artcnn-c4f16": 12240, "artcnn-c4f32": 47520, "fsrcnnx-f8b4": 2856, "fsrcnnx-f16b4": 10448}
 
 
 def macs_for(model):
@@ -418,7 +419,8 @@ def run_ours(args):
                          "traffic": 2119168, "algorithmic_bytes": W * H + 4 * W * H,
                          "kernel": "fused luma network (segment kernel), 1920x1080 Y -> 3840x2160 Y", "kernel_ms": kernel_ms,
                          "launches_per_pass": launches_per_pass, "flop_per_launch": flop_frame, "peak_source": peaks["source"],
-                         "pipe": "fp32 FFMA (CUDA cores), exact engine" if args.engine == 0 else "split-fp16 tensor-core MMA (3 HMMA per product)",
+                         "pipe": "fp32 FFMA (CUDA cores), exact engine" if (args.engine == 0 or args.model.startswith(("artcnn", "fsrcnnx")))
+                                 else "split-fp16 tensor-core MMA (3 HMMA per product)",
                          "fp32_ffma_peak_tflops_nominal": fp32_peak_tf, "frac_of_fp32_ffma_peak": achieved_tf / fp32_peak_tf,
                          "frame_roofline_ms": t_roof_ms, "frame_frac": t_roof_ms / (ms_max / (B * args.steps))},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "yuv420": yuv,

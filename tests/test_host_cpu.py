@@ -143,7 +143,7 @@ def test_pyac_surface():
     assert pyac.core.Processor.CUDA == 2 and pyac.core.Processor.CPU == 0 and pyac.core.Processor.OpenCL == 1
     assert int(pyac.core.RESIZE_CATMULL_ROM) == 1 and int(pyac.core.RESIZE_BILINEAR) == 16 and int(pyac.core.IMREAD_RGBA) == 4
     names = [m["name"] for m in pyac.specs.ModelList]
-    assert "acnet-legacy-hdn0" in names and "arnet-f8b64" in names and len(names) == 33
+    assert "acnet-legacy-hdn0" in names and "arnet-f8b64" in names and "artcnn-c4f32-ds" in names and "fsrcnnx-f16b4" in names and len(names) == 43
     p = pyac.core.Processor("cpu", 0, "acnet-legacy-hdn0")
     assert not p.ok() and "CPU" in p.error()
     with pytest.raises(RuntimeError):
