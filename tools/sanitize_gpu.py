@@ -23,6 +23,12 @@ for name, shape, c in (("acnet-legacy-hdn0", (70, 90), 3), ("acnet-f8b8-hdn", (5
         got = s.process_host(m, img, 2.0)
         ok = c == 4 or O.compare_u8(got, want)[0] <= 1
         print(name, "engine", engine, "impl", impl, O.compare_u8(got, want), "ok" if ok else "MISMATCH")
+# ArtCNN / FSRCNNX per-layer kernels (exact only)
+s.set_engine(2)
+for name, shape, c in (("artcnn-c4f16", (41, 70), 1), ("artcnn-c4f32-dn", (35, 33), 3), ("fsrcnnx-f8b4", (66, 37), 1), ("fsrcnnx-f16b4", (34, 50), 1)):
+    img = O.noise_u8(shape[0], shape[1], c, seed=2)
+    got = s.process_host(A.Model(name), img, 2.0)
+    print(name, "identical" if np.array_equal(got, O.oracle_process(name, img, 2.0)) else "MISMATCH")
 # planar / semi-planar video frames: shift kernels, the tiled chroma-plane kernel (u8 / u16, 1 and 2 channels), 4x
 rs = np.random.RandomState(5)
 m = A.Model("acnet-legacy-hdn0")
