@@ -566,3 +566,34 @@ def test_wide_families_1080p_frame_against_oracle_sample(session):
         assert got.shape == (2160, 3840)
         want = O.oracle_process(name, np.ascontiguousarray(img[:96, :96]), 2.0)
         assert np.array_equal(got[:160, :160], want[:160, :160])     # 96 - 7 layers of context - margin = 80 source pixels
+
+
+@pytest.mark.gpu
+def test_config5_8192_square_factor4_in_eight_bands(session):
+    """SURVEY.md 8d config 5 at full size: one 8192x8192 1-channel u8 image, factor 4 (two 2x passes), 8 row bands.  The bands
+    equal the whole-image result bit for bit, and halo'd crops equal the oracle (which cannot take the whole image)."""
+    name = "acnet-legacy-hdn0"
+    m = gpu_model(name)
+    rs = np.random.RandomState(7)
+    base = O.smooth_u8(1024, 1024, 1, seed=5)
+    img = np.tile(base, (8, 8))
+    img[::7, ::5] = rs.randint(0, 256, img[::7, ::5].shape, dtype=np.uint8)     # break the periodicity
+    session.set_engine(ENGINE_EXACT)
+    whole = session.process_host(m, img, 4.0)
+    assert whole.shape == (32768, 32768)
+    out = np.zeros_like(whole)
+    for b in range(8):
+        A.process_band(session, m, img, 4.0, 8, b, out)
+    assert np.array_equal(out, whole)
+    del out
+    # crops with full context: 2 passes x 9 layers -> 9 + 5 source pixels of halo; compare the interior
+    O.set_order(O.ORDER_FMA)
+    for (y0, x0) in ((0, 0), (4000, 4100), (8192 - 96, 8192 - 96), (1024 * 3 - 40, 17)):
+        crop = np.ascontiguousarray(img[y0:y0 + 96, x0:x0 + 96])
+        want = O.oracle_process(name, crop, 4.0)
+        mt = 0 if y0 == 0 else 16
+        ml = 0 if x0 == 0 else 16
+        mb = 0 if y0 + 96 == 8192 else 16
+        mr = 0 if x0 + 96 == 8192 else 16
+        got = whole[4 * (y0 + mt):4 * (y0 + 96 - mb), 4 * (x0 + ml):4 * (x0 + 96 - mr)]
+        assert np.array_equal(got, want[4 * mt:4 * (96 - mb), 4 * ml:4 * (96 - mr)]), (y0, x0)
