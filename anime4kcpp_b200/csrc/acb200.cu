@@ -16,6 +16,7 @@
 #include "acb200_mma.cuh"
 #include "acb200_tc5.cuh"
 #include "acb200_wide.cuh"
+#include "acb200_wide_tc.cuh"
 #include "acb200_pixel.cuh"
 
 namespace
@@ -281,10 +282,40 @@ namespace
             pack_conv3x3(k + 1152 + 64, 4, m.frags);// pixel-shuffle conv
         }
     }
+    // tcgen05 B operand of one F -> F 3x3 conv of the wide families (acb200_wide_tc.cuh): for every (tap, 8-channel chunk) a
+    // [N = 2F][K = 16] fp16 matrix in the K-major canonical layout (element (n, k) at byte (k/8)*N*16 + n*16 + (k%8)*2).
+    // Row n < F: cout n, both K chunks carry w_hi (they multiply a_hi and a_lo); row F + n: K chunk 0 carries w_lo, chunk 1 is zero.
+    void pack_bop_wide(const float* W, int F, std::vector<uint32_t>& out)
+    {
+        const int NCH = F / 8, N = 2 * F, tap_bytes = 2 * N * 16;
+        const size_t base = out.size();
+        out.resize(base + static_cast<size_t>(9) * NCH * tap_bytes / 4, 0u);
+        uint16_t* h = reinterpret_cast<uint16_t*>(out.data() + base);
+        for (int t = 0; t < 9; t++)
+            for (int c = 0; c < NCH; c++)
+            {
+                uint16_t* blk = h + static_cast<size_t>(t * NCH + c) * tap_bytes / 2;
+                for (int n = 0; n < F; n++)
+                    for (int k = 0; k < 8; k++)
+                    {
+                        uint32_t hi, lo;
+                        split_w(W[(static_cast<size_t>(n) * 9 + t) * F + c * 8 + k], hi, lo);
+                        blk[0 * N * 8 + n * 8 + k] = static_cast<uint16_t>(hi);           // x a_hi
+                        blk[1 * N * 8 + n * 8 + k] = static_cast<uint16_t>(hi);           // x a_lo
+                        blk[0 * N * 8 + (F + n) * 8 + k] = static_cast<uint16_t>(lo);     // x a_hi
+                    }
+            }
+    }
     void pack_model(acb200_model& m)
     {
         m.frags.clear();
         m.bops.clear();
+        if (m.family >= ACB200_FAMILY_ARTCNN && m.features >= 16)
+        {
+            const int F = m.features, ks = m.family == ACB200_FAMILY_ARTCNN ? 3 : 5;
+            const int convs = m.family == ACB200_FAMILY_ARTCNN ? m.blocks + 1 : m.blocks;
+            for (int l = 0; l < convs; l++) pack_bop_wide(m.k.data() + F * ks * ks + static_cast<size_t>(F) * F * 9 * l, F, m.bops);
+        }
         for (SegSpec& sp : m.chain)
             switch (sp.kind)
             {
@@ -499,6 +530,25 @@ namespace
         ACB_CUDA(s, cudaGetLastError());
         return ACB200_OK;
     }
+    // the same layer on the tensor cores (tcgen05, split fp16): one launch, B operand from the model's packed table
+    template<int F>
+    int wide_conv_layer_tc(acb200_session* s, cudaStream_t st, const acb200_model& m, int conv_index, const float* in, float* out, const float* res,
+                           int w, int h, int act, const float* b, const float* a)
+    {
+        const uint32_t* dbops = nullptr;
+        int rc = device_bops(s, st, m, &dbops);
+        if (rc != ACB200_OK) return rc;
+        WideTcParams<F> prm;
+        prm.in = in; prm.out = out; prm.res = res; prm.w = w; prm.h = h; prm.act = act;
+        prm.bop = dbops + static_cast<size_t>(conv_index) * (WideTc<F>::B_BYTES / 4);
+        std::memcpy(prm.b, b, sizeof(prm.b));
+        if (a) std::memcpy(prm.a, a, sizeof(prm.a)); else std::memset(prm.a, 0, sizeof(prm.a));
+        ACB_CUDA(s, cudaFuncSetAttribute(wide_tc_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, WideTc<F>::SMEM_BYTES));
+        wide_tc_kernel<F><<<dim3((w + WTC_TW - 1) / WTC_TW, (h + WideTc<F>::TH - 1) / WideTc<F>::TH), WideTc<F>::THREADS, WideTc<F>::SMEM_BYTES, st>>>(prm);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        ACB_CUDA(s, cudaGetLastError());
+        return ACB200_OK;
+    }
     // F -> F conv layer: output channels in launches of at most 16 (the weights travel as kernel parameters)
     template<int F>
     int wide_conv_layer(acb200_session* s, cudaStream_t st, const float* in, float* out, const float* res, int w, int h, int act,
@@ -514,8 +564,16 @@ namespace
     }
     template<int F>
     int luma_pass_wide(acb200_session* s, cudaStream_t st, const acb200_model& m, const void* src, int src_pitch, void* dst, int dst_pitch,
-                       int w, int h, int type)
+                       int w, int h, int type, bool tensor)
     {
+        // F -> F conv number `ci` (0-based) of the model: tensor engine for 16 / 32 features, exact FFMA kernels otherwise
+        auto conv = [&](int ci, const float* in_, float* out_, const float* res_, int act, const float* k_, const float* b_, const float* a_) -> int {
+            if constexpr (F >= 16)
+            {
+                if (tensor) return wide_conv_layer_tc<F>(s, st, m, ci, in_, out_, res_, w, h, act, b_, a_);
+            }
+            return wide_conv_layer<F>(s, st, in_, out_, res_, w, h, act, k_, b_, a_);
+        };
         const size_t bytes = static_cast<size_t>(w) * h * F * sizeof(float);
         int rc;
         for (int i = 0; i < 3; i++) if ((rc = ensure(s, s->wide[i], bytes)) != ACB200_OK) return rc;
@@ -546,10 +604,10 @@ namespace
             // blocks x (conv + ReLU), then conv + Identity + feat (CPUProcessor.cpp:1535-1545)
             for (int i = 0; i < B; i++, l++)
             {
-                if ((rc = wide_conv_layer<F>(s, st, cur, out, nullptr, w, h, ACT_RELU, layer_k(l), b + F * l, nullptr)) != ACB200_OK) return rc;
+                if ((rc = conv(l - 1, cur, out, nullptr, ACT_RELU, layer_k(l), b + F * l, nullptr)) != ACB200_OK) return rc;
                 cur = out; std::swap(in, out);
             }
-            if ((rc = wide_conv_layer<F>(s, st, cur, out, feat, w, h, ACT_IDENTITY, layer_k(l), b + F * l, nullptr)) != ACB200_OK) return rc;
+            if ((rc = conv(l - 1, cur, out, feat, ACT_IDENTITY, layer_k(l), b + F * l, nullptr)) != ACB200_OK) return rc;
             cur = out; std::swap(in, out); l++;
         }
         else
@@ -557,7 +615,7 @@ namespace
             // (blocks - 1) x (conv + PReLU), then conv + PReLU -> 1x1 -> + feat -> PReLU (CPUProcessor.cpp:1637-1651)
             for (int i = 0; i < B; i++, l++)
             {
-                if ((rc = wide_conv_layer<F>(s, st, cur, out, nullptr, w, h, ACT_PRELU, layer_k(l), b + F * l, a + F * (l - 1))) != ACB200_OK) return rc;
+                if ((rc = conv(l - 1, cur, out, nullptr, ACT_PRELU, layer_k(l), b + F * l, a + F * (l - 1))) != ACB200_OK) return rc;
                 cur = out; std::swap(in, out);
             }
             if constexpr (F <= 16)
@@ -587,9 +645,9 @@ namespace
             if (static_cast<long long>(w) * h * m.features > 0x7fffffffLL / 4) return fail(s, ACB200_EINVAL, "image too large for this model family");
             switch (m.features)
             {
-            case 8: return luma_pass_wide<8>(s, st, m, src, src_pitch, dst, dst_pitch, w, h, type);
-            case 16: return luma_pass_wide<16>(s, st, m, src, src_pitch, dst, dst_pitch, w, h, type);
-            default: return luma_pass_wide<32>(s, st, m, src, src_pitch, dst, dst_pitch, w, h, type);
+            case 8: return luma_pass_wide<8>(s, st, m, src, src_pitch, dst, dst_pitch, w, h, type, tensor);
+            case 16: return luma_pass_wide<16>(s, st, m, src, src_pitch, dst, dst_pitch, w, h, type, tensor);
+            default: return luma_pass_wide<32>(s, st, m, src, src_pitch, dst, dst_pitch, w, h, type, tensor);
             }
         }
         float* maps[2] = { nullptr, nullptr };

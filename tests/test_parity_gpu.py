@@ -553,7 +553,7 @@ def test_wide_families_colour_4x_bands_frames_and_processor_api(session, name):
     import pyac
     p = pyac.core.Processor("cuda", 0, name)
     assert p.ok(), p.error()
-    assert np.array_equal(p(gray, 2.0), whole)
+    check_int(p(gray, 2.0), whole)          # the Processor runs the default engine (tensor cores for F >= 16): tolerance, not identity
 
 
 @pytest.mark.gpu
@@ -597,3 +597,44 @@ def test_config5_8192_square_factor4_in_eight_bands(session):
         mr = 0 if x0 + 96 == 8192 else 16
         got = whole[4 * (y0 + mt):4 * (y0 + 96 - mb), 4 * (x0 + ml):4 * (x0 + 96 - mr)]
         assert np.array_equal(got, want[4 * mt:4 * (96 - mb), 4 * ml:4 * (96 - mr)]), (y0, x0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", sorted(k.split(":", 1)[1] for k in WIDE.files if k.startswith("fma:") and ("f16" in k or "f32" in k)))
+def test_wide_families_tensor_engine_golden(session, key):
+    """tcgen05 split-fp16 engine of the F -> F layers (F = 16 / 32): the north_star tolerance against every reference backend."""
+    kind, name = key.split("/", 1)
+    session.set_engine(ENGINE_TENSOR)
+    out = session.process_host(gpu_model(name), wide_src(kind), 4.0 if kind.endswith("4x") else 2.0)
+    for order in ("fma:", "generic:", "avx512:"):
+        if order + key in WIDE.files:
+            check_close(out, WIDE[order + key], x4=kind.endswith("4x"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["artcnn-c4f16", "artcnn-c4f32-dn", "fsrcnnx-f16b4-distort-plus"])
+@pytest.mark.parametrize("shape", [(3, 3), (1, 9), (15, 64), (16, 65), (33, 130), (70, 97)])
+def test_wide_families_tensor_engine_odd_sizes(session, name, shape):
+    O.set_order(O.ORDER_FMA)
+    img = O.noise_u8(shape[0], shape[1], 1, seed=shape[0] * 7 + shape[1])
+    session.set_engine(ENGINE_TENSOR)
+    mx, same = O.compare_u8(session.process_host(gpu_model(name), img, 2.0), O.oracle_process(name, img, 2.0))
+    assert mx <= 1 and same >= 0.998, (mx, same)        # tiny images: one differing sample is already 0.1-1 %
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["artcnn-c4f16", "artcnn-c4f32", "fsrcnnx-f16b4"])
+def test_wide_families_tensor_engine_1080p_against_exact_engine(session, name):
+    img = O.smooth_u8(1080, 1920, 1, seed=9)
+    m = gpu_model(name)
+    session.set_engine(ENGINE_EXACT)
+    exact = session.process_host(m, img, 2.0)
+    session.set_engine(ENGINE_AUTO)                 # the default: tensor engine on the last (here: only) pass
+    got = session.process_host(m, img, 2.0)
+    mx, same = O.compare_u8(got, exact)
+    assert mx <= LSB_MAX and same >= EXACT_MIN, (mx, same)
+    f = (img[:256, :256] / 255.0).astype(np.float32)
+    session.set_engine(ENGINE_EXACT)
+    e32 = session.process_host(m, f, 2.0)
+    session.set_engine(ENGINE_TENSOR)
+    assert float(np.abs(session.process_host(m, f, 2.0) - e32).max()) <= F32_TOL
