@@ -419,8 +419,9 @@ def run_ours(args):
                          "traffic": 2119168, "algorithmic_bytes": W * H + 4 * W * H,
                          "kernel": "fused luma network (segment kernel), 1920x1080 Y -> 3840x2160 Y", "kernel_ms": kernel_ms,
                          "launches_per_pass": launches_per_pass, "flop_per_launch": flop_frame, "peak_source": peaks["source"],
-                         "pipe": "fp32 FFMA (CUDA cores), exact engine" if (args.engine == 0 or args.model.startswith(("artcnn", "fsrcnnx")))
-                                 else "split-fp16 tensor-core MMA (3 HMMA per product)",
+                         "pipe": "fp32 FFMA (CUDA cores), exact engine" if (args.engine == 0 or args.model.startswith("fsrcnnx-f8"))
+                                 else ("split-fp16 tcgen05 MMA with TMEM accumulators (F->F layers); head / tail fp32 FFMA" if args.model.startswith(("artcnn", "fsrcnnx"))
+                                       else "split-fp16 tensor-core MMA (3 HMMA per product)"),
                          "fp32_ffma_peak_tflops_nominal": fp32_peak_tf, "frac_of_fp32_ffma_peak": achieved_tf / fp32_peak_tf,
                          "frame_roofline_ms": t_roof_ms, "frame_frac": t_roof_ms / (ms_max / (B * args.steps))},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "yuv420": yuv,
