@@ -81,11 +81,6 @@ namespace acb
         uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * WTC_SLOTS + G::NT);
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         const int x0 = blockIdx.x * WTC_TW, y0 = blockIdx.y * G::TH;
-#ifdef ACB_WTC_TRACE
-        __shared__ long long wtr[8];
-        if (threadIdx.x == 0) wtr[0] = clock64();
-        if (threadIdx.x == 32) wtr[4] = 0;
-#endif
 
         if (threadIdx.x == 0)
         {
@@ -118,22 +113,11 @@ namespace acb
             {
                 const uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(G::N >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
                 const uint32_t a_base = tc_smem_u32(wtc_smem), b_base = tc_smem_u32(wtc_smem + G::OFF_B);
-#ifdef ACB_WTC_TRACE
-                wtr[1] = clock64();
-                long long waited = 0;
-#endif
                 for (int j = 0; j < G::NT; j++)
                 {
                     const int slot = j % WTC_SLOTS, batch = j / BT, bslot = batch % NBS, use = batch / NBS;
-#ifdef ACB_WTC_TRACE
-                    const long long tw0 = clock64();
-#endif
                     if (j % BT == 0 && use > 0) tc_mbar_wait(bar0 + (WTC_SLOTS + bslot) * 8, (use - 1) & 1);
                     tc_mbar_wait(bar0 + (2 * WTC_SLOTS + j) * 8, 0);
-#ifdef ACB_WTC_TRACE
-                    waited += clock64() - tw0;
-                    if (j == 0) wtr[2] = clock64();
-#endif
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     int first = 1;
 #pragma unroll 1
@@ -151,9 +135,6 @@ namespace acb
                     }
                     if (j % BT == BT - 1 || j == G::NT - 1) tc_commit(bar0 + bslot * 8);
                 }
-#ifdef ACB_WTC_TRACE
-                wtr[3] = clock64(); wtr[5] = waited;
-#endif
             }
             __syncwarp();
         }
@@ -208,9 +189,6 @@ namespace acb
                 tc_mbar_arrive(bar0 + (2 * WTC_SLOTS + j) * 8);
                 row_lo = row_hi;
             }
-#ifdef ACB_WTC_TRACE
-            if (threadIdx.x == 32) wtr[4] = clock64();
-#endif
             // ---- epilogue (warps 4-7, one per TMEM lane quadrant) ----------------------------------------------------------------
             if (warp >= 4 && warp < 8)
             {
@@ -266,11 +244,6 @@ namespace acb
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
-#ifdef ACB_WTC_TRACE
-        if (threadIdx.x == 0 && blockIdx.x == 7 && blockIdx.y == 9)
-            printf("F=%d: setup %lld | first band ready +%lld | issue loop %lld (of which waiting %lld) | loads done at +%lld | total %lld\n", F, wtr[1] - wtr[0], wtr[2] - wtr[1],
-                   wtr[3] - wtr[1], wtr[5], wtr[4] - wtr[0], clock64() - wtr[0]);
-#endif
         if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(TMEM_COLS));
     }
 }
