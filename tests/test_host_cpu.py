@@ -157,3 +157,20 @@ def test_session_without_device_fails_loudly():
     if A.device_count() == 0:
         with pytest.raises(A.Acb200Error):
             A.Session(0)
+
+
+def test_cpp_model_descriptors_like_reference_modeltest(tmp_path):
+    """tests/cpp/model_check.cpp: the reference's ModelTest.cpp checks (offsets / lengths of every layer add up) over all 43
+    variants of the five families, compiled against the re-created headers and linked with libac_b200.so."""
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++ on this box")
+    exe = str(tmp_path / "model_check")
+    libdir = os.path.join(ROOT, "anime4kcpp_b200", "lib")
+    cmd = ["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "anime4kcpp_b200", "csrc", "host", "include"), "-I" + os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "cpp", "model_check.cpp"), "-o", exe, "-L" + libdir, "-lac_b200", "-Wl,-rpath," + libdir]
+    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+    subprocess.run(cmd, check=True, env=env)
+    out = subprocess.run([exe], capture_output=True, text=True, env=env)
+    assert out.returncode == 0 and "model checks ok" in out.stdout, out.stdout + out.stderr

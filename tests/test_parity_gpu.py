@@ -638,3 +638,22 @@ def test_wide_families_tensor_engine_1080p_against_exact_engine(session, name):
     e32 = session.process_host(m, f, 2.0)
     session.set_engine(ENGINE_TENSOR)
     assert float(np.abs(session.process_host(m, f, 2.0) - e32).max()) <= F32_TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["acnet-legacy-hdn0", "acnet-f8b4", "arnet-f8b8", "artcnn-c4f16", "fsrcnnx-f8b4"])
+def test_reference_processor_test_criterion_psnr_48db(session, name):
+    """The reference's own acceptance test (tests/core/src/ProcessorTest.cpp:113-217): a 64x64 RGB noise image, the processor
+    under test against the Generic CPU backend, PSNR > 48 dB -- here through the Processor front door with its default engine."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "anime4kcpp_b200"))
+    import pyac
+    src = O.noise_u8(64, 64, 3, seed=20)
+    O.set_order(O.ORDER_GENERIC)
+    ref = O.oracle_process(name, src, 2.0).astype(np.float64)
+    p = pyac.core.Processor("cuda", 0, name)
+    assert p.ok(), p.error()
+    dst = p.process(src, 2.0).astype(np.float64)
+    assert p.ok()
+    mse = float(((dst - ref) ** 2).mean())
+    psnr = float("inf") if mse == 0 else 10.0 * np.log10(255.0 ** 2 / mse)
+    assert psnr > 48.0, psnr
