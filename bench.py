@@ -290,7 +290,9 @@ def run_ours(args):
     srcs = [map_image(lib, np_in[i]) for i in range(B)]
     dsts = [map_image(lib, np_out[i]) for i in range(B)]
 
-    def e2e_step():
+    def e2e_steps(n_steps):
+        # n_steps batches of B frames; the caller threads (tools/benchmark's "N concurrent images" mode) live across the steps and
+        # pull frame after frame, every call a full ac_processor_process: H2D, the GPU pass, D2H, synchronise
         nxt = [0]
         lock = threading.Lock()
 
@@ -299,20 +301,18 @@ def run_ours(args):
                 with lock:
                     i = nxt[0]
                     nxt[0] += 1
-                if i >= B:
+                if i >= n_steps * B:
                     return
-                rc = lib.ac_processor_process(proc, srcs[i], dsts[i], C.c_double(FACTOR))
+                rc = lib.ac_processor_process(proc, srcs[i % B], dsts[i % B], C.c_double(FACTOR))
                 assert rc == 0, lib.ac_processor_error(proc)
         ts = [threading.Thread(target=worker) for _ in range(n_threads)]
         [x.start() for x in ts]
         [x.join() for x in ts]
 
-    for _ in range(2):
-        e2e_step()
+    e2e_steps(2)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_steps(args.steps)
     barrier()
     t_e2e = time.perf_counter() - t0
     te = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
@@ -360,7 +360,7 @@ def run_ours(args):
         pl_in = [A._planes_of([t.numpy() for t in f]) for f in hp_in]
         pl_out = [A._planes_of([t.numpy() for t in f]) for f in hp_out]
 
-        def yuv_e2e_step():
+        def yuv_e2e_steps(n_steps):
             nxt = [0]
             lock = threading.Lock()
 
@@ -369,19 +369,17 @@ def run_ours(args):
                     with lock:
                         i = nxt[0]
                         nxt[0] += 1
-                    if i >= B:
+                    if i >= n_steps * B:
                         return
-                    rc = lib.ac_processor_process_frame(proc, pl_in[i], pl_out[i], 3, 1, 0, FACTOR)
+                    rc = lib.ac_processor_process_frame(proc, pl_in[i % B], pl_out[i % B], 3, 1, 0, FACTOR)
                     assert rc == 0, lib.ac_processor_error(proc)
             ts = [threading.Thread(target=worker) for _ in range(n_threads)]
             [x.start() for x in ts]
             [x.join() for x in ts]
-        for _ in range(2):
-            yuv_e2e_step()
+        yuv_e2e_steps(2)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            yuv_e2e_step()
+        yuv_e2e_steps(args.steps)
         barrier()
         tye = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
         if dist is not None:
@@ -393,6 +391,38 @@ def run_ours(args):
                "e2e": {"value": OUT_MP * frames_total / float(tye.item()), "unit": "MP/s", "fps": frames_total / float(tye.item()),
                        "h2d_bytes_per_step": B * W * H * 3 // 2, "d2h_bytes_per_step": B * 4 * W * H * 3 // 2,
                        "api": "ac_processor_process_frame (C binding extension), pinned host planes", "caller_threads": n_threads}}
+
+    # ---- a stream of 256 frames through the ordered multi-worker frame stream (the worker / ordering core
+    #      of the reference's video filter), packed RGB and planar YUV420, host buffers in and out; wall clock, max over ranks -------
+    stream_res = None
+    if not args.no_yuv:
+        NFR = 256
+        fs = A.FrameStream(model, [local], workers_per_device=n_threads, queue_depth=4)
+
+        def run_stream(submit):
+            barrier()
+            t0 = time.perf_counter()
+            done = 0
+            for i in range(NFR):
+                submit(i % B)
+                if i >= 2 * n_threads:
+                    fs.next(); done += 1
+            while done < NFR:
+                fs.next(); done += 1
+            barrier()
+            tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+            if dist is not None:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return NFR * world / float(tt.item())
+        run_stream(lambda i: fs.submit(np_in[i], FACTOR, np_out[i]))                 # warm-up (sessions, scratch)
+        rgb_fps = run_stream(lambda i: fs.submit(np_in[i], FACTOR, np_out[i]))
+        y_in = [[t.numpy() for t in f] for f in hp_in]
+        y_out = [[t.numpy() for t in f] for f in hp_out]
+        run_stream(lambda i: fs.submit_frame(y_in[i], FACTOR, y_out[i]))
+        yuv_fps = run_stream(lambda i: fs.submit_frame(y_in[i], FACTOR, y_out[i]))
+        fs.close()
+        stream_res = {"frames": NFR * world, "workers_per_gpu": n_threads, "queue_depth": 4, "rgb_fps": rgb_fps, "yuv420_fps": yuv_fps,
+                      "api": "acb200_stream_submit / submit_frame / next (in-order delivery), pinned host frames"}
 
     cpu = None
     if rank == 0 and not args.no_cpu:
@@ -424,7 +454,7 @@ def run_ours(args):
                                        else "split-fp16 tensor-core MMA (3 HMMA per product)"),
                          "fp32_ffma_peak_tflops_nominal": fp32_peak_tf, "frac_of_fp32_ffma_peak": achieved_tf / fp32_peak_tf,
                          "frame_roofline_ms": t_roof_ms, "frame_frac": t_roof_ms / (ms_max / (B * args.steps))},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "yuv420": yuv,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "yuv420": yuv, "stream": stream_res,
         }
         print(json.dumps(line))
     if dist is not None:
