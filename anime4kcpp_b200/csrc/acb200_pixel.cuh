@@ -224,6 +224,14 @@ namespace acb
         const int ncols = min(CM_OW, ow - ox0), nrows = min(CM_OH, oh - oy0);
         if (tid < nrows * 8) reinterpret_cast<uint32_t*>(sh_v)[tid] = reinterpret_cast<const uint32_t*>(vtab + oy0)[tid];    // the tile's vertical taps, once
         // source window of the tile (tables are monotonic in n0)
+        // this thread's luma samples of the merge (4 output pixels): requested now, consumed after both resize passes
+        uint8_t ylum[CM_OW * CM_OH / CM_THREADS];
+#pragma unroll
+        for (int k = 0; k < CM_OW * CM_OH / CM_THREADS; k++)
+        {
+            const int idx = tid + k * CM_THREADS, orow = min(idx / CM_OW, nrows - 1), col = min(idx % CM_OW, ncols - 1);
+            ylum[k] = __ldg(yp + static_cast<size_t>(oy0 + orow) * y_pitch + ox0 + col);
+        }
         const Contrib hfirst = htab[ox0], hlast = htab[ox0 + ncols - 1], vfirst = vtab[oy0], vlast = vtab[oy0 + nrows - 1];
         const int sx0 = hfirst.n0, sy0 = vfirst.n0;
         const int sw = min(hlast.n0 + 4, sw_img) - sx0 + 0, shh = min(vlast.n0 + 4, sh_img) - sy0;
@@ -281,8 +289,10 @@ namespace acb
         // vertical pass + re-quantise + merge: consecutive lanes take consecutive output columns (conflict-free reads of the
         // horizontal-pass rows); the finished bytes are staged in shared memory and leave as 16-byte vectors
         __shared__ __align__(16) uint8_t s_out[CM_OH][CM_OW * C];
-        for (int idx = tid; idx < CM_OW * CM_OH; idx += CM_THREADS)
+#pragma unroll
+        for (int it = 0; it < CM_OW * CM_OH / CM_THREADS; it++)
         {
+            const int idx = tid + it * CM_THREADS;
             const int orow = idx / CM_OW, col = idx % CM_OW;
             if (orow >= nrows || col >= ncols) continue;
             const Contrib& k = sh_v[orow];
@@ -317,7 +327,7 @@ namespace acb
                 f = f < 0.0f ? 0.0f : (f > 255.0f ? 255.0f : f);
                 q[ch] = unit_from_int<255>(truncf(f));                  // toFloat<u8>: a true division (Util.hpp:53-54), computed without one
             }
-            const float yv = unit_from_int<255>(static_cast<float>(yp[static_cast<size_t>(oy0 + orow) * y_pitch + ox0 + col]));
+            const float yv = unit_from_int<255>(static_cast<float>(ylum[it]));
             const float u = __fsub_rn(q[0], 0.5f), v = __fsub_rn(q[1], 0.5f);
             float r = __fadd_rn(yv, __fmul_rn(1.403f, v));
             float gch = __fsub_rn(__fsub_rn(yv, __fmul_rn(0.344f, u)), __fmul_rn(0.714f, v));
