@@ -170,14 +170,59 @@ namespace
                 if (p < n0) { volatile float t = c[0] + raw[i]; c[0] = t; }
                 else if (p > n1) { volatile float t = c[n1 - n0] + raw[i]; c[n1 - n0] = t; }
             }
-            // drop leading / trailing zero taps so the device loop stays within 6
+            // Drop trailing zero taps so the device loops stay short.  Leading zeros are kept: the tiled kernels take the
+            // first / last contributor of a tile as its source window, which needs n0 to be monotonic in n (an integer
+            // up-scale such as 3x has phases whose outer taps are exactly zero).
             while (n1 > n0 && c[n1 - n0] == 0.0f) n1--;
-            int lead = 0;
-            while (lead < n1 - n0 && c[lead] == 0.0f) lead++;
             Contrib& o = out[n];
-            o.n0 = n0 + lead; o.cnt = n1 - n0 + 1 - lead;
+            o.n0 = n0; o.cnt = n1 - n0 + 1;
             if (o.cnt > 6) return false;
-            for (int i = 0; i < 6; i++) o.c[i] = i < o.cnt ? c[lead + i] : 0.0f;
+            for (int i = 0; i < 6; i++) o.c[i] = i < o.cnt ? c[i] : 0.0f;
+        }
+        return true;
+    }
+    // Down-scaling contributors (scale in [1/2, 1)): the filter stretched by 1/scale in input space, weights normalised,
+    // out-of-range taps folded onto the edge pixel -- the same arithmetic, in the same order, as oracle/ac_oracle.c make_contribs.
+    bool make_contribs_down(std::vector<ContribW>& out, int in_size, int out_size)
+    {
+        out.resize(out_size);
+        const float scale = static_cast<float>(out_size) / static_cast<float>(in_size);
+        if (!(scale < 1.0f) || scale < 0.5f) return false;
+        const float inv_scale = 1.0f / scale;
+        for (int n = 0; n < out_size; n++)
+        {
+            volatile float out_center = static_cast<float>(n) + 0.5f;
+            volatile float in_center = out_center * inv_scale;
+            volatile float reach = 2.0f * inv_scale;
+            volatile float lo = in_center - reach, hi = in_center + reach;
+            int first = static_cast<int>(std::floor(lo + 0.5f)), last = static_cast<int>(std::floor(hi - 0.5f));
+            if (last < first) last = first;
+            if (last - first > 10) last = first + 10;
+            float raw[12];
+            volatile float total = 0.0f;
+            for (int i = 0; i <= last - first; i++)
+            {
+                volatile float pc = static_cast<float>(first + i) + 0.5f;
+                volatile float d = in_center - pc; d = d * scale;
+                raw[i] = catmull_rom(d);
+                total = total + raw[i];
+            }
+            volatile float fs = 1.0f / total;
+            for (int i = 0; i <= last - first; i++) { volatile float t = raw[i] * fs; raw[i] = t; }
+            int n0 = std::max(first, 0), n1 = std::min(last, in_size - 1);
+            if (n1 < n0) n1 = n0 = (first < 0 ? 0 : in_size - 1);
+            float c[12] = {};
+            for (int i = 0; i <= last - first; i++) { int p = first + i; if (p >= n0 && p <= n1) c[p - n0] = raw[i]; }
+            for (int i = 0; i <= last - first; i++)
+            {
+                int p = first + i;
+                if (p < n0) { volatile float t = c[0] + raw[i]; c[0] = t; }
+                else if (p > n1) { volatile float t = c[n1 - n0] + raw[i]; c[n1 - n0] = t; }
+            }
+            ContribW& o = out[n];
+            o.n0 = n0; o.cnt = n1 - n0 + 1;
+            if (o.cnt > 10) return false;
+            for (int i = 0; i < 10; i++) o.c[i] = i < o.cnt ? c[i] : 0.0f;
         }
         return true;
     }
@@ -346,6 +391,8 @@ struct acb200_session
     Buf src, dst, y[2], uv, map[2], feat, htab, vtab;
     Buf pin[3], pout[3];    // planar video frames: staged source / result planes (host entry)
     Buf wide[3];            // ArtCNN / FSRCNNX: feat + two ping-pong maps, [h][w][F] fp32
+    Buf dhtab, dvtab;       // down-scaling contributor tables of the post-network luma resize (non-power-of-two factors)
+    int dtab_in_w = 0, dtab_in_h = 0, dtab_out_w = 0, dtab_out_h = 0;
     int wide_smem_configured = 0;
     // device copies of models' packed fragments, keyed by acb200_model::uid
     std::map<unsigned long long, void*> dev_frags;
@@ -717,10 +764,40 @@ namespace
         return 0;
     }
 
+    // Processor.cpp:203-204: power = factor > 2 ? ceilLog2(factor) : 1 passes of 2x, then (factor not a power of two) a luma
+    // down-scale by fxy = factor / 2^power in (1/2, 1); the result is int(w * factor) x int(h * factor) (ImageResize.cpp:153-154).
+    struct FactorPlan { int power = 0, dw = 0, dh = 0; };
+    bool plan_factor(double factor, int w, int h, FactorPlan& p)
+    {
+        p.power = passes_for(factor);
+        if (p.power) { p.dw = w << p.power; p.dh = h << p.power; return true; }
+        if (!(factor >= 1.0) || factor > 64.0) return false;
+        p.power = 1;
+        while (static_cast<double>(1 << p.power) < factor) p.power++;
+        p.dw = static_cast<int>(w * factor); p.dh = static_cast<int>(h * factor);
+        return p.dw > 0 && p.dh > 0;
+    }
+    int ensure_down_tables(acb200_session* s, cudaStream_t st, int w, int h, int ow, int oh)
+    {
+        if (s->dtab_in_w == w && s->dtab_in_h == h && s->dtab_out_w == ow && s->dtab_out_h == oh) return ACB200_OK;
+        std::vector<ContribW> ht, vt;
+        if (!make_contribs_down(ht, w, ow) || !make_contribs_down(vt, h, oh)) return fail(s, ACB200_EINVAL, "resize: unsupported down-scale");
+        int rc;
+        if ((rc = ensure(s, s->dhtab, ht.size() * sizeof(ContribW))) != ACB200_OK) return rc;
+        if ((rc = ensure(s, s->dvtab, vt.size() * sizeof(ContribW))) != ACB200_OK) return rc;
+        ACB_CUDA(s, cudaMemcpyAsync(s->dhtab.p, ht.data(), ht.size() * sizeof(ContribW), cudaMemcpyHostToDevice, st));
+        ACB_CUDA(s, cudaMemcpyAsync(s->dvtab.p, vt.data(), vt.size() * sizeof(ContribW), cudaMemcpyHostToDevice, st));
+        ACB_CUDA(s, cudaStreamSynchronize(st));
+        s->dtab_in_w = w; s->dtab_in_h = h; s->dtab_out_w = ow; s->dtab_out_h = oh;
+        return ACB200_OK;
+    }
+
     // The whole Processor::process on device-resident planes (Processor.cpp:199-276).
     int process_on_device(acb200_session* s, const acb200_model* m, cudaStream_t st,
-                          const void* d_src, int w, int h, int c, int src_pitch, int type, int power, void* d_dst, int dst_pitch)
+                          const void* d_src, int w, int h, int c, int src_pitch, int type, const FactorPlan& plan, void* d_dst, int dst_pitch)
     {
+        const int power = plan.power;
+        const bool down = plan.dw != (w << power) || plan.dh != (h << power);
         const int es = type & 0xff;
         const dim3 blk(32, 8);
         const void* cur = d_src;
@@ -739,7 +816,7 @@ namespace
         for (int i = 0; i < power; i++)
         {
             const int nw = cw * 2, nh = ch * 2;
-            const bool to_dst = (c == 1) && (i == power - 1);
+            const bool to_dst = (c == 1) && (i == power - 1) && !down;
             void* out; int out_pitch;
             if (to_dst) { out = d_dst; out_pitch = dst_pitch; }
             else
@@ -752,6 +829,24 @@ namespace
             const bool tensor = s->engine == 1 || (s->engine == 2 && i == power - 1);
             if ((rc = luma_pass(s, st, *m, cur, cur_pitch, out, out_pitch, cw, ch, type, tensor)) != ACB200_OK) return rc;
             cur = out; cur_pitch = out_pitch; cw = nw; ch = nh;
+        }
+        if (down)
+        {
+            // gray: resize(out, dst, 0, 0) straight into dst; colour: resize(out, out, fxy, fxy) into the other luma plane
+            if ((rc = ensure_down_tables(s, st, cw, ch, plan.dw, plan.dh)) != ACB200_OK) return rc;
+            void* out; int out_pitch;
+            if (c == 1) { out = d_dst; out_pitch = dst_pitch; }
+            else
+            {
+                const size_t p = pitch_of(plan.dw, 1, es);
+                if ((rc = ensure(s, s->y[slot], p * plan.dh)) != ACB200_OK) return rc;
+                out = s->y[slot].p; out_pitch = static_cast<int>(p);
+            }
+            resize_wide_kernel<<<dim3((plan.dw + 31) / 32, (plan.dh + 7) / 8), blk, 0, st>>>(cur, cur_pitch, 1, type,
+                static_cast<const ContribW*>(s->dhtab.p), static_cast<const ContribW*>(s->dvtab.p), out, plan.dw, plan.dh, out_pitch);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            ACB_CUDA(s, cudaGetLastError());
+            cur = out; cur_pitch = out_pitch; cw = plan.dw; ch = plan.dh;
         }
         if (c > 1)
         {
@@ -888,14 +983,15 @@ namespace
         return ACB200_OK;
     }
 
-    int check_args(acb200_session* s, const acb200_model* m, const void* src, int w, int h, int c, int type, double factor, void* dst, int& power)
+    int check_args(acb200_session* s, const acb200_model* m, const void* src, int w, int h, int c, int type, double factor, void* dst, FactorPlan& plan,
+                   bool power_of_two_only = false)
     {
         if (!s) return ACB200_EINVAL;
         if (!m || !src || !dst) return fail(s, ACB200_EINVAL, "null argument");
         if (w <= 0 || h <= 0 || !(c == 1 || c == 3 || c == 4) || !valid_type(type)) return fail(s, ACB200_EINVAL, "unsupported image shape or element type");
-        power = passes_for(factor);
-        if (!power) return fail(s, ACB200_EINVAL, "factor must be a power of two >= 2");
-        if ((static_cast<long long>(w) << power) > 0x7fffffffLL / 16 || (static_cast<long long>(h) << power) > 0x7fffffffLL / 16) return fail(s, ACB200_EINVAL, "image too large");
+        if (power_of_two_only && !passes_for(factor)) return fail(s, ACB200_EINVAL, "factor must be a power of two >= 2");
+        if (!plan_factor(factor, w, h, plan)) return fail(s, ACB200_EINVAL, "factor must be at least 1 (and at most 64)");
+        if ((static_cast<long long>(w) << plan.power) > 0x7fffffffLL / 16 || (static_cast<long long>(h) << plan.power) > 0x7fffffffLL / 16) return fail(s, ACB200_EINVAL, "image too large");
         return ACB200_OK;
     }
 }
@@ -981,7 +1077,7 @@ extern "C"
         cudaStreamSynchronize(s->stream);
         acb200_session::Buf* bufs[] = { &s->src, &s->dst, &s->y[0], &s->y[1], &s->uv, &s->map[0], &s->map[1], &s->feat, &s->htab, &s->vtab,
                                         &s->pin[0], &s->pin[1], &s->pin[2], &s->pout[0], &s->pout[1], &s->pout[2],
-                                        &s->wide[0], &s->wide[1], &s->wide[2] };
+                                        &s->wide[0], &s->wide[1], &s->wide[2], &s->dhtab, &s->dvtab };
         for (auto* b : bufs) if (b->p) cudaFreeAsync(b->p, s->stream);
         cudaStreamSynchronize(s->stream);
         for (auto& kv : s->dev_frags) cudaFree(kv.second);
@@ -1000,24 +1096,27 @@ extern "C"
     int acb200_process_device(acb200_session* s, const acb200_model* m, const void* d_src, int w, int h, int c, int src_stride, int type,
                               double factor, void* d_dst, int dst_stride, void* stream)
     {
-        int power, rc;
-        if ((rc = check_args(s, m, d_src, w, h, c, type, factor, d_dst, power)) != ACB200_OK) return rc;
+        FactorPlan plan;
+        int rc;
+        if ((rc = check_args(s, m, d_src, w, h, c, type, factor, d_dst, plan)) != ACB200_OK) return rc;
         ACB_CUDA(s, cudaSetDevice(s->device));
         cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : s->stream;
         const int es = type & 0xff;
         if (src_stride < w * c * es) src_stride = w * c * es;
-        if (dst_stride < (w << power) * c * es) dst_stride = (w << power) * c * es;
-        return process_on_device(s, m, st, d_src, w, h, c, src_stride, type, power, d_dst, dst_stride);
+        if (dst_stride < plan.dw * c * es) dst_stride = plan.dw * c * es;
+        return process_on_device(s, m, st, d_src, w, h, c, src_stride, type, plan, d_dst, dst_stride);
     }
 
     // rows [out_y0, out_y1) of the result only; `dst` points at output row out_y0
     static int process_host_rows(acb200_session* s, const acb200_model* m, const void* src, int w, int h, int c, int src_stride, int type,
-                                 double factor, int out_y0, int out_y1, void* dst, int dst_stride)
+                                 double factor, int out_y0, int out_y1, void* dst, int dst_stride, bool whole)
     {
-        int power, rc;
-        if ((rc = check_args(s, m, src, w, h, c, type, factor, dst, power)) != ACB200_OK) return rc;
+        FactorPlan plan;
+        int rc;
+        if ((rc = check_args(s, m, src, w, h, c, type, factor, dst, plan, !whole)) != ACB200_OK) return rc;
         ACB_CUDA(s, cudaSetDevice(s->device));
-        const int es = type & 0xff, ow = w << power, oh = h << power;
+        const int es = type & 0xff, ow = plan.dw, oh = plan.dh;
+        if (whole) { out_y0 = 0; out_y1 = oh; }
         if (out_y0 < 0 || out_y1 > oh || out_y0 >= out_y1) return fail(s, ACB200_EINVAL, "row range outside the result");
         const size_t line_in = static_cast<size_t>(w) * c * es, line_out = static_cast<size_t>(ow) * c * es;
         if (src_stride < static_cast<int>(line_in)) src_stride = static_cast<int>(line_in);
@@ -1027,7 +1126,7 @@ extern "C"
         if ((rc = ensure(s, s->dst, dp * oh)) != ACB200_OK) return rc;
         ACB_CUDA(s, cudaMemcpy2DAsync(s->src.p, sp, src, src_stride, line_in, h, cudaMemcpyHostToDevice, s->stream));
         ACB_CUDA(s, cudaEventRecord(s->ev0, s->stream));
-        if ((rc = process_on_device(s, m, s->stream, s->src.p, w, h, c, static_cast<int>(sp), type, power, s->dst.p, static_cast<int>(dp))) != ACB200_OK) return rc;
+        if ((rc = process_on_device(s, m, s->stream, s->src.p, w, h, c, static_cast<int>(sp), type, plan, s->dst.p, static_cast<int>(dp))) != ACB200_OK) return rc;
         ACB_CUDA(s, cudaEventRecord(s->ev1, s->stream));
         s->timed = true;
         ACB_CUDA(s, cudaMemcpy2DAsync(dst, dst_stride, static_cast<const uint8_t*>(s->dst.p) + static_cast<size_t>(out_y0) * dp, dp, line_out, out_y1 - out_y0,
@@ -1038,8 +1137,7 @@ extern "C"
     int acb200_process_host(acb200_session* s, const acb200_model* m, const void* src, int w, int h, int c, int src_stride, int type,
                             double factor, void* dst, int dst_stride)
     {
-        int power = passes_for(factor);
-        return process_host_rows(s, m, src, w, h, c, src_stride, type, factor, 0, power ? (h << power) : 1, dst, dst_stride);
+        return process_host_rows(s, m, src, w, h, c, src_stride, type, factor, 0, 0, dst, dst_stride, true);
     }
 
     // ---- planar / semi-planar video frames ---------------------------------------------------------------------------------
@@ -1117,7 +1215,7 @@ extern "C"
         if (dst_stride < (w << power) * c * es) dst_stride = (w << power) * c * es;
         const uint8_t* sub = static_cast<const uint8_t*>(src) + static_cast<size_t>(sy0) * src_stride;
         uint8_t* out = static_cast<uint8_t*>(dst) + static_cast<size_t>(oy0) * dst_stride;
-        return process_host_rows(s, m, sub, w, sy1 - sy0, c, src_stride, type, factor, oy0 - (sy0 << power), oy1 - (sy0 << power), out, dst_stride);
+        return process_host_rows(s, m, sub, w, sy1 - sy0, c, src_stride, type, factor, oy0 - (sy0 << power), oy1 - (sy0 << power), out, dst_stride, false);
     }
     int acb200_session_sync(acb200_session* s)
     {

@@ -181,6 +181,41 @@ namespace acb
         }
     }
 
+    // Contributors of the general resize (up to 10 taps): the post-network luma down-scale of non-power-of-two factors
+    // (Processor.cpp:237,249: resize(out, ..., fxy) with 1/2 < fxy < 1 gathers up to 9 source pixels per axis)
+    struct ContribW
+    {
+        int n0, cnt;
+        float c[10];
+    };
+    __global__ void resize_wide_kernel(const void* __restrict__ src, int src_pitch, int c, int type,
+                                       const ContribW* __restrict__ htab, const ContribW* __restrict__ vtab,
+                                       void* __restrict__ dst, int ow, int oh, int dst_pitch)
+    {
+        const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+        if (x >= ow || y >= oh) return;
+        const ContribW hc = htab[x], vc = vtab[y];
+        void* row = static_cast<uint8_t*>(dst) + static_cast<size_t>(y) * dst_pitch;
+        for (int ch = 0; ch < c; ch++)
+        {
+            // horizontal pass then vertical pass, left-to-right sums with separately rounded products (as catmull_sample)
+            float s = 0.0f;
+            for (int i = 0; i < vc.cnt; i++)
+            {
+                const uint8_t* srow = static_cast<const uint8_t*>(src) + static_cast<size_t>(vc.n0 + i) * src_pitch;
+                float hsum = 0.0f;
+                for (int j = 0; j < hc.cnt; j++)
+                {
+                    const float t = __fmul_rn(hc.c[j], resize_decode(srow, (hc.n0 + j) * c + ch, type));
+                    hsum = j == 0 ? t : __fadd_rn(hsum, t);
+                }
+                const float t = __fmul_rn(vc.c[i], hsum);
+                s = i == 0 ? t : __fadd_rn(s, t);
+            }
+            resize_encode_store(row, x * c + ch, type, s, true);
+        }
+    }
+
     // Processor.cpp:251-253 fused: Catmull-Rom upscale of the (u,v[,a]) plane by the full factor, re-quantised to
     // the element type exactly where the reference materialises the resized plane, then YUV->RGB merge with the
     // network's luma.

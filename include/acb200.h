@@ -106,7 +106,9 @@ ACB200_API void acb200_session_clear_error(acb200_session* session);
  * Processor::process(src, dst, factor) for HOST images: H2D, RGB->YUV split (c = 3/4), ceil(log2(factor))
  * 2x luma passes, Catmull-Rom chroma resize by `factor`, YUV->RGB merge, D2H, stream sync.
  * dst must be preallocated: (int)(w*factor) x (int)(h*factor) x c, same element type.
- * `factor` must be a power of two >= 2 (fxy == 1 in Processor.cpp:204-205); others -> ACB200_EINVAL.
+ * Any `factor` >= 1 (<= 64): for factors that are not powers of two the luma is down-scaled after the passes by
+ * fxy = factor / 2^power with the Catmull-Rom filter (Processor.cpp:203-204, 237, 249); factor < 1 -> ACB200_EINVAL.
+ * Row bands (acb200_process_host_band) and video frames (acb200_process_frame_*) take powers of two only.
  */
 ACB200_API int acb200_process_host(acb200_session* session, const acb200_model* model,
                                    const void* src, int w, int h, int c, int src_stride, int elem_type,

@@ -660,11 +660,17 @@ static void make_contribs(orc_contrib *out, int in_size, int out_size, float sca
     const float support = 2.0f;
     float inv_scale = 1.0f / scale;
     float out_radius = support * scale;
+    /* Down-scaling (scale < 1; the post-network luma resize of non-power-of-two factors, Processor.cpp:237,249,265): the
+     * filter is stretched by 1/scale in input space -- output pixel n gathers every input pixel within 2/scale of its centre
+     * with weight k((centre distance) * scale), normalised to sum 1, out-of-range taps folded onto the edge pixel.  This is the
+     * gather form of stb_image_resize2's down-sampler (unvendored: parity unpinned, like the up-sampler). */
+    const int down = scale < 1.0f;
     for (int n = 0; n < out_size; n++)
     {
         float out_center = (float)n + 0.5f;
         float in_center = out_center * inv_scale;
-        float lo = (out_center - out_radius) * inv_scale, hi = (out_center + out_radius) * inv_scale;
+        float lo = down ? in_center - support * inv_scale : (out_center - out_radius) * inv_scale;
+        float hi = down ? in_center + support * inv_scale : (out_center + out_radius) * inv_scale;
         int first = (int)floorf(lo + 0.5f), last = (int)floorf(hi - 0.5f);
         if (last < first) last = first;
         if (last - first > 10) last = first + 10;
@@ -672,7 +678,7 @@ static void make_contribs(orc_contrib *out, int in_size, int out_size, float sca
         for (int i = 0; i <= last - first; i++)
         {
             float in_pixel_center = (float)(first + i) + 0.5f;
-            raw[i] = catmull_rom(in_center - in_pixel_center);
+            raw[i] = down ? catmull_rom((in_center - in_pixel_center) * scale) : catmull_rom(in_center - in_pixel_center);
             total += raw[i];
         }
         float fs = 1.0f / total;
@@ -706,7 +712,7 @@ int orc_resize_catmull_rom(const void *src_, int w, int h, int c, int src_stride
 {
     const uint8_t *src = (const uint8_t *)src_;
     uint8_t *dst = (uint8_t *)dst_;
-    if (ow < w || oh < h) return -1; /* upsample only */
+    if (ow * 2 < w || oh * 2 < h || ow <= 0 || oh <= 0) return -1; /* down to 1/2 (what Processor::process needs), any up-scale */
     orc_contrib *hc = (orc_contrib *)malloc(sizeof(orc_contrib) * ow), *vc = (orc_contrib *)malloc(sizeof(orc_contrib) * oh);
     float *tmp = (float *)malloc(sizeof(float) * (size_t)h * ow * c);
     if (!hc || !vc || !tmp) { free(hc); free(vc); free(tmp); return -1; }
@@ -780,10 +786,10 @@ static int ceil_log2(double v)
 }
 
 /*
- * The whole-image driver, core/src/processor/Processor.cpp:199-276, for factors that are
- * powers of two (fxy == 1): colour split, `power` 2x passes (luma re-quantised to the image
- * type between passes), ONE Catmull-Rom chroma resize by the full factor, merge.
- * dst must be (w*factor) x (h*factor) x c of the same element type.  Returns 0 / -1.
+ * The whole-image driver, core/src/processor/Processor.cpp:199-276: colour split, `power` 2x passes (luma re-quantised to
+ * the image type between passes), for factors that are not powers of two a Catmull-Rom down-scale of the luma by
+ * fxy = factor / 2^power (:237, :249), ONE Catmull-Rom chroma resize by the full factor, merge.
+ * dst must be int(w*factor) x int(h*factor) x c of the same element type.  Returns 0 / -1.
  */
 int orc_process(int family, int blocks, const float *k, const float *b, const float *a,
                 const void *src, int w, int h, int c, int src_stride, int type, double factor,
@@ -791,7 +797,8 @@ int orc_process(int family, int blocks, const float *k, const float *b, const fl
 {
     int power = factor > 2.0 ? ceil_log2(factor) : 1;
     double fxy = factor / (double)(1 << power);
-    if (fxy != 1.0 || !(c == 1 || c == 3 || c == 4)) return -1;
+    if (!(c == 1 || c == 3 || c == 4) || !(factor >= 1.0)) return -1;
+    const int dw = (int)(w * factor), dh = (int)(h * factor);      /* ImageResize.cpp:153-154 / the caller-sized dst */
     int es = elem_size(type);
     void *y = 0, *uv = 0;
     int y_stride = src_stride, uv_stride = 0, uvc = c - 1, rc = 0;
@@ -809,7 +816,7 @@ int orc_process(int family, int blocks, const float *k, const float *b, const fl
     for (int i = 0; i < power && rc == 0; i++)
     {
         int nw = cw * 2, nh = chh * 2;
-        int last = (i == power - 1) && c == 1;
+        int last = (i == power - 1) && c == 1 && fxy == 1.0;
         int nstride = last ? dst_stride : align4(nw * es);
         void *out = last ? dst : malloc((size_t)nstride * nh);
         if (!out) { rc = -1; break; }
@@ -817,6 +824,20 @@ int orc_process(int family, int blocks, const float *k, const float *b, const fl
         if (owned) free(owned);
         owned = last ? 0 : out;
         cur = out; cw = nw; chh = nh; cstride = nstride;
+    }
+    if (rc == 0 && fxy != 1.0)
+    {
+        /* gray: resize(out, dst, 0, 0) straight into dst; colour: resize(out, out, fxy, fxy) into a new luma plane */
+        int nstride = c == 1 ? dst_stride : align4(dw * es);
+        void *out = c == 1 ? dst : malloc((size_t)nstride * dh);
+        if (!out) rc = -1;
+        else
+        {
+            rc = orc_resize_catmull_rom(cur, cw, chh, 1, cstride, type, out, dw, dh, nstride);
+            if (owned) free(owned);
+            owned = c == 1 ? 0 : out;
+            cur = out; cw = dw; chh = dh; cstride = nstride;
+        }
     }
     if (rc == 0 && c > 1)
     {

@@ -232,3 +232,21 @@ def test_wide_family_reference_backends_agree_within_the_parity_bar():
         for other in ("generic:", "fma:"):
             mx, same = O.compare_u8(WIDE[key], WIDE[other + rest])
             assert mx <= 1 and same >= 0.999, (key, other, mx, same)
+
+
+def test_non_power_of_two_factor_driver_and_downscale_properties():
+    """Processor.cpp:203-204,237,249 restated in orc_process: power = ceilLog2(factor) passes, then the Catmull-Rom luma
+    down-scale by fxy.  Properties that do not depend on the (unpinned) stb arithmetic: sizes, constants, identity at 2^k."""
+    name = "acnet-legacy-hdn0"
+    img = O.smooth_u8(24, 36, 1, seed=1)
+    for factor in (1.0, 1.5, 2.5, 3.0):
+        out = O.oracle_process(name, img, factor)
+        assert out.shape == (int(24 * factor), int(36 * factor))
+        assert abs(float(out.mean()) - float(img.mean())) < 2.0           # brightness preserved
+    c = np.full((20, 30), 77, np.uint8)
+    assert (O.oracle_resize(c, 20, 14) == 77).all() and (O.oracle_resize(c, 15, 10) == 77).all()     # weights sum to 1, also at the edges
+    two = O.oracle_process(name, img, 2.0)
+    # 3x = (4x result) down-scaled by 0.75: equals a resize of the oracle's own 4x output
+    four = O.oracle_process(name, img, 4.0)
+    assert np.array_equal(O.oracle_process(name, img, 3.0), O.oracle_resize(four, 108, 72))
+    assert two.shape == (48, 72)

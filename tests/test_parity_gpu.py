@@ -298,8 +298,10 @@ def test_processor_api_threads_and_errors():
     [t.join() for t in ts]
     for i in range(6):
         check_int(outs[i], O.oracle_process("acnet-legacy-hdn0", imgs[i], 2.0))
-    p.process(imgs[0], 3.0)                     # non power-of-two factors are outside the accelerated path
-    assert not p.ok() and "power of two" in p.error()
+    p.process(imgs[0], 0.5)                     # factors below 1 would need a down-scale by less than 1/2: reported, not aborted
+    assert not p.ok() and "at least 1" in p.error()
+    out3 = p.process(imgs[0], 3.0)              # non power-of-two: two 2x passes, then the Catmull-Rom luma down-scale by 0.75
+    assert p.ok() and out3.shape == (192, 240)
     out4 = p.process(np.ascontiguousarray(imgs[0][:16, :16]), 4.0)      # reference ProcessorTest.cpp:93-104: 4x dims
     assert out4.shape == (64, 64)
     auto = pyac.core.Processor("auto", -1, "acnet-hdn")
@@ -428,6 +430,18 @@ def test_video_frame_1080p_i420_properties(session):
     assert np.array_equal(got[0], session.process_host(m, planes[0], 2.0))
     for i in (1, 2):
         assert np.array_equal(got[i], session.resize_catmull_rom(planes[i], 1920, 1080))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scale", [3, 5, 6])
+def test_video_frame_chroma_planes_at_integer_scales_with_zero_taps(session, scale):
+    """Chroma destination planes need not be 2^k x the source: 3x / 5x / 6x have phases whose outer Catmull-Rom taps are exactly
+    zero (the tiled kernel's source window must not depend on them)."""
+    planes = _yuv_frame(40, 140, "i444", np.uint8, 8, seed=15)
+    out = [np.empty((80, 280), np.uint8), np.empty((40 * scale, 140 * scale), np.uint8), np.empty((40 * scale, 140 * scale), np.uint8)]
+    got = session.process_frame(gpu_model("acnet-legacy-hdn0"), planes, 2.0, out=out)
+    for i in (1, 2):
+        assert np.array_equal(got[i], O.oracle_resize(planes[i], 140 * scale, 40 * scale))
 
 
 @pytest.mark.gpu
@@ -657,3 +671,51 @@ def test_reference_processor_test_criterion_psnr_48db(session, name):
     mse = float(((dst - ref) ** 2).mean())
     psnr = float("inf") if mse == 0 else 10.0 * np.log10(255.0 ** 2 / mse)
     assert psnr > 48.0, psnr
+
+
+
+# ---- factors that are not powers of two (Processor.cpp:203-204, 237, 249): passes up to the next power of two, then the
+#      Catmull-Rom luma down-scale by fxy = factor / 2^power and the chroma resize by the full factor ---------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("factor", [1.0, 1.5, 2.5, 3.0, 3.7])
+@pytest.mark.parametrize("name", ["acnet-legacy-hdn0", "acnet-f8b8-hdn", "artcnn-c4f16"])
+def test_non_power_of_two_factors_gray_and_colour_vs_oracle(session, name, factor):
+    O.set_order(O.ORDER_FMA)
+    m = gpu_model(name)
+    gray = O.smooth_u8(37, 53, 1, seed=3)
+    want = O.oracle_process(name, gray, factor)
+    got = session.process_host(m, gray, factor)
+    assert got.shape == want.shape == (int(37 * factor), int(53 * factor))
+    assert np.array_equal(got, want)
+    rgb = O.smooth_u8(26, 34, 3, seed=4)
+    assert np.array_equal(session.process_host(m, rgb, factor), O.oracle_process(name, rgb, factor))
+
+
+@pytest.mark.gpu
+def test_non_power_of_two_factor_types_engines_and_device_path(session):
+    import torch
+    O.set_order(O.ORDER_FMA)
+    name = "acnet-f8b4"
+    m = gpu_model(name)
+    g8 = O.smooth_u8(40, 48, 1, seed=6)
+    for img in (g8.astype(np.uint16) * 257, (g8 / 255.0).astype(np.float32), O.noise_u8(22, 30, 4, seed=7)):
+        want = O.oracle_process(name, img, 1.5)
+        got = session.process_host(m, img, 1.5)
+        if img.ndim == 3:
+            opaque = np.repeat((want[..., 3:4] >= 128), 4, axis=2)
+            assert np.array_equal(got[opaque], want[opaque])
+        else:
+            assert np.array_equal(got, want)
+    # default engine (tensor cores on the last pass): the north_star tolerance
+    session.set_engine(ENGINE_AUTO)
+    rgb = O.smooth_u8(64, 80, 3, seed=8)
+    check_close(session.process_host(m, rgb, 3.0), O.oracle_process(name, rgb, 3.0), x4=True)
+    # device-resident entry
+    session.set_engine(ENGINE_EXACT)
+    d = torch.from_numpy(rgb).cuda()
+    out = session.process_device(m, d, 1.5)
+    torch.cuda.synchronize()
+    session.sync()
+    assert np.array_equal(out.cpu().numpy(), O.oracle_process(name, rgb, 1.5))
+    with pytest.raises(A.Acb200Error):
+        session.process_host(m, g8, 0.75)
