@@ -444,10 +444,11 @@ def run_ours(args):
                        "parity_spot_check": parity},
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                          "frac": achieved_tf / peaks["bf16_tflops_sustained"],
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full, profiles/r01_mma_flat_ncu_summary.json):
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full, profiles/r01_final_luma_mma_ncu_summary.json):
                          # the 2.07 MB input plane is read once; the 8.3 MB result is still in the 126 MB L2 when the kernel retires
-                         "traffic": 2119168, "algorithmic_bytes": W * H + 4 * W * H,
-                         "kernel": "fused luma network (segment kernel), 1920x1080 Y -> 3840x2160 Y", "kernel_ms": kernel_ms,
+                         "traffic": None if args.model.startswith(("artcnn", "fsrcnnx")) else 2127616, "algorithmic_bytes": W * H + 4 * W * H,
+                         "kernel": ("luma network, one launch per layer (launches_per_pass), 1920x1080 Y -> 3840x2160 Y" if args.model.startswith(("artcnn", "fsrcnnx"))
+                                    else "fused luma network (segment kernel), 1920x1080 Y -> 3840x2160 Y"), "kernel_ms": kernel_ms,
                          "launches_per_pass": launches_per_pass, "flop_per_launch": flop_frame, "peak_source": peaks["source"],
                          "pipe": "fp32 FFMA (CUDA cores), exact engine" if (args.engine == 0 or args.model.startswith("fsrcnnx-f8"))
                                  else ("split-fp16 tcgen05 MMA with TMEM accumulators (F->F layers); head / tail fp32 FFMA" if args.model.startswith(("artcnn", "fsrcnnx"))
