@@ -42,8 +42,7 @@ def _planes_of(arrays):
 
 def frame_result_planes(planes, factor):
     """Destination planes of one video frame: every plane `factor` x its source (what Pipeline::request allocates)."""
-    f = int(factor)
-    return [np.empty((p.shape[0] * f, p.shape[1] * f) + p.shape[2:], p.dtype) for p in planes]
+    return [np.empty((int(p.shape[0] * factor), int(p.shape[1] * factor)) + p.shape[2:], p.dtype) for p in planes]
 
 
 class NativeLibraryMissing(RuntimeError):

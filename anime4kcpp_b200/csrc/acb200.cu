@@ -873,7 +873,7 @@ namespace
 
     // cli/src/Main.cpp:183-206 on device-resident planes: plane 0 -> [shl] network [shr]; planes 1.. -> Catmull-Rom resize.
     int process_frame_on_device(acb200_session* s, const acb200_model* m, cudaStream_t st, const acb200_plane* src, const acb200_plane* dst,
-                                int planes, int type, int shift, int power)
+                                int planes, int type, int shift, const FactorPlan& plan)
     {
         const int es = type & 0xff;
         const dim3 blk(32, 8);
@@ -892,24 +892,12 @@ namespace
             g_launches.fetch_add(1, std::memory_order_relaxed);
             ACB_CUDA(s, cudaGetLastError());
             cur = s->y[slot].p; cur_pitch = static_cast<int>(p);
-            slot ^= 1;
         }
-        for (int i = 0; i < power; i++)
-        {
-            const int nw = cw * 2, nh = ch * 2;
-            void* out; int out_pitch;
-            if (i == power - 1) { out = dst[0].data; out_pitch = frame_stride(dst[0], es); }
-            else
-            {
-                const size_t p = pitch_of(nw, 1, es);
-                if ((rc = ensure(s, s->y[slot], p * nh)) != ACB200_OK) return rc;
-                out = s->y[slot].p; out_pitch = static_cast<int>(p);
-                slot ^= 1;
-            }
-            const bool tensor = s->engine == 1 || (s->engine == 2 && i == power - 1);
-            if ((rc = luma_pass(s, st, *m, cur, cur_pitch, out, out_pitch, cw, ch, type, tensor)) != ACB200_OK) return rc;
-            cur = out; cur_pitch = out_pitch; cw = nw; ch = nh;
-        }
+        // processor->process(srcy, dsty, factor): the 1-channel driver (passes, and the luma down-scale of non-2^k factors).  Its
+        // intermediates start in y[1], so the shifted copy in y[0] is consumed before it can be overwritten.
+        const int dpitch = frame_stride(dst[0], es);
+        if ((rc = process_on_device(s, m, st, cur, cw, ch, 1, cur_pitch, type, plan, dst[0].data, dpitch)) != ACB200_OK) return rc;
+        cw = plan.dw; ch = plan.dh; cur_pitch = dpitch;
         if (sh)
         {
             shift_kernel<<<dim3((cw + 31) / 32, (ch + 7) / 8), blk, 0, st>>>(dst[0].data, cur_pitch, dst[0].data, cur_pitch, cw, ch, es, sh, 0);
@@ -955,14 +943,15 @@ namespace
     }
 
     int check_frame_args(acb200_session* s, const acb200_model* m, const acb200_plane* src, const acb200_plane* dst, int planes, int type, int shift,
-                         double factor, int& power)
+                         double factor, FactorPlan& plan)
     {
         if (!s) return ACB200_EINVAL;
         if (!m || !src || !dst) return fail(s, ACB200_EINVAL, "null argument");
         if (planes < 1 || planes > 3 || !valid_type(type)) return fail(s, ACB200_EINVAL, "frame: 1 to 3 planes of a supported element type");
         if (shift < 0 || shift >= 8 * (type & 0xff)) return fail(s, ACB200_EINVAL, "frame: shift outside the element width");
-        power = passes_for(factor);
-        if (!power) return fail(s, ACB200_EINVAL, "factor must be a power of two >= 2");
+        if (!src[0].data || src[0].width <= 0 || src[0].height <= 0) return fail(s, ACB200_EINVAL, "frame: empty plane");
+        if (!plan_factor(factor, src[0].width, src[0].height, plan)) return fail(s, ACB200_EINVAL, "factor must be at least 1 (and at most 64)");
+        const int power = plan.power;
         for (int i = 0; i < planes; i++)
         {
             const acb200_plane& a = src[i];
@@ -971,7 +960,7 @@ namespace
             if (i == 0)
             {
                 if (a.channel != 1 || b.channel != 1) return fail(s, ACB200_EINVAL, "frame: plane 0 must be the 1-channel luma plane");
-                if (b.width != (a.width << power) || b.height != (a.height << power)) return fail(s, ACB200_EINVAL, "frame: destination luma plane must be factor x the source");
+                if (b.width != plan.dw || b.height != plan.dh) return fail(s, ACB200_EINVAL, "frame: destination luma plane must be factor x the source");
                 if ((static_cast<long long>(a.width) << power) > 0x7fffffffLL / 16 || (static_cast<long long>(a.height) << power) > 0x7fffffffLL / 16) return fail(s, ACB200_EINVAL, "image too large");
             }
             else
@@ -1144,16 +1133,18 @@ extern "C"
     int acb200_process_frame_device(acb200_session* s, const acb200_model* m, const acb200_plane* d_src, const acb200_plane* d_dst, int planes,
                                     int type, int shift, double factor, void* stream)
     {
-        int power, rc;
-        if ((rc = check_frame_args(s, m, d_src, d_dst, planes, type, shift, factor, power)) != ACB200_OK) return rc;
+        FactorPlan plan;
+        int rc;
+        if ((rc = check_frame_args(s, m, d_src, d_dst, planes, type, shift, factor, plan)) != ACB200_OK) return rc;
         ACB_CUDA(s, cudaSetDevice(s->device));
-        return process_frame_on_device(s, m, stream ? static_cast<cudaStream_t>(stream) : s->stream, d_src, d_dst, planes, type, shift, power);
+        return process_frame_on_device(s, m, stream ? static_cast<cudaStream_t>(stream) : s->stream, d_src, d_dst, planes, type, shift, plan);
     }
     int acb200_process_frame_host(acb200_session* s, const acb200_model* m, const acb200_plane* src, const acb200_plane* dst, int planes,
                                   int type, int shift, double factor)
     {
-        int power, rc;
-        if ((rc = check_frame_args(s, m, src, dst, planes, type, shift, factor, power)) != ACB200_OK) return rc;
+        FactorPlan plan;
+        int rc;
+        if ((rc = check_frame_args(s, m, src, dst, planes, type, shift, factor, plan)) != ACB200_OK) return rc;
         ACB_CUDA(s, cudaSetDevice(s->device));
         const int es = type & 0xff;
         acb200_plane din[3], dout[3];
@@ -1168,7 +1159,7 @@ extern "C"
                                           cudaMemcpyHostToDevice, s->stream));
         }
         ACB_CUDA(s, cudaEventRecord(s->ev0, s->stream));
-        if ((rc = process_frame_on_device(s, m, s->stream, din, dout, planes, type, shift, power)) != ACB200_OK) return rc;
+        if ((rc = process_frame_on_device(s, m, s->stream, din, dout, planes, type, shift, plan)) != ACB200_OK) return rc;
         ACB_CUDA(s, cudaEventRecord(s->ev1, s->stream));
         s->timed = true;
         for (int i = 0; i < planes; i++)

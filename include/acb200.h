@@ -108,7 +108,7 @@ ACB200_API void acb200_session_clear_error(acb200_session* session);
  * dst must be preallocated: (int)(w*factor) x (int)(h*factor) x c, same element type.
  * Any `factor` >= 1 (<= 64): for factors that are not powers of two the luma is down-scaled after the passes by
  * fxy = factor / 2^power with the Catmull-Rom filter (Processor.cpp:203-204, 237, 249); factor < 1 -> ACB200_EINVAL.
- * Row bands (acb200_process_host_band) and video frames (acb200_process_frame_*) take powers of two only.
+ * Video frames (acb200_process_frame_*) take the same factors; row bands (acb200_process_host_band) powers of two only.
  */
 ACB200_API int acb200_process_host(acb200_session* session, const acb200_model* model,
                                    const void* src, int w, int h, int c, int src_stride, int elem_type,
@@ -134,7 +134,8 @@ ACB200_API int acb200_session_sync(acb200_session* session);
  *   shift          for 10/12-bit samples stored LSB-aligned in 16-bit words (cli/src/Main.cpp:175): luma is shifted left by
  *                  `shift` bits before the network and the result shifted right again (ac::core::shl / shr,
  *                  core/src/ImageProcess.cpp:601-616); the source plane itself is not modified; chroma is not shifted
- *   dst planes     caller-allocated; plane 0 must be factor x the source luma, chroma planes at least the source size
+ *   dst planes     caller-allocated; plane 0 must be int(w * factor) x int(h * factor), chroma planes at least the source size
+ *   factor         any factor >= 1 (powers of two or not), as for images
  */
 typedef struct acb200_plane
 {

@@ -247,8 +247,7 @@ def oracle_frame(name, planes, factor=2.0, shift=0):
     oy = oracle_process(name, y, factor)
     if shift and integer:
         oy = np.right_shift(oy, shift).astype(oy.dtype)
-    f = int(factor)
-    return [oy] + [oracle_resize(p, p.shape[1] * f, p.shape[0] * f) for p in planes[1:]]
+    return [oy] + [oracle_resize(p, int(p.shape[1] * factor), int(p.shape[0] * factor)) for p in planes[1:]]
 
 
 # ---------------------------------------------------------------------------------------------

@@ -449,7 +449,7 @@ def test_video_frame_errors(session):
     m = gpu_model("acnet-legacy-hdn0")
     planes = _yuv_frame(16, 16, "i420", np.uint8, 8, seed=1)
     with pytest.raises(A.Acb200Error):
-        session.process_frame(m, planes, 3.0)                                   # not a power of two
+        session.process_frame(m, planes, 0.5)                                   # factors below 1 are not provided
     with pytest.raises(A.Acb200Error):
         session.process_frame(m, [planes[0]] * 4, 2.0)                          # too many planes
     bad = A.frame_result_planes(planes, 2.0)
@@ -506,7 +506,7 @@ def test_c_binding_process_frame_extension(session):
         assert np.array_equal(a, b)
     # failure is reported through the processor's sticky status, like ac_processor_process
     assert L.ac_processor_process_frame(p, src, dst, 3, 0x002, 6, 3.0) == -256
-    assert b"power of two" in L.ac_processor_error(p)
+    assert b"factor x the source" in L.ac_processor_error(p)        # the destination planes were sized for 2x
     assert L.ac_processor_process_frame(p, src, dst, 3, 0x002, 6, 2.0) == 0
     assert L.ac_processor_process_frame(None, src, dst, 3, 0x002, 6, 2.0) == -22
     L.ac_processor_free(C.byref(p))
@@ -719,3 +719,17 @@ def test_non_power_of_two_factor_types_engines_and_device_path(session):
     assert np.array_equal(out.cpu().numpy(), O.oracle_process(name, rgb, 1.5))
     with pytest.raises(A.Acb200Error):
         session.process_host(m, g8, 0.75)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("factor,bits,shift", [(1.5, 8, 0), (3.0, 10, 6)])
+def test_video_frame_non_power_of_two_factor(session, factor, bits, shift):
+    """processor->process(srcy, dsty, factor) with any factor >= 1 (cli/src/Main.cpp:188): luma through the passes and the luma
+    down-scale, chroma straight to factor x its size."""
+    O.set_order(O.ORDER_FMA)
+    planes = _yuv_frame(40, 56, "i420", np.uint8 if bits == 8 else np.uint16, bits, seed=31)
+    want = O.oracle_frame("acnet-legacy-hdn0", planes, factor, shift)
+    got = session.process_frame(gpu_model("acnet-legacy-hdn0"), planes, factor, shift)
+    assert got[0].shape == (int(40 * factor), int(56 * factor)) and got[1].shape == (int(20 * factor), int(28 * factor))
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
