@@ -1299,13 +1299,46 @@ extern "C"
     int acb200_resize_catmull_rom_host(acb200_session* s, const void* src, int w, int h, int c, int src_stride, int type, void* dst, int ow, int oh, int dst_stride)
     {
         if (!s) return ACB200_EINVAL;
-        if (!src || !dst || w <= 0 || h <= 0 || c < 1 || c > 4 || !valid_type(type) || ow < w || oh < h) return fail(s, ACB200_EINVAL, "resize: bad argument (upscale only)");
+        if (!src || !dst || w <= 0 || h <= 0 || c < 1 || c > 4 || !valid_type(type) || ow <= 0 || oh <= 0 || 2 * ow < w || 2 * oh < h)
+            return fail(s, ACB200_EINVAL, "resize: bad argument (any up-scale, down-scale to no less than 1/2)");
         ACB_CUDA(s, cudaSetDevice(s->device));
         const int es = type & 0xff;
         const size_t sp = pitch_of(w, c, es), dp = pitch_of(ow, c, es);
         int rc;
         if ((rc = ensure(s, s->src, sp * h)) != ACB200_OK) return rc;
         if ((rc = ensure(s, s->dst, dp * oh)) != ACB200_OK) return rc;
+        if (ow < w || oh < h)
+        {
+            // at least one axis shrinks: general 10-tap contributors per axis (an axis that grows keeps its up-scaling taps)
+            auto axis = [](std::vector<ContribW>& out, int in_size, int out_size) {
+                if (out_size < in_size) return make_contribs_down(out, in_size, out_size);
+                std::vector<Contrib> up;
+                if (!make_contribs(up, in_size, out_size)) return false;
+                out.resize(up.size());
+                for (size_t i = 0; i < up.size(); i++)
+                {
+                    out[i].n0 = up[i].n0; out[i].cnt = up[i].cnt;
+                    for (int k = 0; k < 10; k++) out[i].c[k] = k < 6 ? up[i].c[k] : 0.0f;
+                }
+                return true;
+            };
+            std::vector<ContribW> ht, vt;
+            if (!axis(ht, w, ow) || !axis(vt, h, oh)) return fail(s, ACB200_EINVAL, "resize: unsupported scale");
+            if ((rc = ensure(s, s->dhtab, ht.size() * sizeof(ContribW))) != ACB200_OK) return rc;
+            if ((rc = ensure(s, s->dvtab, vt.size() * sizeof(ContribW))) != ACB200_OK) return rc;
+            s->dtab_in_w = s->dtab_in_h = s->dtab_out_w = s->dtab_out_h = 0;       // the cached luma down-scale tables are gone
+            ACB_CUDA(s, cudaMemcpyAsync(s->dhtab.p, ht.data(), ht.size() * sizeof(ContribW), cudaMemcpyHostToDevice, s->stream));
+            ACB_CUDA(s, cudaMemcpyAsync(s->dvtab.p, vt.data(), vt.size() * sizeof(ContribW), cudaMemcpyHostToDevice, s->stream));
+            ACB_CUDA(s, cudaStreamSynchronize(s->stream));
+            ACB_CUDA(s, cudaMemcpy2DAsync(s->src.p, sp, src, std::max<size_t>(src_stride, static_cast<size_t>(w) * c * es), static_cast<size_t>(w) * c * es, h, cudaMemcpyHostToDevice, s->stream));
+            resize_wide_kernel<<<dim3((ow + 31) / 32, (oh + 7) / 8), dim3(32, 8), 0, s->stream>>>(s->src.p, static_cast<int>(sp), c, type,
+                static_cast<const ContribW*>(s->dhtab.p), static_cast<const ContribW*>(s->dvtab.p), s->dst.p, ow, oh, static_cast<int>(dp));
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            ACB_CUDA(s, cudaGetLastError());
+            ACB_CUDA(s, cudaMemcpy2DAsync(dst, std::max<size_t>(dst_stride, static_cast<size_t>(ow) * c * es), s->dst.p, dp, static_cast<size_t>(ow) * c * es, oh, cudaMemcpyDeviceToHost, s->stream));
+            ACB_CUDA(s, cudaStreamSynchronize(s->stream));
+            return ACB200_OK;
+        }
         if ((rc = ensure_tables(s, s->stream, w, h, ow, oh)) != ACB200_OK) return rc;
         ACB_CUDA(s, cudaMemcpy2DAsync(s->src.p, sp, src, std::max<size_t>(src_stride, static_cast<size_t>(w) * c * es), static_cast<size_t>(w) * c * es, h, cudaMemcpyHostToDevice, s->stream));
         resize_catmull_kernel<<<dim3((ow + 31) / 32, (oh + 7) / 8), dim3(32, 8), 0, s->stream>>>(s->src.p, static_cast<int>(sp), c, type,

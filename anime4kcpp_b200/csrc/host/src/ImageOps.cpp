@@ -106,7 +106,7 @@ namespace
         }
         if (mode != ac::core::RESIZE_CATMULL_ROM)
         {
-            std::fprintf(stderr, "ac::core::resize: only RESIZE_CATMULL_ROM upscaling is on the accelerated path\n");
+            std::fprintf(stderr, "ac::core::resize: only RESIZE_CATMULL_ROM (any up-scale, down-scale to 1/2) is on the accelerated path\n");
             return;
         }
         acb200_session* s = threadSession();

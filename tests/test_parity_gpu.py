@@ -733,3 +733,17 @@ def test_video_frame_non_power_of_two_factor(session, factor, bits, shift):
     assert got[0].shape == (int(40 * factor), int(56 * factor)) and got[1].shape == (int(20 * factor), int(28 * factor))
     for a, b in zip(got, want):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("out_shape", [(20, 30), (23, 37), (29, 50), (15, 22), (45, 30)])
+@pytest.mark.parametrize("c", [1, 3])
+def test_catmull_rom_downscale_and_mixed_resize_vs_oracle(session, out_shape, c):
+    """ac::core::resize with the Catmull-Rom filter below 1x (down to 1/2, what the driver needs for non-2^k factors) and with
+    one axis growing while the other shrinks."""
+    img = O.noise_u8(30, 44, c, seed=12)
+    oh, ow = out_shape
+    if ow >= 44 and oh >= 30:
+        pytest.skip("pure up-scale is covered elsewhere")
+    want = O.oracle_resize(img, ow, oh)
+    assert np.array_equal(session.resize_catmull_rom(img, ow, oh), want)
