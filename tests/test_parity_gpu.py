@@ -747,3 +747,32 @@ def test_catmull_rom_downscale_and_mixed_resize_vs_oracle(session, out_shape, c)
         pytest.skip("pure up-scale is covered elsewhere")
     want = O.oracle_resize(img, ow, oh)
     assert np.array_equal(session.resize_catmull_rom(img, ow, oh), want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(40))
+def test_randomized_model_shape_type_factor_vs_oracle(session, seed):
+    """Seeded random draws over the whole input space of Processor::process -- model family, image size (down to one pixel),
+    channels, element type, factor (powers of two or not) -- exact engine against the FMA-order oracle, bit for bit."""
+    rs = np.random.RandomState(1000 + seed)
+    name = str(rs.choice(["acnet-legacy-gan", "acnet-legacy-hdn2", "acnet-f8b4-box", "acnet-f8b8", "acnet-f8b18-hdn", "arnet-f8b8-hdn", "arnet-f8b16-box",
+                          "artcnn-c4f16-ds", "artcnn-c4f32", "fsrcnnx-f8b4-distort-plus", "fsrcnnx-f16b4"]))
+    h, w = int(rs.randint(1, 90)), int(rs.randint(1, 120))
+    c = int(rs.choice([1, 1, 3, 4]))
+    factor = float(rs.choice([1.0, 1.25, 1.5, 2.0, 2.0, 2.0, 3.0, 4.0]))
+    dtype = [np.uint8, np.uint8, np.uint16, np.float32][int(rs.randint(0, 4))]
+    img = O.noise_u8(h, w, c, seed=seed) if rs.rand() < 0.5 else O.smooth_u8(h, w, c, seed=seed)
+    if dtype == np.uint16:
+        img = img.astype(np.uint16) * 257
+    elif dtype == np.float32:
+        img = (img / 255.0).astype(np.float32)
+    O.set_order(O.ORDER_FMA)
+    want = O.oracle_process(name, img, factor)
+    got = session.process_host(gpu_model(name), img, factor)
+    assert got.shape == want.shape and got.dtype == want.dtype
+    if c == 4:
+        thr = {np.uint8: 128, np.uint16: 32768, np.float32: 0.5}[dtype]
+        opaque = np.repeat(want[..., 3:4] >= thr, 4, axis=2)
+        assert np.array_equal(got[opaque], want[opaque]), (name, h, w, c, factor, np.dtype(dtype).name)
+    else:
+        assert np.array_equal(got, want), (name, h, w, c, factor, np.dtype(dtype).name)
