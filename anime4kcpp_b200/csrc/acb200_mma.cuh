@@ -146,7 +146,7 @@ namespace acb
         for (int i = 0; i < 18; i++) bf[i] = __ldg(frag + i * 32 + lane);
     }
 
-    template<bool BORDER, class Epi>
+    template<bool BORDER, int NT, class Epi>
     __device__ __forceinline__ void mma_conv3x3_impl(const int L, const HalfPlanes& in, const uint32_t (&bf)[18], const TileGeom& g, Epi&& epi)
     {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -167,65 +167,96 @@ namespace acb
             toff[s] = ((tap / 3 - 1) * FT + (tap % 3 - 1)) * 16;
         }
         const int arow = r + ((m & 1) << 3), drow = lane >> 2;
-        for (int it = warp; it < tiles; it += MMA_WARPS)
+        // NT M-tiles of 16 pixels are in flight per warp (their ldmatrix / MMA sequences interleave).  NT = 1 is what ships:
+        // measured with NT = 2 (-DACB_MMA_TILES=2) ACNet-B8 gains 3 % but ACNetLegacy and ARNet lose 3-4 % (coarser work units
+        // balance worse over the 16 warps than the extra instruction-level parallelism buys).
+        for (int it0 = warp * NT; it0 < tiles; it0 += MMA_WARPS * NT)
         {
-            const int q = min(it * 16 + arow, npix - 1);
-            const int qy = static_cast<int>((static_cast<uint32_t>(q) * rcp) >> 20), qx = q - qy * wr;
-            const int px = xa + qx, py = ya + qy;
-            float c0[4] = { 0.0f, 0.0f, 0.0f, 0.0f }, c1[4] = { 0.0f, 0.0f, 0.0f, 0.0f }, c2[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
-            uint32_t addr[5];
-            if (BORDER)
-            {
-                const int cx[3] = { clampi(px - 1, cx_lo, cx_hi), px, clampi(px + 1, cx_lo, cx_hi) };
-                const int ry[3] = { clampi(py - 1, cy_lo, cy_hi) * FT, py * FT, clampi(py + 1, cy_lo, cy_hi) * FT };
+            int px[NT], py[NT];
+            uint32_t addr[NT][5];
+            float c0[NT][4], c1[NT][4], c2[NT][4];
 #pragma unroll
-                for (int s = 0; s < 5; s++)
+            for (int t = 0; t < NT; t++)
+            {
+                const int q = min((it0 + t) * 16 + arow, npix - 1);
+                const int qy = static_cast<int>((static_cast<uint32_t>(q) * rcp) >> 20), qx = q - qy * wr;
+                px[t] = xa + qx; py[t] = ya + qy;
+#pragma unroll
+                for (int e = 0; e < 4; e++) c0[t][e] = c1[t][e] = c2[t][e] = 0.0f;
+                if (BORDER)
                 {
-                    const int t0 = 2 * s, t1 = 2 * s + 1;
-                    addr[s] = hi_base + (((h && s < 4) ? ry[t1 / 3] + cx[t1 % 3] : ry[t0 / 3] + cx[t0 % 3]) << 4);
+                    const int cx[3] = { clampi(px[t] - 1, cx_lo, cx_hi), px[t], clampi(px[t] + 1, cx_lo, cx_hi) };
+                    const int ry[3] = { clampi(py[t] - 1, cy_lo, cy_hi) * FT, py[t] * FT, clampi(py[t] + 1, cy_lo, cy_hi) * FT };
+#pragma unroll
+                    for (int s = 0; s < 5; s++)
+                    {
+                        const int t0 = 2 * s, t1 = 2 * s + 1;
+                        addr[t][s] = hi_base + (((h && s < 4) ? ry[t1 / 3] + cx[t1 % 3] : ry[t0 / 3] + cx[t0 % 3]) << 4);
+                    }
+                }
+                else
+                {
+                    const uint32_t pix = hi_base + ((py[t] * FT + px[t]) << 4);
+#pragma unroll
+                    for (int s = 0; s < 5; s++) addr[t][s] = pix + toff[s];
                 }
             }
-            else
-            {
-                const uint32_t pix = hi_base + ((py * FT + px) << 4);
-#pragma unroll
-                for (int s = 0; s < 5; s++) addr[s] = pix + toff[s];
-            }
-            // Three independent accumulator chains (a_hi*w_hi, a_lo*w_hi, a_hi*w_lo).  An m16n8k8 occupies the tensor pipe exactly
-            // as long as an m16n8k16 (8 cycles per SM partition, tools/microbench_hmma_latency.cu), so the odd ninth tap is loaded as
-            // ONE fragment {hi | lo} and multiplied by [w_hi ; w_hi] in a single k16: 14 MMA slots per tile instead of 15.
+            // Three independent accumulator chains per tile (a_hi*w_hi, a_lo*w_hi, a_hi*w_lo).  An m16n8k8 occupies the tensor pipe
+            // exactly as long as an m16n8k16 (8 cycles per SM partition, tools/microbench_hmma_latency.cu), so the odd ninth tap is
+            // loaded as ONE fragment {hi | lo} and multiplied by [w_hi ; w_hi] in a single k16: 14 MMA slots per tile instead of 15.
 #pragma unroll
             for (int s = 0; s < 4; s++)
             {
-                uint32_t ah[4], al[4];
-                ldmatrix_x4(ah, addr[s]);
-                ldmatrix_x4_off(al, addr[s], 0);
-                mma_k16(c0, ah, bf[2 * s], bf[2 * s + 1]);
-                mma_k16(c2, ah, bf[9 + 2 * s], bf[9 + 2 * s + 1]);
-                mma_k16(c1, al, bf[2 * s], bf[2 * s + 1]);
+                uint32_t ah[NT][4], al[NT][4];
+#pragma unroll
+                for (int t = 0; t < NT; t++)
+                {
+                    ldmatrix_x4(ah[t], addr[t][s]);
+                    ldmatrix_x4_off(al[t], addr[t][s], 0);
+                }
+#pragma unroll
+                for (int t = 0; t < NT; t++)
+                {
+                    mma_k16(c0[t], ah[t], bf[2 * s], bf[2 * s + 1]);
+                    mma_k16(c2[t], ah[t], bf[9 + 2 * s], bf[9 + 2 * s + 1]);
+                    mma_k16(c1[t], al[t], bf[2 * s], bf[2 * s + 1]);
+                }
             }
             {
-                uint32_t f8[4];
-                ldmatrix_x4(f8, addr[4] + (h ? static_cast<uint32_t>(FT * FT * 16) : 0u));     // matrices 0,1: hi plane; 2,3: lo plane
-                mma_k16(c1, f8, bf[8], bf[8]);
-                mma_k8(c2, f8[0], f8[1], bf[17]);
+                uint32_t f8[NT][4];
+#pragma unroll
+                for (int t = 0; t < NT; t++)
+                    ldmatrix_x4(f8[t], addr[t][4] + (h ? static_cast<uint32_t>(FT * FT * 16) : 0u));   // matrices 0,1: hi plane; 2,3: lo plane
+#pragma unroll
+                for (int t = 0; t < NT; t++)
+                {
+                    mma_k16(c1[t], f8[t], bf[8], bf[8]);
+                    mma_k8(c2[t], f8[t][0], f8[t][1], bf[17]);
+                }
             }
 #pragma unroll
-            for (int e = 0; e < 4; e++) c0[e] += c1[e];
-            // D fragment rows are region pixels 16*it + g and + 8: exactly the pixels lanes g and g + 8 addressed above
-            const int packed = (py << 8) | px;
-            const int d0 = __shfl_sync(0xffffffffu, packed, drow), d1 = __shfl_sync(0xffffffffu, packed, drow + 8);
-            const int q0 = it * 16 + drow;
-            epi(d0 & 0xff, d0 >> 8, c0[0] + c2[0], c0[1] + c2[1], q0 < npix);
-            epi(d1 & 0xff, d1 >> 8, c0[2] + c2[2], c0[3] + c2[3], q0 + 8 < npix);
+            for (int t = 0; t < NT; t++)
+            {
+#pragma unroll
+                for (int e = 0; e < 4; e++) c0[t][e] += c1[t][e];
+                // D fragment rows are region pixels 16*it + g and + 8: exactly the pixels lanes g and g + 8 addressed above
+                const int packed = (py[t] << 8) | px[t];
+                const int d0 = __shfl_sync(0xffffffffu, packed, drow), d1 = __shfl_sync(0xffffffffu, packed, drow + 8);
+                const int q0 = (it0 + t) * 16 + drow;
+                epi(d0 & 0xff, d0 >> 8, c0[t][0] + c2[t][0], c0[t][1] + c2[t][1], q0 < npix);
+                epi(d1 & 0xff, d1 >> 8, c0[t][2] + c2[t][2], c0[t][3] + c2[t][3], q0 + 8 < npix);
+            }
         }
     }
     template<class Epi>
     __device__ __forceinline__ void mma_conv3x3(const int L, const HalfPlanes& in, const uint32_t (&bf)[18], const TileGeom& g, Epi&& epi)
     {
         // interior CTA: the image covers the whole frame, no replicate padding anywhere in this tile (uniform branch)
-        if (g.ix0 <= 0 && g.iy0 <= 0 && g.ix1 >= FT - 1 && g.iy1 >= FT - 1) mma_conv3x3_impl<false>(L, in, bf, g, epi);
-        else mma_conv3x3_impl<true>(L, in, bf, g, epi);
+#ifndef ACB_MMA_TILES
+#define ACB_MMA_TILES 1
+#endif
+        if (g.ix0 <= 0 && g.iy0 <= 0 && g.ix1 >= FT - 1 && g.iy1 >= FT - 1) mma_conv3x3_impl<false, ACB_MMA_TILES>(L, in, bf, g, epi);
+        else mma_conv3x3_impl<true, 1>(L, in, bf, g, epi);
     }
 
     template<class S>
