@@ -776,3 +776,48 @@ def test_randomized_model_shape_type_factor_vs_oracle(session, seed):
         assert np.array_equal(got[opaque], want[opaque]), (name, h, w, c, factor, np.dtype(dtype).name)
     else:
         assert np.array_equal(got, want), (name, h, w, c, factor, np.dtype(dtype).name)
+
+
+# ---- SURVEY.md 8d configs 2 and 3 at full size: every real-weight 8-feature model and the largest ARNet on a 1080p frame ------------
+ALL_REAL_8 = ["acnet-legacy-gan", "acnet-legacy-hdn0", "acnet-legacy-hdn1", "acnet-legacy-hdn2", "acnet-legacy-hdn3",
+              "acnet-f8b4", "acnet-f8b4-hdn", "acnet-f8b4-box", "acnet-f8b4-box-hdn", "acnet-f8b8", "acnet-f8b8-hdn", "acnet-f8b8-box",
+              "acnet-f8b8-box-hdn", "acnet-f8b18", "acnet-f8b18-hdn", "acnet-f8b18-box", "acnet-f8b18-box-hdn"]
+_frame_1080p = {}
+
+
+def frame_1080p():
+    if "img" not in _frame_1080p:
+        _frame_1080p["img"] = O.smooth_u8(1080, 1920, 1, seed=77)
+    return _frame_1080p["img"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ALL_REAL_8)
+def test_config2_every_real_model_1080p_default_engine_within_the_bar(session, name):
+    img = frame_1080p()
+    m = gpu_model(name)
+    session.set_engine(ENGINE_EXACT)
+    exact = session.process_host(m, img, 2.0)
+    # the exact engine against the oracle on a crop whose interior does not see the crop border (<= 20 layers of context)
+    O.set_order(O.ORDER_FMA)
+    want = O.oracle_process(name, np.ascontiguousarray(img[500:596, 900:996]), 2.0)
+    assert np.array_equal(exact[2 * 524:2 * 572, 2 * 924:2 * 972], want[48:144, 48:144])
+    session.set_engine(ENGINE_AUTO)
+    mx, same = O.compare_u8(session.process_host(m, img, 2.0), exact)
+    assert mx <= LSB_MAX and same >= EXACT_MIN, (name, mx, same)
+
+
+@pytest.mark.gpu
+def test_config3_arnet_f8b64_small_exact_and_1080p_engines(session):
+    """The largest model of the reference's catalogue (130 3x3 layers, synthetic seeded weights: ARNet.p is absent)."""
+    name = "arnet-f8b64"
+    m = gpu_model(name)
+    O.set_order(O.ORDER_FMA)
+    small = O.noise_u8(40, 56, 1, seed=64)
+    session.set_engine(ENGINE_EXACT)
+    assert np.array_equal(session.process_host(m, small, 2.0), O.oracle_process(name, small, 2.0))
+    img = frame_1080p()
+    exact = session.process_host(m, img, 2.0)
+    session.set_engine(ENGINE_AUTO)
+    mx, same = O.compare_u8(session.process_host(m, img, 2.0), exact)
+    assert mx <= LSB_MAX and same >= EXACT_MIN, (mx, same)
