@@ -23,8 +23,17 @@ for name, shape, c in (("acnet-legacy-hdn0", (70, 90), 3), ("acnet-f8b8-hdn", (5
         got = s.process_host(m, img, 2.0)
         ok = c == 4 or O.compare_u8(got, want)[0] <= 1
         print(name, "engine", engine, "impl", impl, O.compare_u8(got, want), "ok" if ok else "MISMATCH")
-# ArtCNN / FSRCNNX per-layer kernels (exact only)
-s.set_engine(2)
+# ArtCNN / FSRCNNX per-layer kernels: exact FFMA and the tcgen05 engine (F >= 16), plus a non-power-of-two factor
+for eng in (0, 1):
+    s.set_engine(eng)
+    for name, shape in (("artcnn-c4f16", (37, 70)), ("artcnn-c4f32", (20, 66)), ("fsrcnnx-f16b4", (34, 50))):
+        img = O.noise_u8(shape[0], shape[1], 1, seed=3)
+        mx, same = O.compare_u8(s.process_host(A.Model(name), img, 2.0), O.oracle_process(name, img, 2.0))
+        print(name, "engine", eng, (mx, same), "ok" if mx <= 1 else "MISMATCH")
+s.set_engine(0)
+img = O.noise_u8(30, 44, 3, seed=4)
+print("factor 1.5:", "identical" if np.array_equal(s.process_host(A.Model("acnet-f8b4"), img, 1.5), O.oracle_process("acnet-f8b4", img, 1.5)) else "MISMATCH")
+s.set_engine(0)
 for name, shape, c in (("artcnn-c4f16", (41, 70), 1), ("artcnn-c4f32-dn", (35, 33), 3), ("fsrcnnx-f8b4", (66, 37), 1), ("fsrcnnx-f16b4", (34, 50), 1)):
     img = O.noise_u8(shape[0], shape[1], c, seed=2)
     got = s.process_host(A.Model(name), img, 2.0)
