@@ -35,6 +35,11 @@ namespace acb
     constexpr int MMA_WARPS = MMA_THREADS / 32;
     constexpr int FRAG_WORDS_3X3 = 18 * 32;     // uint32 per packed 3x3 layer: (4 x 2 + 1) registers x {hi, lo} x 32 lanes
     constexpr int FRAG_WORDS_1X1 = 2 * 32;      // the ARNet 1x1: one k8 register x {hi, lo}
+#ifndef ACB_MMA_CHAINS
+#define ACB_MMA_CHAINS 3
+#endif
+    constexpr int MMA_CHAINS = ACB_MMA_CHAINS;
+    constexpr int PLANE_BYTES = FT * FT * 16;   // distance between the hi and the lo plane of a map
 
     template<class S>
     struct MmaParams
@@ -69,9 +74,14 @@ namespace acb
     __device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& hi, uint32_t& lo)
     {
         const __half2 h = __floats2half2_rn(v0, v1);        // one packed conversion
-        const float2 hf = __half22float2(h);
-        const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
         hi = *reinterpret_cast<const uint32_t*>(&h);
+        // v - float(hi) in ONE instruction per value: the sm_100 mixed-precision FMA (FHFMA) takes the fp16 halves of `hi`
+        // directly, hi * (-1) + v with a single rounding (the difference is exactly representable, so it is exact)
+        const unsigned short h0 = static_cast<unsigned short>(hi & 0xffffu), h1 = static_cast<unsigned short>(hi >> 16), m1 = 0xBC00;
+        float l0, l1;
+        asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(l0) : "h"(h0), "h"(m1), "f"(v0));
+        asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(l1) : "h"(h1), "h"(m1), "f"(v1));
+        const __half2 l = __floats2half2_rn(l0, l1);
         lo = *reinterpret_cast<const uint32_t*>(&l);
     }
     __device__ __forceinline__ float2 join_pair(uint32_t hi, uint32_t lo)
@@ -132,9 +142,10 @@ namespace acb
     // region pixels 16j .. 16j+15, wrapping across region rows.  ldmatrix takes one row address per lane, so a wrap costs
     // nothing but an occasional 2-way bank conflict, and no MMA row is spent on padding a region width up to a multiple of 16.
     //
-    //   epi(px, py, v0, v1, valid): called by every lane twice per tile -- for the D-fragment rows g and g+8 -- with the
-    //   finished fp32 sums (bias NOT included) of output channels 2t, 2t+1 at frame pixel (px, py).  `valid` is false only in
-    //   the overhang of the last tile: the epilogue may use warp collectives but must not store for those.
+    //   epi(off, v0, v1, valid): called by every lane twice per tile -- for the D-fragment rows g and g+8 -- with the
+    //   finished fp32 sums (bias0 / bias1 included: they are the initial accumulator) of output channels 2t, 2t+1 at frame pixel off = py * FT + px.  `valid` is
+    //   false only in the overhang of the last tile (where `off` aliases the last valid pixel): the epilogue may use warp
+    //   collectives and may read, but must not store for those.
     //   L = number of 3x3 layers between the frame and this layer's output (its region is the frame shrunk by L).
     //   The hi plane and the lo plane of `in` must be FT*FT*16 bytes apart (they are: see the kernel's smem carve-up).
     // B fragments of one 3x3 layer, one register per tap: 0-8 = w_hi, 9-17 = w_lo.  The kernel loads them one layer AHEAD (while
@@ -147,7 +158,7 @@ namespace acb
     }
 
     template<bool BORDER, int NT, class Epi>
-    __device__ __forceinline__ void mma_conv3x3_impl(const int L, const HalfPlanes& in, const uint32_t (&bf)[18], const TileGeom& g, Epi&& epi)
+    __device__ __forceinline__ void mma_conv3x3_impl(const int L, const HalfPlanes& in, const uint32_t (&bf)[18], const TileGeom& g, const float bias0, const float bias1, Epi&& epi)
     {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
@@ -172,7 +183,7 @@ namespace acb
         // balance worse over the 16 warps than the extra instruction-level parallelism buys).
         for (int it0 = warp * NT; it0 < tiles; it0 += MMA_WARPS * NT)
         {
-            int px[NT], py[NT];
+            int px[NT], py[NT], poff[NT];
             uint32_t addr[NT][5];
             float c0[NT][4], c1[NT][4], c2[NT][4];
 #pragma unroll
@@ -181,8 +192,10 @@ namespace acb
                 const int q = min((it0 + t) * 16 + arow, npix - 1);
                 const int qy = static_cast<int>((static_cast<uint32_t>(q) * rcp) >> 20), qx = q - qy * wr;
                 px[t] = xa + qx; py[t] = ya + qy;
+                poff[t] = py[t] * FT + px[t];
 #pragma unroll
-                for (int e = 0; e < 4; e++) c0[t][e] = c1[t][e] = c2[t][e] = 0.0f;
+                for (int e = 0; e < 4; e++) c1[t][e] = c2[t][e] = 0.0f;
+                c0[t][0] = c0[t][2] = bias0; c0[t][1] = c0[t][3] = bias1;      // the bias rides in as the first chain's C operand
                 if (BORDER)
                 {
                     const int cx[3] = { clampi(px[t] - 1, cx_lo, cx_hi), px[t], clampi(px[t] + 1, cx_lo, cx_hi) };
@@ -196,12 +209,13 @@ namespace acb
                 }
                 else
                 {
-                    const uint32_t pix = hi_base + ((py[t] * FT + px[t]) << 4);
+                    const uint32_t pix = hi_base + (poff[t] << 4);
 #pragma unroll
                     for (int s = 0; s < 5; s++) addr[t][s] = pix + toff[s];
                 }
             }
-            // Three independent accumulator chains per tile (a_hi*w_hi, a_lo*w_hi, a_hi*w_lo).  An m16n8k8 occupies the tensor pipe
+            // MMA_CHAINS independent accumulator chains per tile (3: a_hi*w_hi, a_lo*w_hi, a_hi*w_lo; 2: the a_lo*w_hi products
+            // alternate between the other two chains, seven MMAs each, which saves the four adds that join c1).  An m16n8k8 occupies the tensor pipe
             // exactly as long as an m16n8k16 (8 cycles per SM partition, tools/microbench_hmma_latency.cu), so the odd ninth tap is
             // loaded as ONE fragment {hi | lo} and multiplied by [w_hi ; w_hi] in a single k16: 14 MMA slots per tile instead of 15.
 #pragma unroll
@@ -219,7 +233,9 @@ namespace acb
                 {
                     mma_k16(c0[t], ah[t], bf[2 * s], bf[2 * s + 1]);
                     mma_k16(c2[t], ah[t], bf[9 + 2 * s], bf[9 + 2 * s + 1]);
-                    mma_k16(c1[t], al[t], bf[2 * s], bf[2 * s + 1]);
+                    if (MMA_CHAINS == 3) mma_k16(c1[t], al[t], bf[2 * s], bf[2 * s + 1]);
+                    else if (s & 1) mma_k16(c2[t], al[t], bf[2 * s], bf[2 * s + 1]);
+                    else mma_k16(c0[t], al[t], bf[2 * s], bf[2 * s + 1]);
                 }
             }
             {
@@ -230,33 +246,35 @@ namespace acb
 #pragma unroll
                 for (int t = 0; t < NT; t++)
                 {
-                    mma_k16(c1[t], f8[t], bf[8], bf[8]);
+                    mma_k16(MMA_CHAINS == 3 ? c1[t] : c0[t], f8[t], bf[8], bf[8]);
                     mma_k8(c2[t], f8[t][0], f8[t][1], bf[17]);
                 }
             }
 #pragma unroll
             for (int t = 0; t < NT; t++)
             {
+                if (MMA_CHAINS == 3)
+                {
 #pragma unroll
-                for (int e = 0; e < 4; e++) c0[t][e] += c1[t][e];
+                    for (int e = 0; e < 4; e++) c0[t][e] += c1[t][e];
+                }
                 // D fragment rows are region pixels 16*it + g and + 8: exactly the pixels lanes g and g + 8 addressed above
-                const int packed = (py[t] << 8) | px[t];
-                const int d0 = __shfl_sync(0xffffffffu, packed, drow), d1 = __shfl_sync(0xffffffffu, packed, drow + 8);
+                const int d0 = __shfl_sync(0xffffffffu, poff[t], drow), d1 = __shfl_sync(0xffffffffu, poff[t], drow + 8);
                 const int q0 = (it0 + t) * 16 + drow;
-                epi(d0 & 0xff, d0 >> 8, c0[t][0] + c2[t][0], c0[t][1] + c2[t][1], q0 < npix);
-                epi(d1 & 0xff, d1 >> 8, c0[t][2] + c2[t][2], c0[t][3] + c2[t][3], q0 + 8 < npix);
+                epi(d0, c0[t][0] + c2[t][0], c0[t][1] + c2[t][1], q0 < npix);
+                epi(d1, c0[t][2] + c2[t][2], c0[t][3] + c2[t][3], q0 + 8 < npix);
             }
         }
     }
     template<class Epi>
-    __device__ __forceinline__ void mma_conv3x3(const int L, const HalfPlanes& in, const uint32_t (&bf)[18], const TileGeom& g, Epi&& epi)
+    __device__ __forceinline__ void mma_conv3x3(const int L, const HalfPlanes& in, const uint32_t (&bf)[18], const TileGeom& g, const float bias0, const float bias1, Epi&& epi)
     {
         // interior CTA: the image covers the whole frame, no replicate padding anywhere in this tile (uniform branch)
 #ifndef ACB_MMA_TILES
 #define ACB_MMA_TILES 1
 #endif
-        if (g.ix0 <= 0 && g.iy0 <= 0 && g.ix1 >= FT - 1 && g.iy1 >= FT - 1) mma_conv3x3_impl<false, ACB_MMA_TILES>(L, in, bf, g, epi);
-        else mma_conv3x3_impl<true, 1>(L, in, bf, g, epi);
+        if (g.ix0 <= 0 && g.iy0 <= 0 && g.ix1 >= FT - 1 && g.iy1 >= FT - 1) mma_conv3x3_impl<false, ACB_MMA_TILES>(L, in, bf, g, bias0, bias1, epi);
+        else mma_conv3x3_impl<true, 1>(L, in, bf, g, bias0, bias1, epi);
     }
 
     template<class S>
@@ -384,14 +402,14 @@ namespace acb
                 if ((i & 1) == 0) { act = ACT_PRELU; a0 = prm.a[(i >> 1) * 8 + 2 * tq]; a1 = prm.a[(i >> 1) * 8 + 2 * tq + 1]; }
                 else { act = ACT_IDENTITY; res = true; }
             }
-            const HalfPlanes out = oth;
-            auto epi = [&](const int px, const int py, float v0, float v1, const bool valid) {
-                if (!valid) return;
-                v0 += b0; v1 += b1;
+            uint32_t* const out_q = reinterpret_cast<uint32_t*>(oth.hi) + tq;      // this lane's channel pair of pixel 0, hi plane
+            auto epi = [&](const int off, float v0, float v1, const bool valid) {
+                // no early exit for the overhang lanes: straight-line code with predicated stores (one address, the lo plane
+                // is a constant distance away)
                 if (act == ACT_RELU) { v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); }
                 else if (act == ACT_PRELU) { v0 = prelu(v0, a0); v1 = prelu(v1, a1); }
-                uint32_t* ph = reinterpret_cast<uint32_t*>(out.hi + py * FT + px) + tq;
-                uint32_t* pl = reinterpret_cast<uint32_t*>(out.lo + py * FT + px) + tq;
+                uint32_t* ph = out_q + 4 * off;
+                uint32_t* pl = ph + PLANE_BYTES / 4;
                 if (res)
                 {
                     const float2 id = join_pair(*ph, *pl);
@@ -399,9 +417,9 @@ namespace acb
                 }
                 uint32_t hi, lo;
                 split_pair(v0, v1, hi, lo);
-                *ph = hi; *pl = lo;
+                if (valid) { *ph = hi; *pl = lo; }
             };
-            mma_conv3x3(i + 1, cur, bf, g, epi);
+            mma_conv3x3(i + 1, cur, bf, g, b0, b1, epi);
             __syncthreads();
             if (more)
             {
@@ -443,8 +461,9 @@ namespace acb
             static_assert(OPITCH * OT <= LT * LT * 4, "output staging does not fit the luma tile");
             uint8_t* s_out = reinterpret_cast<uint8_t*>(luma);
             const bool staged = prm.type == ACB200_UINT8 && S::HEAD;
-            auto epi = [&](const int px, const int py, float v0, float v1, const bool valid) {
-                v0 = fmaxf(v0 + b0, 0.0f); v1 = fmaxf(v1 + b1, 0.0f);
+            auto epi = [&](const int off, float v0, float v1, const bool valid) {
+                const int py = off / FT, px = off - py * FT;
+                v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f);
                 float o[4];
 #pragma unroll
                 for (int q = 0; q < 4; q++)
@@ -466,7 +485,7 @@ namespace acb
                     }
                 }
             };
-            mma_conv3x3(S::NCONV + 1, cur, bf, g, epi);
+            mma_conv3x3(S::NCONV + 1, cur, bf, g, b0, b1, epi);
             if (staged)
             {
                 __syncthreads();
@@ -499,16 +518,16 @@ namespace acb
                 {
                     const float b0 = prm.b[BT + 2 * tq], b1 = prm.b[BT + 2 * tq + 1], a0 = prm.a[AT + 2 * tq], a1 = prm.a[AT + 2 * tq + 1];
                     const HalfPlanes out = oth;
-                    auto epi = [&](const int px, const int py, float v0, float v1, const bool valid) {
+                    auto epi = [&](const int off, float v0, float v1, const bool valid) {
                         if (!valid) return;
-                        v0 = prelu(v0 + b0, a0); v1 = prelu(v1 + b1, a1);
+                        v0 = prelu(v0, a0); v1 = prelu(v1, a1);
                         uint32_t hi, lo;
                         split_pair(v0, v1, hi, lo);
-                        reinterpret_cast<uint32_t*>(out.hi + py * FT + px)[tq] = hi;
-                        reinterpret_cast<uint32_t*>(out.lo + py * FT + px)[tq] = lo;
+                        reinterpret_cast<uint32_t*>(out.hi + off)[tq] = hi;
+                        reinterpret_cast<uint32_t*>(out.lo + off)[tq] = lo;
                     };
                     mma_load_bfrag(nb, tfrag + FRAG_WORDS_3X3);
-                    mma_conv3x3(S::NCONV + 1, cur, bf, g, epi);
+                    mma_conv3x3(S::NCONV + 1, cur, bf, g, b0, b1, epi);
                     __syncthreads();
 #pragma unroll
                     for (int e = 0; e < 18; e++) bf[e] = nb[e];
@@ -524,15 +543,15 @@ namespace acb
                     // the epilogue is called for (px, py) then (px + 8, py): collect both halves of the fragment, then run
                     // the 1x1 as tensor-core MMAs on the pair
                     float keep[2];
-                    int kx = 0, ky = 0, phase = 0;
+                    int koff = 0, phase = 0;
                     bool kvalid = false;
-                    auto epi = [&](const int px, const int py, float v0, float v1, const bool valid) {
-                        uint32_t* ph = reinterpret_cast<uint32_t*>(out.hi + py * FT + px) + tq;
-                        uint32_t* pl = reinterpret_cast<uint32_t*>(out.lo + py * FT + px) + tq;
+                    auto epi = [&](const int off, float v0, float v1, const bool valid) {
+                        uint32_t* ph = reinterpret_cast<uint32_t*>(out.hi + off) + tq;
+                        uint32_t* pl = reinterpret_cast<uint32_t*>(out.lo + off) + tq;
                         // overhang lanes of the last tile alias its last valid pixel: they must not touch it
                         const float2 id = valid ? join_pair(*ph, *pl) : make_float2(0.0f, 0.0f);
-                        v0 = fmaf(v0 + b0, 0.2f, id.x); v1 = fmaf(v1 + b1, 0.2f, id.y);
-                        if (phase == 0) { keep[0] = v0; keep[1] = v1; kx = px; ky = py; kvalid = valid; phase = 1; return; }
+                        v0 = fmaf(v0, 0.2f, id.x); v1 = fmaf(v1, 0.2f, id.y);
+                        if (phase == 0) { keep[0] = v0; keep[1] = v1; koff = off; kvalid = valid; phase = 1; return; }
                         phase = 0;
                         uint32_t h0, l0, h1, l1;
                         split_pair(keep[0], keep[1], h0, l0);
@@ -541,12 +560,12 @@ namespace acb
                         mma_k8(d, h0, h1, w1h);
                         mma_k8(d, l0, l1, w1h);
                         mma_k8(d, h0, h1, w1l);
-                        const int pxs[2] = { kx, px }, pys[2] = { ky, py };
+                        const int offs[2] = { koff, off };
                         const bool oks[2] = { kvalid, valid };
 #pragma unroll
                         for (int half = 0; half < 2; half++)
                         {
-                            const int qx = pxs[half], qy = pys[half];
+                            const int qo = offs[half], qy = qo / FT, qx = qo - qy * FT;
                             if (!oks[half]) continue;
                             float u0 = prelu(d[2 * half] + c0, a0), u1 = prelu(d[2 * half + 1] + c1, a1);
                             const int gx = clampi(g.ox + qx, 0, prm.w - 1), gy = clampi(g.oy + qy, 0, prm.h - 1);
@@ -554,12 +573,12 @@ namespace acb
                             u0 += ft.x; u1 += ft.y;
                             uint32_t hi, lo;
                             split_pair(u0, u1, hi, lo);
-                            reinterpret_cast<uint32_t*>(out.hi + qy * FT + qx)[tq] = hi;
-                            reinterpret_cast<uint32_t*>(out.lo + qy * FT + qx)[tq] = lo;
+                            reinterpret_cast<uint32_t*>(out.hi + qo)[tq] = hi;
+                            reinterpret_cast<uint32_t*>(out.lo + qo)[tq] = lo;
                         }
                     };
                     mma_load_bfrag(nb, f1 + FRAG_WORDS_1X1);
-                    mma_conv3x3(S::NCONV + 2, oth, bf, g, epi);
+                    mma_conv3x3(S::NCONV + 2, oth, bf, g, b0, b1, epi);
                     __syncthreads();
 #pragma unroll
                     for (int e = 0; e < 18; e++) bf[e] = nb[e];
@@ -571,16 +590,17 @@ namespace acb
             constexpr int BPS = S::FAM == ACB200_FAMILY_ARNET ? BT + 24 : BT;
             const float b0 = tq < 2 ? prm.b[BPS + 2 * tq] : 0.0f, b1 = tq < 2 ? prm.b[BPS + 2 * tq + 1] : 0.0f;
             constexpr int LT_PS = S::FAM == ACB200_FAMILY_ARNET ? S::NCONV + 3 : S::NCONV + 1;
-            auto epi = [&](const int px, const int py, float v0, float v1, const bool valid) {
+            auto epi = [&](const int off, float v0, float v1, const bool valid) {
                 if (tq < 2 && valid)
                 {
+                    const int py = off / FT, px = off - py * FT;
                     const float id = luma[(py + 1) * LT + px + 1];
                     void* row = static_cast<uint8_t*>(prm.dst) + static_cast<size_t>(2 * (g.oy + py) + tq) * prm.dst_pitch;
-                    net_store2(row, 2 * (g.ox + px), prm.type, (v0 + b0) + id, (v1 + b1) + id, aligned);
+                    net_store2(row, 2 * (g.ox + px), prm.type, v0 + id, v1 + id, aligned);
                 }
             };
             (void)LPS;
-            mma_conv3x3(LT_PS, cur, bf, g, epi);
+            mma_conv3x3(LT_PS, cur, bf, g, b0, b1, epi);
         }
     }
 
