@@ -251,7 +251,7 @@ namespace acb
                                                                       int ow, int oh, uint8_t* __restrict__ dst, int dst_pitch)
     {
         constexpr int UVC = C - 1;
-        __shared__ Contrib sh_v[CM_OH];
+        __shared__ __align__(16) Contrib sh_v[CM_OH];
         __shared__ __align__(16) float s_src[CM_SRC_H][CM_SRC_W * UVC];
         __shared__ __align__(16) float s_hp[CM_SRC_H][CM_OW * UVC];
         const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -324,6 +324,51 @@ namespace acb
         // vertical pass + re-quantise + merge: consecutive lanes take consecutive output columns (conflict-free reads of the
         // horizontal-pass rows); the finished bytes are staged in shared memory and leave as 16-byte vectors
         __shared__ __align__(16) uint8_t s_out[CM_OH][CM_OW * C];
+        if constexpr (C == 3)
+        {
+            // RGB: the hot path, written for instruction count (every step of the arithmetic is the one of the general loop
+            // below, value for value).  The contributor comes in as two vector loads; clamps are min / max; trunc(f), the
+            // float -> byte conversions and byte -> float run on the FMA pipe through the 2^23 trick instead of the quarter-rate
+            // conversion unit (exact for 0 <= f < 2^23: a round-toward-zero add of 2^23 leaves trunc(f) in the low mantissa bits);
+            // no per-pixel branch: rows / columns outside a partial tile are computed from clamped indices and not stored.
+            constexpr float MAGIC = 8388608.0f;
+            const int col = tid & (CM_OW - 1), rg = tid / CM_OW;
+            const bool col_ok = col < ncols;
+            const float2* hbase = reinterpret_cast<const float2*>(&s_hp[0][0]) + col;
+#pragma unroll
+            for (int it = 0; it < CM_OW * CM_OH / CM_THREADS; it++)
+            {
+                const int orow = rg + (CM_THREADS / CM_OW) * it;
+                const Contrib* kp = &sh_v[min(orow, nrows - 1)];
+                const uint4 ka = *reinterpret_cast<const uint4*>(kp);               // n0, cnt, c[0], c[1]
+                const float2 kb = *reinterpret_cast<const float2*>(&kp->c[2]);      // c[2], c[3]
+                const float c0 = __uint_as_float(ka.z), c1 = __uint_as_float(ka.w), c2 = kb.x, c3 = kb.y;
+                const float2* h = hbase + (static_cast<int>(ka.x) - sy0) * CM_OW;
+                const float2 t0 = h[0], t1 = h[CM_OW], t2 = h[2 * CM_OW], t3 = h[3 * CM_OW];
+                const float su = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(c0, t0.x), __fmul_rn(c1, t1.x)), __fmul_rn(c2, t2.x)), __fmul_rn(c3, t3.x));
+                const float sv = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(c0, t0.y), __fmul_rn(c1, t1.y)), __fmul_rn(c2, t2.y)), __fmul_rn(c3, t3.y));
+                // stb encode (x 255 + 0.5, clamp, truncate), then toFloat of the stored byte
+                const float fu = fminf(fmaxf(__fadd_rn(__fmul_rn(su, 255.0f), 0.5f), 0.0f), 255.0f);
+                const float fv = fminf(fmaxf(__fadd_rn(__fmul_rn(sv, 255.0f), 0.5f), 0.0f), 255.0f);
+                const float qu = unit_from_int<255>(__fsub_rn(__fadd_rz(fu, MAGIC), MAGIC));
+                const float qv = unit_from_int<255>(__fsub_rn(__fadd_rz(fv, MAGIC), MAGIC));
+                const float yv = unit_from_int<255>(__fsub_rn(__uint_as_float(0x4B000000u | ylum[it]), MAGIC));
+                const float u = __fsub_rn(qu, 0.5f), v = __fsub_rn(qv, 0.5f);
+                const float r = __fadd_rn(yv, __fmul_rn(1.403f, v));
+                const float gch = __fsub_rn(__fsub_rn(yv, __fmul_rn(0.344f, u)), __fmul_rn(0.714f, v));
+                const float b = __fadd_rn(yv, __fmul_rn(1.773f, u));
+                // quant_u8: sat01, x 255 + 0.5, truncate -- the byte is the low mantissa byte of the magic sum
+                const uint32_t rb = __float_as_uint(__fadd_rz(__fadd_rn(__fmul_rn(__saturatef(r), 255.0f), 0.5f), MAGIC));
+                const uint32_t gb = __float_as_uint(__fadd_rz(__fadd_rn(__fmul_rn(__saturatef(gch), 255.0f), 0.5f), MAGIC));
+                const uint32_t bb = __float_as_uint(__fadd_rz(__fadd_rn(__fmul_rn(__saturatef(b), 255.0f), 0.5f), MAGIC));
+                if (col_ok && orow < nrows)
+                {
+                    uint8_t* o = &s_out[orow][col * 3];
+                    o[0] = static_cast<uint8_t>(rb); o[1] = static_cast<uint8_t>(gb); o[2] = static_cast<uint8_t>(bb);
+                }
+            }
+        }
+        else
 #pragma unroll
         for (int it = 0; it < CM_OW * CM_OH / CM_THREADS; it++)
         {
