@@ -38,6 +38,10 @@ namespace
         SEG_ARNET_FIRST,    // <ARNET, head, 8, ->
         SEG_ARNET_MID,      // <ARNET, -, 8, ->
         SEG_ARNET_LAST,     // <ARNET, -, 6, tail>
+        SEG_LEGACY_A,       // <LEGACY, head, 3, ->
+        SEG_LEGACY_B,       // <LEGACY, -, 4, tail>
+        SEG_ACNET_B8_A,     // <ACNET, head, 4, ->
+        SEG_ACNET_B8_B,     // <ACNET, -, 4, tail>
     };
     using SegLegacyFull = Seg<ACB200_FAMILY_ACNET_LEGACY, true, 7, true>;
     using SegAcnetB4 = Seg<ACB200_FAMILY_ACNET, true, 4, true>;
@@ -47,6 +51,13 @@ namespace
     using SegArnetFirst = Seg<ACB200_FAMILY_ARNET, true, 8, false>;
     using SegArnetMid = Seg<ACB200_FAMILY_ARNET, false, 8, false>;
     using SegArnetLast = Seg<ACB200_FAMILY_ARNET, false, 6, true>;
+    using SegLegacyA = Seg<ACB200_FAMILY_ACNET_LEGACY, true, 3, false>;
+    using SegLegacyB = Seg<ACB200_FAMILY_ACNET_LEGACY, false, 4, true>;
+    using SegAcnetB8A = Seg<ACB200_FAMILY_ACNET, true, 4, false>;
+    using SegAcnetB8B = Seg<ACB200_FAMILY_ACNET, false, 4, true>;
+#ifndef ACB_SPLIT_CHAINS
+#define ACB_SPLIT_CHAINS 1
+#endif
 
     struct SegSpec
     {
@@ -99,10 +110,26 @@ namespace
     {
         m.chain.clear();
         if (m.family >= ACB200_FAMILY_ARTCNN) return;       // per-layer kernels (acb200_wide.cuh), no fused segments
-        if (m.family == ACB200_FAMILY_ACNET_LEGACY) m.chain.push_back({ SEG_LEGACY_FULL, 0, 0, 0 });
+        // A tile's halo grows by one pixel per 3x3 layer, so a fused segment recomputes (56 - 2l)^2 / T^2 of layer l per tile: 1.39x
+        // over the eight tensor-core layers of ACNetLegacy in ONE segment (T = 40), 1.15x when the network is cut in two (T = 50
+        // and 46) at the price of one [h][w][8] fp32 map through L2 / HBM.  ACB_SPLIT_CHAINS selects the two-segment chains.
+        if (m.family == ACB200_FAMILY_ACNET_LEGACY)
+        {
+            if (ACB_SPLIT_CHAINS)
+            {
+                m.chain.push_back({ SEG_LEGACY_A, 0, 0, 0 });
+                m.chain.push_back({ SEG_LEGACY_B, 72 + 576 * 3, 8 + 8 * 3, 0 });
+            }
+            else m.chain.push_back({ SEG_LEGACY_FULL, 0, 0, 0 });
+        }
         else if (m.family == ACB200_FAMILY_ACNET)
         {
             if (m.blocks == 4) m.chain.push_back({ SEG_ACNET_B4, 0, 0, 0 });
+            else if (m.blocks == 8 && ACB_SPLIT_CHAINS)
+            {
+                m.chain.push_back({ SEG_ACNET_B8_A, 0, 0, 0 });
+                m.chain.push_back({ SEG_ACNET_B8_B, 72 + 576 * 4, 8 + 8 * 4, 8 + 8 * 4 });
+            }
             else if (m.blocks == 8) m.chain.push_back({ SEG_ACNET_B8, 0, 0, 0 });
             else
             {
@@ -372,6 +399,10 @@ namespace
             case SEG_ARNET_FIRST: pack_segment<SegArnetFirst>(m, sp); break;
             case SEG_ARNET_MID: pack_segment<SegArnetMid>(m, sp); break;
             case SEG_ARNET_LAST: pack_segment<SegArnetLast>(m, sp); break;
+            case SEG_LEGACY_A: pack_segment<SegLegacyA>(m, sp); break;
+            case SEG_LEGACY_B: pack_segment<SegLegacyB>(m, sp); break;
+            case SEG_ACNET_B8_A: pack_segment<SegAcnetB8A>(m, sp); break;
+            case SEG_ACNET_B8_B: pack_segment<SegAcnetB8B>(m, sp); break;
             }
     }
     std::atomic<unsigned long long> g_model_uid{ 1 };
@@ -729,6 +760,10 @@ namespace
             case SEG_ARNET_FIRST: rc = launch_any<SegArnetFirst>(tensor, s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, nullptr, out, feat); break;
             case SEG_ARNET_MID: rc = launch_any<SegArnetMid>(tensor, s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, in, out, feat); break;
             case SEG_ARNET_LAST: rc = launch_any<SegArnetLast>(tensor, s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, in, nullptr, feat); break;
+            case SEG_LEGACY_A: rc = launch_any<SegLegacyA>(tensor, s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, nullptr, out, nullptr); break;
+            case SEG_LEGACY_B: rc = launch_any<SegLegacyB>(tensor, s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, in, nullptr, nullptr); break;
+            case SEG_ACNET_B8_A: rc = launch_any<SegAcnetB8A>(tensor, s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, nullptr, out, nullptr); break;
+            case SEG_ACNET_B8_B: rc = launch_any<SegAcnetB8B>(tensor, s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, in, nullptr, nullptr); break;
             }
             if (rc != ACB200_OK) return rc;
             cur ^= 1;

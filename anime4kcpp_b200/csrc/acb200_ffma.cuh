@@ -186,7 +186,8 @@ namespace acb
 #pragma unroll
         for (int iy = 0; iy < FFMA_P + 2; iy++)
         {
-            const int ry = clampi(y - 1 + iy, g.iy0, g.iy1) * FT;
+            // (rows past the region's last group of FFMA_P feed sums that are dropped: keep their reads inside the frame)
+            const int ry = clampi(y - 1 + iy, g.iy0, min(g.iy1, FT - 1)) * FT;
 #pragma unroll
             for (int dx = 0; dx < 3; dx++)
             {

@@ -412,7 +412,8 @@ namespace acb
                 uint32_t* pl = ph + PLANE_BYTES / 4;
                 if (res)
                 {
-                    const float2 id = join_pair(*ph, *pl);
+                    // (overhang lanes alias the last valid pixel, which its owner rewrites: they must not read it either)
+                    const float2 id = valid ? join_pair(*ph, *pl) : make_float2(0.0f, 0.0f);
                     v0 = fmaf(v0, 0.2f, id.x); v1 = fmaf(v1, 0.2f, id.y);
                 }
                 uint32_t hi, lo;

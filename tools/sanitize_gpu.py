@@ -13,7 +13,8 @@ import oracle_lib as O
 
 s = A.Session(0)
 O.set_order(O.ORDER_FMA)
-for name, shape, c in (("acnet-legacy-hdn0", (70, 90), 3), ("acnet-f8b8-hdn", (50, 64), 1), ("acnet-f8b18", (48, 48), 1), ("arnet-f8b8", (60, 44), 4)):
+# (150 x 150 has interior CTAs -- tiles whose 56 x 56 frame lies inside the image -- which take the unclamped tile loop)
+for name, shape, c in (("acnet-legacy-hdn0", (70, 90), 3), ("acnet-legacy-hdn0", (150, 150), 1), ("arnet-f8b8", (140, 150), 1), ("acnet-f8b8-hdn", (50, 64), 1), ("acnet-f8b18", (48, 48), 1), ("arnet-f8b8", (60, 44), 4)):
     img = O.noise_u8(shape[0], shape[1], c, seed=1)
     want = O.oracle_process(name, img, 2.0)
     m = A.Model(name)
