@@ -328,14 +328,25 @@ namespace acb
         }
         if constexpr (!S::HEAD)
         {
-            for (int i = threadIdx.x; i < FT * FT; i += MMA_THREADS)
+            // the previous segment's map: all of this thread's pixels (7 x 32 bytes) are requested before the first one is
+            // split and stored -- one exposed L2 / HBM latency per CTA instead of one per loop iteration
+            constexpr int PER = (FT * FT + MMA_THREADS - 1) / MMA_THREADS;
+            float4 v0[PER], v1[PER];
+#pragma unroll
+            for (int k = 0; k < PER; k++)
             {
+                const int i = min(threadIdx.x + k * MMA_THREADS, FT * FT - 1);
                 const int fx = i % FT, fy = i / FT;
                 const int gx = clampi(g.ox + fx, 0, prm.w - 1), gy = clampi(g.oy + fy, 0, prm.h - 1);
                 const float4* p = reinterpret_cast<const float4*>(prm.map_in + (static_cast<size_t>(gy) * prm.w + gx) * 8);
-                const float4 v0 = __ldg(p), v1 = __ldg(p + 1);
-                const float v[8] = { v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w };
-                store_pixel_split(A, i, v);
+                v0[k] = __ldg(p); v1[k] = __ldg(p + 1);
+            }
+#pragma unroll
+            for (int k = 0; k < PER; k++)
+            {
+                const int i = threadIdx.x + k * MMA_THREADS;
+                const float v[8] = { v0[k].x, v0[k].y, v0[k].z, v0[k].w, v1[k].x, v1[k].y, v1[k].z, v1[k].w };
+                if (i < FT * FT) store_pixel_split(A, i, v);
             }
         }
         __syncthreads();
