@@ -35,26 +35,33 @@ namespace
         SEG_ACNET_B8,       // <ACNET, head, 8, tail>
         SEG_ACNET_B18_A,    // <ACNET, head, 9, ->
         SEG_ACNET_B18_B,    // <ACNET, -, 9, tail>
-        SEG_ARNET_FIRST,    // <ARNET, head, 8, ->
-        SEG_ARNET_MID,      // <ARNET, -, 8, ->
-        SEG_ARNET_LAST,     // <ARNET, -, 6, tail>
+        SEG_ARNET_FIRST,    // <ARNET, head, ARNET_SEG, ->
+        SEG_ARNET_MID,      // <ARNET, -, ARNET_SEG, ->
+        SEG_ARNET_LAST,     // <ARNET, -, ARNET_SEG - 2, tail>
         SEG_LEGACY_A,       // <LEGACY, head, 3, ->
         SEG_LEGACY_B,       // <LEGACY, -, 4, tail>
         SEG_ACNET_B8_A,     // <ACNET, head, 4, ->
         SEG_ACNET_B8_B,     // <ACNET, -, 4, tail>
+        SEG_ACNET_MID5,     // <ACNET, -, 5, ->
     };
     using SegLegacyFull = Seg<ACB200_FAMILY_ACNET_LEGACY, true, 7, true>;
     using SegAcnetB4 = Seg<ACB200_FAMILY_ACNET, true, 4, true>;
     using SegAcnetB8 = Seg<ACB200_FAMILY_ACNET, true, 8, true>;
     using SegAcnetB18A = Seg<ACB200_FAMILY_ACNET, true, 9, false>;
     using SegAcnetB18B = Seg<ACB200_FAMILY_ACNET, false, 9, true>;
-    using SegArnetFirst = Seg<ACB200_FAMILY_ARNET, true, 8, false>;
-    using SegArnetMid = Seg<ACB200_FAMILY_ARNET, false, 8, false>;
-    using SegArnetLast = Seg<ACB200_FAMILY_ARNET, false, 6, true>;
+    // ARNet: ARNET_SEG body convs per segment (4: T = 48, halo recompute 1.13x; 8: T = 40, 1.39x and half the map traffic)
+#ifndef ACB_ARNET_SEG
+#define ACB_ARNET_SEG 4
+#endif
+    constexpr int ARNET_SEG = ACB_ARNET_SEG;
+    using SegArnetFirst = Seg<ACB200_FAMILY_ARNET, true, ARNET_SEG, false>;
+    using SegArnetMid = Seg<ACB200_FAMILY_ARNET, false, ARNET_SEG, false>;
+    using SegArnetLast = Seg<ACB200_FAMILY_ARNET, false, ARNET_SEG - 2, true>;
     using SegLegacyA = Seg<ACB200_FAMILY_ACNET_LEGACY, true, 3, false>;
     using SegLegacyB = Seg<ACB200_FAMILY_ACNET_LEGACY, false, 4, true>;
     using SegAcnetB8A = Seg<ACB200_FAMILY_ACNET, true, 4, false>;
     using SegAcnetB8B = Seg<ACB200_FAMILY_ACNET, false, 4, true>;
+    using SegAcnetMid5 = Seg<ACB200_FAMILY_ACNET, false, 5, false>;
 #ifndef ACB_SPLIT_CHAINS
 #define ACB_SPLIT_CHAINS 1
 #endif
@@ -131,6 +138,14 @@ namespace
                 m.chain.push_back({ SEG_ACNET_B8_B, 72 + 576 * 4, 8 + 8 * 4, 8 + 8 * 4 });
             }
             else if (m.blocks == 8) m.chain.push_back({ SEG_ACNET_B8, 0, 0, 0 });
+            else if (ACB_SPLIT_CHAINS)
+            {
+                // 18 body convs as head + 4 | 5 | 5 | 4 + tail (T = 48, 46, 46, 46) instead of head + 9 | 9 + tail (T = 38, 36)
+                m.chain.push_back({ SEG_ACNET_B8_A, 0, 0, 0 });
+                m.chain.push_back({ SEG_ACNET_MID5, 72 + 576 * 4, 8 + 8 * 4, 8 + 8 * 4 });
+                m.chain.push_back({ SEG_ACNET_MID5, 72 + 576 * 9, 8 + 8 * 9, 8 + 8 * 9 });
+                m.chain.push_back({ SEG_ACNET_B8_B, 72 + 576 * 14, 8 + 8 * 14, 8 + 8 * 14 });
+            }
             else
             {
                 m.chain.push_back({ SEG_ACNET_B18_A, 0, 0, 0 });
@@ -139,11 +154,12 @@ namespace
         }
         else
         {
-            // 2(B-1) body convs ahead of the last block: 8 with the head, 8 per middle segment, 6 in the tail segment
+            // 2(B-1) body convs ahead of the last block (B = 8, 16, 32, 64: always 2 short of a multiple of 8 and of 4):
+            // ARNET_SEG with the head, ARNET_SEG per middle segment, ARNET_SEG - 2 in the tail segment
             const int body = 2 * (m.blocks - 1);
             m.chain.push_back({ SEG_ARNET_FIRST, 0, 0, 0 });
-            int c0 = 8;
-            for (; c0 + 6 < body; c0 += 8) m.chain.push_back({ SEG_ARNET_MID, 72 + 576 * c0, 8 + 8 * c0, (c0 / 2) * 8 });
+            int c0 = ARNET_SEG;
+            for (; c0 + ARNET_SEG - 2 < body; c0 += ARNET_SEG) m.chain.push_back({ SEG_ARNET_MID, 72 + 576 * c0, 8 + 8 * c0, (c0 / 2) * 8 });
             m.chain.push_back({ SEG_ARNET_LAST, 72 + 576 * c0, 8 + 8 * c0, (c0 / 2) * 8 });
         }
     }
@@ -403,6 +419,7 @@ namespace
             case SEG_LEGACY_B: pack_segment<SegLegacyB>(m, sp); break;
             case SEG_ACNET_B8_A: pack_segment<SegAcnetB8A>(m, sp); break;
             case SEG_ACNET_B8_B: pack_segment<SegAcnetB8B>(m, sp); break;
+            case SEG_ACNET_MID5: pack_segment<SegAcnetMid5>(m, sp); break;
             }
     }
     std::atomic<unsigned long long> g_model_uid{ 1 };
@@ -764,6 +781,7 @@ namespace
             case SEG_LEGACY_B: rc = launch_any<SegLegacyB>(tensor, s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, in, nullptr, nullptr); break;
             case SEG_ACNET_B8_A: rc = launch_any<SegAcnetB8A>(tensor, s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, nullptr, out, nullptr); break;
             case SEG_ACNET_B8_B: rc = launch_any<SegAcnetB8B>(tensor, s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, in, nullptr, nullptr); break;
+            case SEG_ACNET_MID5: rc = launch_any<SegAcnetMid5>(tensor, s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, in, out, nullptr); break;
             }
             if (rc != ACB200_OK) return rc;
             cur ^= 1;
