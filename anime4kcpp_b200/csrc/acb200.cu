@@ -517,6 +517,35 @@ namespace
         return ACB200_OK;
     }
 
+    // TMA descriptor of an inter-segment map of the mma engine (layout in acb200_mma.cuh): 32-bit words, dims {4 w, h, 2 planes},
+    // box {4 * 56, 56, 2}, no swizzle, out-of-bounds coordinates read as zero.  cuTensorMapEncodeTiled comes from the driver
+    // through the runtime (no libcuda link dependency).
+    using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                       const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    int encode_map_tmap(acb200_session* s, CUtensorMap* tm, const void* map, int w, int h)
+    {
+        static std::atomic<EncodeTiledFn> cached{ nullptr };
+        EncodeTiledFn fn = cached.load(std::memory_order_acquire);
+        if (!fn)
+        {
+            void* p = nullptr;
+            cudaDriverEntryPointQueryResult qres = cudaDriverEntryPointSymbolNotFound;
+            const cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+            if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) return fail(s, ACB200_ECUDA, "cuTensorMapEncodeTiled is not available from the driver", e);
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+            cached.store(fn, std::memory_order_release);
+        }
+        // a row of a plane is contiguous over (x, channel): described as 32-bit words so that the 56-pixel box row is ONE 896-byte
+        // extent (224 words, the box limit is 256 elements) instead of 56 extents of 16 bytes
+        const cuuint64_t dims[3] = { static_cast<cuuint64_t>(w) * 4, static_cast<cuuint64_t>(h), 2 };
+        const cuuint64_t strides[2] = { static_cast<cuuint64_t>(w) * 16, static_cast<cuuint64_t>(w) * h * 16 };
+        const cuuint32_t box[3] = { FT * 4, FT, 2 }, estr[3] = { 1, 1, 1 };
+        const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void*>(map), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(s, ACB200_ECUDA, "cuTensorMapEncodeTiled failed");
+        return ACB200_OK;
+    }
+
     template<class S>
     int launch_segment_mma(acb200_session* s, cudaStream_t st, const acb200_model& m, const SegSpec& spec,
                            const void* src, int src_pitch, void* dst, int dst_pitch, int w, int h, int type,
@@ -532,6 +561,8 @@ namespace
         prm.tiles_x = (w + S::T - 1) / S::T;
         const int tiles_y = (h + S::T - 1) / S::T;
         prm.frags = dfrags + spec.frag_off;
+        std::memset(&prm.tmap, 0, sizeof(prm.tmap));
+        if (!S::HEAD && (rc = encode_map_tmap(s, &prm.tmap, map_in, w, h)) != ACB200_OK) return rc;
         std::memset(prm.k, 0, sizeof(prm.k));
         if (S::HEAD) std::memcpy(prm.k, m.k.data() + spec.koff, sizeof(float) * 72);
         if (S::TAIL && S::FAM == ACB200_FAMILY_ACNET_LEGACY)

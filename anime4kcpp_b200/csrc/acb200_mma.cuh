@@ -21,6 +21,7 @@
 // The 1->8 head conv (72 MAC / pixel) and the deconvolution / pixel-shuffle / 1x1 epilogues stay in fp32 FFMA.
 #pragma once
 
+#include <cuda.h>        // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked)
 #include <cuda_fp16.h>
 
 #include "acb200_common.cuh"
@@ -40,10 +41,17 @@ namespace acb
 #endif
     constexpr int MMA_CHAINS = ACB_MMA_CHAINS;
     constexpr int PLANE_BYTES = FT * FT * 16;   // distance between the hi and the lo plane of a map
+    constexpr size_t MMA_SMEM_DATA_BYTES = 4 * FT * FT * sizeof(uint4) + LT * LT * sizeof(float);
 
+    // Inter-segment maps of this engine are stored ALREADY SPLIT: two planes (hi, lo) of [h][w][8 x fp16] = 16 bytes per pixel and
+    // plane -- the shared-memory layout of the frame.  The next segment's 56 x 56 frame (both planes, 100 352 bytes) is then ONE TMA
+    // tensor copy: a 3-D box {56 x 16 bytes, 56 rows, 2 planes} at (ox, oy, 0) lands as [plane][y][x][8] = {A.hi, A.lo}; coordinates outside
+    // the image are zero-filled by the TMA unit, and border CTAs never read them (replicate padding clamps READ coordinates).
+    constexpr uint32_t MAP_BOX_BYTES = 2u * FT * FT * 16u;
     template<class S>
     struct MmaParams
     {
+        alignas(64) CUtensorMap tmap;   // the previous segment's map (!HEAD segments), see above
         const void* src;
         const float* map_in;
         float* map_out;
@@ -280,10 +288,11 @@ namespace acb
     template<class S>
     __global__ void __launch_bounds__(MMA_THREADS, 1) segment_mma_kernel(const __grid_constant__ MmaParams<S> prm)
     {
-        extern __shared__ __align__(16) unsigned char smem_raw[];
-        uint4* base = reinterpret_cast<uint4*>(smem_raw);
+        extern __shared__ __align__(128) unsigned char smem_mma[];
+        uint4* base = reinterpret_cast<uint4*>(smem_mma);
         HalfPlanes A{ base, base + FT * FT }, B{ base + 2 * FT * FT, base + 3 * FT * FT };
         float* luma = reinterpret_cast<float*>(base + 4 * FT * FT);
+        const uint32_t tma_bar = static_cast<uint32_t>(__cvta_generic_to_shared(smem_mma + MMA_SMEM_DATA_BYTES));   // mbarrier of the map copy
 
         const int tx = blockIdx.x % prm.tiles_x, ty = blockIdx.x / prm.tiles_x;
         TileGeom g;
@@ -292,6 +301,20 @@ namespace acb
         g.ix0 = -g.ox; g.ix1 = prm.w - 1 - g.ox;
         g.iy0 = -g.oy; g.iy1 = prm.h - 1 - g.oy;
         const int lane = threadIdx.x & 31, tq = lane & 3;
+        if constexpr (!S::HEAD)
+        {
+            // one thread starts the tensor copy of the whole frame; everybody waits for it after the barrier below
+            if (threadIdx.x == 0)
+            {
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(tma_bar));
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(tma_bar), "r"(MAP_BOX_BYTES) : "memory");
+                asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                             :: "r"(static_cast<uint32_t>(__cvta_generic_to_shared(A.hi))), "l"(reinterpret_cast<uint64_t>(&prm.tmap)),
+                                "r"(4 * g.ox), "r"(g.oy), "r"(0), "r"(tma_bar) : "memory");
+            }
+        }
         uint32_t bf[18], nb[18];        // B fragments of the current / the next 3x3 layer
         mma_load_bfrag(bf, prm.frags);  // consumed after the input load (and the head): the latency is hidden
 
@@ -326,30 +349,13 @@ namespace acb
                     luma[i] = load_elem(static_cast<const uint8_t*>(prm.src) + static_cast<size_t>(gy) * prm.src_pitch, gx, prm.type);
                 }
         }
+        __syncthreads();
         if constexpr (!S::HEAD)
         {
-            // the previous segment's map: all of this thread's pixels (7 x 32 bytes) are requested before the first one is
-            // split and stored -- one exposed L2 / HBM latency per CTA instead of one per loop iteration
-            constexpr int PER = (FT * FT + MMA_THREADS - 1) / MMA_THREADS;
-            float4 v0[PER], v1[PER];
-#pragma unroll
-            for (int k = 0; k < PER; k++)
-            {
-                const int i = min(threadIdx.x + k * MMA_THREADS, FT * FT - 1);
-                const int fx = i % FT, fy = i / FT;
-                const int gx = clampi(g.ox + fx, 0, prm.w - 1), gy = clampi(g.oy + fy, 0, prm.h - 1);
-                const float4* p = reinterpret_cast<const float4*>(prm.map_in + (static_cast<size_t>(gy) * prm.w + gx) * 8);
-                v0[k] = __ldg(p); v1[k] = __ldg(p + 1);
-            }
-#pragma unroll
-            for (int k = 0; k < PER; k++)
-            {
-                const int i = threadIdx.x + k * MMA_THREADS;
-                const float v[8] = { v0[k].x, v0[k].y, v0[k].z, v0[k].w, v1[k].x, v1[k].y, v1[k].z, v1[k].w };
-                if (i < FT * FT) store_pixel_split(A, i, v);
-            }
+            uint32_t done = 0;
+            while (!done)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(tma_bar), "r"(0) : "memory");
         }
-        __syncthreads();
         if constexpr (S::HEAD)
         {
             // 1 -> 8 head conv in fp32 (Common.hpp:166-197), one pixel per thread
@@ -449,14 +455,15 @@ namespace acb
         {
             const int xa = max(S::R, g.ix0), xb = min(FT - S::R, g.ix1 + 1), ya = max(S::R, g.iy0), yb = min(FT - S::R, g.iy1 + 1);
             const int ncols = xb - xa, n = ncols * (yb - ya);
+            // the map leaves as it lies in shared memory: (hi, lo) fp16 planes, 16 bytes per pixel and plane
+            uint4* const mo = reinterpret_cast<uint4*>(prm.map_out);
+            const size_t plane = static_cast<size_t>(prm.w) * prm.h;
             for (int i = threadIdx.x; i < n; i += MMA_THREADS)
             {
-                const int x = xa + i % ncols, y = ya + i / ncols;
-                float v[8];
-                load_pixel_joined(cur, y * FT + x, v);
-                float4* p = reinterpret_cast<float4*>(prm.map_out + (static_cast<size_t>(g.oy + y) * prm.w + (g.ox + x)) * 8);
-                p[0] = make_float4(v[0], v[1], v[2], v[3]);
-                p[1] = make_float4(v[4], v[5], v[6], v[7]);
+                const int x = xa + i % ncols, y = ya + i / ncols, o = y * FT + x;
+                const size_t go = static_cast<size_t>(g.oy + y) * prm.w + (g.ox + x);
+                mo[go] = cur.hi[o];
+                mo[plane + go] = cur.lo[o];
             }
         }
         else if constexpr (S::FAM == ACB200_FAMILY_ACNET_LEGACY)
@@ -472,7 +479,12 @@ namespace acb
             constexpr int OT = 2 * S::T, OPITCH = ((OT + 15) / 16) * 16;
             static_assert(OPITCH * OT <= LT * LT * 4, "output staging does not fit the luma tile");
             uint8_t* s_out = reinterpret_cast<uint8_t*>(luma);
-            const bool staged = prm.type == ACB200_UINT8 && S::HEAD;
+#ifndef ACB_STAGE_HEADLESS_TAIL
+#define ACB_STAGE_HEADLESS_TAIL 0
+#endif
+            // (this family's tail never reads the luma tile, so the space is free with or without a head -- but measured on the
+            // head-less second segment of the two-segment chain the direct byte stores are 2.5 % faster than staging)
+            const bool staged = prm.type == ACB200_UINT8 && (S::HEAD || ACB_STAGE_HEADLESS_TAIL);
             auto epi = [&](const int off, float v0, float v1, const bool valid) {
                 const int py = off / FT, px = off - py * FT;
                 v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f);
@@ -616,5 +628,5 @@ namespace acb
         }
     }
 
-    constexpr size_t MMA_SMEM_BYTES = 4 * FT * FT * sizeof(uint4) + LT * LT * sizeof(float);
+    constexpr size_t MMA_SMEM_BYTES = MMA_SMEM_DATA_BYTES + 16;     // + the mbarrier of the map copy
 }
