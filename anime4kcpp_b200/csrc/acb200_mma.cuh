@@ -469,11 +469,18 @@ namespace acb
         else if constexpr (S::FAM == ACB200_FAMILY_ACNET_LEGACY)
         {
             // conv3x3 + ReLU on the tensor cores, then the 2x2 deconv: each quad of lanes holds the 8 channels of a pixel
-            // (2 per lane) -- partial dots per lane, butterfly over the quad, lane t writes output sub-pixel t
+            // (2 per lane) -- four partial dots per lane (one per output sub-pixel), reduce-scattered over the quad in three shuffles:
+            // lane t ends with sub-pixel t.  The sub-pixels' weights are held in the order {t, t^2, t^1, t^3} so that a lane always
+            // keeps its first two slots and sends the other two (no selects): after the exchange with lane t^1 slots 0 / 1 hold the
+            // pair sums of sub-pixels t and t^2, the exchange with lane t^2 completes sub-pixel t.
             const float b0 = prm.b[BT + 2 * tq], b1 = prm.b[BT + 2 * tq + 1];
             float kd[4][2];
 #pragma unroll
-            for (int q = 0; q < 4; q++) { kd[q][0] = prm.k[(S::HEAD ? 72 : 0) + q * 8 + 2 * tq]; kd[q][1] = prm.k[(S::HEAD ? 72 : 0) + q * 8 + 2 * tq + 1]; }
+            for (int j = 0; j < 4; j++)
+            {
+                const int q = tq ^ (j == 1 ? 2 : j == 2 ? 1 : j == 3 ? 3 : 0);
+                kd[j][0] = prm.k[(S::HEAD ? 72 : 0) + q * 8 + 2 * tq]; kd[j][1] = prm.k[(S::HEAD ? 72 : 0) + q * 8 + 2 * tq + 1];
+            }
             // 8-bit output: the 2T x 2T result tile is staged in shared memory (the luma tile is dead after the head) and leaves
             // as 16-byte vectors; other element types are stored directly
             constexpr int OT = 2 * S::T, OPITCH = ((OT + 15) / 16) * 16;
@@ -490,14 +497,10 @@ namespace acb
                 v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f);
                 float o[4];
 #pragma unroll
-                for (int q = 0; q < 4; q++)
-                {
-                    float s = fmaf(v1, kd[q][1], v0 * kd[q][0]);
-                    s += __shfl_xor_sync(0xffffffffu, s, 1);
-                    s += __shfl_xor_sync(0xffffffffu, s, 2);
-                    o[q] = s;
-                }
-                const float mine = tq == 0 ? o[0] : tq == 1 ? o[1] : tq == 2 ? o[2] : o[3];
+                for (int j = 0; j < 4; j++) o[j] = fmaf(v1, kd[j][1], v0 * kd[j][0]);
+                o[0] += __shfl_xor_sync(0xffffffffu, o[2], 1);
+                o[1] += __shfl_xor_sync(0xffffffffu, o[3], 1);
+                const float mine = o[0] + __shfl_xor_sync(0xffffffffu, o[1], 2);
                 if (valid)
                 {
                     if (staged)
