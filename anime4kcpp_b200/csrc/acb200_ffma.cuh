@@ -91,6 +91,21 @@ namespace acb
         float a[S::NA > 0 ? S::NA : 1];
     };
 
+    // i / d and i % d for the pixel loops over a tile region (0 <= i < 3300, 1 <= d <= 56): one multiply and a shift instead of the
+    // ~35-instruction integer division sequence.  rcp = floor(2^20 / d) + 1 over-estimates 2^20 / d by less than 1, so the
+    // quotient estimate is high by less than i / 2^20 < 0.0032 < 1 / 56 <= 1 - frac(i / d): the floor is exact.
+    struct RegionDiv
+    {
+        uint32_t rcp;
+        int d;
+        __device__ __forceinline__ explicit RegionDiv(int d_) : rcp((1u << 20) / static_cast<uint32_t>(max(d_, 1)) + 1u), d(d_) {}
+        __device__ __forceinline__ void split(int i, int& quo, int& rem) const
+        {
+            quo = static_cast<int>((static_cast<uint32_t>(i) * rcp) >> 20);
+            rem = i - quo * d;
+        }
+    };
+
     struct TileGeom
     {
         int ox, oy;             // image coordinates of frame position (0,0)
@@ -148,9 +163,12 @@ namespace acb
     {
         const int xa = max(0, g.ix0), xb = min(FT, g.ix1 + 1), ya = max(0, g.iy0), yb = min(FT, g.iy1 + 1);
         const int ncols = xb - xa, n = ncols * (yb - ya);
+        const RegionDiv rd(ncols);
         for (int i = threadIdx.x; i < n; i += FFMA_THREADS)
         {
-            const int x = xa + i % ncols, y = ya + i / ncols;
+            int qy, qx;
+            rd.split(i, qy, qx);
+            const int x = xa + qx, y = ya + qy;
             float r[9];
 #pragma unroll
             for (int dy = 0; dy < 3; dy++)
@@ -228,10 +246,13 @@ namespace acb
     {
         const int xa = max(L, g.ix0), xb = min(FT - L, g.ix1 + 1), ya = max(L, g.iy0), yb = min(FT - L, g.iy1 + 1);
         const int ncols = xb - xa, n = ncols * ((yb - ya + FFMA_P - 1) / FFMA_P);
+        const RegionDiv rdiv(ncols);
         float* __restrict__ outf = reinterpret_cast<float*>(out);
         for (int i = threadIdx.x; i < n; i += FFMA_THREADS)
         {
-            const int x = xa + i % ncols, y = ya + FFMA_P * (i / ncols);
+            int qy, qx;
+            rdiv.split(i, qy, qx);
+            const int x = xa + qx, y = ya + FFMA_P * qy;
             conv_cols_rolled<COUT, KOFF, BOFF>(prm, in, g, x, y, [&](const int co, const float (&v)[FFMA_P]) {
                 // channel co lives in plane co/4, component co%4 of the float4 at the pixel
                 float* dst = outf + ((co >> 2) * FT * FT + y * FT + x) * 4 + (co & 3);
@@ -258,9 +279,12 @@ namespace acb
     {
         const int xa = max(L, g.ix0), xb = min(FT - L, g.ix1 + 1), ya = max(L, g.iy0), yb = min(FT - L, g.iy1 + 1);
         const int ncols = xb - xa, n = ncols * (yb - ya);
+        const RegionDiv rdiv(ncols);
         for (int i = threadIdx.x; i < n; i += FFMA_THREADS)
         {
-            const int x = xa + i % ncols, y = ya + i / ncols, o = y * FT + x;
+            int qy, qx;
+            rdiv.split(i, qy, qx);
+            const int x = xa + qx, y = ya + qy, o = y * FT + x;
             const float4 t0 = buf[o], t1 = buf[FT * FT + o];
             const float t[8] = { t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w };
             const float* f = prm.feat_in + (static_cast<size_t>(g.oy + y) * prm.w + (g.ox + x)) * 8;
@@ -287,11 +311,14 @@ namespace acb
     {
         const int xa = max(L, g.ix0), xb = min(FT - L, g.ix1 + 1), ya = max(L, g.iy0), yb = min(FT - L, g.iy1 + 1);
         const int ncols = xb - xa, n = ncols * (yb - ya);
+        const RegionDiv rdiv(ncols);
         const int es = prm.type & 0xff;
         const bool aligned = ((reinterpret_cast<uintptr_t>(prm.dst) | static_cast<uintptr_t>(prm.dst_pitch)) & (2 * es - 1)) == 0;
         for (int i = threadIdx.x; i < n; i += FFMA_THREADS)
         {
-            const int x = xa + i % ncols, y = ya + i / ncols, o = y * FT + x;
+            int qy, qx;
+            rdiv.split(i, qy, qx);
+            const int x = xa + qx, y = ya + qy, o = y * FT + x;
             const float4 t0 = in[o], t1 = in[FT * FT + o];
             const float t[8] = { t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w };
             const int gx = g.ox + x, gy = g.oy + y;
@@ -319,11 +346,14 @@ namespace acb
     {
         const int xa = max(L, g.ix0), xb = min(FT - L, g.ix1 + 1), ya = max(L, g.iy0), yb = min(FT - L, g.iy1 + 1);
         const int ncols = xb - xa, n = ncols * (yb - ya);
+        const RegionDiv rdiv(ncols);
         const int es = prm.type & 0xff;
         const bool aligned = ((reinterpret_cast<uintptr_t>(prm.dst) | static_cast<uintptr_t>(prm.dst_pitch)) & (2 * es - 1)) == 0;
         for (int i = threadIdx.x; i < n; i += FFMA_THREADS)
         {
-            const int x = xa + i % ncols, y = ya + i / ncols;
+            int qy, qx;
+            rdiv.split(i, qy, qx);
+            const int x = xa + qx, y = ya + qy;
             const float4 v = in[y * FT + x];
             const float id = luma[(y + 1) * LT + x + 1];
             const int gx = g.ox + x, gy = g.oy + y;
@@ -402,9 +432,12 @@ namespace acb
                 // keep the head output (`feat`) for the tail segment: centre T x T of this tile
                 const int xa = max(S::R, g.ix0), xb = min(FT - S::R, g.ix1 + 1), ya = max(S::R, g.iy0), yb = min(FT - S::R, g.iy1 + 1);
                 const int ncols = xb - xa, n = ncols * (yb - ya);
+                const RegionDiv rdiv(ncols);
                 for (int i = threadIdx.x; i < n; i += FFMA_THREADS)
                 {
-                    const int x = xa + i % ncols, y = ya + i / ncols;
+                    int qy, qx;
+                    rdiv.split(i, qy, qx);
+                    const int x = xa + qx, y = ya + qy;
                     float4* p = reinterpret_cast<float4*>(prm.feat_out + (static_cast<size_t>(g.oy + y) * prm.w + (g.ox + x)) * 8);
                     p[0] = bufA[y * FT + x];
                     p[1] = bufA[FT * FT + y * FT + x];
@@ -420,9 +453,12 @@ namespace acb
         {
             const int xa = max(S::R, g.ix0), xb = min(FT - S::R, g.ix1 + 1), ya = max(S::R, g.iy0), yb = min(FT - S::R, g.iy1 + 1);
             const int ncols = xb - xa, n = ncols * (yb - ya);
+            const RegionDiv rdiv(ncols);
             for (int i = threadIdx.x; i < n; i += FFMA_THREADS)
             {
-                const int x = xa + i % ncols, y = ya + i / ncols;
+                int qy, qx;
+                rdiv.split(i, qy, qx);
+                const int x = xa + qx, y = ya + qy;
                 float4* p = reinterpret_cast<float4*>(prm.map_out + (static_cast<size_t>(g.oy + y) * prm.w + (g.ox + x)) * 8);
                 p[0] = cur[y * FT + x];
                 p[1] = cur[FT * FT + y * FT + x];

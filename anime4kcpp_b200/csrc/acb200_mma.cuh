@@ -362,9 +362,12 @@ namespace acb
             constexpr int ACT = S::FAM == ACB200_FAMILY_ACNET_LEGACY ? ACT_RELU : S::FAM == ACB200_FAMILY_ACNET ? ACT_PRELU : ACT_IDENTITY;
             const int xa = max(0, g.ix0), xb = min(FT, g.ix1 + 1), ya = max(0, g.iy0), yb = min(FT, g.iy1 + 1);
             const int ncols = xb - xa, n = ncols * (yb - ya);
+            const RegionDiv rd(ncols);
             for (int i = threadIdx.x; i < n; i += MMA_THREADS)
             {
-                const int x = xa + i % ncols, y = ya + i / ncols;
+                int qy, qx;
+                rd.split(i, qy, qx);
+                const int x = xa + qx, y = ya + qy;
                 float r[9];
 #pragma unroll
                 for (int dy = 0; dy < 3; dy++)
@@ -458,9 +461,12 @@ namespace acb
             // the map leaves as it lies in shared memory: (hi, lo) fp16 planes, 16 bytes per pixel and plane
             uint4* const mo = reinterpret_cast<uint4*>(prm.map_out);
             const size_t plane = static_cast<size_t>(prm.w) * prm.h;
+            const RegionDiv rd(ncols);
             for (int i = threadIdx.x; i < n; i += MMA_THREADS)
             {
-                const int x = xa + i % ncols, y = ya + i / ncols, o = y * FT + x;
+                int qy, qx;
+                rd.split(i, qy, qx);
+                const int x = xa + qx, y = ya + qy, o = y * FT + x;
                 const size_t go = static_cast<size_t>(g.oy + y) * prm.w + (g.ox + x);
                 mo[go] = cur.hi[o];
                 mo[plane + go] = cur.lo[o];
