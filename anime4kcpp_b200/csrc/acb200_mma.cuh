@@ -518,7 +518,26 @@ namespace acb
                     }
                 }
             };
-            mma_conv3x3(S::NCONV + 1, cur, bf, g, b0, b1, epi);
+            if (prm.type == ACB200_UINT8 && !staged)
+            {
+                // direct 8-bit stores, written for instruction count: no element-type dispatch per pixel, one 64-bit base per lane
+                // and 32-bit offsets, saturate / FMA / convert
+                uint8_t* const dq = static_cast<uint8_t*>(prm.dst) + static_cast<long long>(2 * g.oy + (tq >> 1)) * prm.dst_pitch + (2 * g.ox + (tq & 1));
+                const int pitch2 = 2 * prm.dst_pitch;
+                auto epi8 = [&](const int off, float v0, float v1, const bool valid) {
+                    const int py = off / FT, px = off - py * FT;
+                    v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f);
+                    float o[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) o[j] = fmaf(v1, kd[j][1], v0 * kd[j][0]);
+                    o[0] += __shfl_xor_sync(0xffffffffu, o[2], 1);
+                    o[1] += __shfl_xor_sync(0xffffffffu, o[3], 1);
+                    const float mine = o[0] + __shfl_xor_sync(0xffffffffu, o[1], 2);
+                    if (valid) dq[py * pitch2 + 2 * px] = static_cast<uint8_t>(fmaf(__saturatef(mine), 255.0f, 0.5f));
+                };
+                mma_conv3x3(S::NCONV + 1, cur, bf, g, b0, b1, epi8);
+            }
+            else mma_conv3x3(S::NCONV + 1, cur, bf, g, b0, b1, epi);
             if (staged)
             {
                 __syncthreads();
