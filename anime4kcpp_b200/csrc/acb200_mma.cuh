@@ -652,7 +652,24 @@ namespace acb
                 }
             };
             (void)LPS;
-            mma_conv3x3(LT_PS, cur, bf, g, b0, b1, epi);
+            if (prm.type == ACB200_UINT8 && aligned)
+            {
+                // 8-bit fast path: no element-type dispatch per pixel, one base pointer per lane and 32-bit offsets
+                uint8_t* const dq = static_cast<uint8_t*>(prm.dst) + static_cast<long long>(2 * g.oy + tq) * prm.dst_pitch + 2 * g.ox;
+                const int pitch2 = 2 * prm.dst_pitch;
+                auto epi8 = [&](const int off, float v0, float v1, const bool valid) {
+                    if (tq < 2 && valid)
+                    {
+                        const int py = off / FT, px = off - py * FT;
+                        const float id = luma[(py + 1) * LT + px + 1];
+                        const uint8_t q0 = static_cast<uint8_t>(__fadd_rn(__fmul_rn(__saturatef(v0 + id), 255.0f), 0.5f));
+                        const uint8_t q1 = static_cast<uint8_t>(__fadd_rn(__fmul_rn(__saturatef(v1 + id), 255.0f), 0.5f));
+                        *reinterpret_cast<uchar2*>(dq + py * pitch2 + 2 * px) = make_uchar2(q0, q1);
+                    }
+                };
+                mma_conv3x3(LT_PS, cur, bf, g, b0, b1, epi8);
+            }
+            else mma_conv3x3(LT_PS, cur, bf, g, b0, b1, epi);
         }
     }
 
