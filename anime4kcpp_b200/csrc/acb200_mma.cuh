@@ -189,6 +189,23 @@ namespace acb
         // NT M-tiles of 16 pixels are in flight per warp (their ldmatrix / MMA sequences interleave).  NT = 1 is what ships:
         // measured with NT = 2 (-DACB_MMA_TILES=2) ACNet-B8 gains 3 % but ACNetLegacy and ARNet lose 3-4 % (coarser work units
         // balance worse over the 16 warps than the extra instruction-level parallelism buys).
+        // Interior CTAs with one tile in flight walk their pixel INCREMENTALLY: a warp's next tile lies 16 * MMA_WARPS region
+        // pixels ahead, i.e. `dq` region rows and `rq` columns further (one conditional wrap), so the frame offset moves by a
+        // constant plus a conditional constant -- five instructions instead of the multiply / shift / multiply-subtract / multiply-
+        // add of the direct mapping.  Lanes past the region's last pixel (last tile only) are not clamped: they read at most one
+        // row and one pixel below the region, which is inside the kernel's shared memory, and their results are dropped.
+        constexpr bool WALK = !BORDER && NT == 1;
+        int wqx = 0, woff = 0, step_off = 0, rq = 0;
+        if (WALK)
+        {
+            const int q = warp * 16 + arow;
+            const int qy = static_cast<int>((static_cast<uint32_t>(q) * rcp) >> 20);
+            wqx = q - qy * wr;
+            woff = (ya + qy) * FT + xa + wqx;
+            const int dq = static_cast<int>((static_cast<uint32_t>(16 * MMA_WARPS) * rcp) >> 20);
+            rq = 16 * MMA_WARPS - dq * wr;
+            step_off = dq * FT + rq;
+        }
         for (int it0 = warp * NT; it0 < tiles; it0 += MMA_WARPS * NT)
         {
             int px[NT], py[NT], poff[NT];
@@ -197,10 +214,20 @@ namespace acb
 #pragma unroll
             for (int t = 0; t < NT; t++)
             {
-                const int q = min((it0 + t) * 16 + arow, npix - 1);
-                const int qy = static_cast<int>((static_cast<uint32_t>(q) * rcp) >> 20), qx = q - qy * wr;
-                px[t] = xa + qx; py[t] = ya + qy;
-                poff[t] = py[t] * FT + px[t];
+                if (WALK)
+                {
+                    poff[t] = woff;
+                    px[t] = py[t] = 0;      // (only the clamped border path needs them)
+                    wqx += rq; woff += step_off;
+                    if (wqx >= wr) { wqx -= wr; woff += FT - wr; }
+                }
+                else
+                {
+                    const int q = min((it0 + t) * 16 + arow, npix - 1);
+                    const int qy = static_cast<int>((static_cast<uint32_t>(q) * rcp) >> 20), qx = q - qy * wr;
+                    px[t] = xa + qx; py[t] = ya + qy;
+                    poff[t] = py[t] * FT + px[t];
+                }
 #pragma unroll
                 for (int e = 0; e < 4; e++) c1[t][e] = c2[t][e] = 0.0f;
                 c0[t][0] = c0[t][2] = bias0; c0[t][1] = c0[t][3] = bias1;      // the bias rides in as the first chain's C operand
