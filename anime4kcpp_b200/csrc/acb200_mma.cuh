@@ -24,6 +24,8 @@
 #include <cuda.h>        // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked)
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "acb200_common.cuh"
 #include "acb200_ffma.cuh"
 
@@ -430,9 +432,11 @@ namespace acb
         constexpr int A0 = (S::FAM == ACB200_FAMILY_ACNET && S::HEAD) ? 8 : 0;
         HalfPlanes cur = A, oth = B;
         // ---- body convs -------------------------------------------------------------------------------------------------
-#pragma unroll 1
-        for (int i = 0; i < S::NCONV; i++)
-        {
+        // A segment without a tail hands its last body conv's results to the next segment: that layer's epilogue stores them
+        // straight into the global map (already split, see MmaParams) instead of into shared memory, which spreads the 80 KB per
+        // CTA over the layer instead of a store burst at the end of every wave, and saves a pass over the tile.
+        auto body_layer = [&](const int i, auto to_map_tag) {
+            constexpr bool TO_MAP = decltype(to_map_tag)::value;
             const bool more = i + 1 < S::NCONV || S::TAIL;      // a further 3x3 layer follows in this segment
             if (more) mma_load_bfrag(nb, prm.frags + (i + 1) * FRAG_WORDS_3X3);
             const float b0 = prm.b[B0 + 8 * i + 2 * tq], b1 = prm.b[B0 + 8 * i + 2 * tq + 1];
@@ -450,6 +454,9 @@ namespace acb
                 else { act = ACT_IDENTITY; res = true; }
             }
             uint32_t* const out_q = reinterpret_cast<uint32_t*>(oth.hi) + tq;      // this lane's channel pair of pixel 0, hi plane
+            // TO_MAP: this lane's channel pair of image pixel (g.ox, g.oy) in the hi plane of the global map (32-bit words)
+            uint32_t* const map_q = reinterpret_cast<uint32_t*>(prm.map_out) + (static_cast<long long>(g.oy) * prm.w + g.ox) * 4 + tq;
+            const size_t map_plane_words = static_cast<size_t>(prm.w) * prm.h * 4;
             auto epi = [&](const int off, float v0, float v1, const bool valid) {
                 // no early exit for the overhang lanes: straight-line code with predicated stores (one address, the lo plane
                 // is a constant distance away)
@@ -465,17 +472,30 @@ namespace acb
                 }
                 uint32_t hi, lo;
                 split_pair(v0, v1, hi, lo);
-                if (valid) { *ph = hi; *pl = lo; }
+                if constexpr (TO_MAP)
+                {
+                    const int py = off / FT, px = off - py * FT;
+                    uint32_t* gp = map_q + (static_cast<long long>(py) * prm.w + px) * 4;
+                    if (valid) { gp[0] = hi; gp[map_plane_words] = lo; }
+                }
+                else if (valid) { *ph = hi; *pl = lo; }
             };
             mma_conv3x3(i + 1, cur, bf, g, b0, b1, epi);
-            __syncthreads();
-            if (more)
+            if constexpr (!TO_MAP)
             {
+                __syncthreads();
+                if (more)
+                {
 #pragma unroll
-                for (int e = 0; e < 18; e++) bf[e] = nb[e];
+                    for (int e = 0; e < 18; e++) bf[e] = nb[e];
+                }
+                const HalfPlanes t = cur; cur = oth; oth = t;
             }
-            const HalfPlanes t = cur; cur = oth; oth = t;
-        }
+        };
+        constexpr int NLOOP = S::TAIL ? S::NCONV : S::NCONV - 1;
+#pragma unroll 1
+        for (int i = 0; i < NLOOP; i++) body_layer(i, std::false_type{});
+        if constexpr (!S::TAIL) body_layer(S::NCONV - 1, std::true_type{});
 
         const uint32_t* tfrag = prm.frags + S::NCONV * FRAG_WORDS_3X3;
         constexpr int BT = B0 + 8 * S::NCONV;
@@ -483,21 +503,7 @@ namespace acb
         const bool aligned = ((reinterpret_cast<uintptr_t>(prm.dst) | static_cast<uintptr_t>(prm.dst_pitch)) & (2 * es - 1)) == 0;
         if constexpr (!S::TAIL)
         {
-            const int xa = max(S::R, g.ix0), xb = min(FT - S::R, g.ix1 + 1), ya = max(S::R, g.iy0), yb = min(FT - S::R, g.iy1 + 1);
-            const int ncols = xb - xa, n = ncols * (yb - ya);
-            // the map leaves as it lies in shared memory: (hi, lo) fp16 planes, 16 bytes per pixel and plane
-            uint4* const mo = reinterpret_cast<uint4*>(prm.map_out);
-            const size_t plane = static_cast<size_t>(prm.w) * prm.h;
-            const RegionDiv rd(ncols);
-            for (int i = threadIdx.x; i < n; i += MMA_THREADS)
-            {
-                int qy, qx;
-                rd.split(i, qy, qx);
-                const int x = xa + qx, y = ya + qy, o = y * FT + x;
-                const size_t go = static_cast<size_t>(g.oy + y) * prm.w + (g.ox + x);
-                mo[go] = cur.hi[o];
-                mo[plane + go] = cur.lo[o];
-            }
+            // (the map went out with the last body conv's epilogue)
         }
         else if constexpr (S::FAM == ACB200_FAMILY_ACNET_LEGACY)
         {
