@@ -891,7 +891,11 @@ namespace
             const size_t yp = pitch_of(w, 1, es), uvp = pitch_of(w, c - 1, es);
             if ((rc = ensure(s, s->y[0], yp * h)) != ACB200_OK) return rc;
             if ((rc = ensure(s, s->uv, uvp * h)) != ACB200_OK) return rc;
-            rgb2yuv_kernel<<<dim3((w + 31) / 32, (h + 7) / 8), blk, 0, st>>>(d_src, src_pitch, w, h, c, type, s->y[0].p, static_cast<int>(yp), 1, s->uv.p, static_cast<int>(uvp), c - 1);
+            if (type == ACB200_UINT8 && c == 3 && ((reinterpret_cast<uintptr_t>(d_src) | static_cast<uintptr_t>(src_pitch)) & 3) == 0)
+                rgb2yuv_u8x4_kernel<<<dim3((w + 127) / 128, (h + 7) / 8), blk, 0, st>>>(static_cast<const uint8_t*>(d_src), src_pitch, w, h,
+                    static_cast<uint8_t*>(s->y[0].p), static_cast<int>(yp), static_cast<uint8_t*>(s->uv.p), static_cast<int>(uvp));
+            else
+                rgb2yuv_kernel<<<dim3((w + 31) / 32, (h + 7) / 8), blk, 0, st>>>(d_src, src_pitch, w, h, c, type, s->y[0].p, static_cast<int>(yp), 1, s->uv.p, static_cast<int>(uvp), c - 1);
             g_launches.fetch_add(1, std::memory_order_relaxed);
             ACB_CUDA(s, cudaGetLastError());
             cur = s->y[0].p; cur_pitch = static_cast<int>(yp);

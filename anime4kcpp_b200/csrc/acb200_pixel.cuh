@@ -53,6 +53,44 @@ namespace acb
         if (c == 4) store_elem(uvo, x * uvstep + 2, type, a);
     }
 
+    // 8-bit RGB -> quantised Y plane + interleaved (u, v) plane, four pixels per thread: three 32-bit loads, one 32-bit and one
+    // 64-bit store.  Same arithmetic as rgb2yuv_kernel value for value.  Requires 4-byte aligned rows (pointers and pitches).
+    __global__ void __launch_bounds__(256) rgb2yuv_u8x4_kernel(const uint8_t* __restrict__ src, int src_pitch, int w, int h,
+                                                               uint8_t* __restrict__ yp, int y_pitch, uint8_t* __restrict__ uvp, int uv_pitch)
+    {
+        const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y * blockDim.y + threadIdx.y;
+        if (x4 >= w || y >= h) return;
+        const uint8_t* in = src + static_cast<size_t>(y) * src_pitch + 3 * x4;
+        uint8_t* yo = yp + static_cast<size_t>(y) * y_pitch + x4;
+        uint8_t* uvo = uvp + static_cast<size_t>(y) * uv_pitch + 2 * x4;
+        uint8_t px[12], qy[4], quv[8];
+        const int n = min(4, w - x4);
+        if (n == 4)
+        {
+            const uint32_t* in4 = reinterpret_cast<const uint32_t*>(in);
+            const uint32_t w0 = __ldg(in4), w1 = __ldg(in4 + 1), w2 = __ldg(in4 + 2);
+#pragma unroll
+            for (int k = 0; k < 4; k++) { px[k] = (w0 >> (8 * k)) & 0xff; px[4 + k] = (w1 >> (8 * k)) & 0xff; px[8 + k] = (w2 >> (8 * k)) & 0xff; }
+        }
+        else
+            for (int k = 0; k < 12; k++) px[k] = k < 3 * n ? in[k] : 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+            const YuvFromRgb o = rgb_to_yuv(unit_from_int<255>(static_cast<float>(px[3 * k])), unit_from_int<255>(static_cast<float>(px[3 * k + 1])),
+                                            unit_from_int<255>(static_cast<float>(px[3 * k + 2])));
+            qy[k] = quant_u8(o.y); quv[2 * k] = quant_u8(o.u); quv[2 * k + 1] = quant_u8(o.v);
+        }
+        if (n == 4)
+        {
+            *reinterpret_cast<uint32_t*>(yo) = qy[0] | (qy[1] << 8) | (qy[2] << 16) | (static_cast<uint32_t>(qy[3]) << 24);
+            *reinterpret_cast<uint2*>(uvo) = make_uint2(quv[0] | (quv[1] << 8) | (quv[2] << 16) | (static_cast<uint32_t>(quv[3]) << 24),
+                                                        quv[4] | (quv[5] << 8) | (quv[6] << 16) | (static_cast<uint32_t>(quv[7]) << 24));
+        }
+        else
+            for (int k = 0; k < n; k++) { yo[k] = qy[k]; uvo[2 * k] = quv[2 * k]; uvo[2 * k + 1] = quv[2 * k + 1]; }
+    }
+
     // r,g,b (+a) from y and the already-decoded u,v(,a) of the same element type
     __device__ __forceinline__ void yuv_to_rgb_store(void* out_row, int x, int c, int type, float y, float uq, float vq, float aq)
     {
