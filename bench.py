@@ -478,10 +478,10 @@ def run_ours(args):
                          "frac": achieved_tf / peaks["bf16_tflops_sustained"],
                          # dram__bytes_read.sum + dram__bytes_write.sum over the pass's two launches (ncu --set full, which flushes the caches
                          # between its replays, profiles/r01_final_luma_mma_ncu_summary.json): segment A reads the 2.07 MB input plane and
-                         # evicts 12.2 MB of the 66 MB inter-segment map, segment B re-reads that map cold (66.4 MB) and writes 2.2 MB of the
+                         # evicts 12.8 MB of the 66 MB inter-segment map, segment B re-reads that map cold (66.4 MB) and writes 1.8 MB of the
                          # 8.3 MB result (the rest is still in the 126 MB L2).  Back to back the map is consumed out of L2; at 6.5 TB/s even
                          # the cold figure is 12 us of a 0.36 ms compute-bound pass.  Captured for acnet-legacy only.
-                         "traffic": 82980096 if (args.model.startswith("acnet-legacy") and args.engine != 0 and args.tensor_impl in (None, 0)) else None,
+                         "traffic": 83077632 if (args.model.startswith("acnet-legacy") and args.engine != 0 and args.tensor_impl in (None, 0)) else None,
                          "traffic_note": "cold-cache ncu replays, sum of both segment launches; includes the 66 MB inter-segment map that stays in L2 in steady state",
                          "algorithmic_bytes": W * H + 4 * W * H,
                          "kernel": ("luma network, one launch per layer (launches_per_pass), 1920x1080 Y -> 3840x2160 Y" if args.model.startswith(("artcnn", "fsrcnnx"))
