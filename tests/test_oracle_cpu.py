@@ -205,6 +205,34 @@ def test_division_free_to_float_is_exact():
         assert np.array_equal(y2, want), m
 
 
+def test_region_index_split_is_exact():
+    """acb200_ffma.cuh RegionDiv and the tile loop of acb200_mma.cuh: i / d == (i * (2^20 / d + 1)) >> 20 in 32-bit unsigned
+    arithmetic for every pixel index of a tile region (i < 3300) and every region width (1 <= d <= 56); the incremental walk of
+    the interior tiles (a warp's next tile is 256 region pixels ahead: dq rows, rq columns, one conditional wrap) visits the
+    same pixels as the direct mapping."""
+    i = np.arange(3300, dtype=np.uint64)
+    for d in range(1, 57):
+        rcp = np.uint64((1 << 20) // d + 1)
+        prod = i * rcp
+        assert int(prod.max()) < 1 << 32, d                    # no 32-bit overflow
+        assert np.array_equal(prod >> np.uint64(20), i // np.uint64(d)), d
+    ft = 56
+    for layers in range(1, 9):                                  # interior region: the frame shrunk by `layers`
+        wr = ft - 2 * layers
+        npix = wr * wr
+        dq, rq = 256 // wr, 256 % wr
+        for lane_q in (0, 7, 15, 16 * 15 + 15):                 # first pixel of a lane: warp * 16 + row of the fragment
+            q, qx, off = lane_q, lane_q % wr, (layers + lane_q // wr) * ft + layers + lane_q % wr
+            while q < npix:
+                assert off == (layers + q // wr) * ft + layers + q % wr, (layers, lane_q, q)
+                q += 256
+                qx += rq
+                off += dq * ft + rq
+                if qx >= wr:
+                    qx -= wr
+                    off += ft - wr
+
+
 # ---- ArtCNN<16/32>, FSRCNNX<8/16>: committed vectors of the compiled reference (travel to the GPU box) ----------------------
 WIDE = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "wide_vectors.npz"))
 
