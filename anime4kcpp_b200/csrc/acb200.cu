@@ -11,81 +11,47 @@
 #include <string>
 #include <vector>
 
-#include "acb200_common.cuh"
-#include "acb200_ffma.cuh"
-#include "acb200_mma.cuh"
+#include "acb200_internal.cuh"
+#include "acb200_mma.cuh"       // packed-table layouts only: the engines' kernels are instantiated in their own translation units
 #include "acb200_tc5.cuh"
-#include "acb200_wide.cuh"
+#include "acb200_tm.cuh"
 #include "acb200_wide_tc.cuh"
 #include "acb200_pixel.cuh"
 
-namespace
+namespace acbh
 {
-    using namespace acb;
-
     std::atomic<unsigned long long> g_launches{ 0 };
 
-    // ------------------------------------------------------------------------------------------------
-    // model: host copy of the flat arrays + the segment chain they are consumed by
-    // ------------------------------------------------------------------------------------------------
-    enum SegKind
+    // Scratch is allocated and freed in the order of the stream its users run on.  (Round-1 allocated on the session's own
+    // stream even when the caller passed another one: a regrown buffer could be handed out again while kernels queued on the
+    // caller's stream were still reading it.)
+    int ensure(acb200_session* s, cudaStream_t st, acb200_session::Buf& b, size_t bytes)
     {
-        SEG_LEGACY_FULL,    // <LEGACY, head, 7, tail>
-        SEG_ACNET_B4,       // <ACNET, head, 4, tail>
-        SEG_ACNET_B8,       // <ACNET, head, 8, tail>
-        SEG_ACNET_B18_A,    // <ACNET, head, 9, ->
-        SEG_ACNET_B18_B,    // <ACNET, -, 9, tail>
-        SEG_ARNET_FIRST,    // <ARNET, head, ARNET_SEG, ->
-        SEG_ARNET_MID,      // <ARNET, -, ARNET_SEG, ->
-        SEG_ARNET_LAST,     // <ARNET, -, ARNET_SEG - 2, tail>
-        SEG_LEGACY_A,       // <LEGACY, head, 3, ->
-        SEG_LEGACY_B,       // <LEGACY, -, 4, tail>
-        SEG_ACNET_B8_A,     // <ACNET, head, 4, ->
-        SEG_ACNET_B8_B,     // <ACNET, -, 4, tail>
-        SEG_ACNET_MID5,     // <ACNET, -, 5, ->
-    };
-    using SegLegacyFull = Seg<ACB200_FAMILY_ACNET_LEGACY, true, 7, true>;
-    using SegAcnetB4 = Seg<ACB200_FAMILY_ACNET, true, 4, true>;
-    using SegAcnetB8 = Seg<ACB200_FAMILY_ACNET, true, 8, true>;
-    using SegAcnetB18A = Seg<ACB200_FAMILY_ACNET, true, 9, false>;
-    using SegAcnetB18B = Seg<ACB200_FAMILY_ACNET, false, 9, true>;
-    // ARNet: ARNET_SEG body convs per segment (4: T = 48, halo recompute 1.13x; 8: T = 40, 1.39x and half the map traffic)
-#ifndef ACB_ARNET_SEG
-#define ACB_ARNET_SEG 4
-#endif
-    constexpr int ARNET_SEG = ACB_ARNET_SEG;
-    using SegArnetFirst = Seg<ACB200_FAMILY_ARNET, true, ARNET_SEG, false>;
-    using SegArnetMid = Seg<ACB200_FAMILY_ARNET, false, ARNET_SEG, false>;
-    using SegArnetLast = Seg<ACB200_FAMILY_ARNET, false, ARNET_SEG - 2, true>;
-    using SegLegacyA = Seg<ACB200_FAMILY_ACNET_LEGACY, true, 3, false>;
-    using SegLegacyB = Seg<ACB200_FAMILY_ACNET_LEGACY, false, 4, true>;
-    using SegAcnetB8A = Seg<ACB200_FAMILY_ACNET, true, 4, false>;
-    using SegAcnetB8B = Seg<ACB200_FAMILY_ACNET, false, 4, true>;
-    using SegAcnetMid5 = Seg<ACB200_FAMILY_ACNET, false, 5, false>;
-#ifndef ACB_SPLIT_CHAINS
-#define ACB_SPLIT_CHAINS 1
-#endif
-
-    struct SegSpec
+        if (b.cap >= bytes) return ACB200_OK;
+        if (b.p) ACB_CUDA(s, cudaFreeAsync(b.p, st));
+        b.p = nullptr; b.cap = 0;
+        ACB_CUDA(s, cudaMallocAsync(&b.p, bytes, st));
+        b.cap = bytes;
+        return ACB200_OK;
+    }
+    int device_table(acb200_session* s, cudaStream_t st, std::map<unsigned long long, void*>& cache, unsigned long long uid, const std::vector<uint32_t>& host,
+                     const char* what, const uint32_t** out)
     {
-        SegKind kind;
-        int koff, boff, aoff;   // slice starts inside the model's flat arrays (contiguous by construction)
-        int frag_off = 0;       // start of this segment's packed B fragments inside acb200_model::frags (uint32 units)
-        int bop_off = 0;        // start of this segment's tcgen05 B operands inside acb200_model::bops (uint32 units)
-    };
+        auto it = cache.find(uid);
+        if (it == cache.end())
+        {
+            void* p = nullptr;
+            ACB_CUDA(s, cudaMalloc(&p, host.size() * sizeof(uint32_t)));
+            cudaError_t e = cudaMemcpyAsync(p, host.data(), host.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) { cudaFree(p); return fail(s, ACB200_ECUDA, what, e); }
+            it = cache.emplace(uid, p).first;
+        }
+        *out = static_cast<const uint32_t*>(it->second);
+        return ACB200_OK;
+    }
 }
-
-struct acb200_model
-{
-    int family = 0, blocks = 0, features = 8;
-    std::vector<float> k, b, a;
-    std::vector<SegSpec> chain;
-    // tensor-core engine: B fragments (split fp16) of every segment, concatenated; chain[i].frag_off indexes into it
-    std::vector<uint32_t> frags;
-    // tcgen05 engine: B operands (split fp16, no-swizzle K-major canonical layout), TC_B_WORDS_LAYER words per 3x3 conv
-    std::vector<uint32_t> bops;
-    unsigned long long uid = 0;
-};
+using namespace acbh;
 
 namespace
 {
@@ -342,9 +308,40 @@ namespace
                         m[0 * (TC_N * 8) + n_lo * 8 + ci] = static_cast<uint16_t>(lo);     // chunk 0 (a_hi) x w_lo
                     }
     }
+    // B operand of one 3x3 conv for the TMEM-resident engine (acb200_tm.cuh): for every alignment al (dx = al - 1) a
+    // [N = 48][K = 16] fp16 matrix in the no-swizzle K-major canonical layout (element (n, k) at byte (k/8)*768 + n*16 + (k%8)*2).
+    // Row n = jo*16 + j: jo selects the output row relative to the input row (o = r - 1 + jo, i.e. dy = 1 - jo); j < 8 -> cout j, both
+    // K chunks (a_hi, a_lo) carry w_hi; j >= 8 -> cout j - 8, chunk 0 carries w_lo and chunk 1 is zero.
+    void pack_bop_tm(const float* W, int cout, std::vector<uint32_t>& out)
+    {
+        const size_t base = out.size();
+        out.resize(base + TM_B_WORDS_LAYER, 0u);
+        uint16_t* h = reinterpret_cast<uint16_t*>(out.data() + base);
+        for (int al = 0; al < 3; al++)
+            for (int jo = 0; jo < 3; jo++)
+                for (int co = 0; co < cout; co++)
+                    for (int ci = 0; ci < 8; ci++)
+                    {
+                        const int dy = 1 - jo, dx = al - 1;
+                        uint32_t hi, lo;
+                        split_w(W[(co * 9 + (dy + 1) * 3 + (dx + 1)) * 8 + ci], hi, lo);
+                        uint16_t* m = h + al * (TM_B_BYTES_AL / 2);
+                        const int n_hi = jo * 16 + co, n_lo = jo * 16 + 8 + co;
+                        m[0 * (48 * 8) + n_hi * 8 + ci] = static_cast<uint16_t>(hi);
+                        m[1 * (48 * 8) + n_hi * 8 + ci] = static_cast<uint16_t>(hi);
+                        m[0 * (48 * 8) + n_lo * 8 + ci] = static_cast<uint16_t>(lo);
+                    }
+    }
     template<class S>
     void pack_segment(acb200_model& m, SegSpec& sp)
     {
+        if (S::FAM != ACB200_FAMILY_ARNET)
+        {
+            sp.tm_off = static_cast<int>(m.tmops.size());
+            const float* kk = m.k.data() + sp.koff + (S::HEAD ? 72 : 0);
+            for (int i = 0; i < S::NCONV; i++, kk += 576) pack_bop_tm(kk, 8, m.tmops);
+            if (S::TAIL) pack_bop_tm(kk, S::FAM == ACB200_FAMILY_ACNET_LEGACY ? 8 : 4, m.tmops);
+        }
         {
             sp.bop_off = static_cast<int>(m.bops.size());
             const float* kk = m.k.data() + sp.koff + (S::HEAD ? 72 : 0);
@@ -398,6 +395,7 @@ namespace
     {
         m.frags.clear();
         m.bops.clear();
+        m.tmops.clear();
         if (m.family >= ACB200_FAMILY_ARTCNN && m.features >= 16)
         {
             const int F = m.features, ks = m.family == ACB200_FAMILY_ARTCNN ? 3 : 5;
@@ -425,369 +423,26 @@ namespace
     std::atomic<unsigned long long> g_model_uid{ 1 };
 }
 
-struct acb200_session
-{
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    bool timed = false;
-    int tensor_impl = 0;    // tensor engine implementation: 0 mma.sync (HMMA), 1 tcgen05 (UTCHMMA + TMEM)
-    int engine = 2;     // 0 exact FFMA, 1 tensor-core MMA, 2 auto: exact for every 2x pass but the last, tensor for the last
-    std::string error = "NO ERROR";
-    // grow-only device scratch
-    struct Buf { void* p = nullptr; size_t cap = 0; };
-    Buf src, dst, y[2], uv, map[2], feat, htab, vtab;
-    Buf pin[3], pout[3];    // planar video frames: staged source / result planes (host entry)
-    Buf wide[3];            // ArtCNN / FSRCNNX: feat + two ping-pong maps, [h][w][F] fp32
-    Buf dhtab, dvtab;       // down-scaling contributor tables of the post-network luma resize (non-power-of-two factors)
-    int dtab_in_w = 0, dtab_in_h = 0, dtab_out_w = 0, dtab_out_h = 0;
-    int wide_smem_configured = 0;
-    // device copies of models' packed fragments, keyed by acb200_model::uid
-    std::map<unsigned long long, void*> dev_frags;
-    std::map<unsigned long long, void*> dev_bops;
-    int tab_in_w = 0, tab_in_h = 0, tab_out_w = 0, tab_out_h = 0, tab_max_cnt = 0;
-    int smem_configured = 0;
-};
-
 namespace
 {
-    int fail(acb200_session* s, int code, const char* what, cudaError_t e = cudaSuccess)
-    {
-        if (s)
-        {
-            s->error = what;
-            if (e != cudaSuccess) { s->error += ": "; s->error += cudaGetErrorString(e); }
-        }
-        return code;
-    }
-#define ACB_CUDA(s, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail((s), ACB200_ECUDA, #call, e__); } while (0)
-
-    int ensure(acb200_session* s, acb200_session::Buf& b, size_t bytes)
-    {
-        if (b.cap >= bytes) return ACB200_OK;
-        // stream-ordered so an in-flight kernel still using the old block finishes first
-        if (b.p) ACB_CUDA(s, cudaFreeAsync(b.p, s->stream));
-        b.p = nullptr; b.cap = 0;
-        ACB_CUDA(s, cudaMallocAsync(&b.p, bytes, s->stream));
-        b.cap = bytes;
-        return ACB200_OK;
-    }
     size_t pitch_of(int w, int c, int es) { return (static_cast<size_t>(w) * c * es + 255) & ~static_cast<size_t>(255); }
-
-    template<class S>
-    int launch_segment(acb200_session* s, cudaStream_t st, const acb200_model& m, const SegSpec& spec,
-                       const void* src, int src_pitch, void* dst, int dst_pitch, int w, int h, int type,
-                       const float* map_in, float* map_out, float* feat)
-    {
-        static_assert(sizeof(SegParams<S>) <= 32764, "kernel parameter block too large");
-        SegParams<S> prm;
-        prm.src = src; prm.map_in = map_in; prm.map_out = map_out; prm.feat_in = feat; prm.feat_out = feat; prm.dst = dst;
-        prm.src_pitch = src_pitch; prm.dst_pitch = dst_pitch; prm.w = w; prm.h = h; prm.type = type;
-        prm.tiles_x = (w + S::T - 1) / S::T;
-        const int tiles_y = (h + S::T - 1) / S::T;
-        std::memcpy(prm.k, m.k.data() + spec.koff, sizeof(float) * S::NK);
-        std::memcpy(prm.b, m.b.data() + spec.boff, sizeof(float) * S::NB);
-        if (S::NA > 0) std::memcpy(prm.a, m.a.data() + spec.aoff, sizeof(float) * S::NA);
-        else prm.a[0] = 0.0f;
-        static std::once_flag once[16];
-        cudaError_t attr_err = cudaSuccess;
-        // the attribute is per device: set it each time the device changes (cheap)
-        attr_err = cudaFuncSetAttribute(segment_ffma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(FFMA_SMEM_BYTES));
-        if (attr_err != cudaSuccess) return fail(s, ACB200_ECUDA, "cudaFuncSetAttribute(max dynamic smem)", attr_err);
-        (void)once;
-        segment_ffma_kernel<S><<<prm.tiles_x * tiles_y, FFMA_THREADS, FFMA_SMEM_BYTES, st>>>(prm);
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-        ACB_CUDA(s, cudaGetLastError());
-        return ACB200_OK;
-    }
-
-    int device_frags(acb200_session* s, cudaStream_t st, const acb200_model& m, const uint32_t** out)
-    {
-        auto it = s->dev_frags.find(m.uid);
-        if (it == s->dev_frags.end())
-        {
-            void* p = nullptr;
-            ACB_CUDA(s, cudaMalloc(&p, m.frags.size() * sizeof(uint32_t)));
-            cudaError_t e = cudaMemcpyAsync(p, m.frags.data(), m.frags.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-            if (e != cudaSuccess) { cudaFree(p); return fail(s, ACB200_ECUDA, "upload of weight fragments", e); }
-            it = s->dev_frags.emplace(m.uid, p).first;
-        }
-        *out = static_cast<const uint32_t*>(it->second);
-        return ACB200_OK;
-    }
-
-    // TMA descriptor of an inter-segment map of the mma engine (layout in acb200_mma.cuh): 32-bit words, dims {4 w, h, 2 planes},
-    // box {4 * 56, 56, 2}, no swizzle, out-of-bounds coordinates read as zero.  cuTensorMapEncodeTiled comes from the driver
-    // through the runtime (no libcuda link dependency).
-    using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                       const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    int encode_map_tmap(acb200_session* s, CUtensorMap* tm, const void* map, int w, int h)
-    {
-        static std::atomic<EncodeTiledFn> cached{ nullptr };
-        EncodeTiledFn fn = cached.load(std::memory_order_acquire);
-        if (!fn)
-        {
-            void* p = nullptr;
-            cudaDriverEntryPointQueryResult qres = cudaDriverEntryPointSymbolNotFound;
-            const cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
-            if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) return fail(s, ACB200_ECUDA, "cuTensorMapEncodeTiled is not available from the driver", e);
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-            cached.store(fn, std::memory_order_release);
-        }
-        // a row of a plane is contiguous over (x, channel): described as 32-bit words so that the 56-pixel box row is ONE 896-byte
-        // extent (224 words, the box limit is 256 elements) instead of 56 extents of 16 bytes
-        const cuuint64_t dims[3] = { static_cast<cuuint64_t>(w) * 4, static_cast<cuuint64_t>(h), 2 };
-        const cuuint64_t strides[2] = { static_cast<cuuint64_t>(w) * 16, static_cast<cuuint64_t>(w) * h * 16 };
-        const cuuint32_t box[3] = { FT * 4, FT, 2 }, estr[3] = { 1, 1, 1 };
-        const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void*>(map), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return fail(s, ACB200_ECUDA, "cuTensorMapEncodeTiled failed");
-        return ACB200_OK;
-    }
-
-    template<class S>
-    int launch_segment_mma(acb200_session* s, cudaStream_t st, const acb200_model& m, const SegSpec& spec,
-                           const void* src, int src_pitch, void* dst, int dst_pitch, int w, int h, int type,
-                           const float* map_in, float* map_out, float* feat)
-    {
-        static_assert(sizeof(MmaParams<S>) <= 32764, "kernel parameter block too large");
-        const uint32_t* dfrags = nullptr;
-        int rc = device_frags(s, st, m, &dfrags);
-        if (rc != ACB200_OK) return rc;
-        MmaParams<S> prm;
-        prm.src = src; prm.map_in = map_in; prm.map_out = map_out; prm.feat_in = feat; prm.feat_out = feat; prm.dst = dst;
-        prm.src_pitch = src_pitch; prm.dst_pitch = dst_pitch; prm.w = w; prm.h = h; prm.type = type;
-        prm.tiles_x = (w + S::T - 1) / S::T;
-        const int tiles_y = (h + S::T - 1) / S::T;
-        prm.frags = dfrags + spec.frag_off;
-        std::memset(&prm.tmap, 0, sizeof(prm.tmap));
-        if (!S::HEAD && (rc = encode_map_tmap(s, &prm.tmap, map_in, w, h)) != ACB200_OK) return rc;
-        std::memset(prm.k, 0, sizeof(prm.k));
-        if (S::HEAD) std::memcpy(prm.k, m.k.data() + spec.koff, sizeof(float) * 72);
-        if (S::TAIL && S::FAM == ACB200_FAMILY_ACNET_LEGACY)
-            std::memcpy(prm.k + (S::HEAD ? 72 : 0), m.k.data() + spec.koff + (S::HEAD ? 72 : 0) + 576 * (S::NCONV + 1), sizeof(float) * 32);
-        std::memcpy(prm.b, m.b.data() + spec.boff, sizeof(float) * S::NB);
-        if (S::NA > 0) std::memcpy(prm.a, m.a.data() + spec.aoff, sizeof(float) * S::NA);
-        else prm.a[0] = 0.0f;
-        cudaError_t attr_err = cudaFuncSetAttribute(segment_mma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(MMA_SMEM_BYTES));
-        if (attr_err != cudaSuccess) return fail(s, ACB200_ECUDA, "cudaFuncSetAttribute(max dynamic smem)", attr_err);
-        segment_mma_kernel<S><<<prm.tiles_x * tiles_y, MMA_THREADS, MMA_SMEM_BYTES, st>>>(prm);
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-        ACB_CUDA(s, cudaGetLastError());
-        return ACB200_OK;
-    }
-
-    int device_bops(acb200_session* s, cudaStream_t st, const acb200_model& m, const uint32_t** out)
-    {
-        auto it = s->dev_bops.find(m.uid);
-        if (it == s->dev_bops.end())
-        {
-            void* p = nullptr;
-            ACB_CUDA(s, cudaMalloc(&p, m.bops.size() * sizeof(uint32_t)));
-            cudaError_t e = cudaMemcpyAsync(p, m.bops.data(), m.bops.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-            if (e != cudaSuccess) { cudaFree(p); return fail(s, ACB200_ECUDA, "upload of tcgen05 B operands", e); }
-            it = s->dev_bops.emplace(m.uid, p).first;
-        }
-        *out = static_cast<const uint32_t*>(it->second);
-        return ACB200_OK;
-    }
-
-    template<class S>
-    int launch_segment_tc5(acb200_session* s, cudaStream_t st, const acb200_model& m, const SegSpec& spec,
-                           const void* src, int src_pitch, void* dst, int dst_pitch, int w, int h, int type,
-                           const float* map_in, float* map_out, float* feat)
-    {
-        static_assert(sizeof(Tc5Params<S>) <= 32764, "kernel parameter block too large");
-        const uint32_t* dbops = nullptr;
-        int rc = device_bops(s, st, m, &dbops);
-        if (rc != ACB200_OK) return rc;
-        Tc5Params<S> prm;
-        prm.src = src; prm.map_in = map_in; prm.map_out = map_out; prm.feat_in = feat; prm.feat_out = feat; prm.dst = dst;
-        prm.src_pitch = src_pitch; prm.dst_pitch = dst_pitch; prm.w = w; prm.h = h; prm.type = type;
-        prm.tiles_x = (w + S::T - 1) / S::T;
-        const int tiles_y = (h + S::T - 1) / S::T;
-        prm.bops = dbops + spec.bop_off;
-        std::memset(prm.k, 0, sizeof(prm.k));
-        constexpr int K0 = S::HEAD ? 72 : 0;
-        if (S::HEAD) std::memcpy(prm.k, m.k.data() + spec.koff, sizeof(float) * 72);
-        if (S::TAIL && S::FAM == ACB200_FAMILY_ACNET_LEGACY)
-            std::memcpy(prm.k + K0 + 64, m.k.data() + spec.koff + K0 + 576 * (S::NCONV + 1), sizeof(float) * 32);
-        if (S::TAIL && S::FAM == ACB200_FAMILY_ARNET)
-            std::memcpy(prm.k + K0, m.k.data() + spec.koff + K0 + 576 * (S::NCONV + 2), sizeof(float) * 64);
-        std::memcpy(prm.b, m.b.data() + spec.boff, sizeof(float) * S::NB);
-        if (S::NA > 0) std::memcpy(prm.a, m.a.data() + spec.aoff, sizeof(float) * S::NA);
-        else prm.a[0] = 0.0f;
-        cudaError_t attr_err = cudaFuncSetAttribute(segment_tc5_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(TC_SMEM_BYTES));
-        if (attr_err != cudaSuccess) return fail(s, ACB200_ECUDA, "cudaFuncSetAttribute(max dynamic smem)", attr_err);
-        segment_tc5_kernel<S><<<prm.tiles_x * tiles_y, TC_THREADS, TC_SMEM_BYTES, st>>>(prm);
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-        ACB_CUDA(s, cudaGetLastError());
-        return ACB200_OK;
-    }
-
-    template<class S>
-    int launch_any(bool tensor, acb200_session* s, cudaStream_t st, const acb200_model& m, const SegSpec& spec,
-                   const void* src, int src_pitch, void* dst, int dst_pitch, int w, int h, int type,
-                   const float* map_in, float* map_out, float* feat)
-    {
-        if (tensor && s->tensor_impl == 1) return launch_segment_tc5<S>(s, st, m, spec, src, src_pitch, dst, dst_pitch, w, h, type, map_in, map_out, feat);
-        return tensor ? launch_segment_mma<S>(s, st, m, spec, src, src_pitch, dst, dst_pitch, w, h, type, map_in, map_out, feat)
-                      : launch_segment<S>(s, st, m, spec, src, src_pitch, dst, dst_pitch, w, h, type, map_in, map_out, feat);
-    }
-
-    // one 2x luma pass: src (w x h) -> dst (2w x 2h), both planes in HBM
-    // ---- ArtCNN<16/32>, FSRCNNX<8/16>: one launch per layer (two for 32 output channels) over fp32 maps in HBM -------------
-    template<int F, int NCO, int MODE>
-    int launch_wide_conv(acb200_session* s, cudaStream_t st, const float* in, float* out, const float* res, void* dst, int dst_pitch, int type,
-                         int w, int h, int co0, int act, const float* k, const float* b, const float* a)
-    {
-        static_assert(sizeof(WideConvParams<F, NCO>) <= 32764, "kernel parameter block too large");
-        WideConvParams<F, NCO> prm;
-        prm.in = in; prm.out = out; prm.res = res; prm.dst = dst; prm.dst_pitch = dst_pitch; prm.type = type;
-        prm.w = w; prm.h = h; prm.co0 = co0; prm.act = act;
-        std::memcpy(prm.k, k + static_cast<size_t>(co0) * 9 * F, sizeof(prm.k));
-        std::memcpy(prm.b, b + co0, sizeof(prm.b));
-        if (a) std::memcpy(prm.a, a + co0, sizeof(prm.a)); else std::memset(prm.a, 0, sizeof(prm.a));
-        ACB_CUDA(s, cudaFuncSetAttribute(wide_conv_kernel<F, NCO, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(wide_smem_bytes<F>())));
-        wide_conv_kernel<F, NCO, MODE><<<dim3((w + WIDE_TW - 1) / WIDE_TW, (h + WIDE_TH - 1) / WIDE_TH), WIDE_THREADS, wide_smem_bytes<F>(), st>>>(prm);
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-        ACB_CUDA(s, cudaGetLastError());
-        return ACB200_OK;
-    }
-    // the same layer on the tensor cores (tcgen05, split fp16): one launch, B operand from the model's packed table
-    template<int F>
-    int wide_conv_layer_tc(acb200_session* s, cudaStream_t st, const acb200_model& m, int conv_index, const float* in, float* out, const float* res,
-                           int w, int h, int act, const float* b, const float* a)
-    {
-        const uint32_t* dbops = nullptr;
-        int rc = device_bops(s, st, m, &dbops);
-        if (rc != ACB200_OK) return rc;
-        WideTcParams<F> prm;
-        prm.in = in; prm.out = out; prm.res = res; prm.w = w; prm.h = h; prm.act = act;
-        prm.bop = dbops + static_cast<size_t>(conv_index) * (WideTc<F>::B_BYTES / 4);
-        std::memcpy(prm.b, b, sizeof(prm.b));
-        if (a) std::memcpy(prm.a, a, sizeof(prm.a)); else std::memset(prm.a, 0, sizeof(prm.a));
-        ACB_CUDA(s, cudaFuncSetAttribute(wide_tc_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, WideTc<F>::SMEM_BYTES));
-        wide_tc_kernel<F><<<dim3((w + WTC_TW - 1) / WTC_TW, (h + WideTc<F>::TH - 1) / WideTc<F>::TH), WideTc<F>::THREADS, WideTc<F>::SMEM_BYTES, st>>>(prm);
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-        ACB_CUDA(s, cudaGetLastError());
-        return ACB200_OK;
-    }
-    // F -> F conv layer: output channels in launches of at most 16 (the weights travel as kernel parameters)
-    template<int F>
-    int wide_conv_layer(acb200_session* s, cudaStream_t st, const float* in, float* out, const float* res, int w, int h, int act,
-                        const float* k, const float* b, const float* a)
-    {
-        constexpr int NCO = F < 16 ? F : 16;
-        for (int co0 = 0; co0 < F; co0 += NCO)
-        {
-            const int rc = launch_wide_conv<F, NCO, WIDE_STORE>(s, st, in, out, res, nullptr, 0, 0, w, h, co0, act, k, b, a);
-            if (rc != ACB200_OK) return rc;
-        }
-        return ACB200_OK;
-    }
-    template<int F>
-    int luma_pass_wide(acb200_session* s, cudaStream_t st, const acb200_model& m, const void* src, int src_pitch, void* dst, int dst_pitch,
-                       int w, int h, int type, bool tensor)
-    {
-        // F -> F conv number `ci` (0-based) of the model: tensor engine for 16 / 32 features, exact FFMA kernels otherwise
-        auto conv = [&](int ci, const float* in_, float* out_, const float* res_, int act, const float* k_, const float* b_, const float* a_) -> int {
-            if constexpr (F >= 16)
-            {
-                if (tensor) return wide_conv_layer_tc<F>(s, st, m, ci, in_, out_, res_, w, h, act, b_, a_);
-            }
-            return wide_conv_layer<F>(s, st, in_, out_, res_, w, h, act, k_, b_, a_);
-        };
-        const size_t bytes = static_cast<size_t>(w) * h * F * sizeof(float);
-        int rc;
-        for (int i = 0; i < 3; i++) if ((rc = ensure(s, s->wide[i], bytes)) != ACB200_OK) return rc;
-        float* feat = static_cast<float*>(s->wide[0].p);
-        float* in = static_cast<float*>(s->wide[2].p);
-        float* out = static_cast<float*>(s->wide[1].p);
-        const bool art = m.family == ACB200_FAMILY_ARTCNN;
-        const int ks = art ? 3 : 5, KH = F * ks * ks, KL = F * F * 9, B = m.blocks;
-        const float* k = m.k.data();
-        const float* b = m.b.data();
-        const float* a = m.a.empty() ? nullptr : m.a.data();
-        // head (CPUProcessor.cpp:1533 / :1635)
-        {
-            WideHeadParams hp;
-            hp.src = src; hp.src_pitch = src_pitch; hp.type = type; hp.out = feat; hp.w = w; hp.h = h; hp.F = F;
-            std::memcpy(hp.k, k, sizeof(float) * KH);
-            std::memcpy(hp.b, b, sizeof(float) * F);
-            const dim3 grid((w + 31) / 32, (h + 7) / 8);
-            if (art) wide_head_kernel<3><<<grid, 256, 0, st>>>(hp); else wide_head_kernel<5><<<grid, 256, 0, st>>>(hp);
-            g_launches.fetch_add(1, std::memory_order_relaxed);
-            ACB_CUDA(s, cudaGetLastError());
-        }
-        int l = 1;
-        const float* cur = feat;
-        auto layer_k = [&](int layer) { return k + KH + static_cast<size_t>(KL) * (layer - 1); };
-        if (art)
-        {
-            // blocks x (conv + ReLU), then conv + Identity + feat (CPUProcessor.cpp:1535-1545)
-            for (int i = 0; i < B; i++, l++)
-            {
-                if ((rc = conv(l - 1, cur, out, nullptr, ACT_RELU, layer_k(l), b + F * l, nullptr)) != ACB200_OK) return rc;
-                cur = out; std::swap(in, out);
-            }
-            if ((rc = conv(l - 1, cur, out, feat, ACT_IDENTITY, layer_k(l), b + F * l, nullptr)) != ACB200_OK) return rc;
-            cur = out; std::swap(in, out); l++;
-        }
-        else
-        {
-            // (blocks - 1) x (conv + PReLU), then conv + PReLU -> 1x1 -> + feat -> PReLU (CPUProcessor.cpp:1637-1651)
-            for (int i = 0; i < B; i++, l++)
-            {
-                if ((rc = conv(l - 1, cur, out, nullptr, ACT_PRELU, layer_k(l), b + F * l, a + F * (l - 1))) != ACB200_OK) return rc;
-                cur = out; std::swap(in, out);
-            }
-            if constexpr (F <= 16)
-            {
-                WidePointParams<F> pp;
-                pp.in = cur; pp.feat = feat; pp.out = out; pp.n_pixels = w * h;
-                std::memcpy(pp.k, k + KH + static_cast<size_t>(KL) * B, sizeof(pp.k));
-                std::memcpy(pp.b, b + F * l, sizeof(pp.b));
-                std::memcpy(pp.a, a + F * (l - 1), sizeof(pp.a));
-                wide_pointwise_kernel<F><<<(w * h + 255) / 256, 256, 0, st>>>(pp);
-                g_launches.fetch_add(1, std::memory_order_relaxed);
-                ACB_CUDA(s, cudaGetLastError());
-            }
-            cur = out; std::swap(in, out); l++;
-        }
-        // F -> 4 + pixel shuffle (CPUProcessor.cpp:1548 / :1654)
-        const float* kt = art ? layer_k(l) : k + KH + static_cast<size_t>(KL) * B + F * F;
-        // launch_wide_conv copies NCO * 9 * F weights starting at co0 = 0
-        return launch_wide_conv<F, 4, WIDE_SHUFFLE>(s, st, cur, nullptr, nullptr, dst, dst_pitch, type, w, h, 0, ACT_IDENTITY, kt, b + F * l, nullptr);
-    }
 
     int luma_pass(acb200_session* s, cudaStream_t st, const acb200_model& m, const void* src, int src_pitch,
                   void* dst, int dst_pitch, int w, int h, int type, bool tensor)
     {
-        if (m.family >= ACB200_FAMILY_ARTCNN)
-        {
-            if (static_cast<long long>(w) * h * m.features > 0x7fffffffLL / 4) return fail(s, ACB200_EINVAL, "image too large for this model family");
-            switch (m.features)
-            {
-            case 8: return luma_pass_wide<8>(s, st, m, src, src_pitch, dst, dst_pitch, w, h, type, tensor);
-            case 16: return luma_pass_wide<16>(s, st, m, src, src_pitch, dst, dst_pitch, w, h, type, tensor);
-            default: return luma_pass_wide<32>(s, st, m, src, src_pitch, dst, dst_pitch, w, h, type, tensor);
-            }
-        }
+        if (m.family >= ACB200_FAMILY_ARTCNN) return luma_pass_wide_any(s, st, m, src, src_pitch, dst, dst_pitch, w, h, type, tensor);
         float* maps[2] = { nullptr, nullptr };
         float* feat = nullptr;
         if (m.chain.size() > 1)
         {
             const size_t bytes = static_cast<size_t>(w) * h * 8 * sizeof(float);
             int rc;
-            if ((rc = ensure(s, s->map[0], bytes)) != ACB200_OK) return rc;
-            if ((rc = ensure(s, s->map[1], bytes)) != ACB200_OK) return rc;
+            if ((rc = ensure(s, st, s->map[0], bytes)) != ACB200_OK) return rc;
+            if ((rc = ensure(s, st, s->map[1], bytes)) != ACB200_OK) return rc;
             maps[0] = static_cast<float*>(s->map[0].p); maps[1] = static_cast<float*>(s->map[1].p);
             if (m.family == ACB200_FAMILY_ARNET)
             {
-                if ((rc = ensure(s, s->feat, bytes)) != ACB200_OK) return rc;
+                if ((rc = ensure(s, st, s->feat, bytes)) != ACB200_OK) return rc;
                 feat = static_cast<float*>(s->feat.p);
             }
         }
@@ -797,23 +452,19 @@ namespace
             const SegSpec& sp = m.chain[i];
             const float* in = maps[cur];
             float* out = maps[cur ^ 1];
-            int rc = ACB200_EINVAL;
-            switch (sp.kind)
-            {
-            case SEG_LEGACY_FULL: rc = launch_any<SegLegacyFull>(tensor, s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, nullptr, nullptr, nullptr); break;
-            case SEG_ACNET_B4: rc = launch_any<SegAcnetB4>(tensor, s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, nullptr, nullptr, nullptr); break;
-            case SEG_ACNET_B8: rc = launch_any<SegAcnetB8>(tensor, s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, nullptr, nullptr, nullptr); break;
-            case SEG_ACNET_B18_A: rc = launch_any<SegAcnetB18A>(tensor, s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, nullptr, out, nullptr); break;
-            case SEG_ACNET_B18_B: rc = launch_any<SegAcnetB18B>(tensor, s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, in, nullptr, nullptr); break;
-            case SEG_ARNET_FIRST: rc = launch_any<SegArnetFirst>(tensor, s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, nullptr, out, feat); break;
-            case SEG_ARNET_MID: rc = launch_any<SegArnetMid>(tensor, s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, in, out, feat); break;
-            case SEG_ARNET_LAST: rc = launch_any<SegArnetLast>(tensor, s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, in, nullptr, feat); break;
-            case SEG_LEGACY_A: rc = launch_any<SegLegacyA>(tensor, s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, nullptr, out, nullptr); break;
-            case SEG_LEGACY_B: rc = launch_any<SegLegacyB>(tensor, s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, in, nullptr, nullptr); break;
-            case SEG_ACNET_B8_A: rc = launch_any<SegAcnetB8A>(tensor, s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, nullptr, out, nullptr); break;
-            case SEG_ACNET_B8_B: rc = launch_any<SegAcnetB8B>(tensor, s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, in, nullptr, nullptr); break;
-            case SEG_ACNET_MID5: rc = launch_any<SegAcnetMid5>(tensor, s, st, m, sp, src, src_pitch, dst, dst_pitch, w, h, type, in, out, nullptr); break;
-            }
+            // map / feat pointers by segment shape: a segment without a head reads `in`, one without a tail writes `out`
+            const bool head = sp.kind == SEG_LEGACY_FULL || sp.kind == SEG_ACNET_B4 || sp.kind == SEG_ACNET_B8 || sp.kind == SEG_ACNET_B18_A || sp.kind == SEG_ARNET_FIRST ||
+                              sp.kind == SEG_LEGACY_A || sp.kind == SEG_ACNET_B8_A;
+            const bool tail = sp.kind == SEG_LEGACY_FULL || sp.kind == SEG_ACNET_B4 || sp.kind == SEG_ACNET_B8 || sp.kind == SEG_ACNET_B18_B || sp.kind == SEG_ARNET_LAST ||
+                              sp.kind == SEG_LEGACY_B || sp.kind == SEG_ACNET_B8_B;
+            SegLaunch a;
+            a.src = src; a.src_pitch = src_pitch; a.dst = dst; a.dst_pitch = dst_pitch; a.w = w; a.h = h; a.type = type;
+            a.map_in = head ? nullptr : in; a.map_out = tail ? nullptr : out; a.feat = feat;
+            int rc;
+            if (!tensor) rc = launch_seg_ffma(s, st, m, sp, a);
+            else if (s->tensor_impl == 2 && seg_tm_supported(m)) rc = launch_seg_tm(s, st, m, sp, a);
+            else if (s->tensor_impl == 1) rc = launch_seg_tc5(s, st, m, sp, a);
+            else rc = launch_seg_mma(s, st, m, sp, a);
             if (rc != ACB200_OK) return rc;
             cur ^= 1;
         }
@@ -826,8 +477,8 @@ namespace
         std::vector<Contrib> ht, vt;
         if (!make_contribs(ht, w, ow) || !make_contribs(vt, h, oh)) return fail(s, ACB200_EINVAL, "resize: unsupported scale");
         int rc;
-        if ((rc = ensure(s, s->htab, ht.size() * sizeof(Contrib))) != ACB200_OK) return rc;
-        if ((rc = ensure(s, s->vtab, vt.size() * sizeof(Contrib))) != ACB200_OK) return rc;
+        if ((rc = ensure(s, st, s->htab, ht.size() * sizeof(Contrib))) != ACB200_OK) return rc;
+        if ((rc = ensure(s, st, s->vtab, vt.size() * sizeof(Contrib))) != ACB200_OK) return rc;
         // pageable -> device: the copy is staged before the call returns, so the vectors may die
         ACB_CUDA(s, cudaMemcpyAsync(s->htab.p, ht.data(), ht.size() * sizeof(Contrib), cudaMemcpyHostToDevice, st));
         ACB_CUDA(s, cudaMemcpyAsync(s->vtab.p, vt.data(), vt.size() * sizeof(Contrib), cudaMemcpyHostToDevice, st));
@@ -867,8 +518,8 @@ namespace
         std::vector<ContribW> ht, vt;
         if (!make_contribs_down(ht, w, ow) || !make_contribs_down(vt, h, oh)) return fail(s, ACB200_EINVAL, "resize: unsupported down-scale");
         int rc;
-        if ((rc = ensure(s, s->dhtab, ht.size() * sizeof(ContribW))) != ACB200_OK) return rc;
-        if ((rc = ensure(s, s->dvtab, vt.size() * sizeof(ContribW))) != ACB200_OK) return rc;
+        if ((rc = ensure(s, st, s->dhtab, ht.size() * sizeof(ContribW))) != ACB200_OK) return rc;
+        if ((rc = ensure(s, st, s->dvtab, vt.size() * sizeof(ContribW))) != ACB200_OK) return rc;
         ACB_CUDA(s, cudaMemcpyAsync(s->dhtab.p, ht.data(), ht.size() * sizeof(ContribW), cudaMemcpyHostToDevice, st));
         ACB_CUDA(s, cudaMemcpyAsync(s->dvtab.p, vt.data(), vt.size() * sizeof(ContribW), cudaMemcpyHostToDevice, st));
         ACB_CUDA(s, cudaStreamSynchronize(st));
@@ -889,8 +540,8 @@ namespace
         if (c > 1)
         {
             const size_t yp = pitch_of(w, 1, es), uvp = pitch_of(w, c - 1, es);
-            if ((rc = ensure(s, s->y[0], yp * h)) != ACB200_OK) return rc;
-            if ((rc = ensure(s, s->uv, uvp * h)) != ACB200_OK) return rc;
+            if ((rc = ensure(s, st, s->y[0], yp * h)) != ACB200_OK) return rc;
+            if ((rc = ensure(s, st, s->uv, uvp * h)) != ACB200_OK) return rc;
             if (type == ACB200_UINT8 && c == 3 && ((reinterpret_cast<uintptr_t>(d_src) | static_cast<uintptr_t>(src_pitch)) & 3) == 0)
                 rgb2yuv_u8x4_kernel<<<dim3((w + 127) / 128, (h + 7) / 8), blk, 0, st>>>(static_cast<const uint8_t*>(d_src), src_pitch, w, h,
                     static_cast<uint8_t*>(s->y[0].p), static_cast<int>(yp), static_cast<uint8_t*>(s->uv.p), static_cast<int>(uvp));
@@ -910,7 +561,7 @@ namespace
             else
             {
                 const size_t p = pitch_of(nw, 1, es);
-                if ((rc = ensure(s, s->y[slot], p * nh)) != ACB200_OK) return rc;
+                if ((rc = ensure(s, st, s->y[slot], p * nh)) != ACB200_OK) return rc;
                 out = s->y[slot].p; out_pitch = static_cast<int>(p);
                 slot ^= 1;
             }
@@ -927,7 +578,7 @@ namespace
             else
             {
                 const size_t p = pitch_of(plan.dw, 1, es);
-                if ((rc = ensure(s, s->y[slot], p * plan.dh)) != ACB200_OK) return rc;
+                if ((rc = ensure(s, st, s->y[slot], p * plan.dh)) != ACB200_OK) return rc;
                 out = s->y[slot].p; out_pitch = static_cast<int>(p);
             }
             resize_wide_kernel<<<dim3((plan.dw + 31) / 32, (plan.dh + 7) / 8), blk, 0, st>>>(cur, cur_pitch, 1, type,
@@ -975,7 +626,7 @@ namespace
         if (sh)
         {
             const size_t p = pitch_of(cw, 1, es);
-            if ((rc = ensure(s, s->y[slot], p * ch)) != ACB200_OK) return rc;
+            if ((rc = ensure(s, st, s->y[slot], p * ch)) != ACB200_OK) return rc;
             shift_kernel<<<dim3((cw + 31) / 32, (ch + 7) / 8), blk, 0, st>>>(cur, cur_pitch, s->y[slot].p, static_cast<int>(p), cw, ch, es, sh, 1);
             g_launches.fetch_add(1, std::memory_order_relaxed);
             ACB_CUDA(s, cudaGetLastError());
@@ -1159,6 +810,7 @@ extern "C"
         cudaStreamSynchronize(s->stream);
         for (auto& kv : s->dev_frags) cudaFree(kv.second);
         for (auto& kv : s->dev_bops) cudaFree(kv.second);
+        for (auto& kv : s->dev_tmops) cudaFree(kv.second);
         cudaEventDestroy(s->ev0); cudaEventDestroy(s->ev1);
         cudaStreamDestroy(s->stream);
         cudaGetLastError();
@@ -1167,7 +819,7 @@ extern "C"
     int acb200_session_device(const acb200_session* s) { return s ? s->device : ACB200_EINVAL; }
     const char* acb200_session_error(const acb200_session* s) { return s ? s->error.c_str() : "invalid session"; }
     void acb200_session_clear_error(acb200_session* s) { if (s) s->error = "NO ERROR"; }
-    int acb200_session_set_tensor_impl(acb200_session* s, int impl) { if (!s || impl < 0 || impl > 1) return ACB200_EINVAL; s->tensor_impl = impl; return ACB200_OK; }
+    int acb200_session_set_tensor_impl(acb200_session* s, int impl) { if (!s || impl < 0 || impl > 2) return ACB200_EINVAL; s->tensor_impl = impl; return ACB200_OK; }
     int acb200_session_set_engine(acb200_session* s, int engine) { if (!s || engine < 0 || engine > 2) return ACB200_EINVAL; s->engine = engine; return ACB200_OK; }
 
     int acb200_process_device(acb200_session* s, const acb200_model* m, const void* d_src, int w, int h, int c, int src_stride, int type,
@@ -1199,8 +851,8 @@ extern "C"
         if (src_stride < static_cast<int>(line_in)) src_stride = static_cast<int>(line_in);
         if (dst_stride < static_cast<int>(line_out)) dst_stride = static_cast<int>(line_out);
         const size_t sp = pitch_of(w, c, es), dp = pitch_of(ow, c, es);
-        if ((rc = ensure(s, s->src, sp * h)) != ACB200_OK) return rc;
-        if ((rc = ensure(s, s->dst, dp * oh)) != ACB200_OK) return rc;
+        if ((rc = ensure(s, s->stream, s->src, sp * h)) != ACB200_OK) return rc;
+        if ((rc = ensure(s, s->stream, s->dst, dp * oh)) != ACB200_OK) return rc;
         ACB_CUDA(s, cudaMemcpy2DAsync(s->src.p, sp, src, src_stride, line_in, h, cudaMemcpyHostToDevice, s->stream));
         ACB_CUDA(s, cudaEventRecord(s->ev0, s->stream));
         if ((rc = process_on_device(s, m, s->stream, s->src.p, w, h, c, static_cast<int>(sp), type, plan, s->dst.p, static_cast<int>(dp))) != ACB200_OK) return rc;
@@ -1239,8 +891,8 @@ extern "C"
         for (int i = 0; i < planes; i++)
         {
             const size_t ip = pitch_of(src[i].width, src[i].channel, es), op = pitch_of(dst[i].width, dst[i].channel, es);
-            if ((rc = ensure(s, s->pin[i], ip * src[i].height)) != ACB200_OK) return rc;
-            if ((rc = ensure(s, s->pout[i], op * dst[i].height)) != ACB200_OK) return rc;
+            if ((rc = ensure(s, s->stream, s->pin[i], ip * src[i].height)) != ACB200_OK) return rc;
+            if ((rc = ensure(s, s->stream, s->pout[i], op * dst[i].height)) != ACB200_OK) return rc;
             din[i] = src[i]; din[i].data = static_cast<unsigned char*>(s->pin[i].p); din[i].stride = static_cast<int>(ip);
             dout[i] = dst[i]; dout[i].data = static_cast<unsigned char*>(s->pout[i].p); dout[i].stride = static_cast<int>(op);
             ACB_CUDA(s, cudaMemcpy2DAsync(din[i].data, ip, src[i].data, frame_stride(src[i], es), static_cast<size_t>(src[i].width) * src[i].channel * es, src[i].height,
@@ -1321,9 +973,9 @@ extern "C"
         const size_t line = static_cast<size_t>(w) * c * es;
         const size_t sp = pitch_of(w, c, es), yp = pitch_of(w, packed ? c : 1, es), uvp = pitch_of(w, c - 1, es);
         int rc;
-        if ((rc = ensure(s, s->src, sp * h)) != ACB200_OK) return rc;
-        if ((rc = ensure(s, s->y[0], yp * h)) != ACB200_OK) return rc;
-        if (!packed && (rc = ensure(s, s->uv, uvp * h)) != ACB200_OK) return rc;
+        if ((rc = ensure(s, s->stream, s->src, sp * h)) != ACB200_OK) return rc;
+        if ((rc = ensure(s, s->stream, s->y[0], yp * h)) != ACB200_OK) return rc;
+        if (!packed && (rc = ensure(s, s->stream, s->uv, uvp * h)) != ACB200_OK) return rc;
         ACB_CUDA(s, cudaMemcpy2DAsync(s->src.p, sp, src, std::max<size_t>(src_stride, line), line, h, cudaMemcpyHostToDevice, s->stream));
         if (packed)
             rgb2yuv_kernel<<<dim3((w + 31) / 32, (h + 7) / 8), dim3(32, 8), 0, s->stream>>>(s->src.p, static_cast<int>(sp), w, h, c, type,
@@ -1348,9 +1000,9 @@ extern "C"
         const int es = type & 0xff;
         const size_t dp = pitch_of(w, c, es), yp = pitch_of(w, packed ? c : 1, es), uvp = pitch_of(w, c - 1, es);
         int rc;
-        if ((rc = ensure(s, s->dst, dp * h)) != ACB200_OK) return rc;
-        if ((rc = ensure(s, s->y[0], yp * h)) != ACB200_OK) return rc;
-        if (!packed && (rc = ensure(s, s->uv, uvp * h)) != ACB200_OK) return rc;
+        if ((rc = ensure(s, s->stream, s->dst, dp * h)) != ACB200_OK) return rc;
+        if ((rc = ensure(s, s->stream, s->y[0], yp * h)) != ACB200_OK) return rc;
+        if (!packed && (rc = ensure(s, s->stream, s->uv, uvp * h)) != ACB200_OK) return rc;
         const size_t yline = static_cast<size_t>(w) * (packed ? c : 1) * es;
         ACB_CUDA(s, cudaMemcpy2DAsync(s->y[0].p, yp, y, std::max<size_t>(y_stride, yline), yline, h, cudaMemcpyHostToDevice, s->stream));
         if (packed)
@@ -1393,8 +1045,8 @@ extern "C"
         const int es = type & 0xff;
         const size_t sp = pitch_of(w, c, es), dp = pitch_of(ow, c, es);
         int rc;
-        if ((rc = ensure(s, s->src, sp * h)) != ACB200_OK) return rc;
-        if ((rc = ensure(s, s->dst, dp * oh)) != ACB200_OK) return rc;
+        if ((rc = ensure(s, s->stream, s->src, sp * h)) != ACB200_OK) return rc;
+        if ((rc = ensure(s, s->stream, s->dst, dp * oh)) != ACB200_OK) return rc;
         if (ow < w || oh < h)
         {
             // at least one axis shrinks: general 10-tap contributors per axis (an axis that grows keeps its up-scaling taps)
@@ -1412,8 +1064,8 @@ extern "C"
             };
             std::vector<ContribW> ht, vt;
             if (!axis(ht, w, ow) || !axis(vt, h, oh)) return fail(s, ACB200_EINVAL, "resize: unsupported scale");
-            if ((rc = ensure(s, s->dhtab, ht.size() * sizeof(ContribW))) != ACB200_OK) return rc;
-            if ((rc = ensure(s, s->dvtab, vt.size() * sizeof(ContribW))) != ACB200_OK) return rc;
+            if ((rc = ensure(s, s->stream, s->dhtab, ht.size() * sizeof(ContribW))) != ACB200_OK) return rc;
+            if ((rc = ensure(s, s->stream, s->dvtab, vt.size() * sizeof(ContribW))) != ACB200_OK) return rc;
             s->dtab_in_w = s->dtab_in_h = s->dtab_out_w = s->dtab_out_h = 0;       // the cached luma down-scale tables are gone
             ACB_CUDA(s, cudaMemcpyAsync(s->dhtab.p, ht.data(), ht.size() * sizeof(ContribW), cudaMemcpyHostToDevice, s->stream));
             ACB_CUDA(s, cudaMemcpyAsync(s->dvtab.p, vt.data(), vt.size() * sizeof(ContribW), cudaMemcpyHostToDevice, s->stream));

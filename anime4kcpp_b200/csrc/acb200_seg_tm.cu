@@ -1,0 +1,84 @@
+// Launches of the TMEM-resident tcgen05 engine (acb200_tm.cuh).
+#include <cstdlib>
+
+#include "acb200_internal.cuh"
+#include "acb200_tm.cuh"
+
+namespace acbh
+{
+    // rows of a strip frame: the CTA count is tiles_x * ceil(h / (G - 2R)) and every CTA costs about G + c row times, so the best G
+    // is the one with the fewest (waves of SM-count CTAs) x (G + c) -- not necessarily the tallest frame
+    int tm_pick_rows(int tiles_x, int h, int R, int sms)
+    {
+        int best = TM_GMAX;
+        double best_cost = 1e30;
+        for (int G = 2 * R + 4; G <= TM_GMAX; G++)
+        {
+            const int tiles_y = (h + G - 2 * R - 1) / (G - 2 * R);
+            const long long tiles = static_cast<long long>(tiles_x) * tiles_y;
+            const double waves = static_cast<double>((tiles + sms - 1) / sms);
+            const double cost = waves * (G + 10.0);
+            if (cost < best_cost - 1e-9) { best_cost = cost; best = G; }
+        }
+        return best;
+    }
+
+    template<class S>
+    int launch_segment_tm(acb200_session* s, cudaStream_t st, const acb200_model& m, const SegSpec& spec,
+                          const void* src, int src_pitch, void* dst, int dst_pitch, int w, int h, int type,
+                          const float* map_in, float* map_out, float* feat)
+    {
+        if constexpr (S::FAM == ACB200_FAMILY_ARNET || S::R > TM_MAX_R) return ACB200_EINVAL;
+        else
+        {
+            static_assert(sizeof(TmParams<S>) <= 32764, "kernel parameter block too large");
+            const uint32_t* dops = nullptr;
+            int rc = device_table(s, st, s->dev_tmops, m.uid, m.tmops, "upload of the TMEM engine's B operands", &dops);
+            if (rc != ACB200_OK) return rc;
+            if (!s->sm_count)
+            {
+                ACB_CUDA(s, cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device));
+                if (s->sm_count <= 0) s->sm_count = 148;
+            }
+            TmParams<S> prm;
+            prm.src = src; prm.map_in = reinterpret_cast<const uint4*>(map_in); prm.map_out = reinterpret_cast<uint4*>(map_out);
+            prm.feat_in = feat; prm.feat_out = feat; prm.dst = dst;
+            prm.src_pitch = src_pitch; prm.dst_pitch = dst_pitch; prm.w = w; prm.h = h; prm.type = type;
+            constexpr int SW = 32 - 2 * S::R;
+            prm.strips_x = (w + SW - 1) / SW;
+            prm.tiles_x = (prm.strips_x + 3) / 4;
+            prm.G = tm_pick_rows(prm.tiles_x, h, S::R, s->sm_count);
+            const int tiles_y = (h + prm.G - 2 * S::R - 1) / (prm.G - 2 * S::R);
+            prm.bops = dops + spec.tm_off;
+            static const int issuers_env = [] { const char* e = std::getenv("ACB200_TM_ISSUERS"); const int v = e ? std::atoi(e) : TM_ISSUERS; return v < 1 ? 1 : (v > TM_ISSUERS ? TM_ISSUERS : v); }();
+            prm.issuers = issuers_env;
+            std::memset(prm.k, 0, sizeof(prm.k));
+            constexpr int K0 = S::HEAD ? 72 : 0;
+            if (S::HEAD) std::memcpy(prm.k, m.k.data() + spec.koff, sizeof(float) * 72);
+            if (S::TAIL && S::FAM == ACB200_FAMILY_ACNET_LEGACY)
+                std::memcpy(prm.k + K0, m.k.data() + spec.koff + K0 + 576 * (S::NCONV + 1), sizeof(float) * 32);
+            std::memcpy(prm.b, m.b.data() + spec.boff, sizeof(float) * S::NB);
+            if (S::NA > 0) std::memcpy(prm.a, m.a.data() + spec.aoff, sizeof(float) * S::NA);
+            else prm.a[0] = 0.0f;
+            cudaError_t attr_err = cudaFuncSetAttribute(segment_tm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(TM_SMEM_BYTES));
+            if (attr_err != cudaSuccess) return fail(s, ACB200_ECUDA, "cudaFuncSetAttribute(max dynamic smem)", attr_err);
+            segment_tm_kernel<S><<<prm.tiles_x * tiles_y, TM_THREADS, TM_SMEM_BYTES, st>>>(prm);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            ACB_CUDA(s, cudaGetLastError());
+            return ACB200_OK;
+        }
+    }
+
+
+    int launch_seg_tm(acb200_session* s, cudaStream_t st, const acb200_model& m, const SegSpec& spec, const SegLaunch& a)
+    {
+        switch (spec.kind)
+        {
+#define ACB_CASE(KIND, TYPE) case KIND: return launch_segment_tm<TYPE>(s, st, m, spec, a.src, a.src_pitch, a.dst, a.dst_pitch, a.w, a.h, a.type, a.map_in, a.map_out, a.feat);
+        ACB_FOR_EACH_SEG(ACB_CASE)
+#undef ACB_CASE
+        }
+        return ACB200_EINVAL;
+    }
+    bool seg_tm_supported(const acb200_model& m) { return m.family == ACB200_FAMILY_ACNET_LEGACY || m.family == ACB200_FAMILY_ACNET; }
+}

@@ -1,0 +1,650 @@
+// TMEM-resident tensor engine of the fused luma network (tcgen05, sm_100a): activations AND accumulators live in tensor
+// memory for a whole segment; shared memory holds only the weights and the luma tile.
+//
+// What the reference does per 2x pass (core/src/processor/cuda/Kernel.cu:246-514, CUDAProcessor.cpp:383-566): one launch per
+// layer, fp16 activations through HBM.  What the round-1 engines do: 56x56 frames in shared memory, the 3x3 taps gathered by
+// ldmatrix (mma.sync) or by SS-mode descriptors (tcgen05, 44 cycles per MMA: the A fetch from shared memory is the bound).
+// Measured facts this engine is built on (tools/microbench_tcgen05_ts.cu, profiles/r02_microbench_tcgen05_ts.txt):
+//   * tcgen05.mma with the A operand in TMEM (M = 128, K = 16) costs N / 2 cycles: 24 cycles for N = 48, no operand fetch.
+//   * the .ashift qualifier (multiply, then shift the A rows by one lane inside every 32-lane quadrant: new[r] = old[r + 1])
+//     is free.  A horizontal tap is therefore a lane shift of the operand -- no data movement by any thread.
+//   * a vertical tap is a different A operand (another 8-column group of TMEM) -- free as well.
+//
+// Layout.  A CTA owns four independent STRIPS, one per TMEM lane quadrant: 32 pixels wide (lane = x) and G <= 48 rows tall.
+// Row y of the current layer's 8-channel map is ONE A operand: columns 8y .. 8y+7 of every lane hold the pixel's eight
+// channels as split fp16 (hi words 0-3, lo words 4-7), i.e. K = 16 = {a_hi | a_lo}.  Per row r of the input map the issuing
+// thread runs three alignments (dx = -1, 0, +1 through two .ashift's), each ONE MMA with N = 48 = 3 output rows x (8 couts
+// with w_hi | 8 couts with w_lo): row r contributes to output rows r+1, r, r-1 with the weights of dy = -1, 0, +1, whose
+// accumulators are adjacent 16-column slots of a ring of eight.  All nine taps and all three split-precision products
+// (a_hi w_hi + a_lo w_hi + a_hi w_lo) are accumulated inside the tensor core: 72 tensor cycles per 128 pixels and layer.
+//   The accumulate flag is always set: the epilogue that drains a slot writes the NEXT user's bias back into it (one
+// tcgen05.st), which also makes the bias add free.
+//   Epilogue (warps 4.., one warp per lane quadrant and row): tcgen05.ld of 16 columns, hi + lo, activation, fp16 split,
+// tcgen05.st of the 8 operand columns of the next layer IN PLACE (row y of layer l overwrites row y of layer l - 1, which is
+// dead once row y + 1 has been multiplied).  Nothing is exchanged between threads and no shared memory is touched.
+//   The lane shift drifts the map by one lane per layer (lane j of layer l is pixel x0 + l + j), which consumes exactly the
+// halo a fused segment loses anyway: after R layers lanes 0 .. 31 - 2R hold the strip's 32 - 2R output columns.
+//   Layers are not separated by barriers: rows flow (mbarrier per row / per accumulator slot), so the tensor pipe runs
+// across layer boundaries and under the head conv / the map load of the first rows.
+//   Replicate padding (border CTAs): the epilogue copies the edge values one pixel outwards -- a warp shuffle in x, a second
+// tcgen05.st in y.  Rows outside the image are skipped.
+#pragma once
+
+#include <cuda_fp16.h>
+
+#include "acb200_common.cuh"
+#include "acb200_ffma.cuh"
+#include "acb200_mma.cuh"
+
+namespace acb
+{
+#ifndef ACB_TM_EPI_SETS
+#define ACB_TM_EPI_SETS 4
+#endif
+    constexpr int TM_NR = 8;                        // accumulator ring: slots of 16 columns
+    constexpr int TM_GMAX = 48;                     // rows of a strip frame: 8 * 48 + 16 * 8 = 512 TMEM columns
+    constexpr int TM_D_COL0 = 8 * TM_GMAX;
+    constexpr int TM_SETS = ACB_TM_EPI_SETS;        // epilogue warp sets (4 warps = 4 lane quadrants each)
+    constexpr int TM_THREADS = 128 + 128 * TM_SETS; // warps 0-3 issue the MMAs
+    constexpr int TM_MAX_R = 8;
+#ifndef ACB_TM_ISSUERS
+#define ACB_TM_ISSUERS 4
+#endif
+    constexpr int TM_ISSUERS = ACB_TM_ISSUERS;      // issuer warps (warps 0 .. 3), each takes every TM_ISSUERS-th chunk of the step program
+    constexpr int TM_CHUNK = 4;                     // consecutive steps (input rows) per chunk, >= 3
+    constexpr int TM_B_BYTES_AL = 2 * 48 * 16;      // one alignment: [2 K chunks][48 rows][8 fp16]
+    constexpr int TM_B_BYTES_LAYER = 3 * TM_B_BYTES_AL;     // 4608
+    constexpr int TM_B_WORDS_LAYER = TM_B_BYTES_LAYER / 4;
+    constexpr int TM_LP = 34;                       // luma tile pitch (floats): lanes 0..31 read columns j .. j + 2
+    constexpr int TM_OFF_LUMA = TM_MAX_R * TM_B_BYTES_LAYER;
+    constexpr int TM_OFF_BAR = TM_OFF_LUMA + 4 * (TM_GMAX + 2) * TM_LP * 4;
+    constexpr int TM_N_BARS = TM_GMAX + 2 * TM_NR + 1;
+    constexpr int TM_OFF_GEOM = TM_OFF_BAR + TM_N_BARS * 8 + 8;
+    constexpr int TM_OFF_STEPS = ((TM_OFF_GEOM + 3 * (TM_MAX_R + 2) * 4 + 4 + 15) / 16) * 16;      // the issuer's step program, 32 bytes per input row and layer
+    constexpr int TM_MAX_STEPS = TM_MAX_R * TM_GMAX;
+    constexpr int TM_SMEM_BYTES = TM_OFF_STEPS + TM_MAX_STEPS * 32;
+
+    template<class S>
+    struct TmParams
+    {
+        const void* src;
+        const uint4* map_in;    // previous segment's map, two planes (hi, lo) of [h][w][8 x fp16] (the mma engine's format)
+        uint4* map_out;
+        const float* feat_in;
+        float* feat_out;
+        void* dst;
+        int src_pitch, dst_pitch;
+        int w, h;
+        int type;
+        int tiles_x, strips_x, G;
+        int issuers;            // issuer warps used (1 .. TM_ISSUERS)
+        const uint32_t* bops;   // B operands of this segment's 3x3 convs, TM_B_WORDS_LAYER words each, in layer order
+        float k[(S::HEAD ? 72 : 0) + 64 + 32];  // fp32 weights used outside the MMAs: head (72) | ARNet 1x1 (64) | legacy deconv (32)
+        float b[S::NB];
+        float a[S::NA > 0 ? S::NA : 1];
+    };
+
+    __device__ __forceinline__ bool tm_elect_one()
+    {
+        uint32_t pred;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+        return pred != 0;
+    }
+    __device__ __forceinline__ void tm_mma(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc)
+    {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+                     :: "r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(1u) : "memory");
+    }
+    __device__ __forceinline__ void tm_mma_ashift(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc)
+    {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16.ashift [%0], [%1], %2, %3, p;\n\t}\n"
+                     :: "r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(1u) : "memory");
+    }
+    __device__ __forceinline__ void tm_commit(uint32_t bar)
+    {
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+    }
+    __device__ __forceinline__ void tm_wait(uint32_t bar, uint32_t parity)
+    {
+        uint32_t ok = 0, spins = 0;
+        do
+        {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+            if (!ok && ++spins > (1u << 22)) __trap();      // a protocol bug must fault, never hang the device
+        } while (!ok);
+    }
+    __device__ __forceinline__ void tm_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory"); }
+    __device__ __forceinline__ void tm_ld16(uint32_t (&v)[16], uint32_t taddr)
+    {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+                       "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) : "r"(taddr));
+    }
+    __device__ __forceinline__ void tm_st8(uint32_t taddr, const uint32_t (&v)[8])
+    {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};"
+                     :: "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(taddr) : "memory");
+    }
+    __device__ __forceinline__ void tm_st16(uint32_t taddr, const uint32_t (&v)[16])
+    {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};"
+                     :: "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+                        "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(taddr) : "memory");
+    }
+#define ACB_TM_WAIT_LD() asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory")
+#define ACB_TM_WAIT_ST() asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory")
+#define ACB_TM_FENCE_BEFORE() asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory")
+#define ACB_TM_FENCE_AFTER() asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory")
+
+    // rows of layer l's output that exist: the frame shrunk by l, clipped to the image (frame row y = image row y0 + y)
+    __device__ __forceinline__ void tm_rows(int l, int G, int y0, int h, int& ya, int& yb)
+    {
+        ya = max(l, -y0);
+        yb = min(G - 1 - l, h - 1 - y0);
+    }
+    // Progress words: one byte per lane quadrant (= per epilogue warp working on the row / slot), holding a MONOTONIC count.  (mbarrier
+    // parity waits cannot be used where a waiter may be two phases ahead of the barrier -- several issuer warps run layers apart on
+    // the same row index -- because a phase parity only distinguishes adjacent phases.)
+    __device__ __forceinline__ void tm_wait_bytes(uint32_t addr, uint32_t need)
+    {
+        const uint32_t want = need * 0x01010101u;
+        uint32_t spins = 0;
+        for (;;)
+        {
+            uint32_t w;
+            asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(w) : "r"(addr) : "memory");
+            if (__vcmpgeu4(w, want) == 0xffffffffu) return;
+            if (++spins > (1u << 24)) __trap();     // a protocol bug must fault, never hang the device
+        }
+    }
+    __device__ __forceinline__ void tm_publish_byte(uint32_t addr, uint32_t value)
+    {
+        asm volatile("st.release.cta.shared.u8 [%0], %1;" :: "r"(addr), "r"(value) : "memory");
+    }
+    __device__ __forceinline__ uint32_t tm_test(uint32_t bar_and_parity)
+    {
+        // non-blocking probe of an mbarrier phase (address in bits 0-23, parity in bit 31); 1 = that phase has completed
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok) : "r"(bar_and_parity & 0xffffffu), "r"(bar_and_parity >> 31) : "memory");
+        return ok;
+    }
+
+    template<class S>
+    __global__ void __launch_bounds__(TM_THREADS, 1) segment_tm_kernel(const __grid_constant__ TmParams<S> prm)
+    {
+        constexpr int R = S::R;                 // 3x3 convs of this segment (all on the tensor cores)
+        constexpr int SW = 32 - 2 * R;          // output columns of a strip
+        static_assert(R >= 1 && R <= TM_MAX_R && SW >= 8, "segment too deep for 32-pixel strips");
+        static_assert(S::FAM == ACB200_FAMILY_ACNET_LEGACY || S::FAM == ACB200_FAMILY_ACNET, "family not on this engine yet");
+        extern __shared__ __align__(128) unsigned char smem_tm[];
+        float* luma_all = reinterpret_cast<float*>(smem_tm + TM_OFF_LUMA);
+        const uint32_t bars = static_cast<uint32_t>(__cvta_generic_to_shared(smem_tm + TM_OFF_BAR));
+        // flag_a[row] / flag_e[slot]: progress words (see tm_wait_bytes); bar_full[slot], bar_bop: mbarriers
+        const uint32_t flag_a = bars, bar_full = bars + 8 * TM_GMAX, flag_e = bar_full + 8 * TM_NR, bar_bop = flag_e + 8 * TM_NR;
+        uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_tm + TM_OFF_BAR + TM_N_BARS * 8);
+        int* s_ya = reinterpret_cast<int*>(smem_tm + TM_OFF_GEOM);      // per layer 0..R+1: first / last existing row, dense index of the first
+        int* s_yb = s_ya + TM_MAX_R + 2;
+        int* s_tb = s_yb + TM_MAX_R + 2;
+        int* s_nsteps = s_tb + TM_MAX_R + 2;
+        uint4* steps = reinterpret_cast<uint4*>(smem_tm + TM_OFF_STEPS);
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int G = prm.G, SH = G - 2 * R;
+        const int tile_x = blockIdx.x % prm.tiles_x, sy = blockIdx.x / prm.tiles_x;
+        const int y0 = sy * SH - R;
+
+        // ---- setup ---------------------------------------------------------------------------------------------------------------
+        if (threadIdx.x == 0)
+        {
+            for (int i = 0; i < TM_GMAX; i++) asm volatile("st.shared.u32 [%0], %1;" :: "r"(flag_a + 8 * i), "r"(0));
+            for (int i = 0; i < TM_NR; i++)
+            {
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" :: "r"(bar_full + 8 * i));
+                asm volatile("st.shared.u32 [%0], %1;" :: "r"(flag_e + 8 * i), "r"(0));
+            }
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_bop));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            // the segment's B operands: one bulk copy (UBLKCP) on an mbarrier
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_bop), "r"(R * TM_B_BYTES_LAYER) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_tm))), "l"(reinterpret_cast<uint64_t>(prm.bops)), "r"(R * TM_B_BYTES_LAYER), "r"(bar_bop) : "memory");
+            int tb = 0, ns = 0;
+            for (int l = 0; l <= R; l++)
+            {
+                int ya, yb;
+                tm_rows(l, G, y0, prm.h, ya, yb);
+                s_ya[l] = ya; s_yb[l] = yb; s_tb[l] = tb;
+                if (l >= 1) { tb += max(yb - ya + 1, 0); ns += yb >= ya ? yb - ya + 3 : 0; }
+            }
+            s_ya[R + 1] = 0; s_yb[R + 1] = -1; s_tb[R + 1] = tb;
+            *s_nsteps = ns;
+        }
+        if (warp == 0)
+        {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(static_cast<uint32_t>(__cvta_generic_to_shared(tmem_slot))), "r"(512u));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+        }
+        if constexpr (S::NEEDS_LUMA)
+        {
+            // luma tile of every strip: frame columns -1 .. 32, frame rows -1 .. G, clamp-to-edge (the head conv's own padding)
+            const int n = 4 * (G + 2) * TM_LP;
+            for (int i = threadIdx.x; i < n; i += TM_THREADS)
+            {
+                const int q = i / ((G + 2) * TM_LP), rem = i - q * (G + 2) * TM_LP, ly = rem / TM_LP, lx = rem - ly * TM_LP;
+                const int strip = min(tile_x * 4 + q, prm.strips_x - 1);
+                const int gx = clampi(strip * SW - R - 1 + lx, 0, prm.w - 1), gy = clampi(y0 - 1 + ly, 0, prm.h - 1);
+                luma_all[(q * (TM_GMAX + 2) + ly) * TM_LP + lx] = load_elem(static_cast<const uint8_t*>(prm.src) + static_cast<size_t>(gy) * prm.src_pitch, gx, prm.type);
+            }
+        }
+        ACB_TM_FENCE_BEFORE();
+        __syncthreads();
+        ACB_TM_FENCE_AFTER();
+        const uint32_t tmem = *tmem_slot;
+        constexpr int B0 = S::HEAD ? 8 : 0;     // bias / alpha offsets of the segment's first 3x3 conv inside prm.b / prm.a
+        constexpr int A0 = (S::FAM == ACB200_FAMILY_ACNET && S::HEAD) ? 8 : 0;
+        // bias of the segment's tensor layer ln (1-based) as the initial accumulator of output channel c (the ACNet tail has 4 couts)
+        auto bias_of = [&](const int ln, const int c) -> float {
+            if (S::TAIL && S::FAM == ACB200_FAMILY_ACNET && ln == R && c >= 4) return 0.0f;
+            return prm.b[B0 + 8 * (ln - 1) + c];
+        };
+        if (warp == 0)
+        {
+            // The issuers' step program: one record per (layer, input row), built by the whole warp.
+            //   x: A-row progress word | layers it must have seen << 24
+            //   y: per touched output row j (6 bits each): slot | wait-for-drain << 3, then commits (0-2) << 18 + 2j
+            //   z: A operand     w: first accumulator     x': B descriptor (low word, alignment 0)     y': output rows | rows before the ring wraps << 8
+            //   z': per touched output row j (8 bits each): drains its slot must have seen
+            // Steps are issued in CHUNKS of TM_CHUNK consecutive steps, chunk c by issuer warp c % TM_ISSUERS: every UTCHMMA holds a
+            // scoreboard on its uniform-register operands until the tensor core dequeues it, so a single issuing thread can never run
+            // ahead of the pipe and each of its barrier waits becomes a bubble (120-150 cycles, profiles/r02_microbench_tcgen05_ts.txt).
+            // With several issuers one warp's waits run under the other warps' queued MMAs.  All MMAs accumulate (the epilogue
+            // re-initialises drained accumulators), so their order across rows does not matter; an output row's three input rows lie
+            // in at most two chunks, hence every `full` barrier takes exactly two commits.
+            const uint32_t bop_s = static_cast<uint32_t>(__cvta_generic_to_shared(smem_tm));
+            int base = 0;
+            for (int l = 1; l <= R; l++)
+            {
+                const int ya = s_ya[l], yb = s_yb[l], tb = s_tb[l];
+                if (yb < ya) continue;
+                const int n = yb - ya + 3;
+                for (int k = lane; k < n; k += 32)
+                {
+                    const int i = base + k, r = ya - 1 + k;
+                    const int oa = max(r - 1, ya), ob = min(r + 1, yb), n_rows = ob - oa + 1;
+                    const uint32_t ta = static_cast<uint32_t>(tb + oa - ya);
+                    const int s0 = ta & (TM_NR - 1), first = min(n_rows, TM_NR - s0), jb0 = oa - (r - 1);
+                    const int c0 = (i / TM_CHUNK) * TM_CHUNK, c1 = c0 + TM_CHUNK - 1;       // this step's chunk
+                    uint4 u, v;
+                    u.x = (flag_a + 8 * r) | (static_cast<uint32_t>(l) << 24);     // layer l - 1 publishes l
+                    u.y = 0; v.z = 0;
+                    for (int jj = 0; jj < n_rows; jj++)
+                    {
+                        const int o = oa + jj;
+                        const uint32_t t = static_cast<uint32_t>(tb + o - ya);
+                        const int i_a = base + (o - ya), i_c = i_a + 2;                     // steps of input rows o - 1 and o + 1
+                        const bool first_touch = i == max(i_a, c0), last_touch = i == min(i_c, c1);
+                        uint32_t f = t & (TM_NR - 1);
+                        if (first_touch && t >= TM_NR) { f |= 8u; v.z |= (t >> 3) << (8 * jj); }
+                        u.y |= f << (6 * jj);
+                        if (last_touch) u.y |= ((i_a >= c0 && i_c <= c1) ? 2u : 1u) << (18 + 2 * jj);
+                    }
+                    u.z = tmem + 8 * r;
+                    u.w = tmem + TM_D_COL0 + 16 * s0;
+                    v.x = ((bop_s + (l - 1) * TM_B_BYTES_LAYER + jb0 * 256) >> 4) & 0x3FFF;
+                    v.y = static_cast<uint32_t>(n_rows) | (static_cast<uint32_t>(first) << 8);
+                    v.w = 0;
+                    steps[2 * i] = u;
+                    steps[2 * i + 1] = v;
+                }
+                base += n;
+            }
+        }
+        if (warp >= 4 && warp < 8)
+        {
+            // accumulator ring: every slot starts with its first user's bias (hi-sum columns) and zeros (lo-sum columns)
+            // (slot s is first used by dense row index s, which belongs to a later layer when the frame has few rows)
+            const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+            for (int s = 0; s < TM_NR; s++)
+            {
+                int ln = 1;
+                while (ln <= R && s >= s_tb[ln + 1]) ln++;
+                if (ln > R) break;
+                uint32_t init[16];
+#pragma unroll
+                for (int c = 0; c < 8; c++) { init[c] = __float_as_uint(bias_of(ln, c)); init[8 + c] = 0u; }
+                tm_st16(tmem + lane_base + TM_D_COL0 + 16 * s, init);
+            }
+            ACB_TM_WAIT_ST();
+        }
+        ACB_TM_FENCE_BEFORE();
+        __syncthreads();
+        ACB_TM_FENCE_AFTER();
+
+        if (warp < prm.issuers)
+        {
+            // ==== MMA issuers: warp w takes chunks w, w + TM_ISSUERS, ... of the step program ===============================================
+            if (tm_elect_one())
+            {
+                tm_wait(bar_bop, 0);
+                constexpr uint32_t IDESC0 = (1u << 4) | (static_cast<uint32_t>(128 >> 4) << 24);       // D f32, A / B f16 K-major, M = 128
+                constexpr uint32_t DESC_HI = ((768u >> 4) & 0x3FFF) << 16;                              // LBO (K chunk distance) in the low word
+                constexpr uint32_t DESC_TOP = ((128u >> 4) & 0x3FFF) | (1u << 14);                      // SBO | descriptor version, high word
+                const int nsteps = *s_nsteps;
+#ifdef ACB_TM_TRACE
+                long long tr_blocked = 0; const long long tr_0 = clock64();
+#endif
+#pragma unroll 1
+                for (int c = warp * TM_CHUNK; c < nsteps; c += prm.issuers * TM_CHUNK)
+                {
+                    const int ce = min(c + TM_CHUNK, nsteps);
+#pragma unroll 1
+                    for (int i = c; i < ce; i++)
+                    {
+                        const uint4 u = steps[2 * i], v = steps[2 * i + 1];
+                        const int n_rows = v.y & 0xff, first = v.y >> 8;
+#ifdef ACB_TM_TRACE
+                        const long long tr_1 = clock64();
+#endif
+                        tm_wait_bytes(u.x & 0xffffffu, u.x >> 24);
+#pragma unroll
+                        for (int jj = 0; jj < 3; jj++)
+                        {
+                            const uint32_t f = (u.y >> (6 * jj)) & 0x3f;
+                            if (jj < n_rows && (f & 8u)) tm_wait_bytes(flag_e + 8 * (f & 7u), (v.z >> (8 * jj)) & 0xffu);
+                        }
+#ifdef ACB_TM_TRACE
+                        tr_blocked += clock64() - tr_1;
+#endif
+                        ACB_TM_FENCE_AFTER();
+#pragma unroll
+                        for (int al = 0; al < 3; al++)
+                        {
+                            const uint32_t blo = (v.x + al * (TM_B_BYTES_AL >> 4)) | DESC_HI;
+                            const uint64_t db = static_cast<uint64_t>(blo) | (static_cast<uint64_t>(DESC_TOP) << 32);
+                            if (first == n_rows)
+                            {
+                                const uint32_t idesc = IDESC0 | (static_cast<uint32_t>(2 * n_rows) << 17);
+                                if (al < 2) tm_mma_ashift(u.w, u.z, db, idesc); else tm_mma(u.w, u.z, db, idesc);
+                            }
+                            else
+                            {
+                                // the ring wraps inside this row's outputs: two MMAs, the shift rides on the second
+                                const uint64_t db2 = static_cast<uint64_t>(blo + first * 16) | (static_cast<uint64_t>(DESC_TOP) << 32);
+                                const uint32_t id1 = IDESC0 | (static_cast<uint32_t>(2 * first) << 17), id2 = IDESC0 | (static_cast<uint32_t>(2 * (n_rows - first)) << 17);
+                                tm_mma(u.w, u.z, db, id1);
+                                if (al < 2) tm_mma_ashift(tmem + TM_D_COL0, u.z, db2, id2); else tm_mma(tmem + TM_D_COL0, u.z, db2, id2);
+                            }
+                        }
+                        // output rows that have received this chunk's last contribution
+#pragma unroll
+                        for (int jj = 0; jj < 3; jj++)
+                        {
+                            const uint32_t m = (u.y >> (18 + 2 * jj)) & 3u, bar = bar_full + 8 * ((u.y >> (6 * jj)) & 7u);
+                            if (m >= 1) tm_commit(bar);
+                            if (m >= 2) tm_commit(bar);
+                        }
+                    }
+                }
+#ifdef ACB_TM_TRACE
+                if (blockIdx.x == gridDim.x / 2 + 3) printf("issuer %d: %d steps, total %lld cycles, in barrier waits %lld\n", warp, nsteps, clock64() - tr_0, tr_blocked);
+#endif
+            }
+            __syncwarp();
+        }
+        else if (warp >= 4)
+        {
+            // ==== producers of layer 0 and epilogue of every layer: one warp per lane quadrant (strip) and row ===============================
+            const int set = (warp - 4) >> 2, q = warp & 3;
+            const int strip = min(tile_x * 4 + q, prm.strips_x - 1);
+            const int x0 = strip * SW - R;
+            const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+            const float* luma = luma_all + q * (TM_GMAX + 2) * TM_LP;
+            const int pad_top = -y0 - 1, pad_bot = prm.h - y0;          // frame rows of image rows -1 and h (replicate padding), if inside the frame
+            const uint32_t my_a = tmem + lane_base;
+#ifdef ACB_TM_TRACE
+            long long tr_full = 0, tr_ld = 0, tr_put = 0, tr_items = 0; const long long tr_0 = clock64(); long long tr_head = 0;
+#endif
+
+            // writes one row of layer l's output map as the next layer's A operand (x-clamped in border strips), with its padding copies
+            auto put_row = [&](const int l, const int y, uint32_t (&w8)[8]) {
+                const int L0 = -x0 - l, L1 = prm.w - 1 - x0 - l;       // lanes of image columns 0 and w - 1 in layer l's map
+                if (L0 > 0 || L1 < 31)
+                {
+                    const int srcl = min(max(lane, L0), L1);
+#pragma unroll
+                    for (int c = 0; c < 8; c++) w8[c] = __shfl_sync(0xffffffffu, w8[c], srcl);
+                }
+                tm_st8(my_a + 8 * y, w8);
+                const bool top = (y == pad_top + 1) && pad_top >= 0, bot = (y == pad_bot - 1) && pad_bot <= G - 1;
+                if (top) tm_st8(my_a + 8 * pad_top, w8);
+                if (bot) tm_st8(my_a + 8 * pad_bot, w8);
+                ACB_TM_WAIT_ST();
+                ACB_TM_FENCE_BEFORE();
+                if (lane == 0)
+                {
+                    tm_publish_byte(flag_a + 8 * y + q, l + 1);
+                    if (top) tm_publish_byte(flag_a + 8 * pad_top + q, l + 1);
+                    if (bot) tm_publish_byte(flag_a + 8 * pad_bot + q, l + 1);
+                }
+            };
+
+            // ---- layer 0: the head conv (fp32 FFMA) or the previous segment's map --------------------------------------------------------
+            {
+                const int ya = s_ya[0], yb = s_yb[0];
+                if constexpr (S::HEAD)
+                {
+                    constexpr int ACT = S::FAM == ACB200_FAMILY_ACNET_LEGACY ? ACT_RELU : S::FAM == ACB200_FAMILY_ACNET ? ACT_PRELU : ACT_IDENTITY;
+                    for (int y = ya + set; y <= yb; y += TM_SETS)
+                    {
+                        float r9[9];
+#pragma unroll
+                        for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+                            for (int dx = 0; dx < 3; dx++) r9[dy * 3 + dx] = luma[(y + dy) * TM_LP + lane + dx];
+                        float v[8];
+#pragma unroll
+                        for (int co = 0; co < 8; co++)
+                        {
+                            float s = prm.b[co];
+#pragma unroll
+                            for (int p = 0; p < 9; p++) s = fmaf(r9[p], prm.k[co * 9 + p], s);
+                            if (ACT == ACT_RELU) s = fmaxf(s, 0.0f);
+                            else if (ACT == ACT_PRELU) s = prelu(s, prm.a[co]);
+                            v[co] = s;
+                        }
+                        uint32_t w8[8];
+                        split_pair(v[0], v[1], w8[0], w8[4]); split_pair(v[2], v[3], w8[1], w8[5]);
+                        split_pair(v[4], v[5], w8[2], w8[6]); split_pair(v[6], v[7], w8[3], w8[7]);
+                        put_row(0, y, w8);
+                    }
+                }
+                else
+                {
+                    // the map is read with clamped coordinates: padding included, every frame row inside the image +- 1 exists
+                    const int la = max(ya - 1, 0), lb = min(yb + 1, G - 1);
+                    const int gx = clampi(x0 + lane, 0, prm.w - 1);
+                    const size_t plane = static_cast<size_t>(prm.w) * prm.h;
+                    for (int y = la + set; y <= lb; y += TM_SETS)
+                    {
+                        const int gy = clampi(y0 + y, 0, prm.h - 1);
+                        const uint4 hi = __ldg(prm.map_in + static_cast<size_t>(gy) * prm.w + gx), lo = __ldg(prm.map_in + plane + static_cast<size_t>(gy) * prm.w + gx);
+                        const uint32_t w8[8] = { hi.x, hi.y, hi.z, hi.w, lo.x, lo.y, lo.z, lo.w };
+                        tm_st8(my_a + 8 * y, w8);
+                        ACB_TM_WAIT_ST();
+                        ACB_TM_FENCE_BEFORE();
+                        if (lane == 0) tm_publish_byte(flag_a + 8 * y + q, 1);
+                    }
+                }
+            }
+#ifdef ACB_TM_TRACE
+            tr_head = clock64() - tr_0;
+#endif
+
+            // ---- layers 1 .. R ---------------------------------------------------------------------------------------------------------------
+            const int es = prm.type & 0xff;
+            const bool aligned = ((reinterpret_cast<uintptr_t>(prm.dst) | static_cast<uintptr_t>(prm.dst_pitch)) & (2 * es - 1)) == 0;
+            (void)aligned;
+#pragma unroll 1
+            for (int l = 1; l <= R; l++)
+            {
+                const int ya = s_ya[l], yb = s_yb[l], tb = s_tb[l], t_end = s_tb[l + 1], t_end2 = l < R ? s_tb[l + 2] : 0;
+                const bool last = l == R;
+                // accumulator re-initialisation blocks: this layer's bias and the next layer's (the slot's next user is 8 rows ahead)
+                uint32_t init_c[16], init_n[16];
+#pragma unroll
+                for (int c = 0; c < 8; c++)
+                {
+                    init_c[c] = __float_as_uint(bias_of(l, c)); init_c[8 + c] = 0u;
+                    init_n[c] = __float_as_uint(bias_of(min(l + 1, R), c)); init_n[8 + c] = 0u;
+                }
+                float alpha[8];
+#pragma unroll
+                for (int c = 0; c < 8; c++) alpha[c] = S::FAM == ACB200_FAMILY_ACNET ? prm.a[A0 + 8 * (min(l, S::NCONV) - 1) + c] : 0.0f;
+                // this set's rows: dense index t = tb + (y - ya) with t % TM_SETS == set
+                int y = ya + ((set - tb) % TM_SETS + TM_SETS) % TM_SETS;
+                for (; y <= yb; y += TM_SETS)
+                {
+                    const uint32_t t = static_cast<uint32_t>(tb + y - ya), slot = t & (TM_NR - 1);
+#ifdef ACB_TM_TRACE
+                    const long long tr_1 = clock64();
+#endif
+                    tm_wait(bar_full + 8 * slot, (t >> 3) & 1);
+                    ACB_TM_FENCE_AFTER();
+#ifdef ACB_TM_TRACE
+                    const long long tr_2 = clock64(); tr_full += tr_2 - tr_1; tr_items++;
+#endif
+                    uint32_t d[16];
+                    const uint32_t d_addr = my_a + TM_D_COL0 + 16 * slot;
+                    tm_ld16(d, d_addr);
+                    ACB_TM_WAIT_LD();
+#ifdef ACB_TM_TRACE
+                    const long long tr_3 = clock64(); tr_ld += tr_3 - tr_2;
+#endif
+                    {
+                        // hand the slot to its next user (dense index t + 8) with that layer's bias
+                        const int tn = static_cast<int>(t) + TM_NR;
+                        if (tn < t_end) tm_st16(d_addr, init_c);
+                        else if (!last && tn < t_end2) tm_st16(d_addr, init_n);
+                        else if (!last)
+                        {
+                            int ln = l + 2;     // (frames with fewer than 8 rows per layer)
+                            while (ln <= R && tn >= s_tb[ln + 1]) ln++;
+                            if (ln <= R)
+                            {
+                                uint32_t init[16];
+#pragma unroll
+                                for (int c = 0; c < 8; c++) { init[c] = __float_as_uint(bias_of(ln, c)); init[8 + c] = 0u; }
+                                tm_st16(d_addr, init);
+                            }
+                        }
+                    }
+                    float v[8];
+#pragma unroll
+                    for (int c = 0; c < 8; c++) v[c] = __uint_as_float(d[c]) + __uint_as_float(d[8 + c]);
+                    if (!last || !S::TAIL)
+                    {
+                        // body conv: activation, split, next layer's operand (or the segment's output map)
+                        if constexpr (S::FAM == ACB200_FAMILY_ACNET_LEGACY)
+                        {
+#pragma unroll
+                            for (int c = 0; c < 8; c++) v[c] = fmaxf(v[c], 0.0f);
+                        }
+                        else
+                        {
+#pragma unroll
+                            for (int c = 0; c < 8; c++) v[c] = prelu(v[c], alpha[c]);
+                        }
+                        uint32_t w8[8];
+                        split_pair(v[0], v[1], w8[0], w8[4]); split_pair(v[2], v[3], w8[1], w8[5]);
+                        split_pair(v[4], v[5], w8[2], w8[6]); split_pair(v[6], v[7], w8[3], w8[7]);
+                        if (!last) put_row(l, y, w8);
+                        else
+                        {
+                            const int gx = x0 + R + lane, gy = y0 + y;
+                            if (lane < SW && gx < prm.w)
+                            {
+                                const size_t o = static_cast<size_t>(gy) * prm.w + gx, plane = static_cast<size_t>(prm.w) * prm.h;
+                                prm.map_out[o] = make_uint4(w8[0], w8[1], w8[2], w8[3]);
+                                prm.map_out[plane + o] = make_uint4(w8[4], w8[5], w8[6], w8[7]);
+                            }
+                            ACB_TM_WAIT_ST();
+                            ACB_TM_FENCE_BEFORE();
+                        }
+                    }
+                    else if constexpr (S::TAIL && S::FAM == ACB200_FAMILY_ACNET_LEGACY)
+                    {
+                        // conv + ReLU, then the 2x2 deconvolution (Common.hpp:344-393): four dots of 8, no bias
+                        constexpr int KD = S::HEAD ? 72 : 0;
+#pragma unroll
+                        for (int c = 0; c < 8; c++) v[c] = fmaxf(v[c], 0.0f);
+                        float o4[4];
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                        {
+                            float s = v[0] * prm.k[KD + j * 8];
+#pragma unroll
+                            for (int c = 1; c < 8; c++) s = fmaf(v[c], prm.k[KD + j * 8 + c], s);
+                            o4[j] = s;
+                        }
+                        const int gx = x0 + R + lane, gy = y0 + y;
+                        if (lane < SW && gx < prm.w)
+                        {
+                            uint8_t* row = static_cast<uint8_t*>(prm.dst) + static_cast<size_t>(2 * gy) * prm.dst_pitch;
+                            if (prm.type == ACB200_UINT8 && aligned)
+                            {
+                                const uint8_t q0 = static_cast<uint8_t>(fmaf(__saturatef(o4[0]), 255.0f, 0.5f)), q1 = static_cast<uint8_t>(fmaf(__saturatef(o4[1]), 255.0f, 0.5f));
+                                const uint8_t q2 = static_cast<uint8_t>(fmaf(__saturatef(o4[2]), 255.0f, 0.5f)), q3 = static_cast<uint8_t>(fmaf(__saturatef(o4[3]), 255.0f, 0.5f));
+                                *reinterpret_cast<uchar2*>(row + 2 * gx) = make_uchar2(q0, q1);
+                                *reinterpret_cast<uchar2*>(row + prm.dst_pitch + 2 * gx) = make_uchar2(q2, q3);
+                            }
+                            else
+                            {
+                                net_store2(row, 2 * gx, prm.type, o4[0], o4[1], aligned);
+                                net_store2(row + prm.dst_pitch, 2 * gx, prm.type, o4[2], o4[3], aligned);
+                            }
+                        }
+                        ACB_TM_WAIT_ST();
+                        ACB_TM_FENCE_BEFORE();
+                    }
+                    else if constexpr (S::TAIL && S::FAM == ACB200_FAMILY_ACNET)
+                    {
+                        // conv 8 -> 4 (+ bias, already in the accumulator), + nearest-upsampled luma, pixel shuffle (Common.hpp:290-342)
+                        const int gx = x0 + R + lane, gy = y0 + y;
+                        const float id = luma[(y + 1) * TM_LP + R + lane + 1];
+                        if (lane < SW && gx < prm.w)
+                        {
+                            uint8_t* row = static_cast<uint8_t*>(prm.dst) + static_cast<size_t>(2 * gy) * prm.dst_pitch;
+                            if (prm.type == ACB200_UINT8 && aligned)
+                            {
+                                const uint8_t q0 = static_cast<uint8_t>(__fadd_rn(__fmul_rn(__saturatef(v[0] + id), 255.0f), 0.5f)), q1 = static_cast<uint8_t>(__fadd_rn(__fmul_rn(__saturatef(v[1] + id), 255.0f), 0.5f));
+                                const uint8_t q2 = static_cast<uint8_t>(__fadd_rn(__fmul_rn(__saturatef(v[2] + id), 255.0f), 0.5f)), q3 = static_cast<uint8_t>(__fadd_rn(__fmul_rn(__saturatef(v[3] + id), 255.0f), 0.5f));
+                                *reinterpret_cast<uchar2*>(row + 2 * gx) = make_uchar2(q0, q1);
+                                *reinterpret_cast<uchar2*>(row + prm.dst_pitch + 2 * gx) = make_uchar2(q2, q3);
+                            }
+                            else
+                            {
+                                net_store2(row, 2 * gx, prm.type, v[0] + id, v[1] + id, aligned);
+                                net_store2(row + prm.dst_pitch, 2 * gx, prm.type, v[2] + id, v[3] + id, aligned);
+                            }
+                        }
+                        ACB_TM_WAIT_ST();
+                        ACB_TM_FENCE_BEFORE();
+                    }
+                    if (lane == 0) tm_publish_byte(flag_e + 8 * slot + q, (t >> 3) + 1);
+#ifdef ACB_TM_TRACE
+                    tr_put += clock64() - tr_3;
+#endif
+                }
+            }
+#ifdef ACB_TM_TRACE
+            if (blockIdx.x == gridDim.x / 2 + 3 && lane == 0 && (warp == 4 || warp == 9)) printf("epilogue warp %d: %lld items, total %lld cycles, layer 0 %lld, waiting for full %lld, ld %lld, rest %lld\n", warp, tr_items, clock64() - tr_0, tr_head, tr_full, tr_ld, tr_put);
+#endif
+        }
+        ACB_TM_FENCE_BEFORE();
+        __syncthreads();
+        if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u));
+    }
+}

@@ -249,6 +249,93 @@ __global__ void __launch_bounds__(128, 1) rate_mma(long long* __restrict__ cycle
     TM_FENCE_BEFORE(); __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u));
 }
+// What the issuing thread pays per "row" of the engine besides the MMAs: VARIANT bit 0 = tcgen05.commit per row, bit 1 = one mbarrier
+// try_wait on an ALREADY COMPLETE barrier per row, bit 2 = tcgen05.fence::after_thread_sync per row, bit 3 = a second try_wait.
+template<int VARIANT>
+__global__ void __launch_bounds__(128, 1) issue_cost(long long* __restrict__ cycles, int rows)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 48 * 1024);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 48 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    if (tid == 0)
+    {
+        for (int i = 0; i < 8; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(bars + i)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bars + 4)) : "memory");     // bars[4], bars[5]: phase 0 complete
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bars + 5)) : "memory");
+    }
+    if (warp == 0)
+    {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    TM_FENCE_BEFORE(); __syncthreads(); TM_FENCE_AFTER();
+    const uint32_t tmem = *tmem_slot;
+    {
+        uint32_t v[16];
+        for (int j = 0; j < 16; j++) v[j] = 0x3c003c00u;
+        for (int c = 0; c < 512; c += 16) tm_st16(tmem + (static_cast<uint32_t>(warp * 32) << 16) + c, v);
+        TM_WAIT_ST();
+    }
+    TM_FENCE_BEFORE(); __syncthreads(); TM_FENCE_AFTER();
+    constexpr uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(48 >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+    const uint32_t b_base = smem_u32(smem);
+    if (warp == 0 && elect_one())
+    {
+        uint64_t db[3];
+        for (int j = 0; j < 3; j++) db[j] = make_desc(b_base + j * 1536, 768, 128);
+        const long long t0 = clock64();
+        for (int r = 0; r < rows; r++)
+        {
+            if (VARIANT & 2) mbar_wait(smem_u32(bars + 4), 0);
+            if (VARIANT & 8) mbar_wait(smem_u32(bars + 5), 0);
+            if (VARIANT & 16)
+            {
+                // plain shared-memory flag poll (what a producer would publish with st.shared after its fences)
+                uint32_t f;
+                do { asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(f) : "r"(smem_u32(bars + 6)) : "memory"); } while (f == 0xdeadbeefu);
+            }
+            if (VARIANT & 32)
+            {
+                uint32_t ok;
+                do { asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(ok) : "r"(smem_u32(bars + 4)), "r"(0) : "memory"); } while (!ok);
+            }
+            if (VARIANT & 64)
+            {
+                // software-pipelined flag: the load for the NEXT row is issued before this row's MMAs, consumed a row later
+                static_assert(true, "");
+            }
+            if (VARIANT & 4) TM_FENCE_AFTER();
+            const uint32_t a = tmem + 8 * (r % 48), d = tmem + 384 + 16 * (r & 3);
+            mma_ts_ashift(d, a, db[0], idesc, 1);
+            mma_ts_ashift(d, a, db[1], idesc, 1);
+            mma_ts(d, a, db[2], idesc, 1);
+            if (VARIANT & 1) tm_commit(smem_u32(bars + 1 + (r & 1)));
+        }
+        tm_commit(smem_u32(bars));
+        mbar_wait(smem_u32(bars), 0);
+        cycles[blockIdx.x] = clock64() - t0;
+    }
+    TM_FENCE_BEFORE(); __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u));
+}
+template<int VARIANT>
+void run_issue(long long* dc)
+{
+    const int rows = 4000;
+    cudaFuncSetAttribute(issue_cost<VARIANT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024 + 128);
+    issue_cost<VARIANT><<<148, 128, 48 * 1024 + 128>>>(dc, rows);
+    cudaError_t e = cudaDeviceSynchronize();
+    std::vector<long long> hc(148);
+    cudaMemcpy(hc.data(), dc, 148 * 8, cudaMemcpyDeviceToHost);
+    double a = 0; for (auto c : hc) a += double(c);
+    printf("issuer row = {ashift, ashift, plain} N=48%s%s%s%s%s%s: %s, %.1f cycles per row\n", (VARIANT & 16) ? " + ld.volatile.shared poll" : "", (VARIANT & 32) ? " + test_wait(complete)" : "", (VARIANT & 1) ? " + commit" : "", (VARIANT & 2) ? " + try_wait(complete)" : "",
+           (VARIANT & 8) ? " + try_wait(complete)" : "", (VARIANT & 4) ? " + fence::after_thread_sync" : "", cudaGetErrorString(e), a / 148 / rows);
+}
+
 template<int N, int PATTERN, int COMMITS>
 void run_rate(long long* dc)
 {
@@ -385,6 +472,7 @@ int main()
         run_rate<16, 4, 0>(dc); run_rate<48, 4, 0>(dc); run_rate<96, 4, 0>(dc);
         run_rate<48, 5, 0>(dc);
         run_rate<24, 3, 1>(dc); run_rate<48, 3, 1>(dc); run_rate<48, 2, 1>(dc); run_rate<48, 4, 1>(dc); run_rate<48, 1, 1>(dc);
+        run_issue<0>(dc); run_issue<1>(dc); run_issue<2>(dc); run_issue<3>(dc); run_issue<4>(dc); run_issue<7>(dc); run_issue<15>(dc); run_issue<16 + 1 + 4>(dc); run_issue<32 + 1 + 4>(dc);
         cudaFree(dc);
     }
     // ---- TMEM load / store rates ---------------------------------------------------------------------------------------------
