@@ -308,10 +308,10 @@ namespace
                         m[0 * (TC_N * 8) + n_lo * 8 + ci] = static_cast<uint16_t>(lo);     // chunk 0 (a_hi) x w_lo
                     }
     }
-    // B operand of one 3x3 conv for the TMEM-resident engine (acb200_tm.cuh): for every alignment al (dx = al - 1) a
-    // [N = 48][K = 16] fp16 matrix in the no-swizzle K-major canonical layout (element (n, k) at byte (k/8)*768 + n*16 + (k%8)*2).
-    // Row n = jo*16 + j: jo selects the output row relative to the input row (o = r - 1 + jo, i.e. dy = 1 - jo); j < 8 -> cout j, both
-    // K chunks (a_hi, a_lo) carry w_hi; j >= 8 -> cout j - 8, chunk 0 carries w_lo and chunk 1 is zero.
+    // B operands of one 3x3 conv for the TMEM-resident engine (acb200_tm.cuh): for every alignment al (dx = al - 1) TWO [N = 24][K = 16]
+    // fp16 matrices in the no-swizzle K-major canonical layout (element (n, k) at byte (k/8)*384 + n*16 + (k%8)*2).  Row n = jo*8 + co:
+    // jo selects the output row relative to the input row (o = r - 1 + jo, i.e. dy = 1 - jo), co the output channel.  First matrix: both
+    // K chunks (a_hi, a_lo) carry w_hi; second matrix: chunk 0 carries w_lo, chunk 1 is zero.  Both accumulate into the same columns.
     void pack_bop_tm(const float* W, int cout, std::vector<uint32_t>& out)
     {
         const size_t base = out.size();
@@ -325,11 +325,12 @@ namespace
                         const int dy = 1 - jo, dx = al - 1;
                         uint32_t hi, lo;
                         split_w(W[(co * 9 + (dy + 1) * 3 + (dx + 1)) * 8 + ci], hi, lo);
-                        uint16_t* m = h + al * (TM_B_BYTES_AL / 2);
-                        const int n_hi = jo * 16 + co, n_lo = jo * 16 + 8 + co;
-                        m[0 * (48 * 8) + n_hi * 8 + ci] = static_cast<uint16_t>(hi);
-                        m[1 * (48 * 8) + n_hi * 8 + ci] = static_cast<uint16_t>(hi);
-                        m[0 * (48 * 8) + n_lo * 8 + ci] = static_cast<uint16_t>(lo);
+                        uint16_t* m1 = h + al * (TM_B_BYTES_AL / 2);
+                        uint16_t* m2 = m1 + TM_B_BYTES_HALF / 2;
+                        const int n = jo * 8 + co;
+                        m1[0 * (24 * 8) + n * 8 + ci] = static_cast<uint16_t>(hi);
+                        m1[1 * (24 * 8) + n * 8 + ci] = static_cast<uint16_t>(hi);
+                        m2[0 * (24 * 8) + n * 8 + ci] = static_cast<uint16_t>(lo);
                     }
     }
     template<class S>

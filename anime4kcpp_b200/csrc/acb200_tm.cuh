@@ -41,18 +41,24 @@ namespace acb
 #ifndef ACB_TM_EPI_SETS
 #define ACB_TM_EPI_SETS 4
 #endif
-    constexpr int TM_NR = 8;                        // accumulator ring: slots of 16 columns
-    constexpr int TM_GMAX = 48;                     // rows of a strip frame: 8 * 48 + 16 * 8 = 512 TMEM columns
+    constexpr int TM_NR = 16;                       // accumulator ring: slots of 8 columns
+    constexpr int TM_GMAX = 48;                     // rows of a strip frame: 8 * 48 + 8 * 16 = 512 TMEM columns
     constexpr int TM_D_COL0 = 8 * TM_GMAX;
+#ifndef ACB_TM_ISSUERS
+#define ACB_TM_ISSUERS 8
+#endif
+    constexpr int TM_ISSUERS_DECL = ACB_TM_ISSUERS;
     constexpr int TM_SETS = ACB_TM_EPI_SETS;        // epilogue warp sets (4 warps = 4 lane quadrants each)
-    constexpr int TM_THREADS = 128 + 128 * TM_SETS; // warps 0-3 issue the MMAs
+    constexpr int TM_THREADS = 32 * TM_ISSUERS_DECL + 128 * TM_SETS;
     constexpr int TM_MAX_R = 8;
 #ifndef ACB_TM_ISSUERS
-#define ACB_TM_ISSUERS 4
+#define ACB_TM_ISSUERS 8
 #endif
-    constexpr int TM_ISSUERS = ACB_TM_ISSUERS;      // issuer warps (warps 0 .. 3), each takes every TM_ISSUERS-th chunk of the step program
+    constexpr int TM_ISSUERS = ACB_TM_ISSUERS;      // issuer warps (warps 0 .. TM_ISSUERS - 1), each takes every TM_ISSUERS-th chunk of the step program
+    constexpr int TM_EPI_WARP0 = TM_ISSUERS;        // first epilogue warp (a multiple of 4: warp w works on TMEM lane quadrant w % 4)
     constexpr int TM_CHUNK = 4;                     // consecutive steps (input rows) per chunk, >= 3
-    constexpr int TM_B_BYTES_AL = 2 * 48 * 16;      // one alignment: [2 K chunks][48 rows][8 fp16]
+    constexpr int TM_B_BYTES_HALF = 2 * 24 * 16;    // one B matrix: [2 K chunks][24 rows][8 fp16]
+    constexpr int TM_B_BYTES_AL = 2 * TM_B_BYTES_HALF;      // one alignment: the w_hi matrix, then the w_lo matrix
     constexpr int TM_B_BYTES_LAYER = 3 * TM_B_BYTES_AL;     // 4608
     constexpr int TM_B_WORDS_LAYER = TM_B_BYTES_LAYER / 4;
     constexpr int TM_LP = 34;                       // luma tile pitch (floats): lanes 0..31 read columns j .. j + 2
@@ -60,9 +66,14 @@ namespace acb
     constexpr int TM_OFF_BAR = TM_OFF_LUMA + 4 * (TM_GMAX + 2) * TM_LP * 4;
     constexpr int TM_N_BARS = TM_GMAX + 2 * TM_NR + 1;
     constexpr int TM_OFF_GEOM = TM_OFF_BAR + TM_N_BARS * 8 + 8;
-    constexpr int TM_OFF_STEPS = ((TM_OFF_GEOM + 3 * (TM_MAX_R + 2) * 4 + 4 + 15) / 16) * 16;      // the issuer's step program, 32 bytes per input row and layer
+    constexpr int TM_OFF_STEPS = ((TM_OFF_GEOM + 3 * (TM_MAX_R + 2) * 4 + 4 + 15) / 16) * 16;      // the issuers' step program, 64 bytes per input row and layer
     constexpr int TM_MAX_STEPS = TM_MAX_R * TM_GMAX;
-    constexpr int TM_SMEM_BYTES = TM_OFF_STEPS + TM_MAX_STEPS * 32;
+#ifdef ACB_TM_TRACE
+    constexpr int TM_OFF_TRACE = TM_OFF_STEPS + TM_MAX_STEPS * 64;
+    constexpr int TM_SMEM_BYTES = TM_OFF_TRACE + 4 * TM_MAX_STEPS * 8;
+#else
+    constexpr int TM_SMEM_BYTES = TM_OFF_STEPS + TM_MAX_STEPS * 64;
+#endif
 
     template<class S>
     struct TmParams
@@ -122,6 +133,11 @@ namespace acb
                      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
                        "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) : "r"(taddr));
     }
+    __device__ __forceinline__ void tm_ld8(uint32_t (&v)[8], uint32_t taddr)
+    {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr));
+    }
     __device__ __forceinline__ void tm_st8(uint32_t taddr, const uint32_t (&v)[8])
     {
         asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};"
@@ -149,19 +165,24 @@ namespace acb
     // the same row index -- because a phase parity only distinguishes adjacent phases.)
     __device__ __forceinline__ void tm_wait_bytes(uint32_t addr, uint32_t need)
     {
+        // every byte of the word >= need (all values < 128): ((b | 0x80) - need) keeps its top bit exactly when b >= need, and no
+        // byte borrows from its neighbour
         const uint32_t want = need * 0x01010101u;
         uint32_t spins = 0;
         for (;;)
         {
             uint32_t w;
             asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(w) : "r"(addr) : "memory");
-            if (__vcmpgeu4(w, want) == 0xffffffffu) return;
-            if (++spins > (1u << 24)) __trap();     // a protocol bug must fault, never hang the device
+            if ((((w | 0x80808080u) - want) & 0x80808080u) == 0x80808080u) return;
+            if (++spins > (1u << 22)) __trap();     // a protocol bug must fault, never hang the device
         }
     }
+    // publish: plain byte stores.  What they publish are TMEM writes whose COMPLETION the publishing thread has already waited for
+    // (tcgen05.wait::st / wait::ld, then tcgen05.fence::before_thread_sync), so no membar is needed in front of the flag store; a
+    // MEMBAR.ALL.CTA per row cost more than the row's arithmetic.
     __device__ __forceinline__ void tm_publish_byte(uint32_t addr, uint32_t value)
     {
-        asm volatile("st.release.cta.shared.u8 [%0], %1;" :: "r"(addr), "r"(value) : "memory");
+        asm volatile("st.volatile.shared.u8 [%0], %1;" :: "r"(addr), "r"(value) : "memory");
     }
     __device__ __forceinline__ uint32_t tm_test(uint32_t bar_and_parity)
     {
@@ -190,6 +211,10 @@ namespace acb
         int* s_tb = s_yb + TM_MAX_R + 2;
         int* s_nsteps = s_tb + TM_MAX_R + 2;
         uint4* steps = reinterpret_cast<uint4*>(smem_tm + TM_OFF_STEPS);
+#ifdef ACB_TM_TRACE
+        long long* trace = reinterpret_cast<long long*>(smem_tm + TM_OFF_TRACE);    // [0] step: start, [1] step: issued, [2] row: full seen, [3] row: published
+        const bool traced = blockIdx.x == gridDim.x / 2 + 3;
+#endif
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         const int G = prm.G, SH = G - 2 * R;
         const int tile_x = blockIdx.x % prm.tiles_x, sy = blockIdx.x / prm.tiles_x;
@@ -252,18 +277,21 @@ namespace acb
         };
         if (warp == 0)
         {
-            // The issuers' step program: one record per (layer, input row), built by the whole warp.
-            //   x: A-row progress word | layers it must have seen << 24
-            //   y: per touched output row j (6 bits each): slot | wait-for-drain << 3, then commits (0-2) << 18 + 2j
-            //   z: A operand     w: first accumulator     x': B descriptor (low word, alignment 0)     y': output rows | rows before the ring wraps << 8
-            //   z': per touched output row j (8 bits each): drains its slot must have seen
-            // Steps are issued in CHUNKS of TM_CHUNK consecutive steps, chunk c by issuer warp c % TM_ISSUERS: every UTCHMMA holds a
+            // The issuers' step program: one record of four uint4 per (layer, input row), built by the whole warp, with every operand the
+            // issue loop needs already in its final form:
+            //   [0] up to four waits (progress word | count << 24; 0 = none): the A row, then the accumulator slots this chunk touches first
+            //   [1] A operand, first run: accumulator / B descriptor low word / instruction descriptor
+            //   [2] second run (only when the accumulator ring wraps inside this row's outputs): accumulator (0 = none) / B / instruction descriptor
+            //   [3] up to four `full` barriers to commit to (0 = none)
+            // Steps are issued in CHUNKS of TM_CHUNK consecutive steps, chunk c by issuer warp c % issuers: every UTCHMMA holds a
             // scoreboard on its uniform-register operands until the tensor core dequeues it, so a single issuing thread can never run
             // ahead of the pipe and each of its barrier waits becomes a bubble (120-150 cycles, profiles/r02_microbench_tcgen05_ts.txt).
             // With several issuers one warp's waits run under the other warps' queued MMAs.  All MMAs accumulate (the epilogue
             // re-initialises drained accumulators), so their order across rows does not matter; an output row's three input rows lie
             // in at most two chunks, hence every `full` barrier takes exactly two commits.
             const uint32_t bop_s = static_cast<uint32_t>(__cvta_generic_to_shared(smem_tm));
+            constexpr uint32_t IDESC0 = (1u << 4) | (static_cast<uint32_t>(128 >> 4) << 24);       // D f32, A / B f16 K-major, M = 128
+            constexpr uint32_t DESC_HI = ((384u >> 4) & 0x3FFF) << 16;                              // LBO (K chunk distance: 24 rows) in the low word
             int base = 0;
             for (int l = 1; l <= R; l++)
             {
@@ -277,34 +305,42 @@ namespace acb
                     const uint32_t ta = static_cast<uint32_t>(tb + oa - ya);
                     const int s0 = ta & (TM_NR - 1), first = min(n_rows, TM_NR - s0), jb0 = oa - (r - 1);
                     const int c0 = (i / TM_CHUNK) * TM_CHUNK, c1 = c0 + TM_CHUNK - 1;       // this step's chunk
-                    uint4 u, v;
-                    u.x = (flag_a + 8 * r) | (static_cast<uint32_t>(l) << 24);     // layer l - 1 publishes l
-                    u.y = 0; v.z = 0;
+                    uint32_t wv[4] = { (flag_a + 8 * r) | (static_cast<uint32_t>(l) << 24), 0u, 0u, 0u };      // layer l - 1 publishes l
+                    uint32_t cv[4] = { 0u, 0u, 0u, 0u };
+                    int nw = 1, nc = 0;
                     for (int jj = 0; jj < n_rows; jj++)
                     {
                         const int o = oa + jj;
-                        const uint32_t t = static_cast<uint32_t>(tb + o - ya);
+                        const uint32_t t = static_cast<uint32_t>(tb + o - ya), slot = t & (TM_NR - 1);
                         const int i_a = base + (o - ya), i_c = i_a + 2;                     // steps of input rows o - 1 and o + 1
-                        const bool first_touch = i == max(i_a, c0), last_touch = i == min(i_c, c1);
-                        uint32_t f = t & (TM_NR - 1);
-                        if (first_touch && t >= TM_NR) { f |= 8u; v.z |= (t >> 3) << (8 * jj); }
-                        u.y |= f << (6 * jj);
-                        if (last_touch) u.y |= ((i_a >= c0 && i_c <= c1) ? 2u : 1u) << (18 + 2 * jj);
+                        if (i == max(i_a, c0) && t >= TM_NR) wv[nw++] = (flag_e + 8 * slot) | ((t >> 4) << 24);    // first touch by this chunk: the slot's previous user must be drained
+                        if (i == min(i_c, c1))                                                                     // last touch by this chunk
+                        {
+                            cv[nc++] = bar_full + 8 * slot;
+                            if (i_a >= c0 && i_c <= c1) cv[nc++] = bar_full + 8 * slot;                          // all three input rows in this chunk: both commits
+                        }
                     }
-                    u.z = tmem + 8 * r;
-                    u.w = tmem + TM_D_COL0 + 16 * s0;
-                    v.x = ((bop_s + (l - 1) * TM_B_BYTES_LAYER + jb0 * 256) >> 4) & 0x3FFF;
-                    v.y = static_cast<uint32_t>(n_rows) | (static_cast<uint32_t>(first) << 8);
-                    v.w = 0;
-                    steps[2 * i] = u;
-                    steps[2 * i + 1] = v;
+                    const uint32_t b1 = (((bop_s + (l - 1) * TM_B_BYTES_LAYER + jb0 * 128) >> 4) & 0x3FFF) | DESC_HI;
+                    uint4 m1, m2;
+                    m1.x = tmem + 8 * r;
+                    m1.y = tmem + TM_D_COL0 + 8 * s0;
+                    m1.z = b1;
+                    m1.w = IDESC0 | (static_cast<uint32_t>(first) << 17);
+                    m2.x = first < n_rows ? tmem + TM_D_COL0 : 0u;
+                    m2.y = b1 + first * 8;
+                    m2.z = IDESC0 | (static_cast<uint32_t>(n_rows - first) << 17);
+                    m2.w = static_cast<uint32_t>(l);
+                    steps[4 * i] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+                    steps[4 * i + 1] = m1;
+                    steps[4 * i + 2] = m2;
+                    steps[4 * i + 3] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
                 }
                 base += n;
             }
         }
-        if (warp >= 4 && warp < 8)
+        if (warp >= TM_EPI_WARP0 && warp < TM_EPI_WARP0 + 4)
         {
-            // accumulator ring: every slot starts with its first user's bias (hi-sum columns) and zeros (lo-sum columns)
+            // accumulator ring: every slot starts with its first user's bias
             // (slot s is first used by dense row index s, which belongs to a later layer when the frame has few rows)
             const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
             for (int s = 0; s < TM_NR; s++)
@@ -312,10 +348,10 @@ namespace acb
                 int ln = 1;
                 while (ln <= R && s >= s_tb[ln + 1]) ln++;
                 if (ln > R) break;
-                uint32_t init[16];
+                uint32_t init[8];
 #pragma unroll
-                for (int c = 0; c < 8; c++) { init[c] = __float_as_uint(bias_of(ln, c)); init[8 + c] = 0u; }
-                tm_st16(tmem + lane_base + TM_D_COL0 + 16 * s, init);
+                for (int c = 0; c < 8; c++) init[c] = __float_as_uint(bias_of(ln, c));
+                tm_st8(tmem + lane_base + TM_D_COL0 + 8 * s, init);
             }
             ACB_TM_WAIT_ST();
         }
@@ -329,9 +365,7 @@ namespace acb
             if (tm_elect_one())
             {
                 tm_wait(bar_bop, 0);
-                constexpr uint32_t IDESC0 = (1u << 4) | (static_cast<uint32_t>(128 >> 4) << 24);       // D f32, A / B f16 K-major, M = 128
-                constexpr uint32_t DESC_HI = ((768u >> 4) & 0x3FFF) << 16;                              // LBO (K chunk distance) in the low word
-                constexpr uint32_t DESC_TOP = ((128u >> 4) & 0x3FFF) | (1u << 14);                      // SBO | descriptor version, high word
+                constexpr uint64_t DESC_TOP = static_cast<uint64_t>(((128u >> 4) & 0x3FFF) | (1u << 14)) << 32;     // SBO | descriptor version, high word
                 const int nsteps = *s_nsteps;
 #ifdef ACB_TM_TRACE
                 long long tr_blocked = 0; const long long tr_0 = clock64();
@@ -339,65 +373,83 @@ namespace acb
 #pragma unroll 1
                 for (int c = warp * TM_CHUNK; c < nsteps; c += prm.issuers * TM_CHUNK)
                 {
-                    const int ce = min(c + TM_CHUNK, nsteps);
-#pragma unroll 1
-                    for (int i = c; i < ce; i++)
-                    {
-                        const uint4 u = steps[2 * i], v = steps[2 * i + 1];
-                        const int n_rows = v.y & 0xff, first = v.y >> 8;
-#ifdef ACB_TM_TRACE
-                        const long long tr_1 = clock64();
-#endif
-                        tm_wait_bytes(u.x & 0xffffffu, u.x >> 24);
+                    // all of the chunk's records, then all of its waits, then its MMAs back to back (a poll between MMAs would wait for
+                    // the MMAs this thread has in flight)
+                    uint4 wv[TM_CHUNK], m1[TM_CHUNK], m2[TM_CHUNK], cv[TM_CHUNK];
 #pragma unroll
-                        for (int jj = 0; jj < 3; jj++)
-                        {
-                            const uint32_t f = (u.y >> (6 * jj)) & 0x3f;
-                            if (jj < n_rows && (f & 8u)) tm_wait_bytes(flag_e + 8 * (f & 7u), (v.z >> (8 * jj)) & 0xffu);
-                        }
+                    for (int k = 0; k < TM_CHUNK; k++)
+                    {
+                        const int i = min(c + k, nsteps - 1);
+                        wv[k] = steps[4 * i]; m1[k] = steps[4 * i + 1]; m2[k] = steps[4 * i + 2]; cv[k] = steps[4 * i + 3];
+                    }
 #ifdef ACB_TM_TRACE
-                        tr_blocked += clock64() - tr_1;
+                    const long long tr_1 = clock64();
+                    trace[c] = tr_1;
 #endif
-                        ACB_TM_FENCE_AFTER();
+                    // (a chunk that spans two layers of a very short frame can depend on its own earlier steps: it waits step by step)
+                    const bool batched = m2[0].w == m2[TM_CHUNK - 1].w;
+                    auto wait_step = [&](const uint4& w) {
+                        tm_wait_bytes(w.x & 0xffffffu, w.x >> 24);
+                        if (w.y) tm_wait_bytes(w.y & 0xffffffu, w.y >> 24);
+                        if (w.z) tm_wait_bytes(w.z & 0xffffffu, w.z >> 24);
+                        if (w.w) tm_wait_bytes(w.w & 0xffffffu, w.w >> 24);
+                    };
+                    if (batched)
+                    {
+#ifdef ACB_TM_TRACE
+#pragma unroll
+                        for (int k = 0; k < TM_CHUNK; k++) if (c + k < nsteps) tm_wait_bytes(wv[k].x & 0xffffffu, wv[k].x >> 24);
+                        trace[c + 1] = clock64();
+#endif
+#pragma unroll
+                        for (int k = 0; k < TM_CHUNK; k++) if (c + k < nsteps) wait_step(wv[k]);
+                    }
+#ifdef ACB_TM_TRACE
+                    tr_blocked += clock64() - tr_1;
+                    trace[TM_MAX_STEPS + c] = clock64();
+#endif
+                    ACB_TM_FENCE_AFTER();
+#pragma unroll
+                    for (int k = 0; k < TM_CHUNK; k++)
+                    {
+                        if (c + k >= nsteps) break;
+                        if (!batched) { wait_step(wv[k]); ACB_TM_FENCE_AFTER(); }
+                        // per alignment: the w_hi matrix ((a_hi + a_lo) w_hi), then the w_lo matrix (a_hi w_lo) into the SAME 8 columns per
+                        // output row; the operand shift rides on the alignment's last MMA
 #pragma unroll
                         for (int al = 0; al < 3; al++)
                         {
-                            const uint32_t blo = (v.x + al * (TM_B_BYTES_AL >> 4)) | DESC_HI;
-                            const uint64_t db = static_cast<uint64_t>(blo) | (static_cast<uint64_t>(DESC_TOP) << 32);
-                            if (first == n_rows)
+                            const uint32_t o_hi = al * (TM_B_BYTES_AL >> 4), o_lo = o_hi + (TM_B_BYTES_HALF >> 4);
+                            if (m2[k].x == 0u)
                             {
-                                const uint32_t idesc = IDESC0 | (static_cast<uint32_t>(2 * n_rows) << 17);
-                                if (al < 2) tm_mma_ashift(u.w, u.z, db, idesc); else tm_mma(u.w, u.z, db, idesc);
+                                tm_mma(m1[k].y, m1[k].x, DESC_TOP | (m1[k].z + o_hi), m1[k].w);
+                                if (al < 2) tm_mma_ashift(m1[k].y, m1[k].x, DESC_TOP | (m1[k].z + o_lo), m1[k].w); else tm_mma(m1[k].y, m1[k].x, DESC_TOP | (m1[k].z + o_lo), m1[k].w);
                             }
                             else
                             {
-                                // the ring wraps inside this row's outputs: two MMAs, the shift rides on the second
-                                const uint64_t db2 = static_cast<uint64_t>(blo + first * 16) | (static_cast<uint64_t>(DESC_TOP) << 32);
-                                const uint32_t id1 = IDESC0 | (static_cast<uint32_t>(2 * first) << 17), id2 = IDESC0 | (static_cast<uint32_t>(2 * (n_rows - first)) << 17);
-                                tm_mma(u.w, u.z, db, id1);
-                                if (al < 2) tm_mma_ashift(tmem + TM_D_COL0, u.z, db2, id2); else tm_mma(tmem + TM_D_COL0, u.z, db2, id2);
+                                tm_mma(m1[k].y, m1[k].x, DESC_TOP | (m1[k].z + o_hi), m1[k].w);
+                                tm_mma(m1[k].y, m1[k].x, DESC_TOP | (m1[k].z + o_lo), m1[k].w);
+                                tm_mma(m2[k].x, m1[k].x, DESC_TOP | (m2[k].y + o_hi), m2[k].z);
+                                if (al < 2) tm_mma_ashift(m2[k].x, m1[k].x, DESC_TOP | (m2[k].y + o_lo), m2[k].z); else tm_mma(m2[k].x, m1[k].x, DESC_TOP | (m2[k].y + o_lo), m2[k].z);
                             }
                         }
                         // output rows that have received this chunk's last contribution
-#pragma unroll
-                        for (int jj = 0; jj < 3; jj++)
-                        {
-                            const uint32_t m = (u.y >> (18 + 2 * jj)) & 3u, bar = bar_full + 8 * ((u.y >> (6 * jj)) & 7u);
-                            if (m >= 1) tm_commit(bar);
-                            if (m >= 2) tm_commit(bar);
-                        }
+                        if (cv[k].x) tm_commit(cv[k].x);
+                        if (cv[k].y) tm_commit(cv[k].y);
+                        if (cv[k].z) tm_commit(cv[k].z);
+                        if (cv[k].w) tm_commit(cv[k].w);
                     }
                 }
 #ifdef ACB_TM_TRACE
-                if (blockIdx.x == gridDim.x / 2 + 3) printf("issuer %d: %d steps, total %lld cycles, in barrier waits %lld\n", warp, nsteps, clock64() - tr_0, tr_blocked);
+                if (traced) printf("issuer %d: %d steps, total %lld cycles, in waits %lld\n", warp, nsteps, clock64() - tr_0, tr_blocked);
 #endif
             }
             __syncwarp();
         }
-        else if (warp >= 4)
+        else if (warp >= TM_EPI_WARP0)
         {
             // ==== producers of layer 0 and epilogue of every layer: one warp per lane quadrant (strip) and row ===============================
-            const int set = (warp - 4) >> 2, q = warp & 3;
+            const int set = (warp - TM_EPI_WARP0) >> 2, q = warp & 3;
             const int strip = min(tile_x * 4 + q, prm.strips_x - 1);
             const int x0 = strip * SW - R;
             const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
@@ -405,10 +457,12 @@ namespace acb
             const int pad_top = -y0 - 1, pad_bot = prm.h - y0;          // frame rows of image rows -1 and h (replicate padding), if inside the frame
             const uint32_t my_a = tmem + lane_base;
 #ifdef ACB_TM_TRACE
-            long long tr_full = 0, tr_ld = 0, tr_put = 0, tr_items = 0; const long long tr_0 = clock64(); long long tr_head = 0;
+            long long tr_full = 0, tr_ld = 0, tr_put = 0, tr_items = 0; const long long tr_wst = 0; const long long tr_0 = clock64(); long long tr_head = 0;
 #endif
 
-            // writes one row of layer l's output map as the next layer's A operand (x-clamped in border strips), with its padding copies
+            // writes one row of layer l's output map as the next layer's A operand (x-clamped in border strips), with its padding copies.
+            // Every lane stores the progress byte (same address, same value: one shared-memory store, no branch).
+            const bool pads = (pad_top >= 0) || (pad_bot <= G - 1);     // the frame reaches over the top / bottom image edge
             auto put_row = [&](const int l, const int y, uint32_t (&w8)[8]) {
                 const int L0 = -x0 - l, L1 = prm.w - 1 - x0 - l;       // lanes of image columns 0 and w - 1 in layer l's map
                 if (L0 > 0 || L1 < 31)
@@ -418,17 +472,21 @@ namespace acb
                     for (int c = 0; c < 8; c++) w8[c] = __shfl_sync(0xffffffffu, w8[c], srcl);
                 }
                 tm_st8(my_a + 8 * y, w8);
+                if (!pads)
+                {
+                    ACB_TM_WAIT_ST();
+                    ACB_TM_FENCE_BEFORE();
+                    tm_publish_byte(flag_a + 8 * y + q, l + 1);
+                    return;
+                }
                 const bool top = (y == pad_top + 1) && pad_top >= 0, bot = (y == pad_bot - 1) && pad_bot <= G - 1;
                 if (top) tm_st8(my_a + 8 * pad_top, w8);
                 if (bot) tm_st8(my_a + 8 * pad_bot, w8);
                 ACB_TM_WAIT_ST();
                 ACB_TM_FENCE_BEFORE();
-                if (lane == 0)
-                {
-                    tm_publish_byte(flag_a + 8 * y + q, l + 1);
-                    if (top) tm_publish_byte(flag_a + 8 * pad_top + q, l + 1);
-                    if (bot) tm_publish_byte(flag_a + 8 * pad_bot + q, l + 1);
-                }
+                tm_publish_byte(flag_a + 8 * y + q, l + 1);
+                if (top) tm_publish_byte(flag_a + 8 * pad_top + q, l + 1);
+                if (bot) tm_publish_byte(flag_a + 8 * pad_bot + q, l + 1);
             };
 
             // ---- layer 0: the head conv (fp32 FFMA) or the previous segment's map --------------------------------------------------------
@@ -463,19 +521,32 @@ namespace acb
                 }
                 else
                 {
-                    // the map is read with clamped coordinates: padding included, every frame row inside the image +- 1 exists
+                    // the map is read with clamped coordinates: padding included, every frame row inside the image +- 1 exists.  Four rows
+                    // (eight 16-byte loads) are requested before the first is stored, and published together.
                     const int la = max(ya - 1, 0), lb = min(yb + 1, G - 1);
                     const int gx = clampi(x0 + lane, 0, prm.w - 1);
                     const size_t plane = static_cast<size_t>(prm.w) * prm.h;
-                    for (int y = la + set; y <= lb; y += TM_SETS)
+                    for (int yb4 = la + set; yb4 <= lb; yb4 += 4 * TM_SETS)
                     {
-                        const int gy = clampi(y0 + y, 0, prm.h - 1);
-                        const uint4 hi = __ldg(prm.map_in + static_cast<size_t>(gy) * prm.w + gx), lo = __ldg(prm.map_in + plane + static_cast<size_t>(gy) * prm.w + gx);
-                        const uint32_t w8[8] = { hi.x, hi.y, hi.z, hi.w, lo.x, lo.y, lo.z, lo.w };
-                        tm_st8(my_a + 8 * y, w8);
+                        uint4 hi[4], lo[4];
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                        {
+                            const int gy = clampi(y0 + min(yb4 + k * TM_SETS, lb), 0, prm.h - 1);
+                            hi[k] = __ldg(prm.map_in + static_cast<size_t>(gy) * prm.w + gx);
+                            lo[k] = __ldg(prm.map_in + plane + static_cast<size_t>(gy) * prm.w + gx);
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                        {
+                            const int y = yb4 + k * TM_SETS;
+                            const uint32_t w8[8] = { hi[k].x, hi[k].y, hi[k].z, hi[k].w, lo[k].x, lo[k].y, lo[k].z, lo[k].w };
+                            if (y <= lb) tm_st8(my_a + 8 * y, w8);
+                        }
                         ACB_TM_WAIT_ST();
                         ACB_TM_FENCE_BEFORE();
-                        if (lane == 0) tm_publish_byte(flag_a + 8 * y + q, 1);
+#pragma unroll
+                        for (int k = 0; k < 4; k++) if (yb4 + k * TM_SETS <= lb) tm_publish_byte(flag_a + 8 * (yb4 + k * TM_SETS) + q, 1);
                     }
                 }
             }
@@ -493,12 +564,12 @@ namespace acb
                 const int ya = s_ya[l], yb = s_yb[l], tb = s_tb[l], t_end = s_tb[l + 1], t_end2 = l < R ? s_tb[l + 2] : 0;
                 const bool last = l == R;
                 // accumulator re-initialisation blocks: this layer's bias and the next layer's (the slot's next user is 8 rows ahead)
-                uint32_t init_c[16], init_n[16];
+                uint32_t init_c[8], init_n[8];
 #pragma unroll
                 for (int c = 0; c < 8; c++)
                 {
-                    init_c[c] = __float_as_uint(bias_of(l, c)); init_c[8 + c] = 0u;
-                    init_n[c] = __float_as_uint(bias_of(min(l + 1, R), c)); init_n[8 + c] = 0u;
+                    init_c[c] = __float_as_uint(bias_of(l, c));
+                    init_n[c] = __float_as_uint(bias_of(min(l + 1, R), c));
                 }
                 float alpha[8];
 #pragma unroll
@@ -511,53 +582,46 @@ namespace acb
 #ifdef ACB_TM_TRACE
                     const long long tr_1 = clock64();
 #endif
-                    tm_wait(bar_full + 8 * slot, (t >> 3) & 1);
+                    tm_wait(bar_full + 8 * slot, (t >> 4) & 1);
                     ACB_TM_FENCE_AFTER();
 #ifdef ACB_TM_TRACE
                     const long long tr_2 = clock64(); tr_full += tr_2 - tr_1; tr_items++;
+                    if (q == 0 && lane == 0) trace[2 * TM_MAX_STEPS + t] = tr_2;
 #endif
-                    uint32_t d[16];
-                    const uint32_t d_addr = my_a + TM_D_COL0 + 16 * slot;
-                    tm_ld16(d, d_addr);
+                    uint32_t d[8];
+                    const uint32_t d_addr = my_a + TM_D_COL0 + 8 * slot;
+                    tm_ld8(d, d_addr);
                     ACB_TM_WAIT_LD();
 #ifdef ACB_TM_TRACE
                     const long long tr_3 = clock64(); tr_ld += tr_3 - tr_2;
 #endif
                     {
-                        // hand the slot to its next user (dense index t + 8) with that layer's bias
+                        // hand the slot to its next user (dense index t + 16) with that layer's bias
                         const int tn = static_cast<int>(t) + TM_NR;
-                        if (tn < t_end) tm_st16(d_addr, init_c);
-                        else if (!last && tn < t_end2) tm_st16(d_addr, init_n);
+                        if (tn < t_end) tm_st8(d_addr, init_c);
+                        else if (!last && tn < t_end2) tm_st8(d_addr, init_n);
                         else if (!last)
                         {
-                            int ln = l + 2;     // (frames with fewer than 8 rows per layer)
+                            int ln = l + 2;     // (frames with fewer than 16 rows per layer)
                             while (ln <= R && tn >= s_tb[ln + 1]) ln++;
                             if (ln <= R)
                             {
-                                uint32_t init[16];
+                                uint32_t init[8];
 #pragma unroll
-                                for (int c = 0; c < 8; c++) { init[c] = __float_as_uint(bias_of(ln, c)); init[8 + c] = 0u; }
-                                tm_st16(d_addr, init);
+                                for (int c = 0; c < 8; c++) init[c] = __float_as_uint(bias_of(ln, c));
+                                tm_st8(d_addr, init);
                             }
                         }
                     }
                     float v[8];
 #pragma unroll
-                    for (int c = 0; c < 8; c++) v[c] = __uint_as_float(d[c]) + __uint_as_float(d[8 + c]);
+                    for (int c = 0; c < 8; c++) v[c] = __uint_as_float(d[c]);
                     if (!last || !S::TAIL)
                     {
                         // body conv: activation, split, next layer's operand (or the segment's output map)
-                        if constexpr (S::FAM == ACB200_FAMILY_ACNET_LEGACY)
-                        {
-#pragma unroll
-                            for (int c = 0; c < 8; c++) v[c] = fmaxf(v[c], 0.0f);
-                        }
-                        else
-                        {
-#pragma unroll
-                            for (int c = 0; c < 8; c++) v[c] = prelu(v[c], alpha[c]);
-                        }
                         uint32_t w8[8];
+#pragma unroll
+                        for (int c = 0; c < 8; c++) v[c] = S::FAM == ACB200_FAMILY_ACNET_LEGACY ? fmaxf(v[c], 0.0f) : prelu(v[c], alpha[c]);
                         split_pair(v[0], v[1], w8[0], w8[4]); split_pair(v[2], v[3], w8[1], w8[5]);
                         split_pair(v[4], v[5], w8[2], w8[6]); split_pair(v[6], v[7], w8[3], w8[7]);
                         if (!last) put_row(l, y, w8);
@@ -633,18 +697,27 @@ namespace acb
                         ACB_TM_WAIT_ST();
                         ACB_TM_FENCE_BEFORE();
                     }
-                    if (lane == 0) tm_publish_byte(flag_e + 8 * slot + q, (t >> 3) + 1);
+                    tm_publish_byte(flag_e + 8 * slot + q, (t >> 4) + 1);
 #ifdef ACB_TM_TRACE
                     tr_put += clock64() - tr_3;
+                    if (q == 0 && lane == 0) trace[3 * TM_MAX_STEPS + t] = clock64();
 #endif
                 }
             }
 #ifdef ACB_TM_TRACE
-            if (blockIdx.x == gridDim.x / 2 + 3 && lane == 0 && (warp == 4 || warp == 9)) printf("epilogue warp %d: %lld items, total %lld cycles, layer 0 %lld, waiting for full %lld, ld %lld, rest %lld\n", warp, tr_items, clock64() - tr_0, tr_head, tr_full, tr_ld, tr_put);
+            if (blockIdx.x == gridDim.x / 2 + 3 && lane == 0 && (warp == TM_EPI_WARP0 || warp == TM_EPI_WARP0 + 5)) printf("epilogue warp %d: %lld items, total %lld cycles, layer 0 %lld, waiting for full %lld, ld %lld, rest %lld (of which wait::st %lld, all put_row calls)\n", warp, tr_items, clock64() - tr_0, tr_head, tr_full, tr_ld, tr_put, tr_wst);
 #endif
         }
         ACB_TM_FENCE_BEFORE();
         __syncthreads();
+#ifdef ACB_TM_TRACE
+        if (traced && threadIdx.x == 0)
+        {
+            const long long t0 = trace[0];
+            for (int i = 0; i < *s_nsteps; i += TM_CHUNK) printf("S %d %lld %lld %lld\n", i, trace[i] - t0, trace[TM_MAX_STEPS + i] - t0, trace[i + 1] - t0);
+            for (int t = 0; t < s_tb[R + 1]; t++) printf("R %d %lld %lld\n", t, trace[2 * TM_MAX_STEPS + t] - t0, trace[3 * TM_MAX_STEPS + t] - t0);
+        }
+#endif
         if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u));
     }
 }

@@ -11,6 +11,7 @@
 //     6. tcgen05.ld / tcgen05.st bytes per cycle and SM with 4 / 8 / 16 warps
 //
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 tools/microbench_tcgen05_ts.cu -o tools/microbench_tcgen05_ts.bin
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -84,7 +85,10 @@ __device__ __forceinline__ bool elect_one()
 __host__ __device__ inline int a_val(int row, int k) { return ((row * 3 + k * 5) % 7) - 3; }
 __host__ __device__ inline int b_val(int k, int n) { return ((n + 2 * k) % 5) - 2; }
 
-constexpr int N_CHK = 48;
+#ifndef N_CHK_VALUE
+#define N_CHK_VALUE 48
+#endif
+constexpr int N_CHK = N_CHK_VALUE;
 constexpr int A_COL = 256;      // A operand columns used by the checks
 // out: [4][128][N_CHK] floats (D0 plain, D1 ashift MMA, D2 plain after ashift, D3 plain after tcgen05.shift), then [2][128][8] u32 (A after 2, after 3)
 __global__ void __launch_bounds__(128, 1) semantics(float* __restrict__ d_out, uint32_t* __restrict__ a_out, int* __restrict__ status)
@@ -336,6 +340,101 @@ void run_issue(long long* dc)
            (VARIANT & 8) ? " + try_wait(complete)" : "", (VARIANT & 4) ? " + fence::after_thread_sync" : "", cudaGetErrorString(e), a / 148 / rows);
 }
 
+// W issuer warps at once, each with its own A operands and accumulators (N = 24, per row {plain, ashift} x 3 as the engine issues them):
+// do MMAs from different warps stream through the tensor pipe as well as MMAs from one warp?
+__global__ void __launch_bounds__(640, 1) multi_issuer(long long* __restrict__ cycles, int rows, int nwarps, int commit_every, int d_slide = 0, int a_rotate = 8, int side_traffic = 0)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 48 * 1024);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 48 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    volatile int* stop = reinterpret_cast<volatile int*>(smem + 48 * 1024 + 200);
+    if (tid == 0) *stop = 0;
+    if (tid == 0)
+    {
+        for (int i = 0; i < 16; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(bars + i)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0)
+    {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    TM_FENCE_BEFORE(); __syncthreads(); TM_FENCE_AFTER();
+    const uint32_t tmem = *tmem_slot;
+    {
+        uint32_t v[16];
+        for (int j = 0; j < 16; j++) v[j] = 0x3c003c00u;
+        if (warp < 4) for (int c = 0; c < 512; c += 16) tm_st16(tmem + (static_cast<uint32_t>(warp * 32) << 16) + c, v);
+        TM_WAIT_ST();
+    }
+    TM_FENCE_BEFORE(); __syncthreads(); TM_FENCE_AFTER();
+    if (warp >= 4)
+    {
+        // side traffic of the engine's epilogue warps: tcgen05.ld / tcgen05.st on columns no MMA touches, `side_traffic` = idle cycles between items
+        if (side_traffic > 0)
+        {
+            uint32_t v[8];
+            const uint32_t col = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + 320 + 8 * ((warp >> 2) & 3);
+            long long n = 0;
+            while (*stop < nwarps)
+            {
+                tm_ld8(v, col); TM_WAIT_LD();
+                for (int j = 0; j < 8; j++) v[j] += 1;
+                tm_st8(col, v); TM_WAIT_ST();
+                const long long t1 = clock64();
+                while (clock64() - t1 < side_traffic) { }
+                n++;
+            }
+            if (tid == 128) cycles[148 * 4 + blockIdx.x] = n;
+        }
+        TM_FENCE_BEFORE(); __syncthreads();
+        return;
+    }
+    constexpr uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(24 >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+    const uint32_t b_base = smem_u32(smem);
+    long long t0 = 0;
+    if (warp < nwarps && elect_one())
+    {
+        uint64_t db[6];
+        for (int j = 0; j < 6; j++) db[j] = make_desc(b_base + j * 768, 384, 128);
+        t0 = clock64();
+        for (int r = 0; r < rows; r++)
+        {
+            // d_slide: the accumulator window moves by d_slide columns per row inside a ring of 128 columns (the engine: 8 -> consecutive rows overlap in 16 of 24 columns)
+            const uint32_t a = tmem + 64 * warp + 8 * (r % a_rotate), d = d_slide ? tmem + 384 + ((r * d_slide) % 104) : tmem + 384 + 32 * warp + 8 * (r & 1);
+            mma_ts(d, a, db[0], idesc, 1); mma_ts_ashift(d, a, db[1], idesc, 1);
+            mma_ts(d, a, db[2], idesc, 1); mma_ts_ashift(d, a, db[3], idesc, 1);
+            mma_ts(d, a, db[4], idesc, 1); mma_ts(d, a, db[5], idesc, 1);
+            if (commit_every && (r + 1) % commit_every == 0) tm_commit(smem_u32(bars + 4 + warp * 2 + (r & 1)));
+        }
+        tm_commit(smem_u32(bars + warp));
+        mbar_wait(smem_u32(bars + warp), 0);
+        cycles[blockIdx.x * 4 + warp] = clock64() - t0;
+        atomicAdd(const_cast<int*>(stop), 1);
+    }
+    else if (warp < 4 && warp >= nwarps) { }
+    TM_FENCE_BEFORE(); __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u));
+}
+void run_multi(long long* dc4, int nwarps, int commit_every, int d_slide = 0, int side_traffic = 0)
+{
+    const int rows = 2000;
+    cudaFuncSetAttribute(multi_issuer, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024 + 256);
+    cudaMemset(dc4, 0, 148 * 5 * 8);
+    multi_issuer<<<148, 640, 48 * 1024 + 256>>>(dc4, rows, nwarps, commit_every, d_slide, 8, side_traffic);
+    cudaError_t e = cudaDeviceSynchronize();
+    std::vector<long long> hc(148 * 5);
+    cudaMemcpy(hc.data(), dc4, 148 * 5 * 8, cudaMemcpyDeviceToHost);
+    double worst = 0;
+    for (int b = 0; b < 148; b++) { double m = 0; for (int w = 0; w < nwarps; w++) m = std::max(m, double(hc[b * 4 + w])); worst += m; }
+    if (side_traffic) printf("[16 side warps: ld8 + st8 every %d cycles, %.0f items per warp] ", side_traffic, double(hc[148 * 4]));
+    printf("%d issuer warp(s), D window slides %d columns per row, commit every %d rows: %s, %.1f cycles per row of 6 MMAs (N=24) per warp, %.1f cycles per row overall\n", nwarps, d_slide, commit_every, cudaGetErrorString(e),
+           worst / 148 / rows, worst / 148 / rows / nwarps);
+}
+
 template<int N, int PATTERN, int COMMITS>
 void run_rate(long long* dc)
 {
@@ -472,6 +571,7 @@ int main()
         run_rate<16, 4, 0>(dc); run_rate<48, 4, 0>(dc); run_rate<96, 4, 0>(dc);
         run_rate<48, 5, 0>(dc);
         run_rate<24, 3, 1>(dc); run_rate<48, 3, 1>(dc); run_rate<48, 2, 1>(dc); run_rate<48, 4, 1>(dc); run_rate<48, 1, 1>(dc);
+        { long long* dc4; cudaMalloc(&dc4, 148 * 5 * 8); for (int w = 1; w <= 4; w++) run_multi(dc4, w, 0); run_multi(dc4, 1, 1); run_multi(dc4, 4, 1); run_multi(dc4, 2, 1); run_multi(dc4, 1, 0, 8); run_multi(dc4, 1, 0, 24); run_multi(dc4, 1, 0, 16); run_multi(dc4, 4, 0, 8); run_multi(dc4, 4, 1, 8); run_multi(dc4, 4, 1, 8, 1); run_multi(dc4, 4, 1, 8, 200); run_multi(dc4, 4, 1, 8, 1000); cudaFree(dc4); }
         run_issue<0>(dc); run_issue<1>(dc); run_issue<2>(dc); run_issue<3>(dc); run_issue<4>(dc); run_issue<7>(dc); run_issue<15>(dc); run_issue<16 + 1 + 4>(dc); run_issue<32 + 1 + 4>(dc);
         cudaFree(dc);
     }
