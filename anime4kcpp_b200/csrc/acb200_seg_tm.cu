@@ -7,14 +7,11 @@
 
 namespace acbh
 {
-    // Frame height and accumulator ring depth.  The CTA count is tiles_x * ceil(h / (G - 2R)) and every CTA costs about G + c row
-    // times, so the best G is the one with the fewest (waves of SM-count CTAs) x (G + c) -- not necessarily the tallest frame.  TMEM
-    // holds 8 columns per frame row plus 32 per ring group (G + 4 groups <= 64): a frame of at most 40 rows leaves room for six groups
-    // instead of four, which lets the issuers run further ahead of the epilogue.
-    void tm_pick_rows(int tiles_x, int h, int R, int sms, int& G_out, int& groups_out)
+    // Frame height: the CTA count is tiles_x * ceil(h / (G - 2R)) and every CTA costs about G + c row times, so the best G is the one
+    // with the fewest (waves of SM-count CTAs) x (G + c) -- not necessarily the tallest frame.
+    int tm_pick_rows(int tiles_x, int h, int R, int sms)
     {
         static const int force_g = [] { const char* e = std::getenv("ACB200_TM_G"); return e ? std::atoi(e) : 0; }();
-        static const int force_ring = [] { const char* e = std::getenv("ACB200_TM_RING"); return e ? std::atoi(e) : 0; }();
         int best = TM_GMAX;
         double best_cost = 1e30;
         for (int G = 2 * R + 4; G <= TM_GMAX; G++)
@@ -22,14 +19,11 @@ namespace acbh
             const int tiles_y = (h + G - 2 * R - 1) / (G - 2 * R);
             const long long tiles = static_cast<long long>(tiles_x) * tiles_y;
             const double waves = static_cast<double>((tiles + sms - 1) / sms);
-            const int groups = std::min(8, (64 - G) / 4);
-            const double cost = waves * (G + 10.0) * (groups >= 6 ? 1.0 : groups == 5 ? 1.1 : 1.25);
+            const double cost = waves * (G + 8.0);
             if (cost < best_cost - 1e-9) { best_cost = cost; best = G; }
         }
         if (force_g >= 2 * R + 4 && force_g <= TM_GMAX) best = force_g;
-        G_out = best;
-        groups_out = std::min(8, (64 - best) / 4);
-        if (force_ring >= 4 && force_ring <= groups_out) groups_out = force_ring;
+        return best;
     }
 
     template<class S>
@@ -56,7 +50,7 @@ namespace acbh
             constexpr int SW = 32 - 2 * S::R;
             prm.strips_x = (w + SW - 1) / SW;
             prm.tiles_x = (prm.strips_x + 3) / 4;
-            tm_pick_rows(prm.tiles_x, h, S::R, s->sm_count, prm.G, prm.ring_groups);
+            prm.G = tm_pick_rows(prm.tiles_x, h, S::R, s->sm_count);
             const int tiles_y = (h + prm.G - 2 * S::R - 1) / (prm.G - 2 * S::R);
             prm.bops = dops + spec.tm_off;
             static const int issuers_env = [] { const char* e = std::getenv("ACB200_TM_ISSUERS"); const int v = e ? std::atoi(e) : TM_ISSUERS; return v < 1 ? 1 : (v > TM_ISSUERS ? TM_ISSUERS : v); }();

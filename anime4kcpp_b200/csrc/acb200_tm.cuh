@@ -5,27 +5,28 @@
 // layer, fp16 activations through HBM.  What the round-1 engines do: 56x56 frames in shared memory, the 3x3 taps gathered by
 // ldmatrix (mma.sync) or by SS-mode descriptors (tcgen05, 44 cycles per MMA: the A fetch from shared memory is the bound).
 // Measured facts this engine is built on (tools/microbench_tcgen05_ts.cu, profiles/r02_microbench_tcgen05_ts.txt):
-//   * tcgen05.mma with the A operand in TMEM (M = 128, K = 16) costs N / 2 cycles: 24 cycles for N = 48, no operand fetch.
+//   * tcgen05.mma with the A operand in TMEM (M = 128, K = 16) costs N / 2 cycles, no operand fetch.
 //   * the .ashift qualifier (multiply, then shift the A rows by one lane inside every 32-lane quadrant: new[r] = old[r + 1])
 //     is free.  A horizontal tap is therefore a lane shift of the operand -- no data movement by any thread.
 //   * a vertical tap is a different A operand (another 8-column group of TMEM) -- free as well.
+//   * the issuing thread cannot run ahead of the tensor pipe (every UTCHMMA holds a scoreboard on its uniform-register
+//     operands until it is dequeued), so anything it waits for becomes a pipe bubble: several issuer warps take turns.
 //
-// Layout.  A CTA owns four independent STRIPS, one per TMEM lane quadrant: 32 pixels wide (lane = x) and G <= 48 rows tall.
-// Row y of the current layer's 8-channel map is ONE A operand: columns 8y .. 8y+7 of every lane hold the pixel's eight
+// Layout.  A CTA owns four independent STRIPS, one per TMEM lane quadrant: 32 pixels wide (lane = x) and G <= 32 rows tall.
+// TMEM holds two frame buffers of 8 columns per row.  Row y of a layer's 8-channel map is ONE A operand: the pixel's eight
 // channels as split fp16 (hi words 0-3, lo words 4-7), i.e. K = 16 = {a_hi | a_lo}.  Per row r of the input map the issuing
-// thread runs three alignments (dx = -1, 0, +1 through two .ashift's), each ONE MMA with N = 48 = 3 output rows x (8 couts
-// with w_hi | 8 couts with w_lo): row r contributes to output rows r+1, r, r-1 with the weights of dy = -1, 0, +1, whose
-// accumulators are adjacent 16-column slots of a ring of eight.  All nine taps and all three split-precision products
-// (a_hi w_hi + a_lo w_hi + a_hi w_lo) are accumulated inside the tensor core: 72 tensor cycles per 128 pixels and layer.
-//   The accumulate flag is always set: the epilogue that drains a slot writes the NEXT user's bias back into it (one
-// tcgen05.st), which also makes the bias add free.
-//   Epilogue (warps 4.., one warp per lane quadrant and row): tcgen05.ld of 16 columns, hi + lo, activation, fp16 split,
-// tcgen05.st of the 8 operand columns of the next layer IN PLACE (row y of layer l overwrites row y of layer l - 1, which is
-// dead once row y + 1 has been multiplied).  Nothing is exchanged between threads and no shared memory is touched.
+// thread runs three alignments (dx = -1, 0, +1 through two .ashift's), each two MMAs with N = 24 = 3 output rows x 8 couts:
+// (a_hi + a_lo) w_hi and a_hi w_lo accumulate into the SAME columns; row r contributes to output rows r+1, r, r-1 with the
+// weights of dy = -1, 0, +1, whose accumulators are adjacent rows of the OTHER frame buffer.  All nine taps and all three
+// split-precision products are accumulated inside the tensor core: 76 tensor cycles per 128 pixels and layer.
+//   The accumulate flag is always set: whoever writes row y of a layer also pre-loads row y of the other buffer (dead by then)
+// with the next layer's bias, which makes the bias add free and the order of the MMAs across rows irrelevant.
+//   Epilogue (warps 4.., one warp per lane quadrant and group of four rows): tcgen05.ld of 32 columns, activation, fp16 split,
+// tcgen05.st of the next layer's operands IN PLACE.  Nothing is exchanged between threads and no shared memory is touched.
 //   The lane shift drifts the map by one lane per layer (lane j of layer l is pixel x0 + l + j), which consumes exactly the
 // halo a fused segment loses anyway: after R layers lanes 0 .. 31 - 2R hold the strip's 32 - 2R output columns.
-//   Layers are not separated by barriers: rows flow (mbarrier per row / per accumulator slot), so the tensor pipe runs
-// across layer boundaries and under the head conv / the map load of the first rows.
+//   Layers are not separated by barriers: rows flow (a progress byte per row and quadrant, a one-shot mbarrier per group of
+// accumulator rows), so the tensor pipe runs across layer boundaries and under the head conv / the map load.
 //   Replicate padding (border CTAs): the epilogue copies the edge values one pixel outwards -- a warp shuffle in x, a second
 // tcgen05.st in y.  Rows outside the image are skipped.
 #pragma once
@@ -41,11 +42,13 @@ namespace acb
 #ifndef ACB_TM_EPI_SETS
 #define ACB_TM_EPI_SETS 4
 #endif
-    // TMEM budget: 8 columns per frame row (the A operands) + 8 columns per accumulator slot = 512: G + 4 * groups <= 64.  The host
-    // picks the frame height G and with it the ring depth (groups of four slots): a deeper ring lets the issuers run further ahead of
-    // the epilogue, a taller frame wastes less on the vertical halo.
-    constexpr int TM_GMAX = 48;                     // rows of a strip frame (ring of 4 groups); 40 rows -> 6 groups
-    constexpr int TM_MAX_GROUPS = 12 * 8;           // one-shot `full` barriers: groups of a segment (<= 12 per layer)
+    // TMEM: two frame buffers of 8 columns per frame row (columns 0 .. 255 and 256 .. 511).  Layer l reads its A operands from
+    // buffer (l - 1) % 2 and accumulates into buffer l % 2; the epilogue converts an accumulator row IN PLACE into the next layer's
+    // operand row and pre-loads the same row of the other buffer (whose operand is dead by then) with the next layer's bias.
+    // Frame row y lives at columns 8 (y + 1) of a buffer: rows -1 and G are scratch (the edge steps of a layer add into the row just
+    // outside its output range, so that every MMA has the same shape: three output rows, weights at row block 0).
+    constexpr int TM_GMAX = 30;                     // rows of a strip frame
+    constexpr int TM_MAX_GROUPS = 8 * 8;            // one-shot `full` barriers: groups of four rows of a segment (<= 8 per layer)
 #ifndef ACB_TM_ISSUERS
 #define ACB_TM_ISSUERS 4
 #endif
@@ -56,8 +59,11 @@ namespace acb
 #ifndef ACB_TM_ISSUERS
 #define ACB_TM_ISSUERS 4
 #endif
-    constexpr int TM_ISSUERS = ACB_TM_ISSUERS;      // issuer warps (warps 0 .. TM_ISSUERS - 1), each takes every TM_ISSUERS-th chunk of the step program
-    constexpr int TM_EPI_WARP0 = TM_ISSUERS;        // first epilogue warp (a multiple of 4: warp w works on TMEM lane quadrant w % 4)
+    constexpr int TM_ISSUERS = ACB_TM_ISSUERS;      // issuer warps, each takes every TM_ISSUERS-th chunk of the step program
+    // Warp roles: the epilogue warps come FIRST (warp w works on TMEM lane quadrant w % 4), the issuer warps LAST: the warp scheduler
+    // favours the higher warp id among eligible warps, and an issuer that cannot get an issue slot starves the tensor pipe.
+    constexpr int TM_EPI_WARP0 = 0;
+    constexpr int TM_ISS_WARP0 = 4 * ACB_TM_EPI_SETS;
     constexpr int TM_CHUNK = 4;                     // consecutive steps (input rows) per chunk, >= 3
     constexpr int TM_B_BYTES_HALF = 2 * 24 * 16;    // one B matrix: [2 K chunks][24 rows][8 fp16]
     constexpr int TM_B_BYTES_AL = 2 * TM_B_BYTES_HALF;      // one alignment: the w_hi matrix, then the w_lo matrix
@@ -66,15 +72,17 @@ namespace acb
     constexpr int TM_LP = 34;                       // luma tile pitch (floats): lanes 0..31 read columns j .. j + 2
     constexpr int TM_OFF_LUMA = TM_MAX_R * TM_B_BYTES_LAYER;
     constexpr int TM_OFF_BAR = TM_OFF_LUMA + 4 * (TM_GMAX + 2) * TM_LP * 4;
-    constexpr int TM_N_BARS = TM_GMAX + TM_MAX_GROUPS + 16 + 1;
+    constexpr int TM_N_BARS = TM_GMAX + TM_MAX_GROUPS + 1;
     constexpr int TM_OFF_GEOM = TM_OFF_BAR + TM_N_BARS * 8 + 8;
-    constexpr int TM_OFF_STEPS = ((TM_OFF_GEOM + 3 * (TM_MAX_R + 2) * 4 + 4 + 15) / 16) * 16;      // the issuers' step program, 64 bytes per input row and layer
-    constexpr int TM_MAX_STEPS = TM_MAX_R * TM_GMAX;
+    constexpr int TM_OFF_STEPS = ((TM_OFF_GEOM + 3 * (TM_MAX_R + 2) * 4 + 4 + 15) / 16) * 16;      // the issuers' step program, 48 bytes per input row and layer
+    constexpr int TM_MAX_CHUNKS = TM_MAX_R * ((TM_GMAX + 2 + 3) / 4);     // chunks of up to four steps, never across layers
+    constexpr int TM_MAX_STEPS = 4 * TM_MAX_CHUNKS;
+    constexpr int TM_CHUNK_WORDS = 20;              // one record per chunk: 4 operand words, 6 waits, 8 commits, 2 spare
 #ifdef ACB_TM_TRACE
-    constexpr int TM_OFF_TRACE = TM_OFF_STEPS + TM_MAX_STEPS * 64;
-    constexpr int TM_SMEM_BYTES = TM_OFF_TRACE + 5 * TM_MAX_STEPS * 8;
+    constexpr int TM_OFF_TRACE = TM_OFF_STEPS + TM_MAX_CHUNKS * TM_CHUNK_WORDS * 4;
+    constexpr int TM_SMEM_BYTES = TM_OFF_TRACE + 4 * TM_MAX_STEPS * 8;
 #else
-    constexpr int TM_SMEM_BYTES = TM_OFF_STEPS + TM_MAX_STEPS * 64;
+    constexpr int TM_SMEM_BYTES = TM_OFF_STEPS + TM_MAX_CHUNKS * TM_CHUNK_WORDS * 4;
 #endif
 
     template<class S>
@@ -90,7 +98,6 @@ namespace acb
         int w, h;
         int type;
         int tiles_x, strips_x, G;
-        int ring_groups;        // accumulator ring depth in groups of four 8-column slots: 8 G + 32 ring_groups <= 512
         int issuers;            // issuer warps used (1 .. TM_ISSUERS)
         const uint32_t* bops;   // B operands of this segment's 3x3 convs, TM_B_WORDS_LAYER words each, in layer order
         float k[(S::HEAD ? 72 : 0) + 64 + 32];  // fp32 weights used outside the MMAs: head (72) | ARNet 1x1 (64) | legacy deconv (32)
@@ -204,9 +211,7 @@ namespace acb
     }
 
     // Row bookkeeping.  The rows a layer produces are handled in GROUPS of four consecutive rows (the last group of a layer may be
-    // shorter): a group is one epilogue work item, one `full` mbarrier phase and one drain count.  Rows are numbered densely across
-    // layers with every layer padded to whole groups: row y of layer l has index T = tb[l] + (y - ya[l]), accumulator slot T % 16,
-    // group T / 4, slot group (T / 4) % 4.
+    // shorter): a group is one epilogue work item and one one-shot `full` mbarrier.
     template<class S>
     __global__ void __launch_bounds__(TM_THREADS, 1) segment_tm_kernel(const __grid_constant__ TmParams<S> prm)
     {
@@ -218,20 +223,15 @@ namespace acb
         extern __shared__ __align__(128) unsigned char smem_tm[];
         float* luma_all = reinterpret_cast<float*>(smem_tm + TM_OFF_LUMA);
         const uint32_t bars = static_cast<uint32_t>(__cvta_generic_to_shared(smem_tm + TM_OFF_BAR));
-        // flag_a[row], flag_e[slot group]: progress words (see tm_wait_bytes); bar_full[group] (one-shot: every group of every layer has its
-        // own mbarrier, so no phase parity can alias), bar_bop: mbarriers
-        const uint32_t flag_a = bars, bar_full = bars + 8 * TM_GMAX, flag_e = bar_full + 8 * TM_MAX_GROUPS, bar_bop = flag_e + 8 * 16;
-        const int NRG = prm.ring_groups, NRS = 4 * NRG;                 // accumulator ring: groups / slots
-        const uint32_t d_col0 = 512u - 32u * static_cast<uint32_t>(NRG);    // ... at the top of the TMEM columns
+        // flag_a[row]: progress words (see tm_wait_bytes); bar_full[group] (one-shot: every group of every layer has its own mbarrier,
+        // so no phase parity can alias), bar_bop: mbarriers
+        const uint32_t flag_a = bars, bar_full = bars + 8 * TM_GMAX, bar_bop = bar_full + 8 * TM_MAX_GROUPS;
         uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_tm + TM_OFF_BAR + TM_N_BARS * 8);
-        int* s_ya = reinterpret_cast<int*>(smem_tm + TM_OFF_GEOM);      // per layer 0..R+1: first / last existing row, padded dense index of the first
-        int* s_yb = s_ya + TM_MAX_R + 2;
-        int* s_tb = s_yb + TM_MAX_R + 2;
-        int* s_nsteps = s_tb + TM_MAX_R + 2;
         uint4* steps = reinterpret_cast<uint4*>(smem_tm + TM_OFF_STEPS);
 #ifdef ACB_TM_TRACE
-        long long* trace = reinterpret_cast<long long*>(smem_tm + TM_OFF_TRACE);    // per chunk: [0] start, [1] issued; per group: [2] full seen, [3] drained, [4] rows published
+        long long* trace = reinterpret_cast<long long*>(smem_tm + TM_OFF_TRACE);    // per chunk: [0] start, [1] issued; per group: [2] full seen, [3] rows published
         const bool traced = blockIdx.x == gridDim.x / 2 + 3;
+        if (threadIdx.x == 0) trace[4 * TM_MAX_STEPS - 1] = clock64();
 #endif
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         const int G = prm.G, SH = G - 2 * R;
@@ -239,60 +239,105 @@ namespace acb
         const int y0 = sy * SH - R;
 
         // ---- setup ---------------------------------------------------------------------------------------------------------------
-        if (threadIdx.x == 0)
+        // geometry: every thread derives it for itself (a handful of integer operations per layer), nothing serial
+        int g_ya[TM_MAX_R + 2], g_yb[TM_MAX_R + 2], g_gb[TM_MAX_R + 2];
+        int nchunks = 0;
         {
-            for (int i = 0; i < TM_GMAX; i++) asm volatile("st.shared.u32 [%0], %1;" :: "r"(flag_a + 8 * i), "r"(0));
-            for (int i = 0; i < 16; i++) asm volatile("st.shared.u32 [%0], %1;" :: "r"(flag_e + 8 * i), "r"(0));
-            {
-                // one `full` barrier per group: two commits per row
-                int gi = 0;
-                for (int l = 1; l <= R; l++)
-                {
-                    int ya, yb;
-                    tm_rows(l, G, y0, prm.h, ya, yb);
-                    for (int y = ya; y <= yb; y += 4, gi++)
-                        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar_full + 8 * gi), "r"(2 * min(4, yb - y + 1)));
-                }
-            }
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_bop));
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            // the segment's B operands: one bulk copy (UBLKCP) on an mbarrier
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_bop), "r"(R * TM_B_BYTES_LAYER) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         :: "r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_tm))), "l"(reinterpret_cast<uint64_t>(prm.bops)), "r"(R * TM_B_BYTES_LAYER), "r"(bar_bop) : "memory");
-            int tb = 0, ns = 0;
+            int gb = 0;
+#pragma unroll
             for (int l = 0; l <= R; l++)
             {
-                int ya, yb;
-                tm_rows(l, G, y0, prm.h, ya, yb);
-                s_ya[l] = ya; s_yb[l] = yb; s_tb[l] = tb;
-                if (l >= 1 && yb >= ya) { tb += 4 * ((yb - ya + 4) >> 2); ns += yb - ya + 3; }
+                tm_rows(l, G, y0, prm.h, g_ya[l], g_yb[l]);
+                g_gb[l] = gb;
+                if (l >= 1 && g_yb[l] >= g_ya[l]) { gb += (g_yb[l] - g_ya[l] + 4) >> 2; nchunks += (g_yb[l] - g_ya[l] + 3 + TM_CHUNK - 1) / TM_CHUNK; }
             }
-            s_ya[R + 1] = 0; s_yb[R + 1] = -1; s_tb[R + 1] = tb;
-            *s_nsteps = ns;
+            g_ya[R + 1] = 0; g_yb[R + 1] = -1; g_gb[R + 1] = gb;
         }
-        if (warp == 0)
+        int* s_geom = reinterpret_cast<int*>(smem_tm + TM_OFF_GEOM);     // [l] = ya | yb << 8 | first group << 16, for loops that are not unrolled
+        if (threadIdx.x == 0)
+        {
+#pragma unroll
+            for (int l = 0; l <= R + 1; l++) s_geom[l] = (g_ya[l] & 0xff) | ((g_yb[l] & 0xff) << 8) | (g_gb[l] << 16);
+        }
+        if (threadIdx.x < TM_GMAX) asm volatile("st.shared.u32 [%0], %1;" :: "r"(flag_a + 8 * threadIdx.x), "r"(0));
+        if (threadIdx.x >= 64 && threadIdx.x < 64 + TM_MAX_GROUPS)
+        {
+            // one `full` barrier per group: two commits per row
+            const int gi = threadIdx.x - 64;
+#pragma unroll
+            for (int l = 1; l <= R; l++)
+                if (gi >= g_gb[l] && gi < g_gb[l + 1])
+                    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar_full + 8 * gi), "r"(2 * min(4, g_yb[l] - (g_ya[l] + 4 * (gi - g_gb[l])) + 1)));
+        }
+        if (threadIdx.x == 32) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_bop));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (warp == TM_ISS_WARP0)
         {
             asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(static_cast<uint32_t>(__cvta_generic_to_shared(tmem_slot))), "r"(512u));
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
         }
         if constexpr (S::NEEDS_LUMA)
         {
-            // luma tile of every strip: frame columns -1 .. 32, frame rows -1 .. G, clamp-to-edge (the head conv's own padding)
-            const int n = 4 * (G + 2) * TM_LP;
-            for (int i = threadIdx.x; i < n; i += TM_THREADS)
+            // luma tile of every strip: frame columns -1 .. 32, frame rows -1 .. G, clamp-to-edge (the head conv's own padding).  One warp
+            // per tile row: lane = column (coalesced), lanes 0 / 1 also take columns 32 / 33.
+            constexpr int NWARPS = TM_THREADS / 32, PER = (4 * (TM_GMAX + 2) + NWARPS - 1) / NWARPS;
+            if (prm.type == ACB200_UINT8)
             {
-                const int q = i / ((G + 2) * TM_LP), rem = i - q * (G + 2) * TM_LP, ly = rem / TM_LP, lx = rem - ly * TM_LP;
-                const int strip = min(tile_x * 4 + q, prm.strips_x - 1);
-                const int gx = clampi(strip * SW - R - 1 + lx, 0, prm.w - 1), gy = clampi(y0 - 1 + ly, 0, prm.h - 1);
-                luma_all[(q * (TM_GMAX + 2) + ly) * TM_LP + lx] = load_elem(static_cast<const uint8_t*>(prm.src) + static_cast<size_t>(gy) * prm.src_pitch, gx, prm.type);
+                // all of this warp's rows are requested before the first is consumed (one exposed memory latency, not one per row)
+                uint8_t p0[PER], p1[PER];
+#pragma unroll
+                for (int i = 0; i < PER; i++)
+                {
+                    const int row = min(warp + i * NWARPS, 4 * (G + 2) - 1);
+                    const int q = row / (G + 2), ly = row - q * (G + 2);
+                    const int strip = min(tile_x * 4 + q, prm.strips_x - 1);
+                    const int gy = clampi(y0 - 1 + ly, 0, prm.h - 1), gx0 = strip * SW - R - 1;
+                    const uint8_t* srow = static_cast<const uint8_t*>(prm.src) + static_cast<size_t>(gy) * prm.src_pitch;
+                    p0[i] = __ldg(srow + clampi(gx0 + lane, 0, prm.w - 1));
+                    p1[i] = __ldg(srow + clampi(gx0 + 32 + (lane & 1), 0, prm.w - 1));
+                }
+#pragma unroll
+                for (int i = 0; i < PER; i++)
+                {
+                    const int row = warp + i * NWARPS;
+                    if (row >= 4 * (G + 2)) break;
+                    const int q = row / (G + 2), ly = row - q * (G + 2);
+                    float* drow = luma_all + (q * (TM_GMAX + 2) + ly) * TM_LP;
+                    drow[lane] = unit_from_int<255>(static_cast<float>(p0[i]));     // toFloat<u8>, exact, no division
+                    if (lane < 2) drow[32 + lane] = unit_from_int<255>(static_cast<float>(p1[i]));
+                }
             }
+            else
+                for (int row = warp; row < 4 * (G + 2); row += NWARPS)
+                {
+                    const int q = row / (G + 2), ly = row - q * (G + 2);
+                    const int strip = min(tile_x * 4 + q, prm.strips_x - 1);
+                    const int gy = clampi(y0 - 1 + ly, 0, prm.h - 1), gx0 = strip * SW - R - 1;
+                    const uint8_t* srow = static_cast<const uint8_t*>(prm.src) + static_cast<size_t>(gy) * prm.src_pitch;
+                    float* drow = luma_all + (q * (TM_GMAX + 2) + ly) * TM_LP;
+                    drow[lane] = load_elem(srow, clampi(gx0 + lane, 0, prm.w - 1), prm.type);
+                    if (lane < 2) drow[32 + lane] = load_elem(srow, clampi(gx0 + 32 + lane, 0, prm.w - 1), prm.type);
+                }
         }
+        if (threadIdx.x == 32)
+        {
+            // the segment's B operands: one bulk copy (UBLKCP) on an mbarrier
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_bop), "r"(R * TM_B_BYTES_LAYER) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_tm))), "l"(reinterpret_cast<uint64_t>(prm.bops)), "r"(R * TM_B_BYTES_LAYER), "r"(bar_bop) : "memory");
+        }
+#ifdef ACB_TM_TRACE
+        if (threadIdx.x == 0) trace[4 * TM_MAX_STEPS - 2] = clock64();
+        if (threadIdx.x == 300) trace[4 * TM_MAX_STEPS - 3] = clock64();
+#endif
         ACB_TM_FENCE_BEFORE();
         __syncthreads();
         ACB_TM_FENCE_AFTER();
         const uint32_t tmem = *tmem_slot;
+#ifdef ACB_TM_TRACE
+        if (threadIdx.x == 0) trace[4 * TM_MAX_STEPS - 4] = clock64() + (tmem & 1);
+#endif
         constexpr int B0 = S::HEAD ? 8 : 0;     // bias / alpha offsets of the segment's first 3x3 conv inside prm.b / prm.a
         constexpr int A0 = (S::FAM == ACB200_FAMILY_ACNET && S::HEAD) ? 8 : 0;
         // bias of the segment's tensor layer ln (1-based) as the initial accumulator of output channel c (the ACNet tail has 4 couts)
@@ -300,132 +345,93 @@ namespace acb
             if (S::TAIL && S::FAM == ACB200_FAMILY_ACNET && ln == R && c >= 4) return 0.0f;
             return prm.b[B0 + 8 * (ln - 1) + c];
         };
+        if (warp >= TM_ISS_WARP0)
         {
-            // The issuers' step program: one record of four uint4 per (layer, input row), built by all threads (one step each), with every operand the
-            // issue loop needs already in its final form:
-            //   [0] up to four waits (progress word | count << 24; 0 = none): the A row, then the slot groups this chunk touches first
-            //   [1] A operand, first run: accumulator / B descriptor low word / instruction descriptor
-            //   [2] second run (only when the accumulator ring wraps inside this row's outputs): accumulator (0 = none) / B / instruction descriptor; layer
-            //   [3] up to three `full` barriers to commit to (barrier | number of commits << 24; 0 = none)
-            // Steps are issued in CHUNKS of TM_CHUNK consecutive steps, chunk c by issuer warp c % issuers: every UTCHMMA holds a
-            // scoreboard on its uniform-register operands until the tensor core dequeues it, so a single issuing thread can never run
-            // ahead of the pipe and each of its waits becomes a bubble (120-150 cycles, profiles/r02_microbench_tcgen05_ts.txt).
-            // With several issuers one warp's waits run under the other warps' queued MMAs.  All MMAs accumulate (the epilogue
-            // re-initialises drained accumulators), so their order across rows does not matter; an output row's three input rows lie
-            // in at most two chunks, hence every row contributes exactly two commits to its group's `full` barrier.
+            // The issuers' program: one record of TM_CHUNK_WORDS words per CHUNK of up to four consecutive input rows of one layer, built by
+            // the issuer warps (the other warps are already producing layer 0) -- one thread per chunk:
+            //   [0] A operand of the first step   [1] accumulator of the first step (output row r - 1)   [2] B descriptor low word (alignment 0)
+            //   [3] steps in the chunk            [4..9] waits (progress word | count << 24; 0 = none): rows r0 - 1 .. r0 + steps of the previous
+            //   layer -- the input rows, and the rows whose producers pre-loaded the accumulators the chunk adds to
+            //   [10..17] `full` barriers to commit to after the chunk's MMAs (0 = none)
+            // Every step has the same shape -- A row r into output rows r - 1 .. r + 1 -- because the first and last steps of a layer simply add
+            // into the scratch rows outside the layer's output range.  Chunk c is issued by issuer warp c % issuers.  All MMAs accumulate, so
+            // their order across rows does not matter; an output row's three input rows lie in at most two chunks, hence every row
+            // contributes exactly two commits to its group's `full` barrier.
             const uint32_t bop_s = static_cast<uint32_t>(__cvta_generic_to_shared(smem_tm));
-            constexpr uint32_t IDESC0 = (1u << 4) | (static_cast<uint32_t>(128 >> 4) << 24);       // D f32, A / B f16 K-major, M = 128
             constexpr uint32_t DESC_HI = ((384u >> 4) & 0x3FFF) << 16;                              // LBO (K chunk distance: 24 rows) in the low word
-            int base = 0;
-            for (int l = 1; l <= R; l++)
+            const int c_mine = threadIdx.x - 32 * TM_ISS_WARP0;
+            if (c_mine < nchunks)
             {
-                const int ya = s_ya[l], yb = s_yb[l], tb = s_tb[l];
-                if (yb < ya) continue;
-                const int n = yb - ya + 3;
-                for (int k = threadIdx.x; k < n; k += TM_THREADS)
+                // which layer, which chunk of it
+                int l = 1, cb = 0;
+                bool found = false;
+#pragma unroll
+                for (int ll = 1; ll <= R; ll++)
                 {
-                    const int i = base + k, r = ya - 1 + k;
-                    const int oa = max(r - 1, ya), ob = min(r + 1, yb), n_rows = ob - oa + 1;
-                    const uint32_t ta = static_cast<uint32_t>(tb + oa - ya);
-                    const int s0 = static_cast<int>(ta % static_cast<uint32_t>(NRS)), first = min(n_rows, NRS - s0), jb0 = oa - (r - 1);
-                    const int c0 = (i / TM_CHUNK) * TM_CHUNK, c1 = c0 + TM_CHUNK - 1;       // this step's chunk
-                    const uint32_t w0 = (flag_a + 8 * r) | (static_cast<uint32_t>(l) << 24);      // layer l - 1 publishes l
-                    uint32_t w1 = 0u, w2 = 0u, cv0 = 0u, cv1 = 0u, cv2 = 0u, cv3 = 0u;
-                    int last_group = -1;
-#pragma unroll
-                    for (int jj = 0; jj < 3; jj++)
+                    const int nc = g_yb[ll] >= g_ya[ll] ? (g_yb[ll] - g_ya[ll] + 3 + TM_CHUNK - 1) / TM_CHUNK : 0;
+                    if (!found)
                     {
-                        if (jj >= n_rows) break;
-                        const int o = oa + jj, rel = o - ya;
-                        const uint32_t t = static_cast<uint32_t>(tb + rel), gidx = t >> 2;
-                        // the group's rows are touched by this layer's steps 4j .. 4j + 5 (j = rel / 4); the first of them inside this chunk waits
-                        // for the slot group's previous user to have been drained
-                        if (static_cast<int>(gidx) != last_group)
-                        {
-                            last_group = static_cast<int>(gidx);
-                            if (i == max(base + (rel & ~3), c0) && gidx >= static_cast<uint32_t>(NRG))
-                            {
-                                const uint32_t wq = (flag_e + 8 * (gidx % NRG)) | ((gidx / NRG) << 24);
-                                if (w1 == 0u) w1 = wq; else w2 = wq;
-                            }
-                        }
-                        const int i_a = base + rel, i_c = i_a + 2;                          // steps of input rows o - 1 and o + 1
-                        if (i == min(i_c, c1))                                              // this chunk's last contribution to row o
-                        {
-                            const uint32_t m = (i_a >= c0 && i_c <= c1) ? 2u : 1u;
-                            const uint32_t cq = (bar_full + 8 * gidx) | (m << 24);
-                            if (jj == 0) cv0 = cq; else if (jj == 1) cv1 = cq; else cv2 = cq;
-                        }
+                        if (c_mine >= cb + nc) { cb += nc; l = ll + 1; } else found = true;
                     }
-                    const uint32_t b1 = (((bop_s + (l - 1) * TM_B_BYTES_LAYER + jb0 * 128) >> 4) & 0x3FFF) | DESC_HI;
-                    uint4 m1, m2;
-                    m1.x = tmem + 8 * r;
-                    m1.y = tmem + d_col0 + 8 * s0;
-                    m1.z = b1;
-                    m1.w = IDESC0 | (static_cast<uint32_t>(first) << 17);
-                    m2.x = first < n_rows ? tmem + d_col0 : 0u;
-                    m2.y = b1 + first * 8;
-                    m2.z = IDESC0 | (static_cast<uint32_t>(n_rows - first) << 17);
-                    m2.w = static_cast<uint32_t>(l);
-                    // A chunk is REGULAR when its four steps are interior rows of one layer (three output rows each, weights at row block
-                    // 0) and none of them wraps around the accumulator ring: the issue loop then derives every operand from the leading
-                    // step's record by uniform arithmetic.  The leading record carries the flag and the dense index of the first touched row.
-                    if (i == c0)
-                    {
-                        bool regular = k >= 2 && k + (TM_CHUNK - 1) <= n - 3;
-                        for (int pp = 0; pp < TM_CHUNK && regular; pp++) regular = static_cast<int>((ta + pp) % static_cast<uint32_t>(NRS)) + 3 <= NRS;
-                        cv3 = (regular ? 0x80000000u : 0u) | ta;
-                    }
-                    steps[4 * i] = make_uint4(w0, w1, w2, 0u);
-                    steps[4 * i + 1] = m1;
-                    steps[4 * i + 2] = m2;
-                    steps[4 * i + 3] = make_uint4(cv0, cv1, cv2, cv3);
                 }
-                base += n;
-            }
-        }
-        if (warp >= TM_EPI_WARP0 && warp < TM_EPI_WARP0 + 4)
-        {
-            // accumulator ring: every slot starts with its first user's bias
-            // (slot s is first used by dense row index s, which belongs to a later layer when the frame has few rows)
-            const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-            for (int s = 0; s < NRS; s++)
-            {
-                int ln = 1;
-                while (ln <= R && s >= s_tb[ln + 1]) ln++;
-                if (ln > R) break;
-                uint32_t init[8];
+                int ya = 0, yb = -1, gb = 0;
 #pragma unroll
-                for (int c = 0; c < 8; c++) init[c] = __float_as_uint(bias_of(ln, c));
-                tm_st8(tmem + lane_base + d_col0 + 8 * s, init);
+                for (int ll = 1; ll <= R; ll++) if (ll == l) { ya = g_ya[ll]; yb = g_yb[ll]; gb = g_gb[ll]; }
+                const int n = yb - ya + 3;                      // steps of the layer: input rows ya - 1 .. yb + 1
+                const int k0 = (c_mine - cb) * TM_CHUNK, nst = min(TM_CHUNK, n - k0);
+                const int r0 = ya - 1 + k0;
+                const uint32_t buf_a = tmem + 256u * static_cast<uint32_t>((l - 1) & 1), buf_d = tmem + 256u * static_cast<uint32_t>(l & 1);
+                uint32_t* rec = reinterpret_cast<uint32_t*>(steps) + TM_CHUNK_WORDS * c_mine;
+                rec[0] = buf_a + 8 * (r0 + 1);
+                rec[1] = buf_d + 8 * (r0 - 1 + 1);
+                rec[2] = (((bop_s + (l - 1) * TM_B_BYTES_LAYER) >> 4) & 0x3FFF) | DESC_HI;
+                rec[3] = static_cast<uint32_t>(nst);
+                const uint32_t need = static_cast<uint32_t>(l) << 24;       // layer l - 1 publishes l
+#pragma unroll
+                for (int w = 0; w < 6; w++)
+                {
+                    const int row = r0 - 1 + w;                 // needed as an input row (r0 .. r0 + nst - 1) or as a pre-loaded accumulator row (inside [ya, yb])
+                    const bool input = w >= 1 && w <= nst, accum = w <= nst + 1 && row >= ya && row <= yb;
+                    rec[4 + w] = (input || accum) ? ((flag_a + 8 * row) | need) : 0u;
+                }
+                // commits (issued after the chunk's last MMA): output row rel (relative to ya) is touched by the layer's steps rel, rel + 1,
+                // rel + 2; every chunk that touches it commits once -- twice when all three steps are its own
+                int ne = 0;
+                const int k1 = k0 + nst - 1;
+#pragma unroll
+                for (int t = 0; t < TM_CHUNK + 2; t++)
+                {
+                    const int rel = k0 - 2 + t;
+                    if (rel < 0 || rel > yb - ya || rel > k1) continue;
+                    const uint32_t bar = bar_full + 8 * (gb + (rel >> 2));
+                    rec[10 + ne++] = bar;
+                    if (rel >= k0 && rel + 2 <= k1) rec[10 + ne++] = bar;
+                }
+                for (; ne < 8; ne++) rec[10 + ne] = 0u;
             }
-            ACB_TM_WAIT_ST();
+#ifdef ACB_TM_TRACE
+            if (threadIdx.x == 32 * TM_ISS_WARP0) trace[4 * TM_MAX_STEPS - 5] = clock64();
+#endif
+            asm volatile("bar.sync 1, %0;" :: "n"(32 * TM_ISSUERS) : "memory");     // the issuer warps only
         }
-        ACB_TM_FENCE_BEFORE();
-        __syncthreads();
-        ACB_TM_FENCE_AFTER();
 
-        if (warp < prm.issuers)
+        if (warp >= TM_ISS_WARP0 && warp - TM_ISS_WARP0 < prm.issuers)
         {
-            // ==== MMA issuers: warp w takes chunks w, w + issuers, ... of the step program =============================================
+            // ==== MMA issuers: warp w takes chunks w, w + issuers, ... of the program ==================================================
             tm_wait(bar_bop, 0);
             constexpr uint64_t DESC_TOP = static_cast<uint64_t>(((128u >> 4) & 0x3FFF) | (1u << 14)) << 32;     // SBO | descriptor version, high word
-            const int nsteps = *s_nsteps;
-            const uint32_t* wait_words = reinterpret_cast<const uint32_t*>(steps);
+            constexpr uint32_t IDESC = (1u << 4) | (static_cast<uint32_t>(128 >> 4) << 24) | (3u << 17);       // D f32, A / B f16 K-major, M = 128, N = 24
+            const uint32_t* prog = reinterpret_cast<const uint32_t*>(steps);
 #pragma unroll 1
-            for (int c = warp * TM_CHUNK; c < nsteps; c += prm.issuers * TM_CHUNK)
+            for (int c = warp - TM_ISS_WARP0; c < nchunks; c += prm.issuers)
             {
-                // A chunk that lies inside one layer polls all of its waits at once, one per lane (a chunk that spans two layers of a very
-                // short frame can depend on its own earlier steps: it waits step by step).
-                const int i_last = min(c + TM_CHUNK, nsteps) - 1;
+                const uint32_t* rec = prog + TM_CHUNK_WORDS * c;
 #ifdef ACB_TM_TRACE
                 if (lane == 0) trace[c] = clock64();
 #endif
-                const bool batched = steps[4 * c + 2].w == steps[4 * i_last + 2].w;
-                if (batched)
+                // all of the chunk's waits are polled at once, one per lane
                 {
-                    const int i = c + (lane >> 2);
-                    const uint32_t w = (lane < 4 * TM_CHUNK && i <= i_last) ? wait_words[16 * i + (lane & 3)] : 0u;
+                    const uint32_t w = lane < 6 ? rec[4 + lane] : 0u;
                     if (w) tm_wait_bytes(w & 0xffffffu, w >> 24);
                     __syncwarp();
                 }
@@ -435,82 +441,42 @@ namespace acb
                     trace[TM_MAX_STEPS + c] = clock64();
 #endif
                     ACB_TM_FENCE_AFTER();
-                    const uint4 lead1 = steps[4 * c + 1];
-                    const uint32_t lead = steps[4 * c + 3].w;
-                    if (batched && (lead & 0x80000000u))
-                    {
-                        // regular chunk: 24 MMAs with operands in uniform registers.  Step p multiplies A row r0 + p into the accumulators of
-                        // output rows T0 + p .. T0 + p + 2 (consecutive slots); the commits follow the fixed pattern of a chunk: row T0 + p
-                        // gets this chunk's last contribution at step p (both of its commits when all three input rows are in the chunk),
-                        // rows T0 + 4 and T0 + 5 at the last step.
-                        const uint32_t T0 = lead & 0x7fffffffu;
-                        const uint32_t bl = lead1.z, idesc = lead1.w;
+                    const uint4 op = *reinterpret_cast<const uint4*>(rec);
+                    const uint2 c0 = *reinterpret_cast<const uint2*>(rec + 10);
+                    const uint4 c1 = *reinterpret_cast<const uint4*>(rec + 12);
+                    const uint2 c2 = *reinterpret_cast<const uint2*>(rec + 16);
+                    const uint32_t bl = op.z;
+                    const int nst = static_cast<int>(op.w);
+                    // step p: A row r0 + p into the accumulators of output rows r0 + p - 1 .. r0 + p + 1, operands in uniform registers; per
+                    // alignment the w_hi matrix ((a_hi + a_lo) w_hi), then the w_lo matrix (a_hi w_lo) into the SAME 8 columns per output row;
+                    // the operand shift rides on the alignment's last MMA
 #pragma unroll
-                        for (int pp = 0; pp < TM_CHUNK; pp++)
-                        {
-                            const uint32_t a = lead1.x + 8 * pp, dd = lead1.y + 8 * pp;
-#pragma unroll
-                            for (int al = 0; al < 3; al++)
-                            {
-                                const uint32_t o_hi = al * (TM_B_BYTES_AL >> 4), o_lo = o_hi + (TM_B_BYTES_HALF >> 4);
-                                tm_mma(dd, a, DESC_TOP | (bl + o_hi), idesc);
-                                if (al < 2) tm_mma_ashift(dd, a, DESC_TOP | (bl + o_lo), idesc); else tm_mma(dd, a, DESC_TOP | (bl + o_lo), idesc);
-                            }
-                            const uint32_t b0 = bar_full + 8 * ((T0 + pp) >> 2);
-                            tm_commit(b0);
-                            if (pp >= 2) tm_commit(b0);
-                            if (pp == TM_CHUNK - 1)
-                            {
-                                tm_commit(bar_full + 8 * ((T0 + pp + 1) >> 2));
-                                tm_commit(bar_full + 8 * ((T0 + pp + 2) >> 2));
-                            }
-                        }
-                    }
-                    else
+                    for (int pp = 0; pp < TM_CHUNK; pp++)
                     {
-#pragma unroll 1
-                    for (int i = c; i <= i_last; i++)
-                    {
-                        const uint4 m1 = steps[4 * i + 1], m2 = steps[4 * i + 2], cv = steps[4 * i + 3];
-                        if (!batched)
-                        {
-                            const uint4 w = steps[4 * i];
-                            tm_wait_bytes(w.x & 0xffffffu, w.x >> 24);
-                            if (w.y) tm_wait_bytes(w.y & 0xffffffu, w.y >> 24);
-                            if (w.z) tm_wait_bytes(w.z & 0xffffffu, w.z >> 24);
-                            if (w.w) tm_wait_bytes(w.w & 0xffffffu, w.w >> 24);
-                            ACB_TM_FENCE_AFTER();
-                        }
-                        // per alignment: the w_hi matrix ((a_hi + a_lo) w_hi), then the w_lo matrix (a_hi w_lo) into the SAME 8 columns per
-                        // output row; the operand shift rides on the alignment's last MMA
+                        if (pp >= nst) break;
+                        const uint32_t a = op.x + 8 * pp, dd = op.y + 8 * pp;
 #pragma unroll
                         for (int al = 0; al < 3; al++)
                         {
                             const uint32_t o_hi = al * (TM_B_BYTES_AL >> 4), o_lo = o_hi + (TM_B_BYTES_HALF >> 4);
-                            if (m2.x == 0u)
-                            {
-                                tm_mma(m1.y, m1.x, DESC_TOP | (m1.z + o_hi), m1.w);
-                                if (al < 2) tm_mma_ashift(m1.y, m1.x, DESC_TOP | (m1.z + o_lo), m1.w); else tm_mma(m1.y, m1.x, DESC_TOP | (m1.z + o_lo), m1.w);
-                            }
-                            else
-                            {
-                                tm_mma(m1.y, m1.x, DESC_TOP | (m1.z + o_hi), m1.w);
-                                tm_mma(m1.y, m1.x, DESC_TOP | (m1.z + o_lo), m1.w);
-                                tm_mma(m2.x, m1.x, DESC_TOP | (m2.y + o_hi), m2.z);
-                                if (al < 2) tm_mma_ashift(m2.x, m1.x, DESC_TOP | (m2.y + o_lo), m2.z); else tm_mma(m2.x, m1.x, DESC_TOP | (m2.y + o_lo), m2.z);
-                            }
+                            tm_mma(dd, a, DESC_TOP | (bl + o_hi), IDESC);
+                            if (al < 2) tm_mma_ashift(dd, a, DESC_TOP | (bl + o_lo), IDESC); else tm_mma(dd, a, DESC_TOP | (bl + o_lo), IDESC);
                         }
-                        // output rows that have received this chunk's last contribution
-                        for (uint32_t m = cv.x >> 24; m > 0; m--) tm_commit(cv.x & 0xffffffu);
-                        for (uint32_t m = cv.y >> 24; m > 0; m--) tm_commit(cv.y & 0xffffffu);
-                        for (uint32_t m = cv.z >> 24; m > 0; m--) tm_commit(cv.z & 0xffffffu);
                     }
-                    }
+                    // output rows that have received this chunk's last contribution
+                    if (c0.x) tm_commit(c0.x);
+                    if (c0.y) tm_commit(c0.y);
+                    if (c1.x) tm_commit(c1.x);
+                    if (c1.y) tm_commit(c1.y);
+                    if (c1.z) tm_commit(c1.z);
+                    if (c1.w) tm_commit(c1.w);
+                    if (c2.x) tm_commit(c2.x);
+                    if (c2.y) tm_commit(c2.y);
                 }
                 __syncwarp();
             }
         }
-        else if (warp >= TM_EPI_WARP0)
+        else if (warp < TM_ISS_WARP0)
         {
             // ==== producers of layer 0 and epilogue of every layer: one warp per lane quadrant (strip) and group of four rows ===============
             const int set = (warp - TM_EPI_WARP0) >> 2, q = warp & 3;
@@ -519,11 +485,12 @@ namespace acb
             const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
             const float* luma = luma_all + q * (TM_GMAX + 2) * TM_LP;
             const int pad_top = -y0 - 1, pad_bot = prm.h - y0;          // frame rows of image rows -1 and h (replicate padding), if inside the frame
-            const uint32_t my_a = tmem + lane_base;
+            const uint32_t my_t = tmem + lane_base;
             const uint32_t my_flag_a = flag_a + q;
             const bool pads = (pad_top >= 0) || (pad_bot <= G - 1);     // the frame reaches over the top / bottom image edge
 
-            // one row of layer l's output map becomes the next layer's A operand (x-clamped in border strips); its padding copies in y
+            // one row of layer l's output map becomes the next layer's A operand in buffer l % 2 (x-clamped in border strips), with its
+            // padding copies in y
             auto put_row = [&](const int l, const int y, uint32_t (&w8)[8]) {
                 const int L0 = -x0 - l, L1 = prm.w - 1 - x0 - l;       // lanes of image columns 0 and w - 1 in layer l's map
                 if (L0 > 0 || L1 < 31)
@@ -532,11 +499,12 @@ namespace acb
 #pragma unroll
                     for (int c = 0; c < 8; c++) w8[c] = __shfl_sync(0xffffffffu, w8[c], srcl);
                 }
-                tm_st8(my_a + 8 * y, w8);
+                const uint32_t buf = my_t + 256u * static_cast<uint32_t>(l & 1);
+                tm_st8(buf + 8 * (y + 1), w8);
                 if (pads)
                 {
-                    if (y == pad_top + 1 && pad_top >= 0) tm_st8(my_a + 8 * pad_top, w8);
-                    if (y == pad_bot - 1 && pad_bot <= G - 1) tm_st8(my_a + 8 * pad_bot, w8);
+                    if (y == pad_top + 1 && pad_top >= 0) tm_st8(buf + 8 * (pad_top + 1), w8);
+                    if (y == pad_bot - 1 && pad_bot <= G - 1) tm_st8(buf + 8 * (pad_bot + 1), w8);
                 }
             };
             // ... and is published (after tcgen05.wait::st): every lane stores the progress byte (same address, same value: one store, no branch)
@@ -549,9 +517,12 @@ namespace acb
                 }
             };
 
-            // ---- layer 0: the head conv (fp32 FFMA) or the previous segment's map --------------------------------------------------------
+            // ---- layer 0: the head conv (fp32 FFMA) or the previous segment's map, into buffer 0; buffer 1 gets layer 1's bias ----------------
             {
-                const int ya = s_ya[0], yb = s_yb[0];
+                const int ya = g_ya[0], yb = g_yb[0];
+                uint32_t bias1[8];
+#pragma unroll
+                for (int c = 0; c < 8; c++) bias1[c] = __float_as_uint(bias_of(1, c));
                 if constexpr (S::HEAD)
                 {
                     constexpr int ACT = S::FAM == ACB200_FAMILY_ACNET_LEGACY ? ACT_RELU : S::FAM == ACB200_FAMILY_ACNET ? ACT_PRELU : ACT_IDENTITY;
@@ -581,6 +552,7 @@ namespace acb
                             split_pair(v[0], v[1], w8[0], w8[4]); split_pair(v[2], v[3], w8[1], w8[5]);
                             split_pair(v[4], v[5], w8[2], w8[6]); split_pair(v[6], v[7], w8[3], w8[7]);
                             put_row(0, y, w8);
+                            tm_st8(my_t + 256u + 8 * (y + 1), bias1);
                         }
                         ACB_TM_WAIT_ST();
                         ACB_TM_FENCE_BEFORE();
@@ -608,7 +580,7 @@ namespace acb
                         for (int k = 0; k < 4; k++)
                         {
                             const uint32_t w8[8] = { hi[k].x, hi[k].y, hi[k].z, hi[k].w, lo[k].x, lo[k].y, lo[k].z, lo[k].w };
-                            if (yg + k <= lb) tm_st8(my_a + 8 * (yg + k), w8);
+                            if (yg + k <= lb) { tm_st8(my_t + 8 * (yg + k + 1), w8); tm_st8(my_t + 256u + 8 * (yg + k + 1), bias1); }
                         }
                         ACB_TM_WAIT_ST();
                         ACB_TM_FENCE_BEFORE();
@@ -621,71 +593,39 @@ namespace acb
             // ---- layers 1 .. R ---------------------------------------------------------------------------------------------------------------
             const int es = prm.type & 0xff;
             const bool aligned = ((reinterpret_cast<uintptr_t>(prm.dst) | static_cast<uintptr_t>(prm.dst_pitch)) & (2 * es - 1)) == 0;
-            const uint32_t my_flag_e = flag_e + q;
             (void)aligned;
 #pragma unroll 1
             for (int l = 1; l <= R; l++)
             {
-                const int ya = s_ya[l], yb = s_yb[l], tb = s_tb[l], t_end = s_tb[l + 1], t_end2 = l < R ? s_tb[l + 2] : 0;
+                const int geom = s_geom[l];
+                const int ya = geom & 0xff, yb = static_cast<int>(static_cast<int8_t>((geom >> 8) & 0xff)), g0 = geom >> 16;
                 const bool last = l == R;
                 const bool xclamp = (-x0 - l > 0) || (prm.w - 1 - x0 - l < 31);      // the strip reaches over the left / right image edge in this layer's map
-                // accumulator re-initialisation blocks: this layer's bias and the next layer's (the slot group's next user is one ring ahead)
-                uint32_t init_c[8], init_n[8];
+                const uint32_t buf_d = my_t + 256u * static_cast<uint32_t>(l & 1), buf_o = my_t + 256u * static_cast<uint32_t>((l + 1) & 1);
+                uint32_t bias_n[8];         // the next layer's bias: pre-loaded into the other buffer's rows (its operands are dead)
 #pragma unroll
-                for (int c = 0; c < 8; c++)
-                {
-                    init_c[c] = __float_as_uint(bias_of(l, c));
-                    init_n[c] = __float_as_uint(bias_of(min(l + 1, R), c));
-                }
+                for (int c = 0; c < 8; c++) bias_n[c] = __float_as_uint(bias_of(min(l + 1, R), c));
                 float alpha[8];
 #pragma unroll
                 for (int c = 0; c < 8; c++) alpha[c] = S::FAM == ACB200_FAMILY_ACNET ? prm.a[A0 + 8 * (min(l, S::NCONV) - 1) + c] : 0.0f;
-                // this set's groups: group index gidx = tb / 4 + j with gidx % 4 == set
-                const int g0 = tb >> 2;
+                // this set's groups: group index g0 + j with (g0 + j) % 4 == set
                 for (int j = (set - g0) & 3; ya + 4 * j <= yb; j += 4)
                 {
                     const int yg = ya + 4 * j, k = min(4, yb - yg + 1);
-                    const uint32_t gidx = static_cast<uint32_t>(g0 + j), use = gidx / static_cast<uint32_t>(NRG), sg = gidx - use * NRG;
-                    const uint32_t d_addr = my_a + d_col0 + 32 * sg;
-                    tm_wait(bar_full + 8 * gidx, 0);
+                    tm_wait(bar_full + 8 * (g0 + j), 0);
                     ACB_TM_FENCE_AFTER();
 #ifdef ACB_TM_TRACE
-                    if (q == 0 && lane == 0) trace[2 * TM_MAX_STEPS + gidx] = clock64();
-#endif
-                    uint32_t d[32];
-                    tm_ld32(d, d_addr);
-                    ACB_TM_WAIT_LD();
-                    {
-                        // hand the slot group to its next user (group gidx + ring depth) with that layer's bias
-                        const int tn = static_cast<int>(gidx + NRG) * 4;
-                        auto reinit = [&](const uint32_t (&b8)[8]) { tm_st8(d_addr, b8); tm_st8(d_addr + 8, b8); tm_st8(d_addr + 16, b8); tm_st8(d_addr + 24, b8); };
-                        if (tn < t_end) reinit(init_c);
-                        else if (!last && tn < t_end2) reinit(init_n);
-                        else if (!last)
-                        {
-                            int ln = l + 2;     // (frames with fewer rows per layer than the ring has slots)
-                            while (ln <= R && tn >= s_tb[ln + 1]) ln++;
-                            if (ln <= R)
-                            {
-                                uint32_t init_x[8];
-#pragma unroll
-                                for (int c = 0; c < 8; c++) init_x[c] = __float_as_uint(bias_of(ln, c));
-                                reinit(init_x);
-                            }
-                        }
-                    }
-                    // the accumulators are free again as soon as they have been read and re-initialised: publish that BEFORE the arithmetic
-                    // (the ring's turn-around time is what bounds how far the issuers can run ahead)
-                    ACB_TM_WAIT_ST();
-                    ACB_TM_FENCE_BEFORE();
-                    tm_publish_byte(my_flag_e + 8 * sg, use + 1);
-#ifdef ACB_TM_TRACE
-                    if (q == 0 && lane == 0) trace[3 * TM_MAX_STEPS + gidx] = clock64();
+                    if (q == 0 && lane == 0) trace[2 * TM_MAX_STEPS + g0 + j] = clock64();
 #endif
                     if (!last && k == 4 && !pads && !xclamp)
                     {
-                        // the common case -- a whole group of a body layer inside an interior strip -- as straight-line code: activation and
-                        // split of the four rows, ONE 32-column store of the next layer's operands, four progress bytes
+                        // the common case -- a whole group of a body layer inside an interior strip -- as straight-line code: one 32-column
+                        // load, activation and split of the four rows, ONE 32-column store of the next layer's operands in place, the next
+                        // layer's bias into the other buffer, four progress bytes
+                        uint32_t d[32];
+                        tm_ld32(d, buf_d + 8 * (yg + 1));
+                        ACB_TM_WAIT_LD();
+                        tm_st8(buf_o + 8 * yg + 8, bias_n); tm_st8(buf_o + 8 * yg + 16, bias_n); tm_st8(buf_o + 8 * yg + 24, bias_n); tm_st8(buf_o + 8 * yg + 32, bias_n);
                         uint32_t w[32];
 #pragma unroll
                         for (int jr = 0; jr < 4; jr++)
@@ -700,21 +640,25 @@ namespace acb
                             split_pair(v[0], v[1], w[8 * jr + 0], w[8 * jr + 4]); split_pair(v[2], v[3], w[8 * jr + 1], w[8 * jr + 5]);
                             split_pair(v[4], v[5], w[8 * jr + 2], w[8 * jr + 6]); split_pair(v[6], v[7], w[8 * jr + 3], w[8 * jr + 7]);
                         }
-                        tm_st32(my_a + 8 * yg, w);
+                        tm_st32(buf_d + 8 * (yg + 1), w);
                         ACB_TM_WAIT_ST();
                         ACB_TM_FENCE_BEFORE();
                         const uint32_t fa = my_flag_a + 8 * yg;
                         tm_publish_byte(fa, l + 1); tm_publish_byte(fa + 8, l + 1); tm_publish_byte(fa + 16, l + 1); tm_publish_byte(fa + 24, l + 1);
+#ifdef ACB_TM_TRACE
+                        if (q == 0 && lane == 0) trace[3 * TM_MAX_STEPS + g0 + j] = clock64();
+#endif
                         continue;
                     }
-#pragma unroll
-                    for (int jr = 0; jr < 4; jr++)
+                    for (int jr = 0; jr < k; jr++)
                     {
-                        if (jr >= k) break;
                         const int y = yg + jr;
+                        uint32_t d[8];
+                        tm_ld8(d, buf_d + 8 * (y + 1));
+                        ACB_TM_WAIT_LD();
                         float v[8];
 #pragma unroll
-                        for (int c = 0; c < 8; c++) v[c] = __uint_as_float(d[8 * jr + c]);
+                        for (int c = 0; c < 8; c++) v[c] = __uint_as_float(d[c]);
                         if (!last || !S::TAIL)
                         {
                             // body conv: activation, split, next layer's operand (or the segment's output map)
@@ -723,7 +667,11 @@ namespace acb
                             uint32_t w8[8];
                             split_pair(v[0], v[1], w8[0], w8[4]); split_pair(v[2], v[3], w8[1], w8[5]);
                             split_pair(v[4], v[5], w8[2], w8[6]); split_pair(v[6], v[7], w8[3], w8[7]);
-                            if (!last) put_row(l, y, w8);
+                            if (!last)
+                            {
+                                put_row(l, y, w8);
+                                tm_st8(buf_o + 8 * (y + 1), bias_n);
+                            }
                             else
                             {
                                 const int gx = x0 + R + lane, gy = y0 + y;
@@ -797,9 +745,6 @@ namespace acb
                         ACB_TM_FENCE_BEFORE();
                         publish_rows(l, yg, k);
                     }
-#ifdef ACB_TM_TRACE
-                    if (q == 0 && lane == 0) trace[4 * TM_MAX_STEPS + gidx] = clock64();
-#endif
                 }
             }
         }
@@ -808,11 +753,13 @@ namespace acb
 #ifdef ACB_TM_TRACE
         if (traced && threadIdx.x == 0)
         {
-            const long long t0 = trace[0];
-            for (int i = 0; i < *s_nsteps; i += TM_CHUNK) printf("S %d %lld %lld\n", i, trace[i] - t0, trace[TM_MAX_STEPS + i] - t0);
-            for (int g = 0; g < s_tb[R + 1] / 4; g++) printf("R %d %lld %lld %lld\n", g, trace[2 * TM_MAX_STEPS + g] - t0, trace[3 * TM_MAX_STEPS + g] - t0, trace[4 * TM_MAX_STEPS + g] - t0);
+            const long long t0 = trace[4 * TM_MAX_STEPS - 1];
+            printf("E %lld\n", clock64() - t0);
+            printf("P thread 0 at barrier 1: %lld, thread 300: %lld, after barrier 1: %lld, steps built: %lld\n", trace[4 * TM_MAX_STEPS - 2] - t0, trace[4 * TM_MAX_STEPS - 3] - t0, trace[4 * TM_MAX_STEPS - 4] - t0, trace[4 * TM_MAX_STEPS - 5] - t0);
+            for (int i = 0; i < nchunks; i++) printf("S %d %lld %lld\n", i, trace[i] - t0, trace[TM_MAX_STEPS + i] - t0);
+            for (int g = 0; g < g_gb[R + 1]; g++) printf("R %d %lld %lld\n", g, trace[2 * TM_MAX_STEPS + g] - t0, trace[3 * TM_MAX_STEPS + g] - t0);
         }
 #endif
-        if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u));
+        if (warp == TM_ISS_WARP0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u));
     }
 }
