@@ -463,9 +463,13 @@ namespace
             a.map_in = head ? nullptr : in; a.map_out = tail ? nullptr : out; a.feat = feat;
             int rc;
             if (!tensor) rc = launch_seg_ffma(s, st, m, sp, a);
-            else if (s->tensor_impl == 2 && seg_tm_supported(m)) rc = launch_seg_tm(s, st, m, sp, a);
             else if (s->tensor_impl == 1) rc = launch_seg_tc5(s, st, m, sp, a);
-            else rc = launch_seg_mma(s, st, m, sp, a);
+            else
+            {
+                // the TMEM-resident engine where it has a kernel for the segment, mma.sync for the rest (ARNet, segments deeper than 8 convs)
+                rc = (s->tensor_impl == 2 && seg_tm_supported(m)) ? launch_seg_tm(s, st, m, sp, a) : ACB_SEG_UNSUPPORTED;
+                if (rc == ACB_SEG_UNSUPPORTED) rc = launch_seg_mma(s, st, m, sp, a);
+            }
             if (rc != ACB200_OK) return rc;
             cur ^= 1;
         }
@@ -782,6 +786,22 @@ extern "C"
         acb200_session* s = new (std::nothrow) acb200_session;
         if (!s) return ACB200_ENOMEM;
         s->device = device;
+        // Engine selection for callers that only see the reference's API (ac::core::Processor / the C binding / pyac never pass a
+        // session): ACB200_ENGINE = exact | tensor | auto, ACB200_TENSOR_IMPL = mma | tc5 | tm.  Unknown values are an error, not a default.
+        if (const char* e = std::getenv("ACB200_ENGINE"))
+        {
+            if (!std::strcmp(e, "exact") || !std::strcmp(e, "0")) s->engine = 0;
+            else if (!std::strcmp(e, "tensor") || !std::strcmp(e, "1")) s->engine = 1;
+            else if (!std::strcmp(e, "auto") || !std::strcmp(e, "2")) s->engine = 2;
+            else { delete s; return ACB200_EINVAL; }
+        }
+        if (const char* e = std::getenv("ACB200_TENSOR_IMPL"))
+        {
+            if (!std::strcmp(e, "mma") || !std::strcmp(e, "0")) s->tensor_impl = 0;
+            else if (!std::strcmp(e, "tc5") || !std::strcmp(e, "1")) s->tensor_impl = 1;
+            else if (!std::strcmp(e, "tm") || !std::strcmp(e, "2")) s->tensor_impl = 2;
+            else { delete s; return ACB200_EINVAL; }
+        }
         if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess)
         {

@@ -91,7 +91,9 @@ struct acb200_session
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
-    int tensor_impl = 0;    // tensor engine implementation: 0 mma.sync (HMMA), 1 tcgen05 SS (UTCHMMA, maps in shared memory), 2 tcgen05 TMEM-resident
+    // tensor engine implementation: 0 mma.sync (HMMA), 1 tcgen05 SS (UTCHMMA, maps in shared memory), 2 tcgen05 TMEM-resident (default; the
+    // families it does not cover -- ARNet, segments deeper than eight convs -- run on mma.sync)
+    int tensor_impl = 2;
     int sm_count = 0;
     int engine = 2;     // 0 exact FFMA, 1 tensor-core MMA, 2 auto: exact for every 2x pass but the last, tensor for the last
     std::string error = "NO ERROR";
@@ -124,6 +126,19 @@ namespace acbh
         }
         return code;
     }
+    // the dynamic shared memory opt-in of a kernel, once per kernel and device (the attribute belongs to the device's context): `mask` is
+    // a static of the launching function template, one bit per device
+    inline int smem_optin_once(acb200_session* s, const void* kernel, size_t bytes, std::atomic<unsigned long long>& mask)
+    {
+        const unsigned long long bit = 1ull << (s->device & 63);
+        if (mask.load(std::memory_order_acquire) & bit) return ACB200_OK;
+        const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+        if (e != cudaSuccess) return fail(s, ACB200_ECUDA, "cudaFuncSetAttribute(max dynamic smem)", e);
+        mask.fetch_or(bit, std::memory_order_release);
+        return ACB200_OK;
+    }
+    // returned by an engine's launcher for a segment it has no kernel for (the caller picks another engine); never leaves the library
+    constexpr int ACB_SEG_UNSUPPORTED = -1000;
 #define ACB_CUDA(s, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return acbh::fail((s), ACB200_ECUDA, #call, e__); } while (0)
 
     // grow-only scratch, allocated and freed in the order of stream `st` (the stream the buffer's users run on)

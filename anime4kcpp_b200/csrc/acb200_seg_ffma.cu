@@ -18,10 +18,8 @@ namespace acbh
         std::memcpy(prm.b, m.b.data() + spec.boff, sizeof(float) * S::NB);
         if (S::NA > 0) std::memcpy(prm.a, m.a.data() + spec.aoff, sizeof(float) * S::NA);
         else prm.a[0] = 0.0f;
-        cudaError_t attr_err = cudaSuccess;
-        // the attribute is per device: set it each time the device changes (cheap)
-        attr_err = cudaFuncSetAttribute(segment_ffma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(FFMA_SMEM_BYTES));
-        if (attr_err != cudaSuccess) return fail(s, ACB200_ECUDA, "cudaFuncSetAttribute(max dynamic smem)", attr_err);
+        static std::atomic<unsigned long long> optin{0};
+        if (int rc = smem_optin_once(s, reinterpret_cast<const void*>(segment_ffma_kernel<S>), FFMA_SMEM_BYTES, optin)) return rc;
         segment_ffma_kernel<S><<<prm.tiles_x * tiles_y, FFMA_THREADS, FFMA_SMEM_BYTES, st>>>(prm);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         ACB_CUDA(s, cudaGetLastError());

@@ -29,8 +29,8 @@ namespace acbh
         std::memcpy(prm.b, m.b.data() + spec.boff, sizeof(float) * S::NB);
         if (S::NA > 0) std::memcpy(prm.a, m.a.data() + spec.aoff, sizeof(float) * S::NA);
         else prm.a[0] = 0.0f;
-        cudaError_t attr_err = cudaFuncSetAttribute(segment_tc5_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(TC_SMEM_BYTES));
-        if (attr_err != cudaSuccess) return fail(s, ACB200_ECUDA, "cudaFuncSetAttribute(max dynamic smem)", attr_err);
+        static std::atomic<unsigned long long> optin{0};
+        if (int rc2 = smem_optin_once(s, reinterpret_cast<const void*>(segment_tc5_kernel<S>), TC_SMEM_BYTES, optin)) return rc2;
         segment_tc5_kernel<S><<<prm.tiles_x * tiles_y, TC_THREADS, TC_SMEM_BYTES, st>>>(prm);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         ACB_CUDA(s, cudaGetLastError());

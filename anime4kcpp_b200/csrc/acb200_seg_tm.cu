@@ -31,7 +31,7 @@ namespace acbh
                           const void* src, int src_pitch, void* dst, int dst_pitch, int w, int h, int type,
                           const float* map_in, float* map_out, float* feat)
     {
-        if constexpr (S::FAM == ACB200_FAMILY_ARNET || S::R > TM_MAX_R) return ACB200_EINVAL;
+        if constexpr (S::FAM == ACB200_FAMILY_ARNET || S::R > TM_MAX_R) return ACB_SEG_UNSUPPORTED;
         else
         {
             static_assert(sizeof(TmParams<S>) <= 32764, "kernel parameter block too large");
@@ -63,8 +63,8 @@ namespace acbh
             std::memcpy(prm.b, m.b.data() + spec.boff, sizeof(float) * S::NB);
             if (S::NA > 0) std::memcpy(prm.a, m.a.data() + spec.aoff, sizeof(float) * S::NA);
             else prm.a[0] = 0.0f;
-            cudaError_t attr_err = cudaFuncSetAttribute(segment_tm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(TM_SMEM_BYTES));
-            if (attr_err != cudaSuccess) return fail(s, ACB200_ECUDA, "cudaFuncSetAttribute(max dynamic smem)", attr_err);
+            static std::atomic<unsigned long long> optin{0};
+            if ((rc = smem_optin_once(s, reinterpret_cast<const void*>(segment_tm_kernel<S>), TM_SMEM_BYTES, optin)) != ACB200_OK) return rc;
             segment_tm_kernel<S><<<prm.tiles_x * tiles_y, TM_THREADS, TM_SMEM_BYTES, st>>>(prm);
             g_launches.fetch_add(1, std::memory_order_relaxed);
             ACB_CUDA(s, cudaGetLastError());

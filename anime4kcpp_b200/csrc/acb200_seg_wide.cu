@@ -17,7 +17,8 @@ namespace acbh
         std::memcpy(prm.k, k + static_cast<size_t>(co0) * 9 * F, sizeof(prm.k));
         std::memcpy(prm.b, b + co0, sizeof(prm.b));
         if (a) std::memcpy(prm.a, a + co0, sizeof(prm.a)); else std::memset(prm.a, 0, sizeof(prm.a));
-        ACB_CUDA(s, cudaFuncSetAttribute(wide_conv_kernel<F, NCO, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(wide_smem_bytes<F>())));
+        static std::atomic<unsigned long long> optin{0};
+        if (int rc = smem_optin_once(s, reinterpret_cast<const void*>(wide_conv_kernel<F, NCO, MODE>), wide_smem_bytes<F>(), optin)) return rc;
         wide_conv_kernel<F, NCO, MODE><<<dim3((w + WIDE_TW - 1) / WIDE_TW, (h + WIDE_TH - 1) / WIDE_TH), WIDE_THREADS, wide_smem_bytes<F>(), st>>>(prm);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         ACB_CUDA(s, cudaGetLastError());
@@ -36,7 +37,8 @@ namespace acbh
         prm.bop = dbops + static_cast<size_t>(conv_index) * (WideTc<F>::B_BYTES / 4);
         std::memcpy(prm.b, b, sizeof(prm.b));
         if (a) std::memcpy(prm.a, a, sizeof(prm.a)); else std::memset(prm.a, 0, sizeof(prm.a));
-        ACB_CUDA(s, cudaFuncSetAttribute(wide_tc_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, WideTc<F>::SMEM_BYTES));
+        static std::atomic<unsigned long long> optin{0};
+        if ((rc = smem_optin_once(s, reinterpret_cast<const void*>(wide_tc_kernel<F>), WideTc<F>::SMEM_BYTES, optin)) != ACB200_OK) return rc;
         wide_tc_kernel<F><<<dim3((w + WTC_TW - 1) / WTC_TW, (h + WideTc<F>::TH - 1) / WideTc<F>::TH), WideTc<F>::THREADS, WideTc<F>::SMEM_BYTES, st>>>(prm);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         ACB_CUDA(s, cudaGetLastError());

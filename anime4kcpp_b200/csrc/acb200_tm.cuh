@@ -65,6 +65,10 @@ namespace acb
     constexpr int TM_EPI_WARP0 = 0;
     constexpr int TM_ISS_WARP0 = 4 * ACB_TM_EPI_SETS;
     constexpr int TM_CHUNK = 4;                     // consecutive steps (input rows) per chunk, >= 3
+#ifndef ACB_TM_LAG
+#define ACB_TM_LAG 4
+#endif
+    constexpr int TM_LAG = ACB_TM_LAG;              // rounds between a layer's chunk k and the next layer's chunk k in the issue order, >= 3
     constexpr int TM_B_BYTES_HALF = 2 * 24 * 16;    // one B matrix: [2 K chunks][24 rows][8 fp16]
     constexpr int TM_B_BYTES_AL = 2 * TM_B_BYTES_HALF;      // one alignment: the w_hi matrix, then the w_lo matrix
     constexpr int TM_B_BYTES_LAYER = 3 * TM_B_BYTES_AL;     // 4608
@@ -260,6 +264,9 @@ namespace acb
             for (int l = 0; l <= R + 1; l++) s_geom[l] = (g_ya[l] & 0xff) | ((g_yb[l] & 0xff) << 8) | (g_gb[l] << 16);
         }
         if (threadIdx.x < TM_GMAX) asm volatile("st.shared.u32 [%0], %1;" :: "r"(flag_a + 8 * threadIdx.x), "r"(0));
+        // tickets[l]: chunks of layer l whose MMAs have been issued (see the issuers)
+        const uint32_t tickets = static_cast<uint32_t>(__cvta_generic_to_shared(smem_tm + TM_OFF_GEOM)) + 4 * (TM_MAX_R + 2);
+        if (threadIdx.x >= 32 && threadIdx.x < 32 + TM_MAX_R + 2) asm volatile("st.shared.u32 [%0], %1;" :: "r"(tickets + 4 * (threadIdx.x - 32)), "r"(0));
         if (threadIdx.x >= 64 && threadIdx.x < 64 + TM_MAX_GROUPS)
         {
             // one `full` barrier per group: two commits per row
@@ -352,9 +359,9 @@ namespace acb
             //   [0] A operand of the first step   [1] accumulator of the first step (output row r - 1)   [2] B descriptor low word (alignment 0)
             //   [3] steps in the chunk            [4..9] waits (progress word | count << 24; 0 = none): rows r0 - 1 .. r0 + steps of the previous
             //   layer -- the input rows, and the rows whose producers pre-loaded the accumulators the chunk adds to
-            //   [10..17] `full` barriers to commit to after the chunk's MMAs (0 = none)
+            //   [10..17] `full` barriers to commit to after the chunk's MMAs (0 = none)   [18] the layer's ticket | chunk index in the layer << 24
             // Every step has the same shape -- A row r into output rows r - 1 .. r + 1 -- because the first and last steps of a layer simply add
-            // into the scratch rows outside the layer's output range.  Chunk c is issued by issuer warp c % issuers.  All MMAs accumulate, so
+            // into the scratch rows outside the layer's output range.  Chunk c of the program is issued by issuer warp c % issuers.  All MMAs accumulate, so
             // their order across rows does not matter; an output row's three input rows lie in at most two chunks, hence every row
             // contributes exactly two commits to its group's `full` barrier.
             const uint32_t bop_s = static_cast<uint32_t>(__cvta_generic_to_shared(smem_tm));
@@ -381,7 +388,24 @@ namespace acb
                 const int k0 = (c_mine - cb) * TM_CHUNK, nst = min(TM_CHUNK, n - k0);
                 const int r0 = ya - 1 + k0;
                 const uint32_t buf_a = tmem + 256u * static_cast<uint32_t>((l - 1) & 1), buf_d = tmem + 256u * static_cast<uint32_t>(l & 1);
-                uint32_t* rec = reinterpret_cast<uint32_t*>(steps) + TM_CHUNK_WORDS * c_mine;
+                // Program order: a WAVEFRONT over the layers, not layer after layer.  Chunk k of layer l needs the rows that chunks <= k + 2 of
+                // layer l - 1 produce (MMAs, commit, epilogue, publish: ~2500 cycles); a frame of 30 rows is only eight chunks per layer,
+                // so issued layer by layer the dependent chunk would follow its producer too closely and every layer would start by waiting.
+                // In round t the program holds chunk t - (l - 1) LAG of every layer l (deepest layer first): producer and consumer are
+                // LAG - 2 rounds apart, with the other layers' chunks in between.
+                int pos = 0;
+                {
+                    const int t = (c_mine - cb) + (l - 1) * TM_LAG;
+#pragma unroll
+                    for (int ll = 1; ll <= R; ll++)
+                    {
+                        const int nc = g_yb[ll] >= g_ya[ll] ? (g_yb[ll] - g_ya[ll] + 3 + TM_CHUNK - 1) / TM_CHUNK : 0;
+                        const int kk = t - (ll - 1) * TM_LAG;           // layer ll's chunk of round t
+                        pos += min(nc, max(0, kk));                     // ... its chunks of earlier rounds
+                        if (ll > l && kk >= 0 && kk < nc) pos++;        // ... and, within the round, the deeper layers come first
+                    }
+                }
+                uint32_t* rec = reinterpret_cast<uint32_t*>(steps) + TM_CHUNK_WORDS * pos;
                 rec[0] = buf_a + 8 * (r0 + 1);
                 rec[1] = buf_d + 8 * (r0 - 1 + 1);
                 rec[2] = (((bop_s + (l - 1) * TM_B_BYTES_LAYER) >> 4) & 0x3FFF) | DESC_HI;
@@ -408,6 +432,7 @@ namespace acb
                     if (rel >= k0 && rel + 2 <= k1) rec[10 + ne++] = bar;
                 }
                 for (; ne < 8; ne++) rec[10 + ne] = 0u;
+                rec[18] = (tickets + 4 * l) | (static_cast<uint32_t>(c_mine - cb) << 24);      // the layer's ticket | chunks of the layer before this one
             }
 #ifdef ACB_TM_TRACE
             if (threadIdx.x == 32 * TM_ISS_WARP0) trace[4 * TM_MAX_STEPS - 5] = clock64();
@@ -418,6 +443,13 @@ namespace acb
         if (warp >= TM_ISS_WARP0 && warp - TM_ISS_WARP0 < prm.issuers)
         {
             // ==== MMA issuers: warp w takes chunks w, w + issuers, ... of the program ==================================================
+            // Neighbouring chunks of a layer add into the two accumulator rows at their boundary, and fp32 sums depend on the order of the
+            // additions: left alone, two warps would race and the last bit of those rows would change from run to run.  So a layer's
+            // chunks are STARTED in order and every chunk issues its rows last to first: chunk k + 1 waits for the layer's ticket to reach
+            // k + 1, which chunk k's issuer sets once its LAST row's MMAs -- the ones that add into the shared rows -- are in the queue, and
+            // chunk k + 1 reaches ITS contribution to those rows (its first row) only after eighteen MMAs of its own.  The tensor pipe
+            // executes in issue order, so the additions into a shared row always happen in the same order, while the bulk of
+            // neighbouring chunks is still issued concurrently by different warps.
             tm_wait(bar_bop, 0);
             constexpr uint64_t DESC_TOP = static_cast<uint64_t>(((128u >> 4) & 0x3FFF) | (1u << 14)) << 32;     // SBO | descriptor version, high word
             constexpr uint32_t IDESC = (1u << 4) | (static_cast<uint32_t>(128 >> 4) << 24) | (3u << 17);       // D f32, A / B f16 K-major, M = 128, N = 24
@@ -431,8 +463,13 @@ namespace acb
 #endif
                 // all of the chunk's waits are polled at once, one per lane
                 {
-                    const uint32_t w = lane < 6 ? rec[4 + lane] : 0u;
-                    if (w) tm_wait_bytes(w & 0xffffffu, w >> 24);
+                    const uint32_t w = lane < 6 ? rec[4 + lane] : (lane == 6 ? rec[18] : 0u);
+                    if (lane < 6) { if (w) tm_wait_bytes(w & 0xffffffu, w >> 24); }
+                    else if (w >> 24)
+                    {
+                        uint32_t t;
+                        do { asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(t) : "r"(w & 0xffffffu) : "memory"); } while (t < (w >> 24));
+                    }
                     __syncwarp();
                 }
                 if (tm_elect_one())
@@ -447,13 +484,15 @@ namespace acb
                     const uint2 c2 = *reinterpret_cast<const uint2*>(rec + 16);
                     const uint32_t bl = op.z;
                     const int nst = static_cast<int>(op.w);
+                    const uint32_t tk = rec[18];
                     // step p: A row r0 + p into the accumulators of output rows r0 + p - 1 .. r0 + p + 1, operands in uniform registers; per
                     // alignment the w_hi matrix ((a_hi + a_lo) w_hi), then the w_lo matrix (a_hi w_lo) into the SAME 8 columns per output row;
                     // the operand shift rides on the alignment's last MMA
 #pragma unroll
-                    for (int pp = 0; pp < TM_CHUNK; pp++)
+                    for (int pq = 0; pq < TM_CHUNK; pq++)
                     {
-                        if (pp >= nst) break;
+                        const int pp = TM_CHUNK - 1 - pq;       // last row first (see above)
+                        if (pp >= nst) continue;
                         const uint32_t a = op.x + 8 * pp, dd = op.y + 8 * pp;
 #pragma unroll
                         for (int al = 0; al < 3; al++)
@@ -462,6 +501,8 @@ namespace acb
                             tm_mma(dd, a, DESC_TOP | (bl + o_hi), IDESC);
                             if (al < 2) tm_mma_ashift(dd, a, DESC_TOP | (bl + o_lo), IDESC); else tm_mma(dd, a, DESC_TOP | (bl + o_lo), IDESC);
                         }
+                        // the chunk's last row is in the queue: the layer's next chunk may start
+                        if (pp == nst - 1) asm volatile("st.volatile.shared.u32 [%0], %1;" :: "r"(tk & 0xffffffu), "r"((tk >> 24) + 1) : "memory");
                     }
                     // output rows that have received this chunk's last contribution
                     if (c0.x) tm_commit(c0.x);

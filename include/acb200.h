@@ -210,7 +210,16 @@ ACB200_API float acb200_session_last_kernel_ms(acb200_session* session);
  *              keep the 8-bit bar because no rounding difference is fed back into a later pass
  */
 ACB200_API int acb200_session_set_engine(acb200_session* session, int engine);
-/* implementation of the tensor engine: 0 = mma.sync (HMMA, operands via ldmatrix), 1 = tcgen05 (UTCHMMA, accumulators in TMEM) */
+/*
+ * implementation of the tensor engine:
+ *   0  mma.sync (HMMA, operands via ldmatrix)
+ *   1  tcgen05 with the feature maps in shared memory (UTCHMMA, SS form; kept for comparison)
+ *   2  (default) tcgen05 with the feature maps resident in TMEM (UTCHMMA, TS form with .ashift): ACNet and ACNet-legacy;
+ *      ARNet and the wide families run on 0 / their own kernels
+ * Both settings can also be given in the environment for callers that never see a session (the reference-facing
+ * ac::core::Processor, the C binding, pyac): ACB200_ENGINE = exact | tensor | auto, ACB200_TENSOR_IMPL = mma | tc5 | tm;
+ * acb200_session_create fails with ACB200_EINVAL on any other value.
+ */
 ACB200_API int acb200_session_set_tensor_impl(acb200_session* session, int impl);
 
 ACB200_API const char* acb200_error_string(int code);

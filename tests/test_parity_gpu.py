@@ -29,9 +29,10 @@ U16_LSB_MAX = 4
 X4_LSB_MAX, X4_EXACT_MIN = 4, 0.995
 ENGINE_EXACT, ENGINE_TENSOR, ENGINE_AUTO = 0, 1, 2
 ENGINES = [ENGINE_EXACT]
-# tensor engine implementations: 0 = mma.sync (library default), 1 = tcgen05; the tensor-engine tests run both
-TENSOR_IMPL = 0
-TENSOR_IMPLS = [0, 1]
+# tensor engine implementations: 0 = mma.sync, 1 = tcgen05 with the maps in shared memory, 2 = tcgen05 with the maps resident in
+# TMEM (library default; ARNet segments fall back to 0 inside the library); the tensor-engine tests run all three
+TENSOR_IMPL = 2
+TENSOR_IMPLS = [0, 1, 2]
 
 
 @pytest.fixture(scope="module")
@@ -330,7 +331,7 @@ def test_frame_stream_delivers_in_order_and_matches_single_calls(session):
     m = gpu_model("acnet-legacy-hdn0")
     frames = [O.noise_u8(72, 120, 3, seed=100 + i) for i in range(12)]
     outs = [np.zeros((144, 240, 3), np.uint8) for _ in frames]
-    session.set_tensor_impl(0)           # the stream's own sessions run the library default implementation
+    session.set_tensor_impl(TENSOR_IMPL)   # the stream's own sessions run the library default implementation
     stream = A.FrameStream(m, [0, 0], workers_per_device=2, queue_depth=2)      # two lanes on the one device of the test box
     got = []
     for i, (f, o) in enumerate(zip(frames, outs)):
@@ -344,6 +345,23 @@ def test_frame_stream_delivers_in_order_and_matches_single_calls(session):
     session.set_engine(ENGINE_AUTO)
     for f, o in zip(frames, outs):
         assert np.array_equal(o, session.process_host(m, f, 2.0))
+
+
+@pytest.mark.parametrize("name", ["acnet-legacy-hdn0", "acnet-f8b8-hdn"])
+def test_default_tensor_engine_is_deterministic(session, name):
+    """The TMEM-resident engine issues MMAs from four warps; the accumulation order into a row must not depend on their timing
+    (acb200_tm.cuh, the issuers' tickets): the same input gives the same bits on every run and on every session."""
+    m = gpu_model(name)
+    session.set_engine(ENGINE_TENSOR)
+    session.set_tensor_impl(2)
+    other = A.Session(0)
+    other.set_engine(ENGINE_TENSOR)
+    for shape in ((72, 120), (300, 500), (1080, 1920)):
+        img = O.noise_u8(shape[0], shape[1], 1, seed=shape[1])
+        first = session.process_host(m, img, 2.0)
+        for _ in range(6):
+            assert np.array_equal(session.process_host(m, img, 2.0), first), shape
+        assert np.array_equal(other.process_host(m, img, 2.0), first), shape
 
 
 # ---- planar / semi-planar video frames (SURVEY.md 8f rank 1, config 4; cli/src/Main.cpp:183-206) -----------------------------
