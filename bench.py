@@ -180,6 +180,45 @@ def map_image(lib, arr):
     return img
 
 
+IMPL_NAMES = {0: "mma.sync", 1: "tcgen05, maps in shared memory", 2: "tcgen05, maps resident in TMEM"}
+
+
+def impl_label(model, tensor_impl):
+    """Name of the tensor-engine implementation that runs `model` (library default: 2; ARNet has no TMEM-resident kernel yet)."""
+    impl = 2 if tensor_impl is None else tensor_impl
+    if model.startswith(("artcnn", "fsrcnnx")):
+        return "per-layer tcgen05 MMA (wide families)"
+    if impl == 2 and model.startswith("arnet"):
+        return IMPL_NAMES[0] + " (ARNet: no TMEM-resident kernel)"
+    return IMPL_NAMES[impl]
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of one luma pass (both segment launches), ncu --set full --cache-control none (caches NOT
+# flushed between replays: the steady-state figure), 1920x1080 u8 plane; profiles/r02_tm_steady_ncu_summary.json
+STEADY_TRAFFIC = {("acnet-legacy", 2): 40646656 + 22812672}     # segment A (head + 3 convs) + segment B (5 convs + tail)
+
+
+def luma_roofline(A, torch, sess, model, name, d_plane, stream, peaks, reps):
+    """The luma network alone on a device-resident 1080p Y plane: CUDA-event time per pass, algorithmic FLOPs against the BURST bf16 peak."""
+    y_out = torch.empty((2 * H, 2 * W), dtype=torch.uint8, device="cuda")
+    for i in range(3):
+        sess.process_device(model, d_plane[i % len(d_plane)], FACTOR, out=y_out, stream=stream)
+    torch.cuda.synchronize()
+    l0 = A.launch_count()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for i in range(reps):
+        sess.process_device(model, d_plane[i % len(d_plane)], FACTOR, out=y_out, stream=stream)
+    k1.record()
+    torch.cuda.synchronize()
+    kernel_ms = k0.elapsed_time(k1) / reps
+    launches = (A.launch_count() - l0) / reps
+    flop = 2.0 * macs_for(name) * W * H
+    tf = flop / (kernel_ms / 1e3) / 1e12
+    return {"kernel_ms": kernel_ms, "launches_per_pass": launches, "flop_per_pass": flop, "flop_per_launch": flop / max(launches, 1.0),
+            "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops"]}
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -277,27 +316,12 @@ def run_ours(args):
 
     # ---- dominant kernel alone: the luma network on a device-resident 1080p Y plane (what the RGB path launches) ----
     y_in = d_in[:, :, :, 0].contiguous()
-    y_out = torch.empty((2 * H, 2 * W), dtype=torch.uint8, device="cuda")
-    for i in range(3):
-        sess.process_device(model, y_in[i % B], FACTOR, out=y_out, stream=stream)
-    torch.cuda.synchronize()
-    l0 = A.launch_count()
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = max(8, min(64, B * args.steps))
-    k0.record()
-    for i in range(reps):
-        sess.process_device(model, y_in[i % B], FACTOR, out=y_out, stream=stream)
-    k1.record()
-    torch.cuda.synchronize()
-    kernel_ms = k0.elapsed_time(k1) / reps
-    launches_per_pass = (A.launch_count() - l0) / reps
     peaks = load_peaks()
-    flop_frame = 2.0 * macs_for(args.model) * W * H
-    achieved_tf = flop_frame / (kernel_ms / 1e3) / 1e12
-    fp32_peak_tf = 148 * 128 * 2 * 1.965e9 / 1e12
+    lr = luma_roofline(A, torch, sess, model, args.model, y_in, stream, peaks, max(8, min(64, B * args.steps)))
+    kernel_ms, launches_per_pass, flop_frame, achieved_tf = lr["kernel_ms"], lr["launches_per_pass"], lr["flop_per_pass"], lr["achieved"]
     # bytes that must cross HBM per RGB frame (in + out) -- the other roofline candidate; compute dominates
     bytes_frame = W * H * CH + 4 * W * H * CH
-    t_roof_ms = max(flop_frame / (peaks["bf16_tflops_sustained"] * 1e12), bytes_frame / (peaks["hbm_gbs"] * 1e9)) * 1e3
+    t_roof_ms = max(flop_frame / (peaks["bf16_tflops"] * 1e12), bytes_frame / (peaks["hbm_gbs"] * 1e9)) * 1e3
 
     # ---- end to end through the C binding with host buffers ---------------------------------------------------------
     e2e = None
@@ -346,8 +370,43 @@ def run_ours(args):
         want = d_out[0].cpu().numpy()
         if args.engine == 2:
             assert np.array_equal(np_out[0], want), "host path and device path disagree"
+
+    # The ceiling of any host-fed path on this box: the SAME bytes (one pinned 1080p RGB frame in, one pinned 2160p RGB frame out, a
+    # synchronise per frame) from the same number of caller threads, each on its own stream, with NO kernel in between.
+    def copy_steps(n_steps):
+        nxt = [0]
+        lock = threading.Lock()
+
+        def worker(k):
+            st_ = torch.cuda.Stream()
+            with torch.cuda.stream(st_):
+                while True:
+                    with lock:
+                        i = nxt[0]
+                        nxt[0] += 1
+                    if i >= n_steps * B:
+                        return
+                    d_in[i % B].copy_(pin_in[i % B], non_blocking=True)
+                    pin_out[i % B].copy_(d_out[i % B], non_blocking=True)
+                    st_.synchronize()
+        ts = [threading.Thread(target=worker, args=(k,)) for k in range(n_threads)]
+        [x.start() for x in ts]
+        [x.join() for x in ts]
+    copy_steps(1)
+    barrier()
+    t0 = time.perf_counter()
+    copy_steps(args.steps)
+    barrier()
+    tcp = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(tcp, op=dist.ReduceOp.MAX)
+    copy_value = OUT_MP * frames_total / float(tcp.item())
+    copy_gbs = frames_total * 5 * W * H * CH / float(tcp.item()) / 1e9
     e2e = {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": B * W * H * CH, "d2h_bytes_per_step": B * 4 * W * H * CH,
-           "fps": frames_total / float(te.item()), "caller_threads": n_threads, "api": "ac_processor_process (libac_c binding), pinned host images"}
+           "fps": frames_total / float(te.item()), "caller_threads": n_threads, "api": "ac_processor_process (libac_c binding), pinned host images",
+           "copy_ceiling": {"value": copy_value, "unit": "MP/s", "gb_per_s_both_directions": copy_gbs,
+                            "what": "the same pinned H2D + D2H bytes per frame from the same caller threads, no kernels; all ranks at once"},
+           "frac_of_copy_ceiling": e2e_value / copy_value}
 
     # ---- the video callers' format: planar YUV420 u8 frames, Y through the network, U and V
     #      through the Catmull-Rom resize, one submission per frame; same metric, counted on the luma plane ----------------
@@ -448,13 +507,138 @@ def run_ours(args):
             return NFR * world / float(tt.item())
         run_stream(lambda i: fs.submit(np_in[i], FACTOR, np_out[i]))                 # warm-up (sessions, scratch)
         rgb_fps = run_stream(lambda i: fs.submit(np_in[i], FACTOR, np_out[i]))
-        y_in = [[t.numpy() for t in f] for f in hp_in]
-        y_out = [[t.numpy() for t in f] for f in hp_out]
-        run_stream(lambda i: fs.submit_frame(y_in[i], FACTOR, y_out[i]))
-        yuv_fps = run_stream(lambda i: fs.submit_frame(y_in[i], FACTOR, y_out[i]))
+        fy_in = [[t.numpy() for t in f] for f in hp_in]
+        fy_out = [[t.numpy() for t in f] for f in hp_out]
+        run_stream(lambda i: fs.submit_frame(fy_in[i], FACTOR, fy_out[i]))
+        yuv_fps = run_stream(lambda i: fs.submit_frame(fy_in[i], FACTOR, fy_out[i]))
         fs.close()
         stream_res = {"frames": NFR * world, "workers_per_gpu": n_threads, "queue_depth": 4, "rgb_fps": rgb_fps, "yuv420_fps": yuv_fps,
                       "api": "acb200_stream_submit / submit_frame / next (in-order delivery), pinned host frames"}
+
+    # ---- BASELINE configs 2 / 3: the other model families on the same frames (device-resident batch + the luma pass alone) ----------
+    models_res = None
+    if not args.no_extra:
+        models_res = {}
+        for name in args.models.split(","):
+            if not name or name == args.model:
+                continue
+            mm = A.Model(name)
+            nb = min(B, 4)
+
+            def mstep():
+                for i in range(nb):
+                    ss, st_ = lanes[i % n_streams]
+                    ss.process_device(mm, d_in[i], FACTOR, out=d_out[i], stream=st_.cuda_stream)
+                for _, st_ in side:
+                    join = torch.cuda.Event()
+                    join.record(st_)
+                    work_stream.wait_event(join)
+            for _ in range(2):
+                mstep()
+            barrier()
+            m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            m0.record()
+            nrep = 3
+            for _ in range(nrep):
+                mstep()
+            m1.record()
+            barrier()
+            tm_ = torch.tensor([m0.elapsed_time(m1)], dtype=torch.float64, device="cuda")
+            if dist is not None:
+                dist.all_reduce(tm_, op=dist.ReduceOp.MAX)
+            r = luma_roofline(A, torch, sess, mm, name, y_in, stream, peaks, 8)
+            crop = np.ascontiguousarray(host_frames[0, :96, :128])
+            mx, exact = O.compare_u8(sess.process_host(mm, crop, FACTOR), O.oracle_process(name, crop, FACTOR))
+            models_res[name] = {"value": OUT_MP * nb * nrep * world / (float(tm_.item()) / 1e3), "unit": "MP/s",
+                                "fps": nb * nrep * world / (float(tm_.item()) / 1e3), "frames_per_step_per_gpu": nb,
+                                "tensor_impl": impl_label(name, args.tensor_impl), "parity_spot_check": {"max_lsb": mx, "bit_exact_frac": exact},
+                                "roofline": dict(r, bound="tensor", kernel="luma network alone, 1920x1080 Y -> 3840x2160 Y")}
+
+    # ---- BASELINE config 5: one 8192 x 8192 image, 4x (two 2x passes), eight halo-overlapped row bands dealt over the ranks; host image
+    #      in, host image out (gray: the 32768^2 RGB result does not fit the reference's int-sized Image) -----------------------------
+    bands_res = None
+    if not args.no_extra:
+        NB_, SZ = 8, args.band_size
+        big = np.random.RandomState(99).randint(0, 256, size=(SZ, SZ), dtype=np.uint8)
+        big_out = np.zeros((4 * SZ, 4 * SZ), np.uint8)
+        mine = [b for b in range(NB_) if b % world == rank]
+        A.process_band(sess, model, big, 4.0, NB_, mine[0], big_out)        # warm-up: scratch at band size
+        barrier()
+        t0 = time.perf_counter()
+        for b in mine:
+            A.process_band(sess, model, big, 4.0, NB_, b, big_out)
+        torch.cuda.synchronize()
+        t_mine = time.perf_counter() - t0
+        barrier()
+        tb = torch.tensor([t_mine], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        flop_big = 2.0 * macs_for(args.model) * (SZ * SZ + 4 * SZ * SZ)
+        tfb = flop_big / float(tb.item()) / 1e12
+        bands_res = {"workload": "%dx%d gray u8 image, 4x, %d row bands, band b on rank b mod N, host image in / host image out" % (SZ, SZ, NB_),
+                     "value": 16 * SZ * SZ / 1e6 / float(tb.item()), "unit": "MP/s", "seconds": float(tb.item()), "bands_per_rank": len(mine),
+                     "h2d_bytes": SZ * SZ, "d2h_bytes": 16 * SZ * SZ,
+                     "roofline": {"bound": "tensor", "achieved": tfb, "peak": peaks["bf16_tflops"] * world, "unit": "TFLOP/s",
+                                  "frac": tfb / (peaks["bf16_tflops"] * world),
+                                  "note": "end to end (copies and both passes inside the timed region) against the burst peak of N GPUs"}}
+        del big_out
+
+    # ---- BASELINE config 4, single process: ONE frame stream over every GPU of the job (rank 0 drives them all; the other ranks wait) ----
+    inproc_res = None
+    if not args.no_extra:
+        barrier()
+        if rank == 0:
+            ndev = min(world, A.device_count())
+            fs = A.FrameStream(model, list(range(ndev)), workers_per_device=n_threads, queue_depth=4)
+            NFR = 128 * ndev
+
+            def run_inproc():
+                t0 = time.perf_counter()
+                done = 0
+                for i in range(NFR):
+                    fs.submit(np_in[i % B], FACTOR, np_out[i % B])
+                    if i >= 2 * n_threads * ndev:
+                        fs.next(); done += 1
+                while done < NFR:
+                    fs.next(); done += 1
+                return time.perf_counter() - t0
+            run_inproc()
+            tt = run_inproc()
+            fs.close()
+            tfi = NFR * flop_frame / tt / 1e12
+            inproc_res = {"workload": "%d synthetic 1080p RGB u8 frames, one process, frame n on GPU n mod %d, in-order delivery, pinned host frames" % (NFR, ndev),
+                          "devices": ndev, "workers_per_gpu": n_threads, "fps": NFR / tt, "value": OUT_MP * NFR / tt, "unit": "MP/s",
+                          "roofline": {"bound": "tensor", "achieved": tfi, "peak": peaks["bf16_tflops"] * ndev, "unit": "TFLOP/s", "frac": tfi / (peaks["bf16_tflops"] * ndev),
+                                       "note": "luma-network FLOPs of the delivered frames over wall time, host copies included"}}
+        barrier()
+
+    # ---- small frames (tools/benchmark's 720x480 gray case): launch-bound -- latency of one synchronous host call, and device-resident rate ----
+    small_res = None
+    if not args.no_extra and rank == 0:
+        sh, sw = 480, 720
+        g = np.random.RandomState(5).randint(0, 256, size=(sh, sw), dtype=np.uint8)
+        for _ in range(5):
+            sess.process_host(model, g, FACTOR)
+        t0 = time.perf_counter()
+        for _ in range(200):
+            sess.process_host(model, g, FACTOR)
+        lat = (time.perf_counter() - t0) / 200
+        dg = torch.from_numpy(g).cuda()
+        dgo = torch.empty((2 * sh, 2 * sw), dtype=torch.uint8, device="cuda")
+        for _ in range(5):
+            sess.process_device(model, dg, FACTOR, out=dgo, stream=stream)
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        s0.record()
+        for _ in range(400):
+            sess.process_device(model, dg, FACTOR, out=dgo, stream=stream)
+        s1.record()
+        t_submit = (time.perf_counter() - t0) / 400
+        torch.cuda.synchronize()
+        small_res = {"workload": "720x480 gray u8, 2x", "host_call_latency_ms": lat * 1e3, "host_call_fps": 1.0 / lat,
+                     "device_resident_fps": 400 / (s0.elapsed_time(s1) / 1e3), "device_resident_ms": s0.elapsed_time(s1) / 400,
+                     "host_submit_us_per_frame": t_submit * 1e6}
 
     cpu = None
     if rank == 0 and not args.no_cpu:
@@ -471,29 +655,25 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "%s 2x on a batch of %d synthetic 1920x1080 RGB u8 frames per GPU (BASELINE configs[1])" % (args.model, B),
                        "frames_per_step_per_gpu": B, "fps": frames_total / (ms_max / 1e3), "engine": args.engine, "streams": n_streams,
-                       "tensor_impl": "mma.sync" if args.tensor_impl in (None, 0) else "tcgen05",
+                       "tensor_impl": impl_label(args.model, args.tensor_impl),
                        "cache": "inputs larger than L2: %d MB in + %d MB out per step" % (B * W * H * CH >> 20, B * 4 * W * H * CH >> 20),
                        "parity_spot_check": parity},
-            "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                         "frac": achieved_tf / peaks["bf16_tflops_sustained"],
-                         # dram__bytes_read.sum + dram__bytes_write.sum over the pass's two launches (ncu --set full, which flushes the caches
-                         # between its replays, profiles/r01_final_luma_mma_ncu_summary.json): segment A reads the 2.07 MB input plane and
-                         # evicts 12.8 MB of the 66 MB inter-segment map, segment B re-reads that map cold (66.4 MB) and writes 1.8 MB of the
-                         # 8.3 MB result (the rest is still in the 126 MB L2).  Back to back the map is consumed out of L2; at 6.5 TB/s even
-                         # the cold figure is 12 us of a 0.36 ms compute-bound pass.  Captured for acnet-legacy only.
-                         "traffic": 83077632 if (args.model.startswith("acnet-legacy") and args.engine != 0 and args.tensor_impl in (None, 0)) else None,
-                         "traffic_note": "cold-cache ncu replays, sum of both segment launches; includes the 66 MB inter-segment map that stays in L2 in steady state",
+            # the dominant kernel timed ALONE against the BURST tensor peak of MEASURED_PEAKS.json (dense bf16; the split-fp16 scheme
+            # spends three tensor products per algorithmic product, so 1/3 is the ceiling of this formulation)
+            "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                         "frac": achieved_tf / peaks["bf16_tflops"],
+                         "traffic": STEADY_TRAFFIC.get((args.model.split("-hdn")[0], 2 if args.tensor_impl is None else args.tensor_impl)) if args.engine != 0 else None,
+                         "traffic_note": "dram bytes read + written by the pass's launches in steady state (ncu --cache-control none: the inter-segment map is consumed out of L2)",
                          "algorithmic_bytes": W * H + 4 * W * H,
                          "kernel": ("luma network, one launch per layer (launches_per_pass), 1920x1080 Y -> 3840x2160 Y" if args.model.startswith(("artcnn", "fsrcnnx"))
                                     else "fused luma network (segment kernels back to back: launches_per_pass), 1920x1080 Y -> 3840x2160 Y"), "kernel_ms": kernel_ms,
                          "launches_per_pass": launches_per_pass, "flop_per_launch": flop_frame / max(launches_per_pass, 1.0), "flop_per_pass": flop_frame,
-                         "peak_source": peaks["source"],
+                         "peak_source": peaks["source"] + ", burst",
                          "pipe": "fp32 FFMA (CUDA cores), exact engine" if (args.engine == 0 or args.model.startswith("fsrcnnx-f8"))
-                                 else ("split-fp16 tcgen05 MMA with TMEM accumulators (F->F layers); head / tail fp32 FFMA" if args.model.startswith(("artcnn", "fsrcnnx"))
-                                       else "split-fp16 tensor-core MMA (3 HMMA per product)"),
-                         "fp32_ffma_peak_tflops_nominal": fp32_peak_tf, "frac_of_fp32_ffma_peak": achieved_tf / fp32_peak_tf,
+                                 else "split-fp16 tensor-core MMA, 3 tensor products per algorithmic product: " + impl_label(args.model, args.tensor_impl),
                          "frame_roofline_ms": t_roof_ms, "frame_frac": t_roof_ms / (ms_max / (B * args.steps))},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "yuv420": yuv, "stream": stream_res,
+            "models": models_res, "bands": bands_res, "stream_inproc": inproc_res, "small_frame": small_res,
         }
         emit(line)
     if dist is not None:
@@ -531,6 +711,9 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=12)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-yuv", action="store_true", help="skip the planar-YUV420 (video caller) section")
+    ap.add_argument("--no-extra", action="store_true", help="skip the models / bands / stream_inproc / small_frame sections")
+    ap.add_argument("--models", default="acnet-f8b8-hdn,arnet-f8b64", help="other models measured on the same frames (BASELINE configs 2 / 3)")
+    ap.add_argument("--band-size", type=int, default=8192, help="edge of the square image of the bands section (BASELINE config 5)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
