@@ -40,6 +40,15 @@ namespace acbh
         auto it = cache.find(uid);
         if (it == cache.end())
         {
+            // Bounded: a long-lived session that has seen many (possibly destroyed) models drops ALL of its cached tables once there are
+            // 32 of them -- after the device has drained, since launches in flight may still read them -- and re-uploads what it meets
+            // again (a table is a few KB; models are identified by uid, which is never reused).
+            if (cache.size() >= 32)
+            {
+                ACB_CUDA(s, cudaDeviceSynchronize());
+                for (auto& kv : cache) cudaFree(kv.second);
+                cache.clear();
+            }
             void* p = nullptr;
             ACB_CUDA(s, cudaMalloc(&p, host.size() * sizeof(uint32_t)));
             cudaError_t e = cudaMemcpyAsync(p, host.data(), host.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st);

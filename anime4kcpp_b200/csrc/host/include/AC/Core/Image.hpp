@@ -100,4 +100,8 @@ namespace ac::core
     // fx, fy > 0: scale factors; otherwise the size of a non-empty dst decides (ImageResize.cpp:136-165)
     AC_CORE_EXPORT void resize(const Image& src, Image& dst, double fx, double fy, int mode = RESIZE_CATMULL_ROM) noexcept;
     AC_CORE_EXPORT Image resize(const Image& src, double fx, double fy, int mode = RESIZE_CATMULL_ROM) noexcept;
+    // Extension (not in the reference): status of the calling thread's most recent free image function above -- 0 when it ran, non-zero
+    // when the operation is not on the accelerated path (e.g. a resize mode other than RESIZE_CATMULL_ROM) or the GPU call failed.  The
+    // reference's functions return void; the C and Python bindings use this to report an error instead of returning unwritten memory.
+    AC_CORE_EXPORT int lastImageOpStatus() noexcept;
 }

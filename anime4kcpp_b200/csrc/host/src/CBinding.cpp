@@ -97,6 +97,8 @@ int ac_resize(const ACImage* const src, ACImage* const dst, const double fx, con
 {
     if (!usable(src) || !usable(dst)) return AC_ERROR(AC_EINVAL);
     ac::core::resize(src->hptr->image, dst->hptr->image, fx, fy, mode);
+    // an unsupported mode (only RESIZE_CATMULL_ROM is on this path) or a failed GPU call is an error, not a silently unwritten image
+    if (ac::core::lastImageOpStatus() != 0) return AC_ERROR(AC_EINVAL);
     publish(dst->hptr->image, dst);
     return AC_SUCCESS;
 }

@@ -39,10 +39,20 @@ namespace ac::core::internal
     }
 }
 
+namespace ac::core::internal
+{
+    int& lastOpStatus() noexcept
+    {
+        static thread_local int status = 0;
+        return status;
+    }
+}
+
 namespace
 {
     using ac::core::Image;
     using ac::core::internal::threadSession;
+    using ac::core::internal::lastOpStatus;
 
     void ensure(Image& img, int w, int h, int c, int type)
     {
@@ -50,6 +60,7 @@ namespace
     }
     void report(acb200_session* s, int rc, const char* what)
     {
+        lastOpStatus() = rc;
         if (rc != ACB200_OK) std::fprintf(stderr, "ac::core::%s failed: %s\n", what, s ? acb200_session_error(s) : acb200_error_string(rc));
     }
     void splitPlanes(const Image& src, Image& y, Image& uv, const char* what)
@@ -89,7 +100,15 @@ namespace
 
     void resizeInto(const Image& src, Image& dst, const double fx, const double fy, const int mode) noexcept
     {
+        lastOpStatus() = ACB200_OK;
         if (src.empty()) return;
+        if (mode != ac::core::RESIZE_CATMULL_ROM)
+        {
+            // nothing is allocated and dst is left untouched: an empty dst stays empty, never "allocated but unwritten"
+            lastOpStatus() = ACB200_EINVAL;
+            std::fprintf(stderr, "ac::core::resize: only RESIZE_CATMULL_ROM (any up-scale, down-scale to 1/2) is on the accelerated path\n");
+            return;
+        }
         if (fx > 0.0 && fy > 0.0)
         {
             if (fx == 1.0 && fy == 1.0) { dst = src; return; }
@@ -104,18 +123,14 @@ namespace
             if (dst.channels() != src.channels() || dst.type() != src.type())
                 dst.create(dst.width(), dst.height(), src.channels(), src.type());
         }
-        if (mode != ac::core::RESIZE_CATMULL_ROM)
-        {
-            std::fprintf(stderr, "ac::core::resize: only RESIZE_CATMULL_ROM (any up-scale, down-scale to 1/2) is on the accelerated path\n");
-            return;
-        }
         acb200_session* s = threadSession();
-        if (!s) return;
+        if (!s) { lastOpStatus() = ACB200_ENODEVICE; return; }
         report(s, acb200_resize_catmull_rom_host(s, src.ptr(), src.width(), src.height(), src.channels(), src.stride(), src.type(),
                                                  dst.ptr(), dst.width(), dst.height(), dst.stride()), "resize");
     }
 }
 
+int ac::core::lastImageOpStatus() noexcept { return ac::core::internal::lastOpStatus(); }
 void ac::core::rgb2yuv(const Image& rgb, Image& yuv) { splitPacked(rgb, yuv, "rgb2yuv"); }
 void ac::core::rgb2yuv(const Image& rgb, Image& y, Image& uv) { splitPlanes(rgb, y, uv, "rgb2yuv"); }
 void ac::core::rgba2yuva(const Image& rgba, Image& yuva) { splitPacked(rgba, yuva, "rgba2yuva"); }

@@ -5,6 +5,7 @@
 // like the reference's per-thread state) and upscales whole frames, and the consumer receives results strictly in frame
 // order through a min-heap keyed on the frame number (AscendingChannel, util/threads/include/AC/Util/Channel.hpp:19-25).
 // Frame n goes to device n mod G; there is no data exchange between GPUs, so no collective and no NCCL.
+#include <atomic>
 #include <condition_variable>
 #include <deque>
 #include <mutex>
@@ -48,7 +49,7 @@ struct acb200_stream
     std::vector<Lane> lanes;
     std::vector<std::thread> workers;
     std::vector<acb200_session*> sessions;
-    bool closing = false;
+    std::atomic<bool> closing{ false };
 
     std::mutex dm;
     std::condition_variable dcv;

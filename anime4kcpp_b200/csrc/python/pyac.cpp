@@ -129,11 +129,14 @@ PYBIND11_MODULE(pyac, m)
                 h = t[1].cast<int>();
             }
             if (w <= 0 || h <= 0) throw py::value_error{ "empty destination size" };
+            if (mode != ac::core::RESIZE_CATMULL_ROM)
+                throw py::value_error{ "pyac.core.resize: only RESIZE_CATMULL_ROM is implemented on the B200 path (pass mode=pyac.core.RESIZE_CATMULL_ROM)" };
             py::array out = allocate(in, h, w, s.c, s.c == 1);
             const py::buffer_info oinfo = out.request();
             Image src{ s.w, s.h, s.c, s.type, s.data, s.stride };
             Image dst{ w, h, s.c, s.type, oinfo.ptr, static_cast<int>(oinfo.strides[0]) };
             ac::core::resize(src, dst, 0.0, 0.0, mode);
+            if (ac::core::lastImageOpStatus() != 0) throw std::runtime_error{ "pyac.core.resize failed on the GPU path (see stderr)" };
             return out;
         }, py::arg("src"), py::arg("dsize"), py::arg("fx") = 0.0, py::arg("fy") = 0.0, py::arg("mode") = ac::core::RESIZE_BILINEAR);
 

@@ -153,6 +153,28 @@ def test_pyac_surface():
         assert not q.ok() and q.error() == "no CUDA device"
 
 
+def test_resize_with_an_unsupported_mode_is_an_error_not_unwritten_memory():
+    """The reference defaults pyac.core.resize / ac_resize to RESIZE_BILINEAR; only RESIZE_CATMULL_ROM exists on this path.  The call
+    must fail through the error path (exception / -AC_EINVAL) and leave the destination untouched -- before any GPU work."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "anime4kcpp_b200"))
+    import pyac
+    src = np.arange(48, dtype=np.uint8).reshape(6, 8)
+    with pytest.raises(ValueError):
+        pyac.core.resize(src, (16, 12))                                     # default mode = RESIZE_BILINEAR
+    with pytest.raises(ValueError):
+        pyac.core.resize(src, None, 2.0, 2.0, pyac.core.RESIZE_BILINEAR)
+    lib = A.lib()
+    lib.ac_resize.argtypes = [C.POINTER(ACImage), C.POINTER(ACImage), C.c_double, C.c_double, C.c_int]
+    a = _cimage(lib, 8, 6, 1, 1)
+    assert lib.ac_image_from(a, src.ctypes.data_as(C.c_void_p)) == 0
+    b = _cimage(lib, 0, 0, 0, 0)
+    assert lib.ac_resize(a, b, 2.0, 2.0, 16) == -22                         # RESIZE_BILINEAR -> -AC_EINVAL
+    assert b.contents.width == 0 and not b.contents.ptr                     # nothing allocated, nothing published
+    for im in (a, b):
+        lib.ac_image_free(C.byref(im))
+
+
 def test_session_without_device_fails_loudly():
     if A.device_count() == 0:
         with pytest.raises(A.Acb200Error):

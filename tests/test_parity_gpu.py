@@ -317,14 +317,24 @@ def test_processor_api_threads_and_errors():
 def test_row_bands_reproduce_the_whole_image_bit_for_bit(session, name, factor, c):
     img = O.noise_u8(150, 96, c, seed=31)
     m = gpu_model(name)
-    for engine in (ENGINE_EXACT, ENGINE_AUTO):
+    # Bit for bit on the exact engine and on the mma.sync tensor implementation (a pixel's sum order does not depend on where its
+    # tile lies).  The TMEM-resident implementation accumulates a row's three input rows in the issue order of its chunks, which
+    # depends on the row's position in the tile grid, and a band has its own tile grid: the last bit of an fp32 sum can differ, so
+    # there the bands are held to the engine's own bar against the whole image (<= 1 LSB, >= 99.9 % identical).
+    for engine, impl in ((ENGINE_EXACT, TENSOR_IMPL), (ENGINE_AUTO, 0), (ENGINE_AUTO, TENSOR_IMPL)):
         session.set_engine(engine)
+        session.set_tensor_impl(impl)
         whole = session.process_host(m, img, factor)
         for n_bands in (2, 3, 8):
             out = np.zeros_like(whole)
             for b in range(n_bands):
                 A.process_band(session, m, img, factor, n_bands, b, out)
-            assert np.array_equal(out, whole), (engine, n_bands)
+            if engine == ENGINE_EXACT or impl == 0:
+                assert np.array_equal(out, whole), (engine, impl, n_bands)
+            else:
+                mx, exact = O.compare_u8(out, whole)
+                assert mx <= 1 and exact >= 0.999, (engine, impl, n_bands, mx, exact)
+    session.set_tensor_impl(TENSOR_IMPL)
 
 
 def test_frame_stream_delivers_in_order_and_matches_single_calls(session):
