@@ -71,6 +71,7 @@ def lib():
         L.acb200_session_sync.argtypes = [_vp]
         L.acb200_session_set_engine.argtypes = [_vp, _i]
         L.acb200_session_set_tensor_impl.argtypes = [_vp, _i]
+        L.acb200_session_set_fusion.argtypes = [_vp, _i]
         L.acb200_session_last_kernel_ms.argtypes = [_vp]
         L.acb200_session_last_kernel_ms.restype = C.c_float
         L.acb200_process_host.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _i, _d, _vp, _i]
@@ -183,6 +184,10 @@ class Session:
 
     def set_tensor_impl(self, impl):
         _check(lib().acb200_session_set_tensor_impl(self.handle, impl), self.handle)
+
+    def set_fusion(self, on):
+        """Colour split / chroma resize / merge inside the TMEM engine's segment kernels (8-bit RGB, 2x); bit-identical either way."""
+        _check(lib().acb200_session_set_fusion(self.handle, 1 if on else 0), self.handle)
 
     def sync(self):
         _check(lib().acb200_session_sync(self.handle), self.handle)

@@ -437,8 +437,17 @@ namespace
 {
     size_t pitch_of(int w, int c, int es) { return (static_cast<size_t>(w) * c * es + 255) & ~static_cast<size_t>(255); }
 
+    // what the fused colour path hands to the first and last segment of a chain (see TmParams)
+    struct FusedColour
+    {
+        const uint8_t* rgb_src; int rgb_pitch;
+        uint8_t* uv; int uv_pitch;
+        const void* htab; const void* vtab;
+        uint8_t* rgb_dst; int rgb_dst_pitch;
+    };
+
     int luma_pass(acb200_session* s, cudaStream_t st, const acb200_model& m, const void* src, int src_pitch,
-                  void* dst, int dst_pitch, int w, int h, int type, bool tensor)
+                  void* dst, int dst_pitch, int w, int h, int type, bool tensor, const FusedColour* fz = nullptr)
     {
         if (m.family >= ACB200_FAMILY_ARTCNN) return luma_pass_wide_any(s, st, m, src, src_pitch, dst, dst_pitch, w, h, type, tensor);
         float* maps[2] = { nullptr, nullptr };
@@ -471,6 +480,16 @@ namespace
             a.src = src; a.src_pitch = src_pitch; a.dst = dst; a.dst_pitch = dst_pitch; a.w = w; a.h = h; a.type = type;
             a.map_in = head ? nullptr : in; a.map_out = tail ? nullptr : out; a.feat = feat;
             int rc;
+            if (fz)
+            {
+                // fused colour handling: TMEM engine only (the caller has checked that every segment has a kernel there)
+                a.rgb_src = fz->rgb_src; a.rgb_pitch = fz->rgb_pitch; a.uv_pitch = fz->uv_pitch;
+                if (head) a.uv_out = fz->uv;
+                if (tail) { a.uv_in = fz->uv; a.htab = fz->htab; a.vtab = fz->vtab; a.rgb_dst = fz->rgb_dst; a.rgb_dst_pitch = fz->rgb_dst_pitch; }
+                if ((rc = launch_seg_tm(s, st, m, sp, a)) != ACB200_OK) return rc == ACB_SEG_UNSUPPORTED ? fail(s, ACB200_EINVAL, "fused colour path: segment without a TMEM kernel") : rc;
+                cur ^= 1;
+                continue;
+            }
             if (!tensor) rc = launch_seg_ffma(s, st, m, sp, a);
             else if (s->tensor_impl == 1) rc = launch_seg_tc5(s, st, m, sp, a);
             else
@@ -551,6 +570,21 @@ namespace
         const dim3 blk(32, 8);
         const void* cur = d_src;
         int cur_pitch = src_pitch, cw = w, ch = h, rc;
+        // 8-bit RGB, exactly 2x, TMEM engine, chains of two or more segments: colour split inside the first segment's tile load, chroma
+        // resize + merge inside the last segment's tail -- two launches per frame, no Y plane, bit-identical to the separate kernels
+        if (s->fuse && c == 3 && type == ACB200_UINT8 && power == 1 && !down && s->engine != 0 && s->tensor_impl == 2 && m->chain.size() >= 2 &&
+            seg_tm_chain_supported(*m) && ((reinterpret_cast<uintptr_t>(d_dst) | static_cast<uintptr_t>(dst_pitch)) & 1) == 0)
+        {
+            const size_t uvp = pitch_of(w, 2, 1);
+            if ((rc = ensure(s, st, s->uv, uvp * h)) != ACB200_OK) return rc;
+            if ((rc = ensure_tables(s, st, w, h, 2 * w, 2 * h)) != ACB200_OK) return rc;
+            if (s->tab_max_cnt <= 4)
+            {
+                const FusedColour fz{ static_cast<const uint8_t*>(d_src), src_pitch, static_cast<uint8_t*>(s->uv.p), static_cast<int>(uvp),
+                                      s->htab.p, s->vtab.p, static_cast<uint8_t*>(d_dst), dst_pitch };
+                return luma_pass(s, st, *m, nullptr, 0, nullptr, 0, w, h, type, true, &fz);
+            }
+        }
         if (c > 1)
         {
             const size_t yp = pitch_of(w, 1, es), uvp = pitch_of(w, c - 1, es);
@@ -811,6 +845,12 @@ extern "C"
             else if (!std::strcmp(e, "tm") || !std::strcmp(e, "2")) s->tensor_impl = 2;
             else { delete s; return ACB200_EINVAL; }
         }
+        if (const char* e = std::getenv("ACB200_FUSE"))
+        {
+            if (!std::strcmp(e, "0")) s->fuse = 0;
+            else if (!std::strcmp(e, "1")) s->fuse = 1;
+            else { delete s; return ACB200_EINVAL; }
+        }
         if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess)
         {
@@ -850,6 +890,7 @@ extern "C"
     const char* acb200_session_error(const acb200_session* s) { return s ? s->error.c_str() : "invalid session"; }
     void acb200_session_clear_error(acb200_session* s) { if (s) s->error = "NO ERROR"; }
     int acb200_session_set_tensor_impl(acb200_session* s, int impl) { if (!s || impl < 0 || impl > 2) return ACB200_EINVAL; s->tensor_impl = impl; return ACB200_OK; }
+    int acb200_session_set_fusion(acb200_session* s, int on) { if (!s || on < 0 || on > 1) return ACB200_EINVAL; s->fuse = on; return ACB200_OK; }
     int acb200_session_set_engine(acb200_session* s, int engine) { if (!s || engine < 0 || engine > 2) return ACB200_EINVAL; s->engine = engine; return ACB200_OK; }
 
     int acb200_process_device(acb200_session* s, const acb200_model* m, const void* d_src, int w, int h, int c, int src_stride, int type,

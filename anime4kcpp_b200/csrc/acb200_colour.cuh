@@ -1,0 +1,109 @@
+// Device-side pieces of the colour path that more than one translation unit needs (no kernels here): the Catmull-Rom contributor
+// record, the RGB -> YUV arithmetic, and the per-lane form of the chroma resize + merge that the TMEM engine's tail runs.
+//
+// Reference semantics: core/src/ImageProcess.cpp:38-61 (rgb2yuv), :191-215 (yuv2rgb); core/src/ImageResize.cpp:136-272 (Catmull-Rom through
+// stb_image_resize2); core/src/processor/Processor.cpp:207-213, 251-253 (where the driver runs them).
+#pragma once
+
+#include "acb200_common.cuh"
+
+namespace acb
+{
+    // one output sample's taps along one axis (already edge-folded): src index n0 .. n0+cnt-1
+    struct Contrib
+    {
+        int n0, cnt;
+        float c[6];
+    };
+
+    struct YuvFromRgb { float y, u, v; };
+    __device__ __forceinline__ YuvFromRgb rgb_to_yuv(float r, float g, float b)
+    {
+        YuvFromRgb o;
+        o.y = __fadd_rn(__fadd_rn(__fmul_rn(0.299f, r), __fmul_rn(0.587f, g)), __fmul_rn(0.114f, b));
+        o.u = __fadd_rn(__fmul_rn(0.564f, __fsub_rn(b, o.y)), 0.5f);
+        o.v = __fadd_rn(__fmul_rn(0.713f, __fsub_rn(r, o.y)), 0.5f);
+        return o;
+    }
+
+    // ---- colour handling fused into the TMEM engine's segment kernels (8-bit RGB, exactly 2x) -----------------------------------
+    // The same arithmetic as rgb2yuv_u8x4_kernel and chroma_merge_u8_kernel<3>, value for value and rounding for rounding, in
+    // a form a single lane can run for the source pixel it owns in the network's tail: the horizontal pass of the lane's two
+    // output columns over a sliding window of five source rows in registers, the vertical pass of its 2 x 2 output pixels, the
+    // re-quantisation (Processor.cpp:251-253 materialises the resized plane) and the YUV->RGB merge.  Nothing is shared
+    // between lanes, so the network's epilogue warps stay free of barriers.
+    constexpr float CM_MAGIC = 8388608.0f;      // 2^23: float(b) = (0x4B000000 | b) - 2^23; trunc(f) = (f +rz 2^23) - 2^23 for 0 <= f < 2^23
+
+    struct HTaps2
+    {
+        int n0, d;          // first source column of output column a = 2 gx; column b = 2 gx + 1 starts at n0 + d, d in {0, 1}
+        float ca[4], cb[4];
+    };
+    __device__ __forceinline__ HTaps2 load_htaps2(const Contrib* __restrict__ htab, int ox)
+    {
+        const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(htab + ox)), b0 = __ldg(reinterpret_cast<const uint4*>(htab + ox + 1));
+        const float2 a1 = __ldg(reinterpret_cast<const float2*>(&htab[ox].c[2])), b1 = __ldg(reinterpret_cast<const float2*>(&htab[ox + 1].c[2]));
+        HTaps2 k;
+        k.n0 = static_cast<int>(a0.x); k.d = static_cast<int>(b0.x) - k.n0;
+        k.ca[0] = __uint_as_float(a0.z); k.ca[1] = __uint_as_float(a0.w); k.ca[2] = a1.x; k.ca[3] = a1.y;
+        k.cb[0] = __uint_as_float(b0.z); k.cb[1] = __uint_as_float(b0.w); k.cb[2] = b1.x; k.cb[3] = b1.y;
+        return k;
+    }
+    // left-to-right sum of four separately rounded products (catmull_sample's order)
+    __device__ __forceinline__ float tap4(float c0, float c1, float c2, float c3, float t0, float t1, float t2, float t3)
+    {
+        return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(c0, t0), __fmul_rn(c1, t1)), __fmul_rn(c2, t2)), __fmul_rn(c3, t3));
+    }
+    // horizontal pass of one source row of the interleaved (u, v) plane for the lane's two output columns: (u_a, v_a, u_b, v_b).
+    // Columns past the image carry zero coefficients and are read clamped (finite), as the tiled kernel zero-fills them.
+    __device__ __forceinline__ float4 chroma_hrow2(const uint8_t* __restrict__ row, int sw_img, const HTaps2& k)
+    {
+        float tu[5], tv[5];
+#pragma unroll
+        for (int j = 0; j < 5; j++)
+        {
+            const uint32_t raw = __ldg(reinterpret_cast<const unsigned short*>(row) + min(k.n0 + j, sw_img - 1));
+            // stb decode: q * (1/255), a multiply
+            tu[j] = __fmul_rn(__fsub_rn(__uint_as_float(0x4B000000u | (raw & 0xffu)), CM_MAGIC), 1.0f / 255.0f);
+            tv[j] = __fmul_rn(__fsub_rn(__uint_as_float(0x4B000000u | (raw >> 8)), CM_MAGIC), 1.0f / 255.0f);
+        }
+        const bool d = k.d != 0;
+        float4 o;
+        o.x = tap4(k.ca[0], k.ca[1], k.ca[2], k.ca[3], tu[0], tu[1], tu[2], tu[3]);
+        o.y = tap4(k.ca[0], k.ca[1], k.ca[2], k.ca[3], tv[0], tv[1], tv[2], tv[3]);
+        o.z = tap4(k.cb[0], k.cb[1], k.cb[2], k.cb[3], d ? tu[1] : tu[0], d ? tu[2] : tu[1], d ? tu[3] : tu[2], d ? tu[4] : tu[3]);
+        o.w = tap4(k.cb[0], k.cb[1], k.cb[2], k.cb[3], d ? tv[1] : tv[0], d ? tv[2] : tv[1], d ? tv[3] : tv[2], d ? tv[4] : tv[3]);
+        return o;
+    }
+    // One output pixel: stb encode of the resized (u, v) (x 255 + 0.5, clamp, truncate), toFloat of the stored byte, YUV -> RGB with
+    // the luma `yv` (already toFloat of ITS stored byte), quant_u8.  Returns the three channel bytes in the low bytes of rb / gb / bb.
+    __device__ __forceinline__ void chroma_merge_px(float su, float sv, float yv, uint32_t& rb, uint32_t& gb, uint32_t& bb)
+    {
+        const float fu = fminf(fmaxf(__fadd_rn(__fmul_rn(su, 255.0f), 0.5f), 0.0f), 255.0f);
+        const float fv = fminf(fmaxf(__fadd_rn(__fmul_rn(sv, 255.0f), 0.5f), 0.0f), 255.0f);
+        const float qu = unit_from_int<255>(__fsub_rn(__fadd_rz(fu, CM_MAGIC), CM_MAGIC));
+        const float qv = unit_from_int<255>(__fsub_rn(__fadd_rz(fv, CM_MAGIC), CM_MAGIC));
+        const float u = __fsub_rn(qu, 0.5f), v = __fsub_rn(qv, 0.5f);
+        const float r = __fadd_rn(yv, __fmul_rn(1.403f, v));
+        const float g = __fsub_rn(__fsub_rn(yv, __fmul_rn(0.344f, u)), __fmul_rn(0.714f, v));
+        const float b = __fadd_rn(yv, __fmul_rn(1.773f, u));
+        rb = __float_as_uint(__fadd_rz(__fadd_rn(__fmul_rn(__saturatef(r), 255.0f), 0.5f), CM_MAGIC));
+        gb = __float_as_uint(__fadd_rz(__fadd_rn(__fmul_rn(__saturatef(g), 255.0f), 0.5f), CM_MAGIC));
+        bb = __float_as_uint(__fadd_rz(__fadd_rn(__fmul_rn(__saturatef(b), 255.0f), 0.5f), CM_MAGIC));
+    }
+    // the two RGB pixels of one output row of a lane (6 bytes at an even address) as three 16-bit stores
+    __device__ __forceinline__ void store_rgb2(uint8_t* o, uint32_t r0, uint32_t g0, uint32_t b0, uint32_t r1, uint32_t g1, uint32_t b1)
+    {
+        unsigned short* o16 = reinterpret_cast<unsigned short*>(o);
+        o16[0] = static_cast<unsigned short>(__byte_perm(r0, g0, 0x0040));
+        o16[1] = static_cast<unsigned short>(__byte_perm(b0, r1, 0x0040));
+        o16[2] = static_cast<unsigned short>(__byte_perm(g1, b1, 0x0040));
+    }
+    // quantised luma byte of the colour split, as the network's toFloat reads it back (rgb2yuv_u8x4_kernel + load_elem)
+    __device__ __forceinline__ float luma_from_rgb_u8(uint32_t r, uint32_t g, uint32_t b, uint8_t& qu, uint8_t& qv)
+    {
+        const YuvFromRgb o = rgb_to_yuv(unit_from_int<255>(static_cast<float>(r)), unit_from_int<255>(static_cast<float>(g)), unit_from_int<255>(static_cast<float>(b)));
+        qu = quant_u8(o.u); qv = quant_u8(o.v);
+        return unit_from_int<255>(static_cast<float>(quant_u8(o.y)));
+    }
+}

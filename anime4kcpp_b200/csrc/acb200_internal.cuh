@@ -96,6 +96,7 @@ struct acb200_session
     int tensor_impl = 2;
     int sm_count = 0;
     int engine = 2;     // 0 exact FFMA, 1 tensor-core MMA, 2 auto: exact for every 2x pass but the last, tensor for the last
+    int fuse = 1;       // colour split / chroma resize / merge inside the TMEM engine's segment kernels where they apply (8-bit RGB, 2x)
     std::string error = "NO ERROR";
     // grow-only device scratch
     struct Buf { void* p = nullptr; size_t cap = 0; };
@@ -154,6 +155,12 @@ namespace acbh
         void* dst; int dst_pitch;
         int w, h, type;
         const float* map_in; float* map_out; float* feat;
+        // Colour handling fused into the TMEM engine's segments (8-bit RGB, 2x; see TmParams): all null = luma plane in / luma plane out.
+        // Only launch_seg_tm understands these; the caller checks seg_tm_chain_supported() before it sets them.
+        const uint8_t* rgb_src = nullptr; int rgb_pitch = 0;
+        uint8_t* uv_out = nullptr; const uint8_t* uv_in = nullptr; int uv_pitch = 0;
+        const void* htab = nullptr; const void* vtab = nullptr;
+        uint8_t* rgb_dst = nullptr; int rgb_dst_pitch = 0;
     };
     // one fused segment on one engine (each defined in its own TU)
     int launch_seg_ffma(acb200_session* s, cudaStream_t st, const acb200_model& m, const SegSpec& spec, const SegLaunch& a);
@@ -161,6 +168,8 @@ namespace acbh
     int launch_seg_tc5(acb200_session* s, cudaStream_t st, const acb200_model& m, const SegSpec& spec, const SegLaunch& a);
     int launch_seg_tm(acb200_session* s, cudaStream_t st, const acb200_model& m, const SegSpec& spec, const SegLaunch& a);
     bool seg_tm_supported(const acb200_model& m);
+    // every segment of the model's chain has a kernel on the TMEM engine (no per-segment fall-back to mma.sync would happen)
+    bool seg_tm_chain_supported(const acb200_model& m);
     // ArtCNN / FSRCNNX: one 2x luma pass, one launch per layer (acb200_seg_wide.cu)
     int luma_pass_wide_any(acb200_session* s, cudaStream_t st, const acb200_model& m, const void* src, int src_pitch, void* dst, int dst_pitch,
                            int w, int h, int type, bool tensor);

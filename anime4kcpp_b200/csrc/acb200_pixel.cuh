@@ -9,26 +9,10 @@
 #pragma once
 
 #include "acb200_common.cuh"
+#include "acb200_colour.cuh"
 
 namespace acb
 {
-    // one output sample's taps along one axis (already edge-folded): src index n0 .. n0+cnt-1
-    struct Contrib
-    {
-        int n0, cnt;
-        float c[6];
-    };
-
-    struct YuvFromRgb { float y, u, v; };
-    __device__ __forceinline__ YuvFromRgb rgb_to_yuv(float r, float g, float b)
-    {
-        YuvFromRgb o;
-        o.y = __fadd_rn(__fadd_rn(__fmul_rn(0.299f, r), __fmul_rn(0.587f, g)), __fmul_rn(0.114f, b));
-        o.u = __fadd_rn(__fmul_rn(0.564f, __fsub_rn(b, o.y)), 0.5f);
-        o.v = __fadd_rn(__fmul_rn(0.713f, __fsub_rn(r, o.y)), 0.5f);
-        return o;
-    }
-
     // ystep / uvstep: element distance between horizontally adjacent samples of the Y and (U,V[,A]) outputs:
     // 1 and c-1 for the 2-plane form, c and c (uvp = yp + 1 element) for the packed YUV[A] form.
     __global__ void rgb2yuv_kernel(const void* __restrict__ src, int src_pitch, int w, int h, int c, int type,

@@ -27,10 +27,10 @@ namespace acbh
     }
 
     template<class S>
-    int launch_segment_tm(acb200_session* s, cudaStream_t st, const acb200_model& m, const SegSpec& spec,
-                          const void* src, int src_pitch, void* dst, int dst_pitch, int w, int h, int type,
-                          const float* map_in, float* map_out, float* feat)
+    int launch_segment_tm(acb200_session* s, cudaStream_t st, const acb200_model& m, const SegSpec& spec, const SegLaunch& a)
     {
+        const void* src = a.src; const int src_pitch = a.src_pitch, dst_pitch = a.dst_pitch, w = a.w, h = a.h, type = a.type;
+        void* dst = a.dst; const float* map_in = a.map_in; float* map_out = a.map_out; float* feat = a.feat;
         if constexpr (S::FAM == ACB200_FAMILY_ARNET || S::R > TM_MAX_R) return ACB_SEG_UNSUPPORTED;
         else
         {
@@ -47,6 +47,10 @@ namespace acbh
             prm.src = src; prm.map_in = reinterpret_cast<const uint4*>(map_in); prm.map_out = reinterpret_cast<uint4*>(map_out);
             prm.feat_in = feat; prm.feat_out = feat; prm.dst = dst;
             prm.src_pitch = src_pitch; prm.dst_pitch = dst_pitch; prm.w = w; prm.h = h; prm.type = type;
+            prm.rgb_src = S::NEEDS_LUMA ? a.rgb_src : nullptr; prm.rgb_pitch = a.rgb_pitch;
+            prm.uv_out = S::HEAD ? a.uv_out : nullptr; prm.uv_in = S::TAIL ? a.uv_in : nullptr; prm.uv_pitch = a.uv_pitch;
+            prm.htab = static_cast<const Contrib*>(a.htab); prm.vtab = static_cast<const Contrib*>(a.vtab);
+            prm.rgb_dst = a.rgb_dst; prm.rgb_dst_pitch = a.rgb_dst_pitch;
             constexpr int SW = 32 - 2 * S::R;
             prm.strips_x = (w + SW - 1) / SW;
             prm.tiles_x = (prm.strips_x + 3) / 4;
@@ -77,11 +81,23 @@ namespace acbh
     {
         switch (spec.kind)
         {
-#define ACB_CASE(KIND, TYPE) case KIND: return launch_segment_tm<TYPE>(s, st, m, spec, a.src, a.src_pitch, a.dst, a.dst_pitch, a.w, a.h, a.type, a.map_in, a.map_out, a.feat);
+#define ACB_CASE(KIND, TYPE) case KIND: return launch_segment_tm<TYPE>(s, st, m, spec, a);
         ACB_FOR_EACH_SEG(ACB_CASE)
 #undef ACB_CASE
         }
         return ACB200_EINVAL;
     }
     bool seg_tm_supported(const acb200_model& m) { return m.family == ACB200_FAMILY_ACNET_LEGACY || m.family == ACB200_FAMILY_ACNET; }
+    bool seg_tm_chain_supported(const acb200_model& m)
+    {
+        if (!seg_tm_supported(m)) return false;
+        for (const SegSpec& sp : m.chain)
+            switch (sp.kind)
+            {
+#define ACB_CASE(KIND, TYPE) case KIND: if (TYPE::FAM == ACB200_FAMILY_ARNET || TYPE::R > TM_MAX_R) return false; break;
+            ACB_FOR_EACH_SEG(ACB_CASE)
+#undef ACB_CASE
+            }
+        return true;
+    }
 }

@@ -36,6 +36,7 @@
 #include "acb200_common.cuh"
 #include "acb200_ffma.cuh"
 #include "acb200_mma.cuh"
+#include "acb200_colour.cuh"
 
 namespace acb
 {
@@ -103,6 +104,15 @@ namespace acb
         int type;
         int tiles_x, strips_x, G;
         int issuers;            // issuer warps used (1 .. TM_ISSUERS)
+        // Colour handling fused into the segments (8-bit RGB, exactly 2x; all null: luma plane in, luma plane out).  Reference:
+        // Processor.cpp:207-213 (rgb2yuv before the network), :251-253 (chroma resize + yuv2rgb after it), run there as separate CPU steps.
+        const uint8_t* rgb_src; // NEEDS_LUMA segments: the luma tile is computed from this packed RGB image instead of read from `src`
+        uint8_t* uv_out;        // HEAD segments: every pixel's quantised (u, v) is written here by the CTA that owns the pixel
+        const uint8_t* uv_in;   // TAIL segments: Catmull-Rom of this (u, v) plane, re-quantise, YUV -> RGB merge, RGB to rgb_dst
+        uint8_t* rgb_dst;
+        const Contrib* htab;    // contributors of the 2x chroma resize, per output column / row
+        const Contrib* vtab;
+        int rgb_pitch, uv_pitch, rgb_dst_pitch;
         const uint32_t* bops;   // B operands of this segment's 3x3 convs, TM_B_WORDS_LAYER words each, in layer order
         float k[(S::HEAD ? 72 : 0) + 64 + 32];  // fp32 weights used outside the MMAs: head (72) | ARNet 1x1 (64) | legacy deconv (32)
         float b[S::NB];
@@ -288,7 +298,49 @@ namespace acb
             // luma tile of every strip: frame columns -1 .. 32, frame rows -1 .. G, clamp-to-edge (the head conv's own padding).  One warp
             // per tile row: lane = column (coalesced), lanes 0 / 1 also take columns 32 / 33.
             constexpr int NWARPS = TM_THREADS / 32, PER = (4 * (TM_GMAX + 2) + NWARPS - 1) / NWARPS;
-            if (prm.type == ACB200_UINT8)
+            if (prm.rgb_src != nullptr)
+            {
+                // Fused colour split (ImageProcess.cpp:38-61): luma = toFloat(quantised Y of the packed RGB pixel); the CTA that OWNS a pixel
+                // (its output region, not the halo) also stores the pixel's quantised (u, v) for the tail segment's chroma resize.
+                constexpr int BATCH = 4;
+                const int own_y0 = y0 + R, own_y1 = min(own_y0 + G - 2 * R, prm.h);
+#pragma unroll 1
+                for (int i0 = 0; i0 < PER; i0 += BATCH)
+                {
+                    uint32_t c0[BATCH], c1[BATCH];
+#pragma unroll
+                    for (int i = 0; i < BATCH; i++)
+                    {
+                        const int row = min(warp + (i0 + i) * NWARPS, 4 * (G + 2) - 1);
+                        const int q = row / (G + 2), ly = row - q * (G + 2);
+                        const int strip = min(tile_x * 4 + q, prm.strips_x - 1);
+                        const int gy = clampi(y0 - 1 + ly, 0, prm.h - 1), gx0 = strip * SW - R - 1;
+                        const uint8_t* srow = prm.rgb_src + static_cast<size_t>(gy) * prm.rgb_pitch;
+                        const uint8_t* pa = srow + 3 * clampi(gx0 + lane, 0, prm.w - 1);
+                        const uint8_t* pb = srow + 3 * clampi(gx0 + 32 + (lane & 1), 0, prm.w - 1);
+                        c0[i] = __ldg(pa) | (static_cast<uint32_t>(__ldg(pa + 1)) << 8) | (static_cast<uint32_t>(__ldg(pa + 2)) << 16);
+                        c1[i] = __ldg(pb) | (static_cast<uint32_t>(__ldg(pb + 1)) << 8) | (static_cast<uint32_t>(__ldg(pb + 2)) << 16);
+                    }
+#pragma unroll
+                    for (int i = 0; i < BATCH; i++)
+                    {
+                        const int row = warp + (i0 + i) * NWARPS;
+                        if (row >= 4 * (G + 2)) break;
+                        const int q = row / (G + 2), ly = row - q * (G + 2);
+                        float* drow = luma_all + (q * (TM_GMAX + 2) + ly) * TM_LP;
+                        uint8_t qu, qv;
+                        drow[lane] = luma_from_rgb_u8(c0[i] & 0xffu, (c0[i] >> 8) & 0xffu, c0[i] >> 16, qu, qv);
+                        if (S::HEAD && prm.uv_out != nullptr)
+                        {
+                            const int strip = tile_x * 4 + q, gy = y0 - 1 + ly, gx = strip * SW - R - 1 + lane;
+                            if (strip < prm.strips_x && gy >= own_y0 && gy < own_y1 && gx >= strip * SW && gx < min(strip * SW + SW, prm.w))
+                                *reinterpret_cast<uchar2*>(prm.uv_out + static_cast<size_t>(gy) * prm.uv_pitch + 2 * gx) = make_uchar2(qu, qv);
+                        }
+                        if (lane < 2) drow[32 + lane] = luma_from_rgb_u8(c1[i] & 0xffu, (c1[i] >> 8) & 0xffu, c1[i] >> 16, qu, qv);
+                    }
+                }
+            }
+            else if (prm.type == ACB200_UINT8)
             {
                 // all of this warp's rows are requested before the first is consumed (one exposed memory latency, not one per row)
                 uint8_t p0[PER], p1[PER];
@@ -691,6 +743,64 @@ namespace acb
 #endif
                         continue;
                     }
+                    // Fused chroma resize + merge (tail segments, prm.uv_in): the lane's horizontal taps and a sliding window of the horizontal
+                    // pass over five source rows, W0 .. W4 = rows gy - 2 .. gy + 2 of the (u, v) plane for the row gy being finished
+                    [[maybe_unused]] HTaps2 hk;
+                    [[maybe_unused]] float4 W0, W1, W2, W3, W4;
+                    const bool fused = S::TAIL && last && prm.uv_in != nullptr;
+                    if constexpr (S::TAIL)
+                        if (fused)
+                        {
+                            hk = load_htaps2(prm.htab, 2 * min(x0 + R + lane, prm.w - 1));
+                            const int gy0 = y0 + yg;
+                            W0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                            W1 = chroma_hrow2(prm.uv_in + static_cast<size_t>(clampi(gy0 - 2, 0, prm.h - 1)) * prm.uv_pitch, prm.w, hk);
+                            W2 = chroma_hrow2(prm.uv_in + static_cast<size_t>(clampi(gy0 - 1, 0, prm.h - 1)) * prm.uv_pitch, prm.w, hk);
+                            W3 = chroma_hrow2(prm.uv_in + static_cast<size_t>(gy0) * prm.uv_pitch, prm.w, hk);
+                            W4 = chroma_hrow2(prm.uv_in + static_cast<size_t>(min(gy0 + 1, prm.h - 1)) * prm.uv_pitch, prm.w, hk);
+                        }
+                    // yl[dy * 2 + dx]: the lane's four luma results as the value BEFORE truncation to the byte (x 255 + 0.5 applied)
+                    [[maybe_unused]] auto fused_store = [&](const int gx, const int gy, const float (&yl)[4], const bool ok) {
+                        W0 = W1; W1 = W2; W2 = W3; W3 = W4;
+                        W4 = chroma_hrow2(prm.uv_in + static_cast<size_t>(min(gy + 2, prm.h - 1)) * prm.uv_pitch, prm.w, hk);
+                        const Contrib* vp = prm.vtab + 2 * gy;
+                        const uint4 va0 = __ldg(reinterpret_cast<const uint4*>(vp)), vb0 = __ldg(reinterpret_cast<const uint4*>(vp + 1));
+                        const float2 va1 = __ldg(reinterpret_cast<const float2*>(&vp[0].c[2])), vb1 = __ldg(reinterpret_cast<const float2*>(&vp[1].c[2]));
+                        const float ca[4] = { __uint_as_float(va0.z), __uint_as_float(va0.w), va1.x, va1.y };
+                        const float cb[4] = { __uint_as_float(vb0.z), __uint_as_float(vb0.w), vb1.x, vb1.y };
+                        float4 sa, sb;      // vertical pass: (u, v) of columns a, b in output rows 2 gy (sa) and 2 gy + 1 (sb)
+                        if (static_cast<int>(va0.x) == gy - 2 && static_cast<int>(vb0.x) == gy - 1)
+                        {
+                            // interior rows: the window holds exactly the rows both contributors read
+                            sa.x = tap4(ca[0], ca[1], ca[2], ca[3], W0.x, W1.x, W2.x, W3.x); sa.y = tap4(ca[0], ca[1], ca[2], ca[3], W0.y, W1.y, W2.y, W3.y);
+                            sa.z = tap4(ca[0], ca[1], ca[2], ca[3], W0.z, W1.z, W2.z, W3.z); sa.w = tap4(ca[0], ca[1], ca[2], ca[3], W0.w, W1.w, W2.w, W3.w);
+                            sb.x = tap4(cb[0], cb[1], cb[2], cb[3], W1.x, W2.x, W3.x, W4.x); sb.y = tap4(cb[0], cb[1], cb[2], cb[3], W1.y, W2.y, W3.y, W4.y);
+                            sb.z = tap4(cb[0], cb[1], cb[2], cb[3], W1.z, W2.z, W3.z, W4.z); sb.w = tap4(cb[0], cb[1], cb[2], cb[3], W1.w, W2.w, W3.w, W4.w);
+                        }
+                        else
+                        {
+                            // rows at the top image edge (folded taps start at another row): the contributors' own rows, recomputed.  Rows past
+                            // the image carry zero coefficients and are read clamped.
+                            float4 t[4];
+#pragma unroll
+                            for (int j = 0; j < 4; j++) t[j] = chroma_hrow2(prm.uv_in + static_cast<size_t>(min(static_cast<int>(va0.x) + j, prm.h - 1)) * prm.uv_pitch, prm.w, hk);
+                            sa.x = tap4(ca[0], ca[1], ca[2], ca[3], t[0].x, t[1].x, t[2].x, t[3].x); sa.y = tap4(ca[0], ca[1], ca[2], ca[3], t[0].y, t[1].y, t[2].y, t[3].y);
+                            sa.z = tap4(ca[0], ca[1], ca[2], ca[3], t[0].z, t[1].z, t[2].z, t[3].z); sa.w = tap4(ca[0], ca[1], ca[2], ca[3], t[0].w, t[1].w, t[2].w, t[3].w);
+#pragma unroll
+                            for (int j = 0; j < 4; j++) t[j] = chroma_hrow2(prm.uv_in + static_cast<size_t>(min(static_cast<int>(vb0.x) + j, prm.h - 1)) * prm.uv_pitch, prm.w, hk);
+                            sb.x = tap4(cb[0], cb[1], cb[2], cb[3], t[0].x, t[1].x, t[2].x, t[3].x); sb.y = tap4(cb[0], cb[1], cb[2], cb[3], t[0].y, t[1].y, t[2].y, t[3].y);
+                            sb.z = tap4(cb[0], cb[1], cb[2], cb[3], t[0].z, t[1].z, t[2].z, t[3].z); sb.w = tap4(cb[0], cb[1], cb[2], cb[3], t[0].w, t[1].w, t[2].w, t[3].w);
+                        }
+                        float yv[4];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) yv[i] = unit_from_int<255>(__fsub_rn(__fadd_rz(yl[i], CM_MAGIC), CM_MAGIC));     // toFloat of the stored luma byte
+                        uint32_t r0, g0, b0, r1, g1, b1;
+                        uint8_t* o = prm.rgb_dst + static_cast<size_t>(2 * gy) * prm.rgb_dst_pitch + 6 * gx;
+                        chroma_merge_px(sa.x, sa.y, yv[0], r0, g0, b0); chroma_merge_px(sa.z, sa.w, yv[1], r1, g1, b1);
+                        if (ok) store_rgb2(o, r0, g0, b0, r1, g1, b1);
+                        chroma_merge_px(sb.x, sb.y, yv[2], r0, g0, b0); chroma_merge_px(sb.z, sb.w, yv[3], r1, g1, b1);
+                        if (ok) store_rgb2(o + prm.rgb_dst_pitch, r0, g0, b0, r1, g1, b1);
+                    };
                     for (int jr = 0; jr < k; jr++)
                     {
                         const int y = yg + jr;
@@ -740,7 +850,13 @@ namespace acb
                                 o4[jo] = s;
                             }
                             const int gx = x0 + R + lane, gy = y0 + y;
-                            if (lane < SW && gx < prm.w)
+                            if (fused)
+                            {
+                                const float yl[4] = { fmaf(__saturatef(o4[0]), 255.0f, 0.5f), fmaf(__saturatef(o4[1]), 255.0f, 0.5f),
+                                                      fmaf(__saturatef(o4[2]), 255.0f, 0.5f), fmaf(__saturatef(o4[3]), 255.0f, 0.5f) };
+                                fused_store(gx, gy, yl, lane < SW && gx < prm.w);
+                            }
+                            else if (lane < SW && gx < prm.w)
                             {
                                 uint8_t* row = static_cast<uint8_t*>(prm.dst) + static_cast<size_t>(2 * gy) * prm.dst_pitch;
                                 if (prm.type == ACB200_UINT8 && aligned)
@@ -762,7 +878,13 @@ namespace acb
                             // conv 8 -> 4 (+ bias, already in the accumulator), + nearest-upsampled luma, pixel shuffle (Common.hpp:290-342)
                             const int gx = x0 + R + lane, gy = y0 + y;
                             const float id = luma[(y + 1) * TM_LP + R + lane + 1];
-                            if (lane < SW && gx < prm.w)
+                            if (fused)
+                            {
+                                const float yl[4] = { __fadd_rn(__fmul_rn(__saturatef(v[0] + id), 255.0f), 0.5f), __fadd_rn(__fmul_rn(__saturatef(v[1] + id), 255.0f), 0.5f),
+                                                      __fadd_rn(__fmul_rn(__saturatef(v[2] + id), 255.0f), 0.5f), __fadd_rn(__fmul_rn(__saturatef(v[3] + id), 255.0f), 0.5f) };
+                                fused_store(gx, gy, yl, lane < SW && gx < prm.w);
+                            }
+                            else if (lane < SW && gx < prm.w)
                             {
                                 uint8_t* row = static_cast<uint8_t*>(prm.dst) + static_cast<size_t>(2 * gy) * prm.dst_pitch;
                                 if (prm.type == ACB200_UINT8 && aligned)

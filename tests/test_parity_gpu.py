@@ -271,6 +271,70 @@ def test_full_size_1080p_properties(session):
     assert np.array_equal(sub[2 * halo:-2 * halo, 2 * halo:-2 * halo], full[2 * y0:2 * y1, 2 * x0:2 * x1])
 
 
+def test_full_size_1080p_rgb_exact_engine_equals_the_fma_order_oracle(session):
+    """BASELINE configs 1 / 2 name a 1920x1080 RGB image: the whole frame through colour split, network (exact engine), Catmull-Rom chroma
+    and merge equals the FMA-order oracle bit for bit (24.9 M samples); the default engine (fused colour path) is within the 8-bit bar."""
+    img = O.smooth_u8(1080, 1920, 3, seed=12)
+    m = gpu_model("acnet-legacy-hdn0")
+    O.set_order(O.ORDER_FMA)
+    want = O.oracle_process("acnet-legacy-hdn0", img, 2.0)
+    O.set_order(O.ORDER_GENERIC)
+    session.set_engine(ENGINE_EXACT)
+    got = session.process_host(m, img, 2.0)
+    assert got.shape == (2160, 3840, 3) and np.array_equal(got, want)
+    session.set_engine(ENGINE_AUTO)
+    mx, exact = O.compare_u8(session.process_host(m, img, 2.0), want)
+    assert mx <= 1 and exact >= 0.999, (mx, exact)
+
+
+FUSED_SHAPES = [(96, 128), (150, 96), (57, 71), (5, 7), (1, 9), (9, 1), (2, 2), (3, 200), (200, 3), (40, 301), (131, 260)]
+
+
+@pytest.mark.parametrize("name", ["acnet-legacy-hdn0", "acnet-legacy-hdn2", "acnet-f8b8-hdn", "acnet-f8b8-gan", "acnet-f8b18"])
+def test_fused_colour_path_is_bit_identical_to_the_separate_kernels(session, name):
+    """Colour split inside the first segment's tile load, chroma resize + merge inside the last segment's tail (TmParams): the RGB
+    result must equal the three-extra-kernel path bit for bit on every shape -- tile seams, image borders (folded Catmull-Rom taps),
+    images smaller than a strip -- and take exactly one launch per segment."""
+    m = gpu_model(name)
+    session.set_engine(ENGINE_AUTO)
+    for i, (h, w) in enumerate(FUSED_SHAPES):
+        img = O.noise_u8(h, w, 3, seed=500 + i)
+        session.set_fusion(False)
+        n0 = A.launch_count()
+        want = session.process_host(m, img, 2.0)
+        n1 = A.launch_count()
+        session.set_fusion(True)
+        got = session.process_host(m, img, 2.0)
+        n2 = A.launch_count()
+        assert np.array_equal(got, want), (name, h, w, int((got != want).sum()))
+        assert (n1 - n0) - (n2 - n1) == 2, (name, n1 - n0, n2 - n1)       # rgb2yuv and chroma_merge are gone
+    session.set_fusion(True)
+
+
+def test_fused_colour_path_1080p_and_strided_device_buffers(session):
+    import torch
+    m = gpu_model("acnet-legacy-hdn0")
+    session.set_engine(ENGINE_AUTO)
+    img = O.noise_u8(1080, 1920, 3, seed=77)
+    session.set_fusion(False)
+    want = session.process_host(m, img, 2.0)
+    session.set_fusion(True)
+    n0 = A.launch_count()
+    got = session.process_host(m, img, 2.0)
+    assert A.launch_count() - n0 == 2                       # two launches for the whole RGB frame
+    assert np.array_equal(got, want)
+    # device-resident, padded pitches (odd destination pitches fall back to the separate kernels: the fused stores are 16-bit)
+    srcbuf = torch.zeros((1080, 1920 * 3 + 64), dtype=torch.uint8, device="cuda")
+    srcbuf[:, :1920 * 3] = torch.from_numpy(img.reshape(1080, -1)).cuda()
+    src = srcbuf[:, :1920 * 3].unflatten(1, (1920, 3))
+    for pad in (0, 32, 7):
+        dstbuf = torch.zeros((2160, 3840 * 3 + pad), dtype=torch.uint8, device="cuda")
+        session.process_device(m, src, 2.0, out=dstbuf[:, :3840 * 3].unflatten(1, (3840, 3)))
+        session.sync()
+        assert np.array_equal(dstbuf[:, :3840 * 3].cpu().numpy().reshape(2160, 3840, 3), want), pad
+        assert int(dstbuf[:, 3840 * 3:].sum()) == 0         # nothing written past the row
+
+
 def test_device_resident_path_matches_host_path(session):
     import torch
     img = O.noise_u8(120, 200, 3, seed=21)
