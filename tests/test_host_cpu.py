@@ -175,6 +175,22 @@ def test_resize_with_an_unsupported_mode_is_an_error_not_unwritten_memory():
         lib.ac_image_free(C.byref(im))
 
 
+def test_reference_benchmark_tool_links_against_the_drop_in():
+    """oracle/_ref/ac_benchmark = the reference's tools/benchmark/src/Benchmark.cpp compiled unchanged against the re-created headers and
+    libac_b200.so (oracle/Makefile ref_callers; built where /root/reference exists).  Without a GPU it must start, list the backends and
+    report the processor error the way the reference tool does -- not crash, not fall back."""
+    import subprocess
+    exe = os.path.join(ROOT, "oracle", "_ref", "ac_benchmark")
+    if not os.path.isfile(exe):
+        pytest.skip("oracle/_ref/ac_benchmark not built (needs /root/reference at build time)")
+    out = subprocess.run([exe, "acnet-legacy-hdn0", "cuda", "0", "64", "48", "4", "2"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "core version:" in out.stdout and "CUDA:" in out.stdout, out.stdout + out.stderr
+    if A.device_count() == 0:
+        assert "no CUDA device" in out.stdout and "FPS:" not in out.stdout
+    else:
+        assert "FPS:" in out.stdout
+
+
 def test_session_without_device_fails_loudly():
     if A.device_count() == 0:
         with pytest.raises(A.Acb200Error):

@@ -12,6 +12,7 @@ import anime4kcpp_b200 as A
 import oracle_lib as O
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.npz"))
 ALL_REAL = sorted(O.models().keys())
@@ -333,6 +334,24 @@ def test_fused_colour_path_1080p_and_strided_device_buffers(session):
         session.sync()
         assert np.array_equal(dstbuf[:, :3840 * 3].cpu().numpy().reshape(2160, 3840, 3), want), pad
         assert int(dstbuf[:, 3840 * 3:].sum()) == 0         # nothing written past the row
+
+
+@pytest.mark.parametrize("w,h,batch,threads", [(720, 480, 600, 1), (720, 480, 600, 8), (1920, 1080, 120, 8)])
+def test_reference_benchmark_tool_runs_unchanged_against_the_drop_in(w, h, batch, threads):
+    """tools/benchmark/src/Benchmark.cpp of the reference, compiled unchanged (oracle/Makefile ref_callers), at its default 720x480 gray
+    shape and at 1080p: creates the "cuda" processor through ac::core::Processor::create, warms up, runs `batch` images over a thread
+    pool sharing the processor, prints FPS."""
+    import re
+    import subprocess
+    exe = os.path.join(ROOT, "oracle", "_ref", "ac_benchmark")
+    if not os.path.isfile(exe):
+        pytest.skip("oracle/_ref/ac_benchmark not built (needs /root/reference at build time)")
+    out = subprocess.run([exe, "acnet-legacy-hdn0", "cuda", "0", str(w), str(h), str(batch), str(threads)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    m = re.search(r"FPS: ([0-9.]+)", out.stdout)
+    assert m and "processor: CUDA" in out.stdout, out.stdout
+    print("reference benchmark tool %dx%d batch %d threads %d: %s FPS" % (w, h, batch, threads, m.group(1)))
+    assert float(m.group(1)) > 50.0
 
 
 def test_device_resident_path_matches_host_path(session):
