@@ -36,15 +36,21 @@ namespace acb
 
     struct HTaps2
     {
-        int n0, d;          // first source column of output column a = 2 gx; column b = 2 gx + 1 starts at n0 + d, d in {0, 1}
+        int off[5];         // byte offsets of source columns n0 .. n0 + 4 (clamped to the row) inside a (u, v) row; n0 = first tap of column a
+        int d;              // output column b = 2 gx + 1 starts at source column n0 + d, d in {0, 1}
+        bool all_d1;        // every lane of the warp has d == 1 (true away from the left / right image edge)
         float ca[4], cb[4];
     };
-    __device__ __forceinline__ HTaps2 load_htaps2(const Contrib* __restrict__ htab, int ox)
+    __device__ __forceinline__ HTaps2 load_htaps2(const Contrib* __restrict__ htab, int ox, int sw_img)
     {
         const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(htab + ox)), b0 = __ldg(reinterpret_cast<const uint4*>(htab + ox + 1));
         const float2 a1 = __ldg(reinterpret_cast<const float2*>(&htab[ox].c[2])), b1 = __ldg(reinterpret_cast<const float2*>(&htab[ox + 1].c[2]));
         HTaps2 k;
-        k.n0 = static_cast<int>(a0.x); k.d = static_cast<int>(b0.x) - k.n0;
+        const int n0 = static_cast<int>(a0.x);
+        k.d = static_cast<int>(b0.x) - n0;
+        k.all_d1 = __all_sync(0xffffffffu, k.d == 1);
+#pragma unroll
+        for (int j = 0; j < 5; j++) k.off[j] = 2 * min(n0 + j, sw_img - 1);
         k.ca[0] = __uint_as_float(a0.z); k.ca[1] = __uint_as_float(a0.w); k.ca[2] = a1.x; k.ca[3] = a1.y;
         k.cb[0] = __uint_as_float(b0.z); k.cb[1] = __uint_as_float(b0.w); k.cb[2] = b1.x; k.cb[3] = b1.y;
         return k;
@@ -54,25 +60,39 @@ namespace acb
     {
         return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(c0, t0), __fmul_rn(c1, t1)), __fmul_rn(c2, t2)), __fmul_rn(c3, t3));
     }
+    // stb decode of a byte b, float(b) * (1/255) rounded once, from the magic form m = 2^23 + b (exact): fma(m, r, -2^23 r) -- the product
+    // m r is exact inside the FMA and 2^23 r is a float, so the single rounding is that of b r: equal to __fmul_rn(float(b), 1/255) for every b
+    __device__ __forceinline__ float decode_u8_magic(uint32_t magic_bits)
+    {
+        constexpr float R = 1.0f / 255.0f;
+        return __fmaf_rn(__uint_as_float(magic_bits), R, -CM_MAGIC * R);
+    }
     // horizontal pass of one source row of the interleaved (u, v) plane for the lane's two output columns: (u_a, v_a, u_b, v_b).
     // Columns past the image carry zero coefficients and are read clamped (finite), as the tiled kernel zero-fills them.
-    __device__ __forceinline__ float4 chroma_hrow2(const uint8_t* __restrict__ row, int sw_img, const HTaps2& k)
+    __device__ __forceinline__ float4 chroma_hrow2(const uint8_t* __restrict__ row, const HTaps2& k)
     {
         float tu[5], tv[5];
 #pragma unroll
         for (int j = 0; j < 5; j++)
         {
-            const uint32_t raw = __ldg(reinterpret_cast<const unsigned short*>(row) + min(k.n0 + j, sw_img - 1));
-            // stb decode: q * (1/255), a multiply
-            tu[j] = __fmul_rn(__fsub_rn(__uint_as_float(0x4B000000u | (raw & 0xffu)), CM_MAGIC), 1.0f / 255.0f);
-            tv[j] = __fmul_rn(__fsub_rn(__uint_as_float(0x4B000000u | (raw >> 8)), CM_MAGIC), 1.0f / 255.0f);
+            const uint32_t raw = __ldg(reinterpret_cast<const unsigned short*>(row + k.off[j]));
+            tu[j] = decode_u8_magic(__byte_perm(raw, 0x4B000000u, 0x7640));     // bytes: raw.b0, 0x00, 0x00, 0x4B
+            tv[j] = decode_u8_magic(__byte_perm(raw, 0x4B000000u, 0x7641));
         }
-        const bool d = k.d != 0;
         float4 o;
         o.x = tap4(k.ca[0], k.ca[1], k.ca[2], k.ca[3], tu[0], tu[1], tu[2], tu[3]);
         o.y = tap4(k.ca[0], k.ca[1], k.ca[2], k.ca[3], tv[0], tv[1], tv[2], tv[3]);
-        o.z = tap4(k.cb[0], k.cb[1], k.cb[2], k.cb[3], d ? tu[1] : tu[0], d ? tu[2] : tu[1], d ? tu[3] : tu[2], d ? tu[4] : tu[3]);
-        o.w = tap4(k.cb[0], k.cb[1], k.cb[2], k.cb[3], d ? tv[1] : tv[0], d ? tv[2] : tv[1], d ? tv[3] : tv[2], d ? tv[4] : tv[3]);
+        if (k.all_d1)
+        {
+            o.z = tap4(k.cb[0], k.cb[1], k.cb[2], k.cb[3], tu[1], tu[2], tu[3], tu[4]);
+            o.w = tap4(k.cb[0], k.cb[1], k.cb[2], k.cb[3], tv[1], tv[2], tv[3], tv[4]);
+        }
+        else
+        {
+            const bool d = k.d != 0;
+            o.z = tap4(k.cb[0], k.cb[1], k.cb[2], k.cb[3], d ? tu[1] : tu[0], d ? tu[2] : tu[1], d ? tu[3] : tu[2], d ? tu[4] : tu[3]);
+            o.w = tap4(k.cb[0], k.cb[1], k.cb[2], k.cb[3], d ? tv[1] : tv[0], d ? tv[2] : tv[1], d ? tv[3] : tv[2], d ? tv[4] : tv[3]);
+        }
         return o;
     }
     // One output pixel: stb encode of the resized (u, v) (x 255 + 0.5, clamp, truncate), toFloat of the stored byte, YUV -> RGB with

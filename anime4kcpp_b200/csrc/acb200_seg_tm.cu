@@ -68,8 +68,8 @@ namespace acbh
             if (S::NA > 0) std::memcpy(prm.a, m.a.data() + spec.aoff, sizeof(float) * S::NA);
             else prm.a[0] = 0.0f;
             static std::atomic<unsigned long long> optin{0};
-            if ((rc = smem_optin_once(s, reinterpret_cast<const void*>(segment_tm_kernel<S>), TM_SMEM_BYTES, optin)) != ACB200_OK) return rc;
-            segment_tm_kernel<S><<<prm.tiles_x * tiles_y, TM_THREADS, TM_SMEM_BYTES, st>>>(prm);
+            if ((rc = smem_optin_once(s, reinterpret_cast<const void*>(segment_tm_kernel<S>), TM_SMEM_BYTES_FUSED, optin)) != ACB200_OK) return rc;
+            segment_tm_kernel<S><<<prm.tiles_x * tiles_y, TM_THREADS, (prm.uv_in || ACB_TM_PROGRESS_MBAR) ? TM_SMEM_BYTES_FUSED : TM_SMEM_BYTES, st>>>(prm);
             g_launches.fetch_add(1, std::memory_order_relaxed);
             ACB_CUDA(s, cudaGetLastError());
             return ACB200_OK;

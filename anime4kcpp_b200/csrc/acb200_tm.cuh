@@ -90,6 +90,15 @@ namespace acb
     constexpr int TM_SMEM_BYTES = TM_OFF_STEPS + TM_MAX_CHUNKS * TM_CHUNK_WORDS * 4;
 #endif
 
+#ifndef ACB_TM_CHROMA_LUT
+#define ACB_TM_CHROMA_LUT 1
+#endif
+    // fused chroma merge: two tables of 256 float2 after the engine's own shared memory (see the tail)
+    constexpr int TM_OFF_LUT = (TM_SMEM_BYTES + 15) / 16 * 16;
+    // progress barriers (ACB_TM_PROGRESS_MBAR): one one-shot mbarrier per (published layer 1 .. R, frame row), four arrivals (one per lane quadrant)
+    constexpr int TM_OFF_PROG = TM_OFF_LUT + 2 * 256 * 8;
+    constexpr int TM_SMEM_BYTES_FUSED = TM_OFF_PROG + TM_MAX_R * TM_GMAX * 8;
+
     template<class S>
     struct TmParams
     {
@@ -203,6 +212,19 @@ namespace acb
     // Progress words: one byte per lane quadrant (= per epilogue warp working on the row / slot group), holding a MONOTONIC count.
     // (mbarrier parity waits cannot be used where a waiter may be two phases ahead of the barrier -- several issuer warps run layers
     // apart on the same row index -- because a phase parity only distinguishes adjacent phases.)
+#ifndef ACB_TM_PROGRESS_MBAR
+#define ACB_TM_PROGRESS_MBAR 0
+#endif
+// Nanoseconds an issuer warp sleeps between two polls of a progress word / a layer ticket.  Measured (tools/time_tm.py, 1080p luma pass,
+// same box): 0 (spin) 0.2372 ms, 5 .. 40 ns 0.2245 ms, 200 ns 0.2417 ms -- a spinning issuer takes issue slots from the epilogue warps
+// of its scheduler (the polling loop was 18 % of all executed instructions), a long sleep turns into tensor-pipe bubbles.  Progress
+// mbarriers instead of polled bytes (ACB_TM_PROGRESS_MBAR) measured 0.2337 ms alone and 0.2257 ms with the ticket sleep: no better.
+#ifndef ACB_TM_POLL_SLEEP
+#define ACB_TM_POLL_SLEEP 20
+#endif
+#ifndef ACB_TM_TICKET_SLEEP
+#define ACB_TM_TICKET_SLEEP ACB_TM_POLL_SLEEP
+#endif
     __device__ __forceinline__ void tm_wait_bytes(uint32_t addr, uint32_t need)
     {
         // every byte of the word >= need (all values < 128): ((b | 0x80) - need) keeps its top bit exactly when b >= need, and no
@@ -215,6 +237,7 @@ namespace acb
             asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(w) : "r"(addr) : "memory");
             if ((((w | 0x80808080u) - want) & 0x80808080u) == 0x80808080u) return;
             if (++spins > (1u << 24)) __trap();     // a protocol bug must fault, never hang the device
+            if (ACB_TM_POLL_SLEEP > 0) __nanosleep(ACB_TM_POLL_SLEEP);
         }
     }
     // publish: plain byte stores.  What they publish are TMEM writes whose COMPLETION the publishing thread has already waited for
@@ -287,6 +310,10 @@ namespace acb
                     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar_full + 8 * gi), "r"(2 * min(4, g_yb[l] - (g_ya[l] + 4 * (gi - g_gb[l])) + 1)));
         }
         if (threadIdx.x == 32) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_bop));
+        [[maybe_unused]] const uint32_t prog = static_cast<uint32_t>(__cvta_generic_to_shared(smem_tm + TM_OFF_PROG));
+#if ACB_TM_PROGRESS_MBAR
+        for (int i = threadIdx.x; i < R * TM_GMAX; i += TM_THREADS) asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" :: "r"(prog + 8 * i));
+#endif
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (warp == TM_ISS_WARP0)
         {
@@ -378,6 +405,16 @@ namespace acb
                     if (lane < 2) drow[32 + lane] = load_elem(srow, clampi(gx0 + 32 + lane, 0, prm.w - 1), prm.type);
                 }
         }
+        if constexpr (S::TAIL)
+            if (prm.uv_in != nullptr && threadIdx.x < 512)
+            {
+                // Fused merge: everything the YUV -> RGB step derives from a quantised chroma byte q, tabulated once per CTA with the very
+                // operations the merge kernel applies per pixel (toFloat<u8>, - 0.5, the four products of ImageProcess.cpp:191-215):
+                // lut[q] = (0.344 u, 1.773 u), lut[256 + q] = (1.403 v, 0.714 v)
+                const float c = __fsub_rn(unit_from_int<255>(static_cast<float>(threadIdx.x & 255)), 0.5f);
+                reinterpret_cast<float2*>(smem_tm + TM_OFF_LUT)[threadIdx.x] =
+                    threadIdx.x < 256 ? make_float2(__fmul_rn(0.344f, c), __fmul_rn(1.773f, c)) : make_float2(__fmul_rn(1.403f, c), __fmul_rn(0.714f, c));
+            }
         if (threadIdx.x == 32)
         {
             // the segment's B operands: one bulk copy (UBLKCP) on an mbarrier
@@ -468,7 +505,11 @@ namespace acb
                 {
                     const int row = r0 - 1 + w;                 // needed as an input row (r0 .. r0 + nst - 1) or as a pre-loaded accumulator row (inside [ya, yb])
                     const bool input = w >= 1 && w <= nst, accum = w <= nst + 1 && row >= ya && row <= yb;
+#if ACB_TM_PROGRESS_MBAR
+                    rec[4 + w] = (input || accum) ? (prog + 8 * ((l - 1) * TM_GMAX + row)) : 0u;
+#else
                     rec[4 + w] = (input || accum) ? ((flag_a + 8 * row) | need) : 0u;
+#endif
                 }
                 // commits (issued after the chunk's last MMA): output row rel (relative to ya) is touched by the layer's steps rel, rel + 1,
                 // rel + 2; every chunk that touches it commits once -- twice when all three steps are its own
@@ -516,11 +557,19 @@ namespace acb
                 // all of the chunk's waits are polled at once, one per lane
                 {
                     const uint32_t w = lane < 6 ? rec[4 + lane] : (lane == 6 ? rec[18] : 0u);
+#if ACB_TM_PROGRESS_MBAR
+                    if (lane < 6) { if (w) tm_wait(w, 0); }
+#else
                     if (lane < 6) { if (w) tm_wait_bytes(w & 0xffffffu, w >> 24); }
+#endif
                     else if (w >> 24)
                     {
                         uint32_t t;
-                        do { asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(t) : "r"(w & 0xffffffu) : "memory"); } while (t < (w >> 24));
+                        do
+                        {
+                            asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(t) : "r"(w & 0xffffffu) : "memory");
+                            if (ACB_TM_TICKET_SLEEP > 0 && t < (w >> 24)) __nanosleep(ACB_TM_TICKET_SLEEP);
+                        } while (t < (w >> 24));
                     }
                     __syncwarp();
                 }
@@ -580,6 +629,14 @@ namespace acb
             const int pad_top = -y0 - 1, pad_bot = prm.h - y0;          // frame rows of image rows -1 and h (replicate padding), if inside the frame
             const uint32_t my_t = tmem + lane_base;
             const uint32_t my_flag_a = flag_a + q;
+            // a row of the map that layer `value - 1` produced is complete in this quadrant
+            auto tm_publish = [&](const uint32_t flag_addr, const uint32_t value) {
+#if ACB_TM_PROGRESS_MBAR
+                if (lane == 0) tm_arrive(prog + 8 * ((value - 1) * TM_GMAX + ((flag_addr - my_flag_a) >> 3)));
+#else
+                tm_publish_byte(flag_addr, value);
+#endif
+            };
             const bool pads = (pad_top >= 0) || (pad_bot <= G - 1);     // the frame reaches over the top / bottom image edge
 
             // one row of layer l's output map becomes the next layer's A operand in buffer l % 2 (x-clamped in border strips), with its
@@ -602,11 +659,11 @@ namespace acb
             };
             // ... and is published (after tcgen05.wait::st): every lane stores the progress byte (same address, same value: one store, no branch)
             auto publish_rows = [&](const int l, const int ya_, const int k) {
-                for (int j = 0; j < k; j++) tm_publish_byte(my_flag_a + 8 * (ya_ + j), l + 1);
+                for (int j = 0; j < k; j++) tm_publish(my_flag_a + 8 * (ya_ + j), l + 1);
                 if (pads)
                 {
-                    if (ya_ == pad_top + 1 && pad_top >= 0) tm_publish_byte(my_flag_a + 8 * pad_top, l + 1);
-                    if (ya_ + k - 1 == pad_bot - 1 && pad_bot <= G - 1) tm_publish_byte(my_flag_a + 8 * pad_bot, l + 1);
+                    if (ya_ == pad_top + 1 && pad_top >= 0) tm_publish(my_flag_a + 8 * pad_top, l + 1);
+                    if (ya_ + k - 1 == pad_bot - 1 && pad_bot <= G - 1) tm_publish(my_flag_a + 8 * pad_bot, l + 1);
                 }
             };
 
@@ -678,7 +735,7 @@ namespace acb
                         ACB_TM_WAIT_ST();
                         ACB_TM_FENCE_BEFORE();
 #pragma unroll
-                        for (int k = 0; k < 4; k++) if (yg + k <= lb) tm_publish_byte(my_flag_a + 8 * (yg + k), 1);
+                        for (int k = 0; k < 4; k++) if (yg + k <= lb) tm_publish(my_flag_a + 8 * (yg + k), 1);
                     }
                 }
             }
@@ -705,6 +762,101 @@ namespace acb
                 for (int j = (set - g0) & 3; ya + 4 * j <= yb; j += 4)
                 {
                     const int yg = ya + 4 * j, k = min(4, yb - yg + 1);
+                    // Fused chroma resize + merge (tail segments, prm.uv_in).  Everything that does not depend on the network -- the horizontal
+                    // pass of the lane's two output columns over the group's source rows, the vertical pass, the re-quantisation of the resized
+                    // (u, v) -- runs BEFORE the wait for the group's accumulators, in time the warp would otherwise spend asleep; what is kept
+                    // is one word per output row: the quantised (u_a, v_a, u_b, v_b) bytes.  After the wait only the merge with the luma is left.
+                    [[maybe_unused]] uint2 cq0 = make_uint2(0u, 0u), cq1 = cq0, cq2 = cq0, cq3 = cq0;
+                    const bool fused = S::TAIL && last && prm.uv_in != nullptr;
+                    if constexpr (S::TAIL)
+                        if (fused)
+                        {
+                            const HTaps2 hk = load_htaps2(prm.htab, 2 * min(x0 + R + lane, prm.w - 1), prm.w);
+                            const int gy0 = y0 + yg;
+                            auto hrow_at = [&](const int gyr) { return chroma_hrow2(prm.uv_in + static_cast<size_t>(clampi(gyr, 0, prm.h - 1)) * prm.uv_pitch, hk); };
+                            float4 H[8];        // rows gy0 - 2 .. gy0 + 5
+#pragma unroll
+                            for (int i = 0; i < 8; i++) H[i] = hrow_at(gy0 - 2 + min(i, k + 3));
+                            auto encode4 = [](const float4 sv) {
+                                // stb encode (x 255 + 0.5, clamp, truncate): the byte is the low mantissa byte of the round-toward-zero magic sum
+                                const uint32_t b0 = __float_as_uint(__fadd_rz(fminf(fmaxf(__fadd_rn(__fmul_rn(sv.x, 255.0f), 0.5f), 0.0f), 255.0f), CM_MAGIC));
+                                const uint32_t b1 = __float_as_uint(__fadd_rz(fminf(fmaxf(__fadd_rn(__fmul_rn(sv.y, 255.0f), 0.5f), 0.0f), 255.0f), CM_MAGIC));
+                                const uint32_t b2 = __float_as_uint(__fadd_rz(fminf(fmaxf(__fadd_rn(__fmul_rn(sv.z, 255.0f), 0.5f), 0.0f), 255.0f), CM_MAGIC));
+                                const uint32_t b3 = __float_as_uint(__fadd_rz(fminf(fmaxf(__fadd_rn(__fmul_rn(sv.w, 255.0f), 0.5f), 0.0f), 255.0f), CM_MAGIC));
+                                return __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
+                            };
+                            auto vrows = [&](const int jr, const float4& w0, const float4& w1, const float4& w2, const float4& w3, const float4& w4) {
+                                const int gy = gy0 + jr;
+                                const Contrib* vp = prm.vtab + 2 * gy;
+                                const uint4 va0 = __ldg(reinterpret_cast<const uint4*>(vp)), vb0 = __ldg(reinterpret_cast<const uint4*>(vp + 1));
+                                const float2 va1 = __ldg(reinterpret_cast<const float2*>(&vp[0].c[2])), vb1 = __ldg(reinterpret_cast<const float2*>(&vp[1].c[2]));
+                                const float ca[4] = { __uint_as_float(va0.z), __uint_as_float(va0.w), va1.x, va1.y };
+                                const float cb[4] = { __uint_as_float(vb0.z), __uint_as_float(vb0.w), vb1.x, vb1.y };
+                                float4 sa, sb;      // vertical pass: (u, v) of columns a, b in output rows 2 gy (sa) and 2 gy + 1 (sb)
+                                if (static_cast<int>(va0.x) == gy - 2 && static_cast<int>(vb0.x) == gy - 1)
+                                {
+                                    // interior rows: the window holds exactly the rows both contributors read
+                                    sa.x = tap4(ca[0], ca[1], ca[2], ca[3], w0.x, w1.x, w2.x, w3.x); sa.y = tap4(ca[0], ca[1], ca[2], ca[3], w0.y, w1.y, w2.y, w3.y);
+                                    sa.z = tap4(ca[0], ca[1], ca[2], ca[3], w0.z, w1.z, w2.z, w3.z); sa.w = tap4(ca[0], ca[1], ca[2], ca[3], w0.w, w1.w, w2.w, w3.w);
+                                    sb.x = tap4(cb[0], cb[1], cb[2], cb[3], w1.x, w2.x, w3.x, w4.x); sb.y = tap4(cb[0], cb[1], cb[2], cb[3], w1.y, w2.y, w3.y, w4.y);
+                                    sb.z = tap4(cb[0], cb[1], cb[2], cb[3], w1.z, w2.z, w3.z, w4.z); sb.w = tap4(cb[0], cb[1], cb[2], cb[3], w1.w, w2.w, w3.w, w4.w);
+                                }
+                                else
+                                {
+                                    // rows at the top image edge (folded taps start at another row): the contributors' own rows, recomputed.  Rows past
+                                    // the image carry zero coefficients and are read clamped.
+                                    float4 t[4];
+#pragma unroll
+                                    for (int i = 0; i < 4; i++) t[i] = hrow_at(static_cast<int>(va0.x) + i);
+                                    sa.x = tap4(ca[0], ca[1], ca[2], ca[3], t[0].x, t[1].x, t[2].x, t[3].x); sa.y = tap4(ca[0], ca[1], ca[2], ca[3], t[0].y, t[1].y, t[2].y, t[3].y);
+                                    sa.z = tap4(ca[0], ca[1], ca[2], ca[3], t[0].z, t[1].z, t[2].z, t[3].z); sa.w = tap4(ca[0], ca[1], ca[2], ca[3], t[0].w, t[1].w, t[2].w, t[3].w);
+#pragma unroll
+                                    for (int i = 0; i < 4; i++) t[i] = hrow_at(static_cast<int>(vb0.x) + i);
+                                    sb.x = tap4(cb[0], cb[1], cb[2], cb[3], t[0].x, t[1].x, t[2].x, t[3].x); sb.y = tap4(cb[0], cb[1], cb[2], cb[3], t[0].y, t[1].y, t[2].y, t[3].y);
+                                    sb.z = tap4(cb[0], cb[1], cb[2], cb[3], t[0].z, t[1].z, t[2].z, t[3].z); sb.w = tap4(cb[0], cb[1], cb[2], cb[3], t[0].w, t[1].w, t[2].w, t[3].w);
+                                }
+                                return make_uint2(encode4(sa), encode4(sb));
+                            };
+                            cq0 = vrows(0, H[0], H[1], H[2], H[3], H[4]);
+                            if (k > 1) cq1 = vrows(1, H[1], H[2], H[3], H[4], H[5]);
+                            if (k > 2) cq2 = vrows(2, H[2], H[3], H[4], H[5], H[6]);
+                            if (k > 3) cq3 = vrows(3, H[3], H[4], H[5], H[6], H[7]);
+                        }
+                    // yl[dy * 2 + dx]: the lane's four luma results as the value BEFORE truncation to the byte (x 255 + 0.5 applied)
+                    [[maybe_unused]] auto fused_store = [&](const int jr, const int gx, const int gy, const float (&yl)[4], const bool ok) {
+                        const uint2 cq = jr == 0 ? cq0 : jr == 1 ? cq1 : jr == 2 ? cq2 : cq3;
+                        uint8_t* o = prm.rgb_dst + static_cast<size_t>(2 * gy) * prm.rgb_dst_pitch + 6 * gx;
+#pragma unroll
+                        for (int dy = 0; dy < 2; dy++)
+                        {
+                            const uint32_t c4 = dy ? cq.y : cq.x;
+                            uint32_t ch[6];
+#pragma unroll
+                            for (int dx = 0; dx < 2; dx++)
+                            {
+                                // toFloat of the stored luma byte; the chroma terms of YUV -> RGB (ImageProcess.cpp:191-215) from the per-CTA tables
+                                const float yv = unit_from_int<255>(__fsub_rn(__fadd_rz(yl[2 * dy + dx], CM_MAGIC), CM_MAGIC));
+#if ACB_TM_CHROMA_LUT
+                                const float2 tu = *reinterpret_cast<const float2*>(smem_tm + TM_OFF_LUT + 8 * __byte_perm(c4, 0u, dx ? 0x4442 : 0x4440));
+                                const float2 tv = *reinterpret_cast<const float2*>(smem_tm + TM_OFF_LUT + 2048 + 8 * __byte_perm(c4, 0u, dx ? 0x4443 : 0x4441));
+                                const float r = __fadd_rn(yv, tv.x);
+                                const float g = __fsub_rn(__fsub_rn(yv, tu.x), tv.y);
+                                const float b = __fadd_rn(yv, tu.y);
+#else
+                                const float qu = unit_from_int<255>(__fsub_rn(__uint_as_float(__byte_perm(c4, 0x4B000000u, dx ? 0x7642 : 0x7640)), CM_MAGIC));
+                                const float qv = unit_from_int<255>(__fsub_rn(__uint_as_float(__byte_perm(c4, 0x4B000000u, dx ? 0x7643 : 0x7641)), CM_MAGIC));
+                                const float u = __fsub_rn(qu, 0.5f), v = __fsub_rn(qv, 0.5f);
+                                const float r = __fadd_rn(yv, __fmul_rn(1.403f, v));
+                                const float g = __fsub_rn(__fsub_rn(yv, __fmul_rn(0.344f, u)), __fmul_rn(0.714f, v));
+                                const float b = __fadd_rn(yv, __fmul_rn(1.773f, u));
+#endif
+                                ch[3 * dx + 0] = __float_as_uint(__fadd_rz(__fadd_rn(__fmul_rn(__saturatef(r), 255.0f), 0.5f), CM_MAGIC));
+                                ch[3 * dx + 1] = __float_as_uint(__fadd_rz(__fadd_rn(__fmul_rn(__saturatef(g), 255.0f), 0.5f), CM_MAGIC));
+                                ch[3 * dx + 2] = __float_as_uint(__fadd_rz(__fadd_rn(__fmul_rn(__saturatef(b), 255.0f), 0.5f), CM_MAGIC));
+                            }
+                            if (ok) store_rgb2(o + dy * prm.rgb_dst_pitch, ch[0], ch[1], ch[2], ch[3], ch[4], ch[5]);
+                        }
+                    };
                     tm_wait(bar_full + 8 * (g0 + j), 0);
                     ACB_TM_FENCE_AFTER();
 #ifdef ACB_TM_TRACE
@@ -737,70 +889,12 @@ namespace acb
                         ACB_TM_WAIT_ST();
                         ACB_TM_FENCE_BEFORE();
                         const uint32_t fa = my_flag_a + 8 * yg;
-                        tm_publish_byte(fa, l + 1); tm_publish_byte(fa + 8, l + 1); tm_publish_byte(fa + 16, l + 1); tm_publish_byte(fa + 24, l + 1);
+                        tm_publish(fa, l + 1); tm_publish(fa + 8, l + 1); tm_publish(fa + 16, l + 1); tm_publish(fa + 24, l + 1);
 #ifdef ACB_TM_TRACE
                         if (q == 0 && lane == 0) trace[3 * TM_MAX_STEPS + g0 + j] = clock64();
 #endif
                         continue;
                     }
-                    // Fused chroma resize + merge (tail segments, prm.uv_in): the lane's horizontal taps and a sliding window of the horizontal
-                    // pass over five source rows, W0 .. W4 = rows gy - 2 .. gy + 2 of the (u, v) plane for the row gy being finished
-                    [[maybe_unused]] HTaps2 hk;
-                    [[maybe_unused]] float4 W0, W1, W2, W3, W4;
-                    const bool fused = S::TAIL && last && prm.uv_in != nullptr;
-                    if constexpr (S::TAIL)
-                        if (fused)
-                        {
-                            hk = load_htaps2(prm.htab, 2 * min(x0 + R + lane, prm.w - 1));
-                            const int gy0 = y0 + yg;
-                            W0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                            W1 = chroma_hrow2(prm.uv_in + static_cast<size_t>(clampi(gy0 - 2, 0, prm.h - 1)) * prm.uv_pitch, prm.w, hk);
-                            W2 = chroma_hrow2(prm.uv_in + static_cast<size_t>(clampi(gy0 - 1, 0, prm.h - 1)) * prm.uv_pitch, prm.w, hk);
-                            W3 = chroma_hrow2(prm.uv_in + static_cast<size_t>(gy0) * prm.uv_pitch, prm.w, hk);
-                            W4 = chroma_hrow2(prm.uv_in + static_cast<size_t>(min(gy0 + 1, prm.h - 1)) * prm.uv_pitch, prm.w, hk);
-                        }
-                    // yl[dy * 2 + dx]: the lane's four luma results as the value BEFORE truncation to the byte (x 255 + 0.5 applied)
-                    [[maybe_unused]] auto fused_store = [&](const int gx, const int gy, const float (&yl)[4], const bool ok) {
-                        W0 = W1; W1 = W2; W2 = W3; W3 = W4;
-                        W4 = chroma_hrow2(prm.uv_in + static_cast<size_t>(min(gy + 2, prm.h - 1)) * prm.uv_pitch, prm.w, hk);
-                        const Contrib* vp = prm.vtab + 2 * gy;
-                        const uint4 va0 = __ldg(reinterpret_cast<const uint4*>(vp)), vb0 = __ldg(reinterpret_cast<const uint4*>(vp + 1));
-                        const float2 va1 = __ldg(reinterpret_cast<const float2*>(&vp[0].c[2])), vb1 = __ldg(reinterpret_cast<const float2*>(&vp[1].c[2]));
-                        const float ca[4] = { __uint_as_float(va0.z), __uint_as_float(va0.w), va1.x, va1.y };
-                        const float cb[4] = { __uint_as_float(vb0.z), __uint_as_float(vb0.w), vb1.x, vb1.y };
-                        float4 sa, sb;      // vertical pass: (u, v) of columns a, b in output rows 2 gy (sa) and 2 gy + 1 (sb)
-                        if (static_cast<int>(va0.x) == gy - 2 && static_cast<int>(vb0.x) == gy - 1)
-                        {
-                            // interior rows: the window holds exactly the rows both contributors read
-                            sa.x = tap4(ca[0], ca[1], ca[2], ca[3], W0.x, W1.x, W2.x, W3.x); sa.y = tap4(ca[0], ca[1], ca[2], ca[3], W0.y, W1.y, W2.y, W3.y);
-                            sa.z = tap4(ca[0], ca[1], ca[2], ca[3], W0.z, W1.z, W2.z, W3.z); sa.w = tap4(ca[0], ca[1], ca[2], ca[3], W0.w, W1.w, W2.w, W3.w);
-                            sb.x = tap4(cb[0], cb[1], cb[2], cb[3], W1.x, W2.x, W3.x, W4.x); sb.y = tap4(cb[0], cb[1], cb[2], cb[3], W1.y, W2.y, W3.y, W4.y);
-                            sb.z = tap4(cb[0], cb[1], cb[2], cb[3], W1.z, W2.z, W3.z, W4.z); sb.w = tap4(cb[0], cb[1], cb[2], cb[3], W1.w, W2.w, W3.w, W4.w);
-                        }
-                        else
-                        {
-                            // rows at the top image edge (folded taps start at another row): the contributors' own rows, recomputed.  Rows past
-                            // the image carry zero coefficients and are read clamped.
-                            float4 t[4];
-#pragma unroll
-                            for (int j = 0; j < 4; j++) t[j] = chroma_hrow2(prm.uv_in + static_cast<size_t>(min(static_cast<int>(va0.x) + j, prm.h - 1)) * prm.uv_pitch, prm.w, hk);
-                            sa.x = tap4(ca[0], ca[1], ca[2], ca[3], t[0].x, t[1].x, t[2].x, t[3].x); sa.y = tap4(ca[0], ca[1], ca[2], ca[3], t[0].y, t[1].y, t[2].y, t[3].y);
-                            sa.z = tap4(ca[0], ca[1], ca[2], ca[3], t[0].z, t[1].z, t[2].z, t[3].z); sa.w = tap4(ca[0], ca[1], ca[2], ca[3], t[0].w, t[1].w, t[2].w, t[3].w);
-#pragma unroll
-                            for (int j = 0; j < 4; j++) t[j] = chroma_hrow2(prm.uv_in + static_cast<size_t>(min(static_cast<int>(vb0.x) + j, prm.h - 1)) * prm.uv_pitch, prm.w, hk);
-                            sb.x = tap4(cb[0], cb[1], cb[2], cb[3], t[0].x, t[1].x, t[2].x, t[3].x); sb.y = tap4(cb[0], cb[1], cb[2], cb[3], t[0].y, t[1].y, t[2].y, t[3].y);
-                            sb.z = tap4(cb[0], cb[1], cb[2], cb[3], t[0].z, t[1].z, t[2].z, t[3].z); sb.w = tap4(cb[0], cb[1], cb[2], cb[3], t[0].w, t[1].w, t[2].w, t[3].w);
-                        }
-                        float yv[4];
-#pragma unroll
-                        for (int i = 0; i < 4; i++) yv[i] = unit_from_int<255>(__fsub_rn(__fadd_rz(yl[i], CM_MAGIC), CM_MAGIC));     // toFloat of the stored luma byte
-                        uint32_t r0, g0, b0, r1, g1, b1;
-                        uint8_t* o = prm.rgb_dst + static_cast<size_t>(2 * gy) * prm.rgb_dst_pitch + 6 * gx;
-                        chroma_merge_px(sa.x, sa.y, yv[0], r0, g0, b0); chroma_merge_px(sa.z, sa.w, yv[1], r1, g1, b1);
-                        if (ok) store_rgb2(o, r0, g0, b0, r1, g1, b1);
-                        chroma_merge_px(sb.x, sb.y, yv[2], r0, g0, b0); chroma_merge_px(sb.z, sb.w, yv[3], r1, g1, b1);
-                        if (ok) store_rgb2(o + prm.rgb_dst_pitch, r0, g0, b0, r1, g1, b1);
-                    };
                     for (int jr = 0; jr < k; jr++)
                     {
                         const int y = yg + jr;
@@ -854,7 +948,7 @@ namespace acb
                             {
                                 const float yl[4] = { fmaf(__saturatef(o4[0]), 255.0f, 0.5f), fmaf(__saturatef(o4[1]), 255.0f, 0.5f),
                                                       fmaf(__saturatef(o4[2]), 255.0f, 0.5f), fmaf(__saturatef(o4[3]), 255.0f, 0.5f) };
-                                fused_store(gx, gy, yl, lane < SW && gx < prm.w);
+                                fused_store(jr, gx, gy, yl, lane < SW && gx < prm.w);
                             }
                             else if (lane < SW && gx < prm.w)
                             {
@@ -882,7 +976,7 @@ namespace acb
                             {
                                 const float yl[4] = { __fadd_rn(__fmul_rn(__saturatef(v[0] + id), 255.0f), 0.5f), __fadd_rn(__fmul_rn(__saturatef(v[1] + id), 255.0f), 0.5f),
                                                       __fadd_rn(__fmul_rn(__saturatef(v[2] + id), 255.0f), 0.5f), __fadd_rn(__fmul_rn(__saturatef(v[3] + id), 255.0f), 0.5f) };
-                                fused_store(gx, gy, yl, lane < SW && gx < prm.w);
+                                fused_store(jr, gx, gy, yl, lane < SW && gx < prm.w);
                             }
                             else if (lane < SW && gx < prm.w)
                             {
