@@ -442,6 +442,7 @@ namespace
     {
         const uint8_t* rgb_src; int rgb_pitch;
         uint8_t* uv; int uv_pitch;
+        uint8_t* y; int y_pitch;            // quantised luma plane, written by the head segment for a tail that adds the source luma (ACNet); else null
         const void* htab; const void* vtab;
         uint8_t* rgb_dst; int rgb_dst_pitch;
     };
@@ -483,8 +484,9 @@ namespace
             if (fz)
             {
                 // fused colour handling: TMEM engine only (the caller has checked that every segment has a kernel there)
-                a.rgb_src = fz->rgb_src; a.rgb_pitch = fz->rgb_pitch; a.uv_pitch = fz->uv_pitch;
-                if (head) a.uv_out = fz->uv;
+                a.uv_pitch = fz->uv_pitch;
+                if (head) { a.rgb_src = fz->rgb_src; a.rgb_pitch = fz->rgb_pitch; a.uv_out = fz->uv; a.y_out = fz->y; a.y_pitch = fz->y_pitch; }
+                else { a.src = fz->y; a.src_pitch = fz->y_pitch; }
                 if (tail) { a.uv_in = fz->uv; a.htab = fz->htab; a.vtab = fz->vtab; a.rgb_dst = fz->rgb_dst; a.rgb_dst_pitch = fz->rgb_dst_pitch; }
                 if ((rc = launch_seg_tm(s, st, m, sp, a)) != ACB200_OK) return rc == ACB_SEG_UNSUPPORTED ? fail(s, ACB200_EINVAL, "fused colour path: segment without a TMEM kernel") : rc;
                 cur ^= 1;
@@ -578,9 +580,14 @@ namespace
             const size_t uvp = pitch_of(w, 2, 1);
             if ((rc = ensure(s, st, s->uv, uvp * h)) != ACB200_OK) return rc;
             if ((rc = ensure_tables(s, st, w, h, 2 * w, 2 * h)) != ACB200_OK) return rc;
+            // ACNet's tail adds the nearest-upsampled source luma (Common.hpp:290-342): the head segment leaves the quantised Y plane for it
+            const bool needs_y = m->family != ACB200_FAMILY_ACNET_LEGACY;
+            const size_t yp = pitch_of(w, 1, 1);
+            if (needs_y && (rc = ensure(s, st, s->y[0], yp * h)) != ACB200_OK) return rc;
             if (s->tab_max_cnt <= 4)
             {
                 const FusedColour fz{ static_cast<const uint8_t*>(d_src), src_pitch, static_cast<uint8_t*>(s->uv.p), static_cast<int>(uvp),
+                                      needs_y ? static_cast<uint8_t*>(s->y[0].p) : nullptr, static_cast<int>(yp),
                                       s->htab.p, s->vtab.p, static_cast<uint8_t*>(d_dst), dst_pitch };
                 return luma_pass(s, st, *m, nullptr, 0, nullptr, 0, w, h, type, true, &fz);
             }

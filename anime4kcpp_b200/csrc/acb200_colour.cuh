@@ -120,10 +120,10 @@ namespace acb
         o16[2] = static_cast<unsigned short>(__byte_perm(g1, b1, 0x0040));
     }
     // quantised luma byte of the colour split, as the network's toFloat reads it back (rgb2yuv_u8x4_kernel + load_elem)
-    __device__ __forceinline__ float luma_from_rgb_u8(uint32_t r, uint32_t g, uint32_t b, uint8_t& qu, uint8_t& qv)
+    __device__ __forceinline__ float luma_from_rgb_u8(uint32_t r, uint32_t g, uint32_t b, uint8_t& qy, uint8_t& qu, uint8_t& qv)
     {
         const YuvFromRgb o = rgb_to_yuv(unit_from_int<255>(static_cast<float>(r)), unit_from_int<255>(static_cast<float>(g)), unit_from_int<255>(static_cast<float>(b)));
-        qu = quant_u8(o.u); qv = quant_u8(o.v);
-        return unit_from_int<255>(static_cast<float>(quant_u8(o.y)));
+        qy = quant_u8(o.y); qu = quant_u8(o.u); qv = quant_u8(o.v);
+        return unit_from_int<255>(static_cast<float>(qy));
     }
 }

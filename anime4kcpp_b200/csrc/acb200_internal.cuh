@@ -159,6 +159,7 @@ namespace acbh
         // Only launch_seg_tm understands these; the caller checks seg_tm_chain_supported() before it sets them.
         const uint8_t* rgb_src = nullptr; int rgb_pitch = 0;
         uint8_t* uv_out = nullptr; const uint8_t* uv_in = nullptr; int uv_pitch = 0;
+        uint8_t* y_out = nullptr; int y_pitch = 0;
         const void* htab = nullptr; const void* vtab = nullptr;
         uint8_t* rgb_dst = nullptr; int rgb_dst_pitch = 0;
     };

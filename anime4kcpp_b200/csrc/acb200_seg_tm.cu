@@ -47,7 +47,8 @@ namespace acbh
             prm.src = src; prm.map_in = reinterpret_cast<const uint4*>(map_in); prm.map_out = reinterpret_cast<uint4*>(map_out);
             prm.feat_in = feat; prm.feat_out = feat; prm.dst = dst;
             prm.src_pitch = src_pitch; prm.dst_pitch = dst_pitch; prm.w = w; prm.h = h; prm.type = type;
-            prm.rgb_src = S::NEEDS_LUMA ? a.rgb_src : nullptr; prm.rgb_pitch = a.rgb_pitch;
+            prm.rgb_src = S::HEAD ? a.rgb_src : nullptr; prm.rgb_pitch = a.rgb_pitch;
+            prm.y_out = S::HEAD ? a.y_out : nullptr; prm.y_pitch = a.y_pitch;
             prm.uv_out = S::HEAD ? a.uv_out : nullptr; prm.uv_in = S::TAIL ? a.uv_in : nullptr; prm.uv_pitch = a.uv_pitch;
             prm.htab = static_cast<const Contrib*>(a.htab); prm.vtab = static_cast<const Contrib*>(a.vtab);
             prm.rgb_dst = a.rgb_dst; prm.rgb_dst_pitch = a.rgb_dst_pitch;
