@@ -1170,6 +1170,19 @@ extern "C"
 
     unsigned long long acb200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+    void* acb200_host_alloc(size_t bytes)
+    {
+        static const bool usable = acb200_device_count() > 0;
+        if (!usable || bytes == 0) return nullptr;
+        void* p = nullptr;
+        if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        return p;
+    }
+    void acb200_host_free(void* p)
+    {
+        if (p && cudaFreeHost(p) != cudaSuccess) cudaGetLastError();
+    }
+
     const char* acb200_error_string(int code)
     {
         switch (code)

@@ -4,8 +4,12 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 
 #include "AC/Core/Image.hpp"
+
+#include "Internal.hpp"
 
 namespace
 {
@@ -20,12 +24,93 @@ namespace
     }
 }
 
+namespace
+{
+    // Image storage comes from a pool of page-locked memory when a CUDA device is present: the host-fed path is PCIe-bound and a
+    // pageable buffer is copied at about a quarter of the pinned rate (and synchronously, through the driver's staging buffer).
+    // Page-locking is slow and serialises with the GPU work in flight (measured: tens of milliseconds per call under load), so the
+    // pool pins SLABS of 128 MB or more and carves blocks out of them; a released block goes to its capacity bucket's free list and
+    // is handed out again -- tools/benchmark's loop allocates a result image per call (the reference's Processor::process creates
+    // dst, core/src/processor/Processor.cpp:199-276).  Pinned memory is never returned while the process lives (bounded by kMaxPinned;
+    // beyond it, for small images, and on boxes without a GPU: malloc).
+    class HostPool
+    {
+    public:
+        static HostPool& get()
+        {
+            static HostPool* pool = new HostPool;       // never destroyed: static teardown must not call into a CUDA runtime that is gone
+            return *pool;
+        }
+        // capacity buckets: powers of two and the three eighth-steps between them (at most 25 % slack)
+        static std::size_t bucket(std::size_t n)
+        {
+            std::size_t p = kMinPinned;
+            while (p < n) p <<= 1;
+            const std::size_t q = p >> 3;
+            for (std::size_t c = (p >> 1) + q; c < p; c += q) if (c >= n) return c;
+            return p;
+        }
+        void* alloc(const std::size_t size, std::size_t& cap, bool& pinned)
+        {
+            pinned = false;
+            cap = (size + kMallocAlign - 1) / kMallocAlign * kMallocAlign;
+            if (enabled && size >= kMinPinned)
+            {
+                const std::size_t b = bucket(size);
+                std::lock_guard<std::mutex> lock(m);
+                auto it = cache.find(b);
+                if (it != cache.end())
+                {
+                    void* p = it->second;
+                    cache.erase(it);
+                    cap = b; pinned = true;
+                    return p;
+                }
+                if (slabLeft < b && total + std::max(kSlab, b) <= kMaxPinned)
+                {
+                    // what is left of the old slab stays unused (at most one block's worth per slab)
+                    const std::size_t bytes = std::max(kSlab, b);
+                    if (void* p = acb200_host_alloc(bytes)) { slab = static_cast<unsigned char*>(p); slabLeft = bytes; total += bytes; }
+                }
+                if (slabLeft >= b)
+                {
+                    void* p = slab;
+                    slab += b; slabLeft -= b;
+                    cap = b; pinned = true;
+                    return p;
+                }
+            }
+            return std::aligned_alloc(kMallocAlign, cap);
+        }
+        void release(void* p, const std::size_t cap, const bool pinned)
+        {
+            if (!p) return;
+            if (!pinned) { std::free(p); return; }
+            std::lock_guard<std::mutex> lock(m);
+            cache.emplace(cap, p);
+        }
+    private:
+        HostPool()
+        {
+            const char* e = std::getenv("ACB200_PINNED_IMAGES");
+            enabled = !(e && e[0] == '0') && acb200_device_count() > 0;
+        }
+        static constexpr std::size_t kMinPinned = 64 * 1024, kSlab = std::size_t{ 128 } << 20, kMaxPinned = std::size_t{ 8 } << 30;
+        std::mutex m;
+        std::multimap<std::size_t, void*> cache;
+        unsigned char* slab = nullptr;
+        std::size_t slabLeft = 0, total = 0;
+        bool enabled = false;
+    };
+}
+
 struct ac::core::Image::ImageData
 {
-    void* data;
-    explicit ImageData(std::size_t size) noexcept
-        : data(std::aligned_alloc(kMallocAlign, (size + kMallocAlign - 1) / kMallocAlign * kMallocAlign)) {}
-    ~ImageData() noexcept { std::free(data); }
+    void* data = nullptr;
+    std::size_t cap = 0;
+    bool pinned = false;
+    explicit ImageData(std::size_t size) noexcept { data = HostPool::get().alloc(size, cap, pinned); }
+    ~ImageData() noexcept { HostPool::get().release(data, cap, pinned); }
     ImageData(const ImageData&) = delete;
     ImageData& operator=(const ImageData&) = delete;
 };

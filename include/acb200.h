@@ -198,6 +198,13 @@ ACB200_API int acb200_stream_submit_frame(acb200_stream* stream, const acb200_pl
 ACB200_API int acb200_stream_next(acb200_stream* stream, long long* seq_out, int* status_out);
 ACB200_API void acb200_stream_destroy(acb200_stream* stream);
 
+/*
+ * Page-locked host memory for images that are fed from / delivered to host memory (the host-fed path is PCIe-bound: pageable buffers
+ * reach about a quarter of the pinned copy rate).  acb200_host_alloc returns NULL when no CUDA device is usable or pinning fails;
+ * the drop-in's ac::core::Image allocates its own storage through a pool of these (ACB200_PINNED_IMAGES=0 turns that off).
+ */
+ACB200_API void* acb200_host_alloc(size_t bytes);
+ACB200_API void acb200_host_free(void* p);
 /* number of kernels this library has launched since load (all sessions); for bench.py's gpu_launches */
 ACB200_API unsigned long long acb200_launch_count(void);
 /* elapsed GPU milliseconds of the most recent process_* call's kernels on this session (CUDA events) */
