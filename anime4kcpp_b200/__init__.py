@@ -292,12 +292,14 @@ def frame_owner(seq, n_devices):
     return lib().acb200_frame_owner(seq, n_devices)
 
 
-def process_band(session, model, img, factor, n_bands, band, out):
-    """Upscale row band `band` of `n_bands` of a host image on `session`'s GPU, writing only that band's rows of `out`."""
+def process_band(session, model, img, factor, n_bands, band, out, out_y0=0):
+    """Upscale row band `band` of `n_bands` of a host image on `session`'s GPU, writing only that band's rows of `out`.  `out` is the whole
+    result image, or -- with `out_y0` = the band's first output row (band_plan) -- a buffer that holds just the band's rows (the shape a
+    multi-GPU job uses: every rank keeps its own band of the result)."""
     h, w = img.shape[:2]
     c = 1 if img.ndim == 2 else img.shape[2]
     _check(lib().acb200_process_host_band(session.handle, model.handle, img.ctypes.data, w, h, c, img.strides[0], _NP_TYPES[img.dtype], float(factor),
-                                          n_bands, band, out.ctypes.data, out.strides[0]), session.handle)
+                                          n_bands, band, out.ctypes.data - out_y0 * out.strides[0], out.strides[0]), session.handle)
 
 
 class FrameStream:
