@@ -345,12 +345,18 @@ namespace
     template<class S>
     void pack_segment(acb200_model& m, SegSpec& sp)
     {
-        if (S::FAM != ACB200_FAMILY_ARNET)
         {
             sp.tm_off = static_cast<int>(m.tmops.size());
             const float* kk = m.k.data() + sp.koff + (S::HEAD ? 72 : 0);
             for (int i = 0; i < S::NCONV; i++, kk += 576) pack_bop_tm(kk, 8, m.tmops);
-            if (S::TAIL) pack_bop_tm(kk, S::FAM == ACB200_FAMILY_ACNET_LEGACY ? 8 : 4, m.tmops);
+            if (S::TAIL && S::FAM == ACB200_FAMILY_ARNET)
+            {
+                // PReLU conv, residual conv, [1x1: 64 weights, on the CUDA cores], pixel-shuffle conv
+                pack_bop_tm(kk, 8, m.tmops);
+                pack_bop_tm(kk + 576, 8, m.tmops);
+                pack_bop_tm(kk + 1152 + 64, 4, m.tmops);
+            }
+            else if (S::TAIL) pack_bop_tm(kk, S::FAM == ACB200_FAMILY_ACNET_LEGACY ? 8 : 4, m.tmops);
         }
         {
             sp.bop_off = static_cast<int>(m.bops.size());

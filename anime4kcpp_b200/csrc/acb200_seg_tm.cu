@@ -31,7 +31,7 @@ namespace acbh
     {
         const void* src = a.src; const int src_pitch = a.src_pitch, dst_pitch = a.dst_pitch, w = a.w, h = a.h, type = a.type;
         void* dst = a.dst; const float* map_in = a.map_in; float* map_out = a.map_out; float* feat = a.feat;
-        if constexpr (S::FAM == ACB200_FAMILY_ARNET || S::R > TM_MAX_R) return ACB_SEG_UNSUPPORTED;
+        if constexpr (S::R > TM_MAX_R) return ACB_SEG_UNSUPPORTED;
         else
         {
             static_assert(sizeof(TmParams<S>) <= 32764, "kernel parameter block too large");
@@ -65,12 +65,16 @@ namespace acbh
             if (S::HEAD) std::memcpy(prm.k, m.k.data() + spec.koff, sizeof(float) * 72);
             if (S::TAIL && S::FAM == ACB200_FAMILY_ACNET_LEGACY)
                 std::memcpy(prm.k + K0, m.k.data() + spec.koff + K0 + 576 * (S::NCONV + 1), sizeof(float) * 32);
+            if (S::TAIL && S::FAM == ACB200_FAMILY_ARNET)       // the 1x1 between the tail's residual conv and the pixel-shuffle conv
+                std::memcpy(prm.k + K0, m.k.data() + spec.koff + K0 + 576 * (S::NCONV + 2), sizeof(float) * 64);
             std::memcpy(prm.b, m.b.data() + spec.boff, sizeof(float) * S::NB);
             if (S::NA > 0) std::memcpy(prm.a, m.a.data() + spec.aoff, sizeof(float) * S::NA);
             else prm.a[0] = 0.0f;
             static std::atomic<unsigned long long> optin{0};
-            if ((rc = smem_optin_once(s, reinterpret_cast<const void*>(segment_tm_kernel<S>), TM_SMEM_BYTES_FUSED, optin)) != ACB200_OK) return rc;
-            segment_tm_kernel<S><<<prm.tiles_x * tiles_y, TM_THREADS, (prm.uv_in || ACB_TM_PROGRESS_MBAR) ? TM_SMEM_BYTES_FUSED : TM_SMEM_BYTES, st>>>(prm);
+            constexpr int SMEM_MAX = S::FAM == ACB200_FAMILY_ARNET ? TM_SMEM_BYTES_ARNET : TM_SMEM_BYTES_FUSED;
+            if ((rc = smem_optin_once(s, reinterpret_cast<const void*>(segment_tm_kernel<S>), SMEM_MAX, optin)) != ACB200_OK) return rc;
+            const int smem = S::FAM == ACB200_FAMILY_ARNET ? TM_SMEM_BYTES_ARNET : (prm.uv_in || ACB_TM_PROGRESS_MBAR) ? TM_SMEM_BYTES_FUSED : TM_SMEM_BYTES;
+            segment_tm_kernel<S><<<prm.tiles_x * tiles_y, TM_THREADS, smem, st>>>(prm);
             g_launches.fetch_add(1, std::memory_order_relaxed);
             ACB_CUDA(s, cudaGetLastError());
             return ACB200_OK;
@@ -88,14 +92,14 @@ namespace acbh
         }
         return ACB200_EINVAL;
     }
-    bool seg_tm_supported(const acb200_model& m) { return m.family == ACB200_FAMILY_ACNET_LEGACY || m.family == ACB200_FAMILY_ACNET; }
+    bool seg_tm_supported(const acb200_model& m) { return m.family == ACB200_FAMILY_ACNET_LEGACY || m.family == ACB200_FAMILY_ACNET || m.family == ACB200_FAMILY_ARNET; }
     bool seg_tm_chain_supported(const acb200_model& m)
     {
         if (!seg_tm_supported(m)) return false;
         for (const SegSpec& sp : m.chain)
             switch (sp.kind)
             {
-#define ACB_CASE(KIND, TYPE) case KIND: if (TYPE::FAM == ACB200_FAMILY_ARNET || TYPE::R > TM_MAX_R) return false; break;
+#define ACB_CASE(KIND, TYPE) case KIND: if (TYPE::R > TM_MAX_R) return false; break;
             ACB_FOR_EACH_SEG(ACB_CASE)
 #undef ACB_CASE
             }

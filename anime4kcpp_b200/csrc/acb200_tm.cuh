@@ -98,6 +98,11 @@ namespace acb
     // progress barriers (ACB_TM_PROGRESS_MBAR): one one-shot mbarrier per (published layer 1 .. R, frame row), four arrivals (one per lane quadrant)
     constexpr int TM_OFF_PROG = TM_OFF_LUT + 2 * 256 * 8;
     constexpr int TM_SMEM_BYTES_FUSED = TM_OFF_PROG + TM_MAX_R * TM_GMAX * 8;
+    // ARNet: the block input x of the residual `conv * 0.2 + x` (CPUProcessor.cpp:1479,1483), fp32, one 32-byte slot per frame row, lane and
+    // quadrant.  Written by the epilogue that produces x, read two layers later by the epilogue of the block's second conv -- two lanes to
+    // the left, because the map drifts by one lane per layer.
+    constexpr int TM_OFF_X = (TM_SMEM_BYTES_FUSED + 127) / 128 * 128;
+    constexpr int TM_SMEM_BYTES_ARNET = TM_OFF_X + 4 * (TM_GMAX + 2) * 32 * 32;
 
     template<class S>
     struct TmParams
@@ -262,7 +267,8 @@ namespace acb
         constexpr int R = S::R;                 // 3x3 convs of this segment (all on the tensor cores)
         constexpr int SW = 32 - 2 * R;          // output columns of a strip
         static_assert(R >= 1 && R <= TM_MAX_R && SW >= 8, "segment too deep for 32-pixel strips");
-        static_assert(S::FAM == ACB200_FAMILY_ACNET_LEGACY || S::FAM == ACB200_FAMILY_ACNET, "family not on this engine yet");
+        constexpr bool ARNET = S::FAM == ACB200_FAMILY_ARNET;
+        static_assert(!ARNET || (S::NCONV % 2) == 0, "ARNet segments start and end on block boundaries");
         static_assert(TM_SETS == 4, "groups are dealt to the epilogue sets by group index % 4");
         extern __shared__ __align__(128) unsigned char smem_tm[];
         float* luma_all = reinterpret_cast<float*>(smem_tm + TM_OFF_LUMA);
@@ -448,8 +454,9 @@ namespace acb
         constexpr int A0 = (S::FAM == ACB200_FAMILY_ACNET && S::HEAD) ? 8 : 0;
         // bias of the segment's tensor layer ln (1-based) as the initial accumulator of output channel c (the ACNet tail has 4 couts)
         auto bias_of = [&](const int ln, const int c) -> float {
-            if (S::TAIL && S::FAM == ACB200_FAMILY_ACNET && ln == R && c >= 4) return 0.0f;
-            return prm.b[B0 + 8 * (ln - 1) + c];
+            if (S::TAIL && S::FAM != ACB200_FAMILY_ACNET_LEGACY && ln == R && c >= 4) return 0.0f;       // the pixel-shuffle conv has four couts
+            // (ARNet's tail: PReLU conv, residual conv, [1x1 bias], pixel-shuffle conv -- the 1x1's bias sits between the last two)
+            return prm.b[B0 + 8 * (ln - 1) + ((ARNET && S::TAIL && ln == R) ? 8 : 0) + c];
         };
         if (warp >= TM_ISS_WARP0)
         {
@@ -649,6 +656,19 @@ namespace acb
             };
             const bool pads = (pad_top >= 0) || (pad_bot <= G - 1);     // the frame reaches over the top / bottom image edge
 
+            // ARNet: the residual store (see TM_OFF_X): slot [frame row + 1][lane] of this quadrant, two float4
+            [[maybe_unused]] float4* const sx = reinterpret_cast<float4*>(smem_tm + TM_OFF_X) + static_cast<size_t>(q) * (TM_GMAX + 2) * 64;
+            [[maybe_unused]] auto sx_store = [&](const int y, const float (&v)[8]) {
+                float4* p = sx + ((y + 1) * 32 + lane) * 2;
+                p[0] = make_float4(v[0], v[1], v[2], v[3]);
+                p[1] = make_float4(v[4], v[5], v[6], v[7]);
+            };
+            // x of the pixel this lane holds TWO layers after the one that stored it: two lanes to the right (lanes 30 / 31 lie in the consumed halo)
+            [[maybe_unused]] auto sx_load = [&](const int y, float (&x)[8]) {
+                const float4* p = sx + ((y + 1) * 32 + min(lane + 2, 31)) * 2;
+                const float4 a = p[0], b = p[1];
+                x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+            };
             // one row of layer l's output map becomes the next layer's A operand in buffer l % 2 (x-clamped in border strips), with its
             // padding copies in y
             auto put_row = [&](const int l, const int y, uint32_t (&w8)[8]) {
@@ -708,6 +728,18 @@ namespace acb
                                 else if (ACT == ACT_PRELU) s = prelu(s, prm.a[co]);
                                 v[co] = s;
                             }
+                            if constexpr (ARNET)
+                            {
+                                // feat: the first block's residual input, and (through global memory) the long skip the last segment adds
+                                sx_store(y, v);
+                                const int su = tile_x * 4 + q, gx = x0 + lane, gy = y0 + y;
+                                if (su < prm.strips_x && gx >= su * SW && gx < min(su * SW + SW, prm.w) && gy >= y0 + R && gy < min(y0 + G - R, prm.h))
+                                {
+                                    float4* f = reinterpret_cast<float4*>(prm.feat_out + (static_cast<size_t>(gy) * prm.w + gx) * 8);
+                                    f[0] = make_float4(v[0], v[1], v[2], v[3]);
+                                    f[1] = make_float4(v[4], v[5], v[6], v[7]);
+                                }
+                            }
                             uint32_t w8[8];
                             split_pair(v[0], v[1], w8[0], w8[4]); split_pair(v[2], v[3], w8[1], w8[5]);
                             split_pair(v[4], v[5], w8[2], w8[6]); split_pair(v[6], v[7], w8[3], w8[7]);
@@ -716,6 +748,7 @@ namespace acb
                         }
                         ACB_TM_WAIT_ST();
                         ACB_TM_FENCE_BEFORE();
+                        if constexpr (ARNET) __threadfence_block();      // the residual store is read by another warp, ordered through the progress flags
                         publish_rows(0, yg, k);
                     }
                 }
@@ -741,9 +774,17 @@ namespace acb
                         {
                             const uint32_t w8[8] = { hi[k].x, hi[k].y, hi[k].z, hi[k].w, lo[k].x, lo[k].y, lo[k].z, lo[k].w };
                             if (yg + k <= lb) { tm_st8(my_t + 8 * (yg + k + 1), w8); tm_st8(my_t + 256u + 8 * (yg + k + 1), bias1); }
+                            if constexpr (ARNET)
+                                if (yg + k <= lb)
+                                {
+                                    const float2 f0 = join_pair(hi[k].x, lo[k].x), f1 = join_pair(hi[k].y, lo[k].y), f2 = join_pair(hi[k].z, lo[k].z), f3 = join_pair(hi[k].w, lo[k].w);
+                                    const float xv[8] = { f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y };
+                                    sx_store(yg + k, xv);
+                                }
                         }
                         ACB_TM_WAIT_ST();
                         ACB_TM_FENCE_BEFORE();
+                        if constexpr (ARNET) __threadfence_block();
 #pragma unroll
                         for (int k = 0; k < 4; k++) if (yg + k <= lb) tm_publish(my_flag_a + 8 * (yg + k), 1);
                     }
@@ -767,7 +808,13 @@ namespace acb
                 for (int c = 0; c < 8; c++) bias_n[c] = __float_as_uint(bias_of(min(l + 1, R), c));
                 float alpha[8];
 #pragma unroll
-                for (int c = 0; c < 8; c++) alpha[c] = S::FAM == ACB200_FAMILY_ACNET ? prm.a[A0 + 8 * (min(l, S::NCONV) - 1) + c] : 0.0f;
+                for (int c = 0; c < 8; c++)
+                    alpha[c] = S::FAM == ACB200_FAMILY_ACNET ? prm.a[A0 + 8 * (min(l, S::NCONV) - 1) + c]
+                             : ARNET ? prm.a[((l - 1) >> 1) * 8 + c] : 0.0f;      // ARNet: the PReLU of the block's first conv (odd l; in bounds for every l <= R)
+                // ARNet layer roles: odd l = conv + PReLU; even l = conv * 0.2 + x (x = the block's input, from the residual store); the tail's
+                // even layer continues with the 1x1 conv, PReLU and the long skip (CPUProcessor.cpp:1479-1483)
+                [[maybe_unused]] const bool is_res = ARNET && (l & 1) == 0;
+                [[maybe_unused]] const bool is_1x1 = ARNET && S::TAIL && l == S::NCONV + 2;
                 // this set's groups: group index g0 + j with (g0 + j) % 4 == set
                 for (int j = (set - g0) & 3; ya + 4 * j <= yb; j += 4)
                 {
@@ -871,7 +918,7 @@ namespace acb
 #ifdef ACB_TM_TRACE
                     if (q == 0 && lane == 0) trace[2 * TM_MAX_STEPS + g0 + j] = clock64();
 #endif
-                    if (!last && k == 4 && !pads && !xclamp)
+                    if (!last && k == 4 && !pads && !xclamp && !is_1x1)
                     {
                         // the common case -- a whole group of a body layer inside an interior strip -- as straight-line code: one 32-column
                         // load, activation and split of the four rows, ONE 32-column store of the next layer's operands in place, the next
@@ -886,10 +933,20 @@ namespace acb
                         {
                             float v[8];
 #pragma unroll
-                            for (int c = 0; c < 8; c++)
+                            for (int c = 0; c < 8; c++) v[c] = __uint_as_float(d[8 * jr + c]);
+                            if (is_res)
                             {
-                                v[c] = __uint_as_float(d[8 * jr + c]);
-                                v[c] = S::FAM == ACB200_FAMILY_ACNET_LEGACY ? fmaxf(v[c], 0.0f) : prelu(v[c], alpha[c]);
+                                float x[8];
+                                sx_load(yg + jr, x);
+                                __syncwarp();           // every lane has read its slot before its owner overwrites it
+#pragma unroll
+                                for (int c = 0; c < 8; c++) v[c] = fmaf(v[c], 0.2f, x[c]);
+                                sx_store(yg + jr, v);
+                            }
+                            else
+                            {
+#pragma unroll
+                                for (int c = 0; c < 8; c++) v[c] = S::FAM == ACB200_FAMILY_ACNET_LEGACY ? fmaxf(v[c], 0.0f) : prelu(v[c], alpha[c]);
                             }
                             split_pair(v[0], v[1], w[8 * jr + 0], w[8 * jr + 4]); split_pair(v[2], v[3], w[8 * jr + 1], w[8 * jr + 5]);
                             split_pair(v[4], v[5], w[8 * jr + 2], w[8 * jr + 6]); split_pair(v[6], v[7], w[8 * jr + 3], w[8 * jr + 7]);
@@ -897,6 +954,7 @@ namespace acb
                         tm_st32(buf_d + 8 * (yg + 1), w);
                         ACB_TM_WAIT_ST();
                         ACB_TM_FENCE_BEFORE();
+                        if constexpr (ARNET) __threadfence_block();
                         const uint32_t fa = my_flag_a + 8 * yg;
                         tm_publish(fa, l + 1); tm_publish(fa + 8, l + 1); tm_publish(fa + 16, l + 1); tm_publish(fa + 24, l + 1);
 #ifdef ACB_TM_TRACE
@@ -916,8 +974,49 @@ namespace acb
                         if (!last || !S::TAIL)
                         {
                             // body conv: activation, split, next layer's operand (or the segment's output map)
+                            if (is_res)
+                            {
+                                float x[8];
+                                sx_load(y, x);
+                                __syncwarp();
 #pragma unroll
-                            for (int c = 0; c < 8; c++) v[c] = S::FAM == ACB200_FAMILY_ACNET_LEGACY ? fmaxf(v[c], 0.0f) : prelu(v[c], alpha[c]);
+                                for (int c = 0; c < 8; c++) v[c] = fmaf(v[c], 0.2f, x[c]);
+                                if constexpr (ARNET && S::TAIL)
+                                    if (is_1x1)
+                                    {
+                                        // 1x1 conv over the eight channels, PReLU, + feat (the head's output, kept in global memory by the first segment)
+                                        constexpr int K1 = S::HEAD ? 72 : 0, BT = B0 + 8 * S::NCONV, AT = (S::NCONV / 2) * 8;
+                                        const int gx = clampi(x0 + l + lane, 0, prm.w - 1), gy = y0 + y;
+                                        const float4* f = reinterpret_cast<const float4*>(prm.feat_in + (static_cast<size_t>(gy) * prm.w + gx) * 8);
+                                        const float4 f0 = __ldg(f), f1 = __ldg(f + 1);
+                                        const float ft[8] = { f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w };
+                                        float u[8];
+#pragma unroll
+                                        for (int co = 0; co < 8; co++)
+                                        {
+                                            float t = prm.b[BT + 16 + co];
+#pragma unroll
+                                            for (int ci = 0; ci < 8; ci++) t = fmaf(v[ci], prm.k[K1 + co * 8 + ci], t);
+                                            u[co] = prelu(t, prm.a[AT + 8 + co]) + ft[co];
+                                        }
+#pragma unroll
+                                        for (int c = 0; c < 8; c++) v[c] = u[c];
+                                    }
+                                if (xclamp)
+                                {
+                                    // border strips: lanes outside the image take the edge pixel's value here already, so that what the residual
+                                    // store keeps for them is the replicate-padded map (put_row repeats the shuffle on the packed words)
+                                    const int srcl = min(max(lane, -x0 - l), prm.w - 1 - x0 - l);
+#pragma unroll
+                                    for (int c = 0; c < 8; c++) v[c] = __shfl_sync(0xffffffffu, v[c], srcl);
+                                }
+                                if (!is_1x1) sx_store(y, v);
+                            }
+                            else
+                            {
+#pragma unroll
+                                for (int c = 0; c < 8; c++) v[c] = S::FAM == ACB200_FAMILY_ACNET_LEGACY ? fmaxf(v[c], 0.0f) : prelu(v[c], alpha[c]);
+                            }
                             uint32_t w8[8];
                             split_pair(v[0], v[1], w8[0], w8[4]); split_pair(v[2], v[3], w8[1], w8[5]);
                             split_pair(v[4], v[5], w8[2], w8[6]); split_pair(v[6], v[7], w8[3], w8[7]);
@@ -976,7 +1075,7 @@ namespace acb
                                 }
                             }
                         }
-                        else if constexpr (S::TAIL && S::FAM == ACB200_FAMILY_ACNET)
+                        else if constexpr (S::TAIL && S::FAM != ACB200_FAMILY_ACNET_LEGACY)
                         {
                             // conv 8 -> 4 (+ bias, already in the accumulator), + nearest-upsampled luma, pixel shuffle (Common.hpp:290-342)
                             const int gx = x0 + R + lane, gy = y0 + y;
@@ -1009,6 +1108,7 @@ namespace acb
                     {
                         ACB_TM_WAIT_ST();
                         ACB_TM_FENCE_BEFORE();
+                        if constexpr (ARNET) __threadfence_block();
                         publish_rows(l, yg, k);
                     }
                 }

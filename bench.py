@@ -184,12 +184,10 @@ IMPL_NAMES = {0: "mma.sync", 1: "tcgen05, maps in shared memory", 2: "tcgen05, m
 
 
 def impl_label(model, tensor_impl):
-    """Name of the tensor-engine implementation that runs `model` (library default: 2; ARNet has no TMEM-resident kernel yet)."""
+    """Name of the tensor-engine implementation that runs `model` (library default: 2, the TMEM-resident engine, for ACNetLegacy / ACNet / ARNet)."""
     impl = 2 if tensor_impl is None else tensor_impl
     if model.startswith(("artcnn", "fsrcnnx")):
         return "per-layer tcgen05 MMA (wide families)"
-    if impl == 2 and model.startswith("arnet"):
-        return IMPL_NAMES[0] + " (ARNet: no TMEM-resident kernel)"
     return IMPL_NAMES[impl]
 
 

@@ -291,7 +291,7 @@ def test_full_size_1080p_rgb_exact_engine_equals_the_fma_order_oracle(session):
 FUSED_SHAPES = [(96, 128), (150, 96), (57, 71), (5, 7), (1, 9), (9, 1), (2, 2), (3, 200), (200, 3), (40, 301), (131, 260)]
 
 
-@pytest.mark.parametrize("name", ["acnet-legacy-hdn0", "acnet-legacy-hdn2", "acnet-f8b8-hdn", "acnet-f8b8-gan", "acnet-f8b18"])
+@pytest.mark.parametrize("name", ["acnet-legacy-hdn0", "acnet-legacy-hdn2", "acnet-f8b8-hdn", "acnet-f8b8-gan", "acnet-f8b18", "arnet-f8b8", "arnet-f8b16-hdn"])
 def test_fused_colour_path_is_bit_identical_to_the_separate_kernels(session, name):
     """Colour split inside the first segment's tile load, chroma resize + merge inside the last segment's tail (TmParams): the RGB
     result must equal the three-extra-kernel path bit for bit on every shape -- tile seams, image borders (folded Catmull-Rom taps),
@@ -352,6 +352,27 @@ def test_reference_benchmark_tool_runs_unchanged_against_the_drop_in(w, h, batch
     assert m and "processor: CUDA" in out.stdout, out.stdout
     print("reference benchmark tool %dx%d batch %d threads %d: %s FPS" % (w, h, batch, threads, m.group(1)))
     assert float(m.group(1)) > 50.0
+
+
+@pytest.mark.parametrize("name", ARNETS)
+def test_arnet_on_the_tmem_engine_vs_exact_engine_and_mma_engine(session, name):
+    """ARNet on the TMEM-resident engine (residual through the per-lane store in shared memory, 1x1 + long skip in the tail's epilogue):
+    within the 8-bit bar of the exact engine on odd shapes that cross tile seams and image borders, as close to it as the mma.sync
+    implementation is, and identical from run to run."""
+    m = gpu_model(name)
+    for h, w in ((150, 96), (57, 131), (9, 200), (64, 3)):
+        img = O.noise_u8(h, w, 1, seed=900 + h)
+        session.set_engine(ENGINE_EXACT)
+        want = session.process_host(m, img, 2.0)
+        session.set_engine(ENGINE_TENSOR)
+        got = {}
+        for impl in (0, 2):
+            session.set_tensor_impl(impl)
+            got[impl] = session.process_host(m, img, 2.0)
+            mx, exact = O.compare_u8(got[impl], want)
+            assert mx <= LSB_MAX and exact >= EXACT_MIN, (name, h, w, impl, mx, exact)
+        assert np.array_equal(got[2], session.process_host(m, img, 2.0))
+    session.set_tensor_impl(TENSOR_IMPL)
 
 
 def test_device_resident_path_matches_host_path(session):
