@@ -97,6 +97,13 @@ namespace ac::core
     };
     enum ImreadModes { IMREAD_UNCHANGED = 0, IMREAD_GRAYSCALE = 1, IMREAD_COLOR = 3, IMREAD_RGB = 3, IMREAD_RGBA = 4 };
 
+    // Image file I/O (reference core/src/ImageIO.cpp:20-87, there on stb_image / stb_image_write): own codecs on zlib.  Reads PNG
+    // (non-interlaced), BMP, binary PNM and uncompressed TGA into an 8-bit image with `mode` channels; writes .png / .bmp / .tga by
+    // extension.  JPEG is not supported (imread gives an empty image, imwrite false).  Never throws.
+    AC_CORE_EXPORT Image imdecode(const void* buffer, int size, int mode = IMREAD_UNCHANGED) noexcept;
+    AC_CORE_EXPORT Image imread(const char* filename, int mode = IMREAD_UNCHANGED) noexcept;
+    AC_CORE_EXPORT bool imwrite(const char* filename, const Image& image) noexcept;
+
     // fx, fy > 0: scale factors; otherwise the size of a non-empty dst decides (ImageResize.cpp:136-165)
     AC_CORE_EXPORT void resize(const Image& src, Image& dst, double fx, double fy, int mode = RESIZE_CATMULL_ROM) noexcept;
     AC_CORE_EXPORT Image resize(const Image& src, double fx, double fy, int mode = RESIZE_CATMULL_ROM) noexcept;

@@ -93,6 +93,20 @@ int ac_image_to(const ACImage* const image, void* const data, const int stride)
     return AC_SUCCESS;
 }
 
+int ac_imread(const char* const filename, const int mode, ACImage* const image)
+{
+    if (!image || !filename) return AC_ERROR(AC_EINVAL);
+    ac::core::Image loaded = ac::core::imread(filename, mode);
+    if (loaded.empty()) return AC_ERROR(AC_EIO);
+    assign(image, loaded);
+    return AC_SUCCESS;
+}
+int ac_imwrite(const char* const filename, const ACImage* const image)
+{
+    if (!usable(image) || !filename) return AC_ERROR(AC_EINVAL);
+    return ac::core::imwrite(filename, image->hptr->image) ? AC_SUCCESS : AC_ERROR(AC_EIO);
+}
+
 int ac_resize(const ACImage* const src, ACImage* const dst, const double fx, const double fy, const int mode)
 {
     if (!usable(src) || !usable(dst)) return AC_ERROR(AC_EINVAL);

@@ -2,7 +2,7 @@
 // -- pyac.core.Processor(type="auto", device=0, model="acnet-f8b8-hdn"), .process(src, factor=2.0), __call__ (raises
 // RuntimeError(error()) when !ok()), .ok/.error/.name/__str__, InfoList/CPU/OpenCL/CUDA, pyac.core.resize,
 // ResizeModes / ImreadModes, pyac.specs.ModelList / ProcessorList -- over this library's ac::core.
-// imread / imwrite are not part of this build (no image file I/O on the accelerated path).
+// imread / imwrite run on the drop-in's own PNG / BMP / PNM / TGA codecs (no JPEG).
 #include <cstdint>
 #include <iterator>
 #include <memory>
@@ -116,6 +116,22 @@ PYBIND11_MODULE(pyac, m)
         .value("IMREAD_RGB", ac::core::IMREAD_RGB)
         .value("IMREAD_RGBA", ac::core::IMREAD_RGBA)
         .export_values();
+
+    // binding/python/src/Binding.cpp:142-157: imread returns an (H,W[,C]) uint8 array that owns its image, imwrite takes such an array
+    core.def("imread", [](const char* filename, const ac::core::ImreadModes mode) {
+            auto* img = new Image{ ac::core::imread(filename, mode) };
+            py::capsule owner{ img, [](void* v) { delete static_cast<Image*>(v); } };
+            if (img->empty()) throw std::runtime_error{ std::string{ "pyac.core.imread: cannot read or decode " } + filename };
+            if (img->channels() == 1)
+                return py::array{ py::dtype::of<std::uint8_t>(), { img->height(), img->width() }, { img->stride(), img->pixelSize() }, img->data(), owner };
+            return py::array{ py::dtype::of<std::uint8_t>(), { img->height(), img->width(), img->channels() }, { img->stride(), img->pixelSize(), img->elementSize() }, img->data(), owner };
+        }, py::arg("filename"), py::arg("mode") = ac::core::IMREAD_UNCHANGED);
+    core.def("imwrite", [](const char* filename, const py::array_t<std::uint8_t>& in) {
+            const py::buffer_info src = in.request();
+            if (src.ndim != 2 && src.ndim != 3) throw py::buffer_error{ "Incompatible dimension: expected 2 or 3." };
+            return ac::core::imwrite(filename, Image{ static_cast<int>(src.shape[1]), static_cast<int>(src.shape[0]), src.ndim == 3 ? static_cast<int>(src.shape[2]) : 1,
+                                                       Image::UInt8, src.ptr, static_cast<int>(src.strides[0]) });
+        }, py::arg("filename"), py::arg("image"));
 
     // the reference defaults `mode` to RESIZE_BILINEAR; only RESIZE_CATMULL_ROM upscaling exists on this path
     core.def("resize", [](const py::array& in, const py::object& dsize, const double fx, const double fy, const ac::core::ResizeModes mode) {

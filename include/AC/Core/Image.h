@@ -2,7 +2,7 @@
  * C image API of the B200 drop-in.  Binary-compatible with the reference's libac_c
  * (binding/c/include/AC/Core/Image.h:15-127, implemented in binding/c/src/Binding.cpp:19-159): same POD
  * layout, enum values, function names and ownership rules -- the caller fills the plain fields, the library
- * owns `hptr`.  File I/O (ac_imread / ac_imwrite) is not part of this build (AC_CORE_DISABLE_IMAGE_IO).
+ * owns `hptr`.  File I/O (ac_imread / ac_imwrite) runs on this build's own PNG / BMP / PNM / TGA codecs.
  */
 #ifndef AC_BINDING_C_CORE_IMAGE_H
 #define AC_BINDING_C_CORE_IMAGE_H
@@ -21,9 +21,6 @@
 #   define AC_C_API extern "C" AC_C_EXPORT
 #else
 #   define AC_C_API AC_C_EXPORT
-#endif
-#ifndef AC_CORE_DISABLE_IMAGE_IO
-#   define AC_CORE_DISABLE_IMAGE_IO 1
 #endif
 
 /* (kind << 8) | bytes per element */
@@ -60,6 +57,10 @@ AC_C_API int ac_image_from(ACImage* image, const void* data);
 AC_C_API int ac_image_view(const ACImage* src, ACImage* dst, int x, int y, int w, int h);
 AC_C_API int ac_image_clone(const ACImage* src, ACImage* dst);
 AC_C_API int ac_image_to(const ACImage* image, void* data, int stride);
+/* file I/O (binding/c/include/AC/Core/Image.h:75-76): PNG / BMP / PNM / TGA in, .png / .bmp / .tga out; -AC_EIO when the file cannot
+ * be read, decoded or written (JPEG is not supported by this build's codecs) */
+AC_C_API int ac_imread(const char* filename, int mode, ACImage* image);
+AC_C_API int ac_imwrite(const char* filename, const ACImage* image);
 /* image operations; both images need a handle (create/map/from/...) */
 AC_C_API int ac_resize(const ACImage* src, ACImage* dst, double fx, double fy, int mode);
 AC_C_API int ac_rgb2yuv(const ACImage* rgb, ACImage* yuv);

@@ -191,6 +191,102 @@ def test_reference_benchmark_tool_links_against_the_drop_in():
         assert "FPS:" in out.stdout
 
 
+def _png_bytes(arr, depth=8, palette=None, interlace=0):
+    """A PNG file built by hand with zlib (filter 0 on even rows, filter 2 'up' on odd rows), for the decoder tests."""
+    import struct
+    import zlib
+
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d))
+    h, w = arr.shape[:2]
+    c = 1 if arr.ndim == 2 else arr.shape[2]
+    ctype = 3 if palette is not None else {1: 0, 2: 4, 3: 2, 4: 6}[c]
+    rows = arr.reshape(h, -1).astype(">u2" if depth == 16 else np.uint8)
+    raw = b""
+    prev = np.zeros(rows.shape[1] * rows.dtype.itemsize, np.uint8)
+    for y in range(h):
+        cur = np.frombuffer(rows[y].tobytes(), np.uint8)
+        if y % 2:
+            raw += b"\x02" + ((cur.astype(np.int16) - prev) & 255).astype(np.uint8).tobytes()
+        else:
+            raw += b"\x00" + cur.tobytes()
+        prev = cur
+    out = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, interlace))
+    if palette is not None:
+        out += chunk(b"PLTE", palette.astype(np.uint8).tobytes())
+    return out + chunk(b"IDAT", zlib.compress(raw)) + chunk(b"IEND", b"")
+
+
+def test_image_file_io_roundtrips_and_decodes(tmp_path):
+    """ac::core::imread / imwrite (reference core/src/ImageIO.cpp:20-87) on the drop-in's own codecs, through pyac and the C binding:
+    write -> read round trips for .png / .bmp / .tga, hand-built PNGs (8 / 16 bit, palette, padded rows), PNM, the decoder's channel
+    conversions, and the failure paths (JPEG, missing file, interlaced PNG) -- all without a GPU."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "anime4kcpp_b200"))
+    import pyac
+    rs = np.random.RandomState(7)
+    for c in (1, 3, 4):
+        img = rs.randint(0, 256, size=(37, 53) if c == 1 else (37, 53, c), dtype=np.uint8)
+        for ext in ("png", "bmp", "tga"):
+            path = str(tmp_path / ("rt%d.%s" % (c, ext)))
+            assert pyac.core.imwrite(path, img)
+            back = pyac.core.imread(path)
+            want = img if not (ext == "bmp" and c == 1) else np.repeat(img[:, :, None], 3, axis=2)     # BMP has no gray form
+            assert back.dtype == np.uint8 and back.shape == want.shape and np.array_equal(back, want), (c, ext)
+    # a strided view (padded rows) is written row by row
+    big = rs.randint(0, 256, size=(20, 64, 3), dtype=np.uint8)
+    view = big[:, 5:40]
+    assert pyac.core.imwrite(str(tmp_path / "view.png"), view) and np.array_equal(pyac.core.imread(str(tmp_path / "view.png")), view)
+    # hand-built PNGs: 8-bit RGB / gray+alpha with the 'up' filter, 16-bit gray (high byte kept), palette
+    rgb = rs.randint(0, 256, size=(9, 11, 3), dtype=np.uint8)
+    (tmp_path / "a.png").write_bytes(_png_bytes(rgb))
+    assert np.array_equal(pyac.core.imread(str(tmp_path / "a.png")), rgb)
+    ga = rs.randint(0, 256, size=(6, 7, 2), dtype=np.uint8)
+    (tmp_path / "ga.png").write_bytes(_png_bytes(ga))
+    assert np.array_equal(pyac.core.imread(str(tmp_path / "ga.png")), ga)
+    g16 = rs.randint(0, 65536, size=(5, 8)).astype(np.uint16)
+    (tmp_path / "g16.png").write_bytes(_png_bytes(g16, depth=16))
+    assert np.array_equal(pyac.core.imread(str(tmp_path / "g16.png")), (g16 >> 8).astype(np.uint8))
+    pal = rs.randint(0, 256, size=(16, 3), dtype=np.uint8)
+    idx = rs.randint(0, 16, size=(7, 9)).astype(np.uint8)
+    (tmp_path / "p.png").write_bytes(_png_bytes(idx, palette=pal))
+    assert np.array_equal(pyac.core.imread(str(tmp_path / "p.png")), pal[idx])
+    # PNM
+    (tmp_path / "g.pgm").write_bytes(b"P5\n# comment\n11 9\n255\n" + rgb[:, :, 0].tobytes())
+    assert np.array_equal(pyac.core.imread(str(tmp_path / "g.pgm")), rgb[:, :, 0])
+    (tmp_path / "c.ppm").write_bytes(b"P6 11 9 255\n" + rgb.tobytes())
+    assert np.array_equal(pyac.core.imread(str(tmp_path / "c.ppm")), rgb)
+    # channel conversions of the decoder: luma = (77 r + 150 g + 29 b) >> 8, alpha filled with 255 / dropped
+    gray = pyac.core.imread(str(tmp_path / "a.png"), pyac.core.IMREAD_GRAYSCALE)
+    want = ((rgb[:, :, 0].astype(np.int32) * 77 + rgb[:, :, 1].astype(np.int32) * 150 + rgb[:, :, 2].astype(np.int32) * 29) >> 8).astype(np.uint8)
+    assert gray.shape == (9, 11) and np.array_equal(gray, want)
+    rgba = pyac.core.imread(str(tmp_path / "a.png"), pyac.core.IMREAD_RGBA)
+    assert rgba.shape == (9, 11, 4) and np.array_equal(rgba[:, :, :3], rgb) and (rgba[:, :, 3] == 255).all()
+    assert np.array_equal(pyac.core.imread(str(tmp_path / "g.pgm"), pyac.core.IMREAD_COLOR), np.repeat(rgb[:, :, :1], 3, axis=2))
+    # failure paths: never a crash, never garbage
+    assert not pyac.core.imwrite(str(tmp_path / "x.jpg"), rgb) and not pyac.core.imwrite(str(tmp_path / "noext"), rgb)
+    with pytest.raises(RuntimeError):
+        pyac.core.imread(str(tmp_path / "missing.png"))
+    (tmp_path / "i.png").write_bytes(_png_bytes(rgb, interlace=1))
+    with pytest.raises(RuntimeError):
+        pyac.core.imread(str(tmp_path / "i.png"))
+    (tmp_path / "t.png").write_bytes(_png_bytes(rgb)[:60])
+    with pytest.raises(RuntimeError):
+        pyac.core.imread(str(tmp_path / "t.png"))
+    # the C binding: ac_imread / ac_imwrite with the reference's return codes
+    lib = A.lib()
+    lib.ac_imread.argtypes = [C.c_char_p, C.c_int, C.POINTER(ACImage)]
+    lib.ac_imwrite.argtypes = [C.c_char_p, C.POINTER(ACImage)]
+    im = _cimage(lib, 0, 0, 0, 0)
+    assert lib.ac_imread(str(tmp_path / "a.png").encode(), 0, im) == 0
+    assert (im.contents.width, im.contents.height, im.contents.channels, im.contents.element_type) == (11, 9, 3, 1)
+    got = np.ctypeslib.as_array(C.cast(im.contents.ptr, C.POINTER(C.c_ubyte)), shape=(9, im.contents.stride))[:, :33].reshape(9, 11, 3)
+    assert np.array_equal(got, rgb)
+    assert lib.ac_imwrite(str(tmp_path / "c.bmp").encode(), im) == 0 and np.array_equal(pyac.core.imread(str(tmp_path / "c.bmp")), rgb)
+    assert lib.ac_imread(str(tmp_path / "missing.png").encode(), 0, im) == -5 and lib.ac_imwrite(str(tmp_path / "c.jpg").encode(), im) == -5       # -AC_EIO
+    lib.ac_image_free(C.byref(im))
+
+
 def test_session_without_device_fails_loudly():
     if A.device_count() == 0:
         with pytest.raises(A.Acb200Error):
