@@ -439,6 +439,16 @@ def test_row_bands_reproduce_the_whole_image_bit_for_bit(session, name, factor, 
                 mx, exact = O.compare_u8(out, whole)
                 assert mx <= 1 and exact >= 0.999, (engine, impl, n_bands, mx, exact)
     session.set_tensor_impl(TENSOR_IMPL)
+    # the multi-GPU shape: every band written into a buffer that holds just its own rows (process_band(out_y0=)), then concatenated
+    session.set_engine(ENGINE_EXACT)
+    whole = session.process_host(m, img, factor)
+    parts = []
+    for b in range(3):
+        _, _, oy0, oy1 = A.band_plan(img.shape[0], factor, m.halo(), 3, b)
+        part = np.zeros((oy1 - oy0,) + whole.shape[1:], np.uint8)
+        A.process_band(session, m, img, factor, 3, b, part, out_y0=oy0)
+        parts.append(part)
+    assert np.array_equal(np.concatenate(parts, axis=0), whole)
 
 
 def test_frame_stream_delivers_in_order_and_matches_single_calls(session):
