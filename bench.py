@@ -323,7 +323,9 @@ def run_ours(args):
 
     # ---- end to end through the C binding with host buffers ---------------------------------------------------------
     e2e = None
-    n_threads = args.threads
+    # workers of the ordered streams: 4 per GPU; callers of the e2e legs: see --threads
+    n_threads = 4
+    e2e_threads = args.threads if args.threads else (4 if world <= 2 else 2 if world <= 4 else 1)
     pin_in = torch.from_numpy(host_frames).pin_memory()
     pin_out = torch.empty((B, 2 * H, 2 * W, CH), dtype=torch.uint8).pin_memory()
     lib.ac_processor_alloc.restype = C.POINTER(ACProcessor)
@@ -350,7 +352,7 @@ def run_ours(args):
                     return
                 rc = lib.ac_processor_process(proc, srcs[i % B], dsts[i % B], C.c_double(FACTOR))
                 assert rc == 0, lib.ac_processor_error(proc)
-        ts = [threading.Thread(target=worker) for _ in range(n_threads)]
+        ts = [threading.Thread(target=worker) for _ in range(e2e_threads)]
         [x.start() for x in ts]
         [x.join() for x in ts]
 
@@ -387,7 +389,7 @@ def run_ours(args):
                     d_in[i % B].copy_(pin_in[i % B], non_blocking=True)
                     pin_out[i % B].copy_(d_out[i % B], non_blocking=True)
                     st_.synchronize()
-        ts = [threading.Thread(target=worker, args=(k,)) for k in range(n_threads)]
+        ts = [threading.Thread(target=worker, args=(k,)) for k in range(e2e_threads)]
         [x.start() for x in ts]
         [x.join() for x in ts]
     copy_steps(1)
@@ -401,7 +403,7 @@ def run_ours(args):
     copy_value = OUT_MP * frames_total / float(tcp.item())
     copy_gbs = frames_total * 5 * W * H * CH / float(tcp.item()) / 1e9
     e2e = {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": B * W * H * CH, "d2h_bytes_per_step": B * 4 * W * H * CH,
-           "fps": frames_total / float(te.item()), "caller_threads": n_threads, "api": "ac_processor_process (libac_c binding), pinned host images",
+           "fps": frames_total / float(te.item()), "caller_threads": e2e_threads, "api": "ac_processor_process (libac_c binding), pinned host images",
            "copy_ceiling": {"value": copy_value, "unit": "MP/s", "gb_per_s_both_directions": copy_gbs,
                             "what": "the same pinned H2D + D2H bytes per frame from the same caller threads, no kernels; all ranks at once"},
            "frac_of_copy_ceiling": e2e_value / copy_value}
@@ -743,7 +745,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="acnet-legacy-hdn0")
     ap.add_argument("--batch", type=int, default=16)
-    ap.add_argument("--threads", type=int, default=4, help="caller threads sharing the processor in the e2e leg")
+    ap.add_argument("--threads", type=int, default=None,
+                    help="caller threads per rank sharing the processor in the host-fed e2e legs (default: 4 on 1-2 GPUs, 2 on 4, 1 on 8 -- the "
+                         "boxes' aggregate copy ceiling is reached with fewer callers as ranks are added, profiles/r02_e2e_caller_thread_sweep_n8.txt)")
     ap.add_argument("--streams", type=int, default=2, help="sessions / CUDA streams the device-resident batch is dealt over")
     ap.add_argument("--engine", type=int, default=2, help="0 exact FFMA, 1 tensor MMA, 2 auto")
     ap.add_argument("--tensor-impl", type=int, default=None, help="0 mma.sync, 1 tcgen05 (default: library default)")
