@@ -65,7 +65,11 @@ namespace acb
     // favours the higher warp id among eligible warps, and an issuer that cannot get an issue slot starves the tensor pipe.
     constexpr int TM_EPI_WARP0 = 0;
     constexpr int TM_ISS_WARP0 = 4 * ACB_TM_EPI_SETS;
-    constexpr int TM_CHUNK = 4;                     // consecutive steps (input rows) per chunk, >= 3
+#ifndef ACB_TM_CHUNK
+#define ACB_TM_CHUNK 4
+#endif
+    constexpr int TM_CHUNK = ACB_TM_CHUNK;          // consecutive steps (input rows) per chunk: 3 or 4 (a chunk record holds TM_CHUNK + 2 <= 6 waits)
+    static_assert(TM_CHUNK == 3 || TM_CHUNK == 4, "chunk records are laid out for three or four steps");
 #ifndef ACB_TM_LAG
 #define ACB_TM_LAG 4
 #endif
@@ -80,7 +84,8 @@ namespace acb
     constexpr int TM_N_BARS = TM_GMAX + TM_MAX_GROUPS + 1;
     constexpr int TM_OFF_GEOM = TM_OFF_BAR + TM_N_BARS * 8 + 8;
     constexpr int TM_OFF_STEPS = ((TM_OFF_GEOM + 3 * (TM_MAX_R + 2) * 4 + 4 + 15) / 16) * 16;      // the issuers' step program, 48 bytes per input row and layer
-    constexpr int TM_MAX_CHUNKS = TM_MAX_R * ((TM_GMAX + 2 + 3) / 4);     // chunks of up to four steps, never across layers
+    constexpr int TM_MAX_CHUNKS = TM_MAX_R * ((TM_GMAX + 2 + TM_CHUNK - 1) / TM_CHUNK);     // chunks of up to TM_CHUNK steps, never across layers
+    static_assert(TM_MAX_CHUNKS <= 32 * TM_ISSUERS_DECL, "one issuer-warp thread builds one chunk record");
     constexpr int TM_MAX_STEPS = 4 * TM_MAX_CHUNKS;
     constexpr int TM_CHUNK_WORDS = 20;              // one record per chunk: 4 operand words, 6 waits, 8 commits, 2 spare
 #ifdef ACB_TM_TRACE
