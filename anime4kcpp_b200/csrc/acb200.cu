@@ -100,7 +100,7 @@ namespace
             if (ACB_SPLIT_CHAINS)
             {
                 m.chain.push_back({ SEG_LEGACY_A, 0, 0, 0 });
-                m.chain.push_back({ SEG_LEGACY_B, 72 + 576 * 3, 8 + 8 * 3, 0 });
+                m.chain.push_back({ SEG_LEGACY_B, 72 + 576 * LEGACY_SPLIT, 8 + 8 * LEGACY_SPLIT, 0 });
             }
             else m.chain.push_back({ SEG_LEGACY_FULL, 0, 0, 0 });
         }
@@ -110,16 +110,18 @@ namespace
             else if (m.blocks == 8 && ACB_SPLIT_CHAINS)
             {
                 m.chain.push_back({ SEG_ACNET_B8_A, 0, 0, 0 });
-                m.chain.push_back({ SEG_ACNET_B8_B, 72 + 576 * 4, 8 + 8 * 4, 8 + 8 * 4 });
+                m.chain.push_back({ SEG_ACNET_B8_B, 72 + 576 * ACNET_SPLIT, 8 + 8 * ACNET_SPLIT, 8 + 8 * ACNET_SPLIT });
             }
             else if (m.blocks == 8) m.chain.push_back({ SEG_ACNET_B8, 0, 0, 0 });
             else if (ACB_SPLIT_CHAINS)
             {
                 // 18 body convs as head + 4 | 5 | 5 | 4 + tail (T = 48, 46, 46, 46) instead of head + 9 | 9 + tail (T = 38, 36)
                 m.chain.push_back({ SEG_ACNET_B8_A, 0, 0, 0 });
-                m.chain.push_back({ SEG_ACNET_MID5, 72 + 576 * 4, 8 + 8 * 4, 8 + 8 * 4 });
-                m.chain.push_back({ SEG_ACNET_MID5, 72 + 576 * 9, 8 + 8 * 9, 8 + 8 * 9 });
-                m.chain.push_back({ SEG_ACNET_B8_B, 72 + 576 * 14, 8 + 8 * 14, 8 + 8 * 14 });
+                constexpr int S1 = ACNET_SPLIT, S2 = S1 + 5, S3 = S2 + 5;
+                static_assert(S3 + (8 - ACNET_SPLIT) == 18, "ACNet-B18: head + S | 5 | 5 | (8 - S) + tail");
+                m.chain.push_back({ SEG_ACNET_MID5, 72 + 576 * S1, 8 + 8 * S1, 8 + 8 * S1 });
+                m.chain.push_back({ SEG_ACNET_MID5, 72 + 576 * S2, 8 + 8 * S2, 8 + 8 * S2 });
+                m.chain.push_back({ SEG_ACNET_B8_B, 72 + 576 * S3, 8 + 8 * S3, 8 + 8 * S3 });
             }
             else
             {

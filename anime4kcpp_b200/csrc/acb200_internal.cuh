@@ -27,8 +27,8 @@ namespace acbh
         SEG_ARNET_FIRST,    // <ARNET, head, ARNET_SEG, ->
         SEG_ARNET_MID,      // <ARNET, -, ARNET_SEG, ->
         SEG_ARNET_LAST,     // <ARNET, -, ARNET_SEG - 2, tail>
-        SEG_LEGACY_A,       // <LEGACY, head, 3, ->
-        SEG_LEGACY_B,       // <LEGACY, -, 4, tail>
+        SEG_LEGACY_A,       // <LEGACY, head, LEGACY_SPLIT, ->
+        SEG_LEGACY_B,       // <LEGACY, -, 7 - LEGACY_SPLIT, tail>
         SEG_ACNET_B8_A,     // <ACNET, head, 4, ->
         SEG_ACNET_B8_B,     // <ACNET, -, 4, tail>
         SEG_ACNET_MID5,     // <ACNET, -, 5, ->
@@ -46,10 +46,20 @@ namespace acbh
     using SegArnetFirst = Seg<ACB200_FAMILY_ARNET, true, ARNET_SEG, false>;
     using SegArnetMid = Seg<ACB200_FAMILY_ARNET, false, ARNET_SEG, false>;
     using SegArnetLast = Seg<ACB200_FAMILY_ARNET, false, ARNET_SEG - 2, true>;
-    using SegLegacyA = Seg<ACB200_FAMILY_ACNET_LEGACY, true, 3, false>;
-    using SegLegacyB = Seg<ACB200_FAMILY_ACNET_LEGACY, false, 4, true>;
-    using SegAcnetB8A = Seg<ACB200_FAMILY_ACNET, true, 4, false>;
-    using SegAcnetB8B = Seg<ACB200_FAMILY_ACNET, false, 4, true>;
+    // ACNetLegacy's seven body convs (+ the tail's conv) as head + LEGACY_SPLIT | (7 - LEGACY_SPLIT) + tail
+#ifndef ACB_LEGACY_SPLIT
+#define ACB_LEGACY_SPLIT 4
+#endif
+    constexpr int LEGACY_SPLIT = ACB_LEGACY_SPLIT;
+    using SegLegacyA = Seg<ACB200_FAMILY_ACNET_LEGACY, true, LEGACY_SPLIT, false>;
+    using SegLegacyB = Seg<ACB200_FAMILY_ACNET_LEGACY, false, 7 - LEGACY_SPLIT, true>;
+    // ACNet-B8 as head + ACNET_SPLIT | (8 - ACNET_SPLIT) + tail; ACNet-B18 as head + ACNET_SPLIT | 5 | 5 | (8 - ACNET_SPLIT) + tail
+#ifndef ACB_ACNET_SPLIT
+#define ACB_ACNET_SPLIT 4
+#endif
+    constexpr int ACNET_SPLIT = ACB_ACNET_SPLIT;
+    using SegAcnetB8A = Seg<ACB200_FAMILY_ACNET, true, ACNET_SPLIT, false>;
+    using SegAcnetB8B = Seg<ACB200_FAMILY_ACNET, false, 8 - ACNET_SPLIT, true>;
     using SegAcnetMid5 = Seg<ACB200_FAMILY_ACNET, false, 5, false>;
 #ifndef ACB_SPLIT_CHAINS
 #define ACB_SPLIT_CHAINS 1
