@@ -191,9 +191,10 @@ def impl_label(model, tensor_impl):
     return IMPL_NAMES[impl]
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one luma pass (both segment launches), ncu --set full --cache-control none (caches NOT
-# flushed between replays: the steady-state figure), 1920x1080 u8 plane; profiles/r02_tm_steady_ncu_summary.json
-STEADY_TRAFFIC = {("acnet-legacy", 2): 40646656 + 22812672}     # segment A (head + 3 convs) + segment B (5 convs + tail)
+# dram__bytes_read.sum + dram__bytes_write.sum of one luma pass (both segment launches), ncu --cache-control none (caches NOT flushed
+# between replays: the steady-state figure), 1920x1080 u8 plane, ACNetLegacy as head + 4 | 3 + tail: profiles/r02_final_luma_pass_traffic.csv
+# (two consecutive passes: 66.8 and 61.3 MB; segment A writes the inter-segment map through to DRAM, segment B reads it out of L2)
+STEADY_TRAFFIC = {("acnet-legacy", 2): (66821632 + 61305856) // 2}
 
 
 def luma_roofline(A, torch, sess, model, name, d_plane, stream, peaks, reps):
