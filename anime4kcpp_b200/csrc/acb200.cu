@@ -445,6 +445,27 @@ namespace
 {
     size_t pitch_of(int w, int c, int es) { return (static_cast<size_t>(w) * c * es + 255) & ~static_cast<size_t>(255); }
 
+    // Staging a host image on the device: when the host rows are 16-byte multiples and not much wider than a line, the device copy
+    // keeps the HOST pitch, so the transfer is one contiguous block instead of a row-by-row (2-D) copy -- a 2-D copy of short rows
+    // (960-byte chroma rows, 1920-byte luma rows) reaches well under the PCIe rate.  Every kernel takes arbitrary pitches.
+    // `to_host`: the block is WRITTEN to host memory, so it may only be used for tight rows -- the bytes between the rows of a strided
+    // view belong to someone else.  Towards the device a padded host pitch is fine (the padding is read, never used).
+    size_t staging_pitch(int host_stride, size_t line, int w, int c, int es, bool to_host)
+    {
+        static const bool off = [] { const char* e = std::getenv("ACB200_CONTIG_COPY"); return e && e[0] == '0'; }();     // A/B switch
+        const size_t hs = static_cast<size_t>(host_stride);
+        const bool ok = to_host ? (hs == line && line % 4 == 0) : (hs >= line && hs % 16 == 0 && hs <= line + line / 4 + 256);
+        return (!off && ok) ? hs : pitch_of(w, c, es);
+    }
+    // rows of `line` bytes between host memory (pitch hp) and device memory (pitch dp): one block when the pitches agree
+    cudaError_t copy_rows(void* dst, size_t dpitch, const void* src, size_t spitch, size_t line, int rows, cudaMemcpyKind kind, cudaStream_t st)
+    {
+        // (towards the host only tight rows: equal pitches alone do not make the bytes between the rows ours to write)
+        if (dpitch == spitch && rows > 0 && (kind == cudaMemcpyHostToDevice || spitch == line))
+            return cudaMemcpyAsync(dst, src, spitch * static_cast<size_t>(rows - 1) + line, kind, st);
+        return cudaMemcpy2DAsync(dst, dpitch, src, spitch, line, rows, kind, st);
+    }
+
     // what the fused colour path hands to the first and last segment of a chain (see TmParams)
     struct FusedColour
     {
@@ -936,16 +957,16 @@ extern "C"
         const size_t line_in = static_cast<size_t>(w) * c * es, line_out = static_cast<size_t>(ow) * c * es;
         if (src_stride < static_cast<int>(line_in)) src_stride = static_cast<int>(line_in);
         if (dst_stride < static_cast<int>(line_out)) dst_stride = static_cast<int>(line_out);
-        const size_t sp = pitch_of(w, c, es), dp = pitch_of(ow, c, es);
+        const size_t sp = staging_pitch(src_stride, line_in, w, c, es, false), dp = staging_pitch(dst_stride, line_out, ow, c, es, true);
         if ((rc = ensure(s, s->stream, s->src, sp * h)) != ACB200_OK) return rc;
         if ((rc = ensure(s, s->stream, s->dst, dp * oh)) != ACB200_OK) return rc;
-        ACB_CUDA(s, cudaMemcpy2DAsync(s->src.p, sp, src, src_stride, line_in, h, cudaMemcpyHostToDevice, s->stream));
+        ACB_CUDA(s, copy_rows(s->src.p, sp, src, src_stride, line_in, h, cudaMemcpyHostToDevice, s->stream));
         ACB_CUDA(s, cudaEventRecord(s->ev0, s->stream));
         if ((rc = process_on_device(s, m, s->stream, s->src.p, w, h, c, static_cast<int>(sp), type, plan, s->dst.p, static_cast<int>(dp))) != ACB200_OK) return rc;
         ACB_CUDA(s, cudaEventRecord(s->ev1, s->stream));
         s->timed = true;
-        ACB_CUDA(s, cudaMemcpy2DAsync(dst, dst_stride, static_cast<const uint8_t*>(s->dst.p) + static_cast<size_t>(out_y0) * dp, dp, line_out, out_y1 - out_y0,
-                                      cudaMemcpyDeviceToHost, s->stream));
+        ACB_CUDA(s, copy_rows(dst, dst_stride, static_cast<const uint8_t*>(s->dst.p) + static_cast<size_t>(out_y0) * dp, dp, line_out, out_y1 - out_y0,
+                              cudaMemcpyDeviceToHost, s->stream));
         ACB_CUDA(s, cudaStreamSynchronize(s->stream));
         return ACB200_OK;
     }
@@ -976,21 +997,22 @@ extern "C"
         acb200_plane din[3], dout[3];
         for (int i = 0; i < planes; i++)
         {
-            const size_t ip = pitch_of(src[i].width, src[i].channel, es), op = pitch_of(dst[i].width, dst[i].channel, es);
+            const size_t iline = static_cast<size_t>(src[i].width) * src[i].channel * es, oline = static_cast<size_t>(dst[i].width) * dst[i].channel * es;
+            const size_t ip = staging_pitch(frame_stride(src[i], es), iline, src[i].width, src[i].channel, es, false);
+            const size_t op = staging_pitch(frame_stride(dst[i], es), oline, dst[i].width, dst[i].channel, es, true);
             if ((rc = ensure(s, s->stream, s->pin[i], ip * src[i].height)) != ACB200_OK) return rc;
             if ((rc = ensure(s, s->stream, s->pout[i], op * dst[i].height)) != ACB200_OK) return rc;
             din[i] = src[i]; din[i].data = static_cast<unsigned char*>(s->pin[i].p); din[i].stride = static_cast<int>(ip);
             dout[i] = dst[i]; dout[i].data = static_cast<unsigned char*>(s->pout[i].p); dout[i].stride = static_cast<int>(op);
-            ACB_CUDA(s, cudaMemcpy2DAsync(din[i].data, ip, src[i].data, frame_stride(src[i], es), static_cast<size_t>(src[i].width) * src[i].channel * es, src[i].height,
-                                          cudaMemcpyHostToDevice, s->stream));
+            ACB_CUDA(s, copy_rows(din[i].data, ip, src[i].data, frame_stride(src[i], es), iline, src[i].height, cudaMemcpyHostToDevice, s->stream));
         }
         ACB_CUDA(s, cudaEventRecord(s->ev0, s->stream));
         if ((rc = process_frame_on_device(s, m, s->stream, din, dout, planes, type, shift, plan)) != ACB200_OK) return rc;
         ACB_CUDA(s, cudaEventRecord(s->ev1, s->stream));
         s->timed = true;
         for (int i = 0; i < planes; i++)
-            ACB_CUDA(s, cudaMemcpy2DAsync(dst[i].data, frame_stride(dst[i], es), dout[i].data, dout[i].stride, static_cast<size_t>(dst[i].width) * dst[i].channel * es, dst[i].height,
-                                          cudaMemcpyDeviceToHost, s->stream));
+            ACB_CUDA(s, copy_rows(dst[i].data, frame_stride(dst[i], es), dout[i].data, dout[i].stride, static_cast<size_t>(dst[i].width) * dst[i].channel * es, dst[i].height,
+                                  cudaMemcpyDeviceToHost, s->stream));
         ACB_CUDA(s, cudaStreamSynchronize(s->stream));
         return ACB200_OK;
     }

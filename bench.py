@@ -327,6 +327,7 @@ def run_ours(args):
     # workers of the ordered streams: 4 per GPU; callers of the e2e legs: see --threads
     n_threads = 4
     e2e_threads = args.threads if args.threads else (4 if world <= 2 else 2 if world <= 4 else 1)
+    yuv_threads = args.yuv_threads if args.yuv_threads else 4
     pin_in = torch.from_numpy(host_frames).pin_memory()
     pin_out = torch.empty((B, 2 * H, 2 * W, CH), dtype=torch.uint8).pin_memory()
     lib.ac_processor_alloc.restype = C.POINTER(ACProcessor)
@@ -465,7 +466,7 @@ def run_ours(args):
                         return
                     rc = lib.ac_processor_process_frame(proc, pl_in[i % B], pl_out[i % B], 3, 1, 0, FACTOR)
                     assert rc == 0, lib.ac_processor_error(proc)
-            ts = [threading.Thread(target=worker) for _ in range(n_threads)]
+            ts = [threading.Thread(target=worker) for _ in range(yuv_threads)]
             [x.start() for x in ts]
             [x.join() for x in ts]
         yuv_e2e_steps(2)
@@ -482,7 +483,7 @@ def run_ours(args):
                "value": OUT_MP * frames_total / (yuv_ms / 1e3), "unit": "MP/s", "fps": frames_total / (yuv_ms / 1e3),
                "e2e": {"value": OUT_MP * frames_total / float(tye.item()), "unit": "MP/s", "fps": frames_total / float(tye.item()),
                        "h2d_bytes_per_step": B * W * H * 3 // 2, "d2h_bytes_per_step": B * 4 * W * H * 3 // 2,
-                       "api": "ac_processor_process_frame (C binding extension), pinned host planes", "caller_threads": n_threads}}
+                       "api": "ac_processor_process_frame (C binding extension), pinned host planes", "caller_threads": yuv_threads}}
 
     # ---- a stream of 256 frames through the ordered multi-worker frame stream (the worker / ordering core
     #      of the reference's video filter), packed RGB and planar YUV420, host buffers in and out; wall clock, max over ranks -------
@@ -749,6 +750,7 @@ def main():
     ap.add_argument("--threads", type=int, default=None,
                     help="caller threads per rank sharing the processor in the host-fed e2e legs (default: 4 on 1-2 GPUs, 2 on 4, 1 on 8 -- the "
                          "boxes' aggregate copy ceiling is reached with fewer callers as ranks are added, profiles/r02_e2e_caller_thread_sweep_n8.txt)")
+    ap.add_argument("--yuv-threads", type=int, default=None, help="caller threads per rank of the planar-YUV420 e2e leg (default 4)")
     ap.add_argument("--streams", type=int, default=2, help="sessions / CUDA streams the device-resident batch is dealt over")
     ap.add_argument("--engine", type=int, default=2, help="0 exact FFMA, 1 tensor MMA, 2 auto")
     ap.add_argument("--tensor-impl", type=int, default=None, help="0 mma.sync, 1 tcgen05 (default: library default)")
