@@ -287,6 +287,26 @@ def test_image_file_io_roundtrips_and_decodes(tmp_path):
     lib.ac_image_free(C.byref(im))
 
 
+def test_pinned_host_allocation_entry_points():
+    """acb200_host_alloc / acb200_host_free (page-locked staging memory, also what ac::core::Image's pool is built on): NULL without a
+    usable device -- callers fall back to their own memory, nothing is emulated -- and a writable block with one."""
+    lib = A.lib()
+    lib.acb200_host_alloc.restype = C.c_void_p
+    lib.acb200_host_alloc.argtypes = [C.c_size_t]
+    lib.acb200_host_free.argtypes = [C.c_void_p]
+    lib.acb200_host_free.restype = None
+    p = lib.acb200_host_alloc(1 << 20)
+    if A.device_count() == 0:
+        assert not p
+    else:
+        assert p
+        C.memset(p, 0x5a, 1 << 20)
+        assert C.string_at(p + (1 << 20) - 1, 1) == b"\x5a"
+        lib.acb200_host_free(p)
+    lib.acb200_host_free(None)          # harmless
+    assert not lib.acb200_host_alloc(0)
+
+
 def test_session_without_device_fails_loudly():
     if A.device_count() == 0:
         with pytest.raises(A.Acb200Error):
