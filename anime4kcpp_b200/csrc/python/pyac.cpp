@@ -54,12 +54,22 @@ namespace
     py::array upscale(Processor& self, const py::array& in, const double factor)
     {
         const ArrayView s = describe(in.request());
-        py::array out = allocate(in, static_cast<int>(s.h * factor), static_cast<int>(s.w * factor), s.c, s.planar);
-        const py::buffer_info oinfo = out.request();
-        Image src{ s.w, s.h, s.c, s.type, s.data, s.stride };
-        Image dst{ static_cast<int>(s.w * factor), static_cast<int>(s.h * factor), s.c, s.type, oinfo.ptr, static_cast<int>(oinfo.strides[0]) };
-        self.process(src, dst, factor);
-        return out;
+        const int ow = static_cast<int>(s.w * factor), oh = static_cast<int>(s.h * factor);
+        if (ow <= 0 || oh <= 0) throw py::value_error{ "empty result size" };
+        // The result lives in an ac::core::Image with tight rows -- page-locked memory from the image pool on a GPU box, so the
+        // device-to-host copy runs at the PCIe rate -- and the returned array keeps that image alive (as imread's does).  The GIL is
+        // released for the call: Python threads sharing one processor overlap like the C++ callers of tools/benchmark.
+        const int es = s.type & 0xff;
+        auto* dst = new Image{ ow, oh, s.c, static_cast<Image::ElementType>(s.type), ow * s.c * es };
+        py::capsule owner{ dst, [](void* v) { delete static_cast<Image*>(v); } };
+        if (dst->empty()) throw std::bad_alloc{};
+        {
+            Image src{ s.w, s.h, s.c, static_cast<Image::ElementType>(s.type), s.data, s.stride };
+            py::gil_scoped_release release;
+            self.process(src, *dst, factor);
+        }
+        if (s.planar) return py::array{ in.dtype(), { oh, ow }, { dst->stride(), es }, dst->data(), owner };
+        return py::array{ in.dtype(), { oh, ow, s.c }, { dst->stride(), s.c * es, es }, dst->data(), owner };
     }
 }
 
