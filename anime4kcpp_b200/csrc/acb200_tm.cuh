@@ -352,7 +352,7 @@ namespace acb
 #pragma unroll 1
                 for (int i0 = 0; i0 < PER; i0 += BATCH)
                 {
-                    uint32_t c0[BATCH], c1[BATCH];
+                    uint32_t c0[BATCH];
 #pragma unroll
                     for (int i = 0; i < BATCH; i++)
                     {
@@ -362,9 +362,7 @@ namespace acb
                         const int gy = clampi(y0 - 1 + ly, 0, prm.h - 1), gx0 = strip * SW - R - 1;
                         const uint8_t* srow = prm.rgb_src + static_cast<size_t>(gy) * prm.rgb_pitch;
                         const uint8_t* pa = srow + 3 * clampi(gx0 + lane, 0, prm.w - 1);
-                        const uint8_t* pb = srow + 3 * clampi(gx0 + 32 + (lane & 1), 0, prm.w - 1);
                         c0[i] = __ldg(pa) | (static_cast<uint32_t>(__ldg(pa + 1)) << 8) | (static_cast<uint32_t>(__ldg(pa + 2)) << 16);
-                        c1[i] = __ldg(pb) | (static_cast<uint32_t>(__ldg(pb + 1)) << 8) | (static_cast<uint32_t>(__ldg(pb + 2)) << 16);
                     }
 #pragma unroll
                     for (int i = 0; i < BATCH; i++)
@@ -384,8 +382,18 @@ namespace acb
                                 if (prm.y_out != nullptr) prm.y_out[static_cast<size_t>(gy) * prm.y_pitch + gx] = qy;
                             }
                         }
-                        if (lane < 2) drow[32 + lane] = luma_from_rgb_u8(c1[i] & 0xffu, (c1[i] >> 8) & 0xffu, c1[i] >> 16, qy, qu, qv);
                     }
+                }
+                // the two extra tile columns (32, 33) of every row: one pixel per thread in ONE pass (done per row by lanes 0 / 1 they cost
+                // every warp a full conversion per row)
+                for (int t = threadIdx.x; t < 8 * (G + 2); t += TM_THREADS)
+                {
+                    const int row = t >> 1, q = row / (G + 2), ly = row - q * (G + 2);
+                    const int strip = min(tile_x * 4 + q, prm.strips_x - 1);
+                    const int gy = clampi(y0 - 1 + ly, 0, prm.h - 1), gx = clampi(strip * SW - R - 1 + 32 + (t & 1), 0, prm.w - 1);
+                    const uint8_t* pb = prm.rgb_src + static_cast<size_t>(gy) * prm.rgb_pitch + 3 * gx;
+                    uint8_t qy, qu, qv;
+                    luma_all[(q * (TM_GMAX + 2) + ly) * TM_LP + 32 + (t & 1)] = luma_from_rgb_u8(__ldg(pb), __ldg(pb + 1), __ldg(pb + 2), qy, qu, qv);
                 }
             }
             else if (prm.type == ACB200_UINT8)
