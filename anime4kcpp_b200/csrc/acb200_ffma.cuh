@@ -196,9 +196,68 @@ namespace acb
     // OpImplX86SIMD256<true>::conv<8,COUT,9>, X86/AVX.hpp:32-58,126-146.  The output-channel loop stays rolled
     // (runtime `co`) so ptxas cannot hoist a whole layer's worth of constant loads into the 63 uniform registers
     // and spill them.  `emit(co, v)` receives the FFMA_P finished sums (bias included) of output channel `co`.
+#ifndef ACB_FFMA2
+#define ACB_FFMA2 1
+#endif
+    // packed fp32 FMA of sm_100 (FFMA2): two independent IEEE fused multiply-adds per instruction, each rounded exactly like fmaf
+    __device__ __forceinline__ float2 fma2(const float2 a, const float2 b, const float2 c)
+    {
+        unsigned long long ra, rb, rc, rd;
+        ra = *reinterpret_cast<const unsigned long long*>(&a); rb = *reinterpret_cast<const unsigned long long*>(&b); rc = *reinterpret_cast<const unsigned long long*>(&c);
+        asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+        return *reinterpret_cast<float2*>(&rd);
+    }
+
     template<int COUT, int KOFF, int BOFF, class P, class Emit>
     __device__ __forceinline__ void conv_cols_rolled(const P& prm, const float4* __restrict__ in, const TileGeom& g, int x, int y, Emit&& emit)
     {
+#if ACB_FFMA2
+        // Packed form: input channels (2c, 2c + 1) of a pixel are one register pair, their weights one 64-bit constant load, their
+        // accumulators one pair -- 36 FFMA2 instead of 72 FFMA per pixel and output channel.  Every accumulator lane still sees the same
+        // products in the same order, so the sums are bit-identical to the scalar form (X86/AVX.hpp:32-58 lane for lane).
+        float2 r2[FFMA_P + 2][3][4];
+        const int cx2[3] = { clampi(x - 1, g.ix0, g.ix1), x, clampi(x + 1, g.ix0, g.ix1) };
+#pragma unroll
+        for (int iy = 0; iy < FFMA_P + 2; iy++)
+        {
+            const int ry = clampi(y - 1 + iy, g.iy0, min(g.iy1, FT - 1)) * FT;
+#pragma unroll
+            for (int dx = 0; dx < 3; dx++)
+            {
+                const float4 v0 = in[ry + cx2[dx]], v1 = in[FT * FT + ry + cx2[dx]];
+                r2[iy][dx][0] = make_float2(v0.x, v0.y); r2[iy][dx][1] = make_float2(v0.z, v0.w);
+                r2[iy][dx][2] = make_float2(v1.x, v1.y); r2[iy][dx][3] = make_float2(v1.z, v1.w);
+            }
+        }
+#pragma unroll 1
+        for (int co = 0; co < COUT; co++)
+        {
+            const float2* __restrict__ wk2 = reinterpret_cast<const float2*>(prm.k + KOFF + co * 72);
+            float2 s2[FFMA_P][4];
+#pragma unroll
+            for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+                for (int dx = 0; dx < 3; dx++)
+#pragma unroll
+                    for (int c2 = 0; c2 < 4; c2++)
+                    {
+                        const float2 wgt = wk2[(dy * 3 + dx) * 4 + c2];
+#pragma unroll
+                        for (int p = 0; p < FFMA_P; p++)
+                            s2[p][c2] = fma2(r2[p + dy][dx][c2], wgt, (dy == 0 && dx == 0) ? make_float2(0.0f, 0.0f) : s2[p][c2]);
+                    }
+            float v[FFMA_P];
+            const float bias = prm.b[BOFF + co];
+#pragma unroll
+            for (int p = 0; p < FFMA_P; p++)
+            {
+                const float s8[8] = { s2[p][0].x, s2[p][0].y, s2[p][1].x, s2[p][1].y, s2[p][2].x, s2[p][2].y, s2[p][3].x, s2[p][3].y };
+                v[p] = __fadd_rn(bias, hsum8(s8));
+            }
+            emit(co, v);
+        }
+        return;
+#endif
         float r[FFMA_P + 2][3][8];
         const int cx[3] = { clampi(x - 1, g.ix0, g.ix1), x, clampi(x + 1, g.ix0, g.ix1) };
 #pragma unroll
