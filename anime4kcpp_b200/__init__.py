@@ -187,7 +187,7 @@ class Session:
 
     def set_fusion(self, on):
         """Colour split / chroma resize / merge inside the TMEM engine's segment kernels (8-bit RGB, 2x); bit-identical either way."""
-        _check(lib().acb200_session_set_fusion(self.handle, 1 if on else 0), self.handle)
+        _check(lib().acb200_session_set_fusion(self.handle, int(on)), self.handle)        # False / True, or 2: RGBA as well
 
     def sync(self):
         _check(lib().acb200_session_sync(self.handle), self.handle)

@@ -471,6 +471,7 @@ namespace
     {
         const uint8_t* rgb_src; int rgb_pitch;
         uint8_t* uv; int uv_pitch;
+        int uvc;                            // channels of the chroma plane (2: RGB, 3: RGBA)
         uint8_t* y; int y_pitch;            // quantised luma plane, written by the head segment for a tail that adds the source luma (ACNet); else null
         const void* htab; const void* vtab;
         uint8_t* rgb_dst; int rgb_dst_pitch;
@@ -513,7 +514,7 @@ namespace
             if (fz)
             {
                 // fused colour handling: TMEM engine only (the caller has checked that every segment has a kernel there)
-                a.uv_pitch = fz->uv_pitch;
+                a.uv_pitch = fz->uv_pitch; a.uvc = fz->uvc;
                 if (head) { a.rgb_src = fz->rgb_src; a.rgb_pitch = fz->rgb_pitch; a.uv_out = fz->uv; a.y_out = fz->y; a.y_pitch = fz->y_pitch; }
                 else { a.src = fz->y; a.src_pitch = fz->y_pitch; }
                 if (tail) { a.uv_in = fz->uv; a.htab = fz->htab; a.vtab = fz->vtab; a.rgb_dst = fz->rgb_dst; a.rgb_dst_pitch = fz->rgb_dst_pitch; }
@@ -603,10 +604,13 @@ namespace
         int cur_pitch = src_pitch, cw = w, ch = h, rc;
         // 8-bit RGB, exactly 2x, TMEM engine, chains of two or more segments: colour split inside the first segment's tile load, chroma
         // resize + merge inside the last segment's tail -- two launches per frame, no Y plane, bit-identical to the separate kernels
-        if (s->fuse && c == 3 && type == ACB200_UINT8 && power == 1 && !down && s->engine != 0 && s->tensor_impl == 2 && m->chain.size() >= 2 &&
-            seg_tm_chain_supported(*m) && ((reinterpret_cast<uintptr_t>(d_dst) | static_cast<uintptr_t>(dst_pitch)) & 1) == 0)
+        // (RGB results leave as 16-bit stores; RGBA pixels are read and written as 32-bit words)
+        const uintptr_t align_bits = (reinterpret_cast<uintptr_t>(d_dst) | static_cast<uintptr_t>(dst_pitch)) |
+                                     (c == 4 ? (reinterpret_cast<uintptr_t>(d_src) | static_cast<uintptr_t>(src_pitch)) : 0);
+        if (((c == 3 && s->fuse >= 1) || (c == 4 && s->fuse >= 2)) && type == ACB200_UINT8 && power == 1 && !down && s->engine != 0 && s->tensor_impl == 2 && m->chain.size() >= 2 &&
+            seg_tm_chain_supported(*m) && (align_bits & (c == 4 ? 3 : 1)) == 0)
         {
-            const size_t uvp = pitch_of(w, 2, 1);
+            const size_t uvp = pitch_of(w, c - 1, 1);
             if ((rc = ensure(s, st, s->uv, uvp * h)) != ACB200_OK) return rc;
             if ((rc = ensure_tables(s, st, w, h, 2 * w, 2 * h)) != ACB200_OK) return rc;
             // ACNet's tail adds the nearest-upsampled source luma (Common.hpp:290-342): the head segment leaves the quantised Y plane for it
@@ -615,7 +619,7 @@ namespace
             if (needs_y && (rc = ensure(s, st, s->y[0], yp * h)) != ACB200_OK) return rc;
             if (s->tab_max_cnt <= 4)
             {
-                const FusedColour fz{ static_cast<const uint8_t*>(d_src), src_pitch, static_cast<uint8_t*>(s->uv.p), static_cast<int>(uvp),
+                const FusedColour fz{ static_cast<const uint8_t*>(d_src), src_pitch, static_cast<uint8_t*>(s->uv.p), static_cast<int>(uvp), c - 1,
                                       needs_y ? static_cast<uint8_t*>(s->y[0].p) : nullptr, static_cast<int>(yp),
                                       s->htab.p, s->vtab.p, static_cast<uint8_t*>(d_dst), dst_pitch };
                 return luma_pass(s, st, *m, nullptr, 0, nullptr, 0, w, h, type, true, &fz);
@@ -885,6 +889,7 @@ extern "C"
         {
             if (!std::strcmp(e, "0")) s->fuse = 0;
             else if (!std::strcmp(e, "1")) s->fuse = 1;
+            else if (!std::strcmp(e, "2")) s->fuse = 2;
             else { delete s; return ACB200_EINVAL; }
         }
         if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -926,7 +931,7 @@ extern "C"
     const char* acb200_session_error(const acb200_session* s) { return s ? s->error.c_str() : "invalid session"; }
     void acb200_session_clear_error(acb200_session* s) { if (s) s->error = "NO ERROR"; }
     int acb200_session_set_tensor_impl(acb200_session* s, int impl) { if (!s || impl < 0 || impl > 2) return ACB200_EINVAL; s->tensor_impl = impl; return ACB200_OK; }
-    int acb200_session_set_fusion(acb200_session* s, int on) { if (!s || on < 0 || on > 1) return ACB200_EINVAL; s->fuse = on; return ACB200_OK; }
+    int acb200_session_set_fusion(acb200_session* s, int on) { if (!s || on < 0 || on > 2) return ACB200_EINVAL; s->fuse = on; return ACB200_OK; }
     int acb200_session_set_engine(acb200_session* s, int engine) { if (!s || engine < 0 || engine > 2) return ACB200_EINVAL; s->engine = engine; return ACB200_OK; }
 
     int acb200_process_device(acb200_session* s, const acb200_model* m, const void* d_src, int w, int h, int c, int src_stride, int type,

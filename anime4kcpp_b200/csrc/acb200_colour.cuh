@@ -41,7 +41,8 @@ namespace acb
         bool all_d1;        // every lane of the warp has d == 1 (true away from the left / right image edge)
         float ca[4], cb[4];
     };
-    __device__ __forceinline__ HTaps2 load_htaps2(const Contrib* __restrict__ htab, int ox, int sw_img)
+    // pix_bytes: bytes per pixel of the chroma plane, 2 for (u, v) and 3 for (u, v, a)
+    __device__ __forceinline__ HTaps2 load_htaps2(const Contrib* __restrict__ htab, int ox, int sw_img, int pix_bytes)
     {
         const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(htab + ox)), b0 = __ldg(reinterpret_cast<const uint4*>(htab + ox + 1));
         const float2 a1 = __ldg(reinterpret_cast<const float2*>(&htab[ox].c[2])), b1 = __ldg(reinterpret_cast<const float2*>(&htab[ox + 1].c[2]));
@@ -50,7 +51,7 @@ namespace acb
         k.d = static_cast<int>(b0.x) - n0;
         k.all_d1 = __all_sync(0xffffffffu, k.d == 1);
 #pragma unroll
-        for (int j = 0; j < 5; j++) k.off[j] = 2 * min(n0 + j, sw_img - 1);
+        for (int j = 0; j < 5; j++) k.off[j] = pix_bytes * min(n0 + j, sw_img - 1);
         k.ca[0] = __uint_as_float(a0.z); k.ca[1] = __uint_as_float(a0.w); k.ca[2] = a1.x; k.ca[3] = a1.y;
         k.cb[0] = __uint_as_float(b0.z); k.cb[1] = __uint_as_float(b0.w); k.cb[2] = b1.x; k.cb[3] = b1.y;
         return k;
@@ -69,15 +70,31 @@ namespace acb
     }
     // horizontal pass of one source row of the interleaved (u, v) plane for the lane's two output columns: (u_a, v_a, u_b, v_b).
     // Columns past the image carry zero coefficients and are read clamped (finite), as the tiled kernel zero-fills them.
+    // MODE 0: (u, v) plane, one 16-bit load per tap.  MODE 1: the (u, v) of a (u, v, a) plane, two byte loads per tap.  MODE 2: the alpha of
+    // a (u, v, a) plane in BOTH halves of the pair (the caller keeps one machinery for every pair of channels).
+    template<int MODE>
     __device__ __forceinline__ float4 chroma_hrow2(const uint8_t* __restrict__ row, const HTaps2& k)
     {
         float tu[5], tv[5];
 #pragma unroll
         for (int j = 0; j < 5; j++)
         {
-            const uint32_t raw = __ldg(reinterpret_cast<const unsigned short*>(row + k.off[j]));
-            tu[j] = decode_u8_magic(__byte_perm(raw, 0x4B000000u, 0x7640));     // bytes: raw.b0, 0x00, 0x00, 0x4B
-            tv[j] = decode_u8_magic(__byte_perm(raw, 0x4B000000u, 0x7641));
+            if constexpr (MODE == 0)
+            {
+                const uint32_t raw = __ldg(reinterpret_cast<const unsigned short*>(row + k.off[j]));
+                tu[j] = decode_u8_magic(__byte_perm(raw, 0x4B000000u, 0x7640));     // bytes: raw.b0, 0x00, 0x00, 0x4B
+                tv[j] = decode_u8_magic(__byte_perm(raw, 0x4B000000u, 0x7641));
+            }
+            else if constexpr (MODE == 1)
+            {
+                tu[j] = decode_u8_magic(0x4B000000u | __ldg(row + k.off[j]));
+                tv[j] = decode_u8_magic(0x4B000000u | __ldg(row + k.off[j] + 1));
+            }
+            else
+            {
+                tu[j] = decode_u8_magic(0x4B000000u | __ldg(row + k.off[j] + 2));
+                tv[j] = tu[j];
+            }
         }
         float4 o;
         o.x = tap4(k.ca[0], k.ca[1], k.ca[2], k.ca[3], tu[0], tu[1], tu[2], tu[3]);
@@ -118,6 +135,15 @@ namespace acb
         o16[0] = static_cast<unsigned short>(__byte_perm(r0, g0, 0x0040));
         o16[1] = static_cast<unsigned short>(__byte_perm(b0, r1, 0x0040));
         o16[2] = static_cast<unsigned short>(__byte_perm(g1, b1, 0x0040));
+    }
+    // rgba2yuva (ImageProcess.cpp:113-138): colour premultiplied by alpha, alpha kept as the third channel of the chroma plane
+    __device__ __forceinline__ float luma_from_rgba_u8(uint32_t r, uint32_t g, uint32_t b, uint32_t a, uint8_t& qy, uint8_t& qu, uint8_t& qv, uint8_t& qa)
+    {
+        const float af = unit_from_int<255>(static_cast<float>(a));
+        const YuvFromRgb o = rgb_to_yuv(__fmul_rn(unit_from_int<255>(static_cast<float>(r)), af), __fmul_rn(unit_from_int<255>(static_cast<float>(g)), af),
+                                        __fmul_rn(unit_from_int<255>(static_cast<float>(b)), af));
+        qy = quant_u8(o.y); qu = quant_u8(o.u); qv = quant_u8(o.v); qa = quant_u8(af);
+        return unit_from_int<255>(static_cast<float>(qy));
     }
     // quantised luma byte of the colour split, as the network's toFloat reads it back (rgb2yuv_u8x4_kernel + load_elem)
     __device__ __forceinline__ float luma_from_rgb_u8(uint32_t r, uint32_t g, uint32_t b, uint8_t& qy, uint8_t& qu, uint8_t& qv)

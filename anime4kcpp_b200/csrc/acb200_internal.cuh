@@ -106,7 +106,7 @@ struct acb200_session
     int tensor_impl = 2;
     int sm_count = 0;
     int engine = 2;     // 0 exact FFMA, 1 tensor-core MMA, 2 auto: exact for every 2x pass but the last, tensor for the last
-    int fuse = 1;       // colour split / chroma resize / merge inside the TMEM engine's segment kernels where they apply (8-bit RGB, 2x)
+    int fuse = 1;       // colour split / chroma resize / merge inside the TMEM engine's segment kernels: 0 never, 1 8-bit RGB at 2x, 2 RGBA as well
     std::string error = "NO ERROR";
     // grow-only device scratch
     struct Buf { void* p = nullptr; size_t cap = 0; };
@@ -170,6 +170,7 @@ namespace acbh
         const uint8_t* rgb_src = nullptr; int rgb_pitch = 0;
         uint8_t* uv_out = nullptr; const uint8_t* uv_in = nullptr; int uv_pitch = 0;
         uint8_t* y_out = nullptr; int y_pitch = 0;
+        int uvc = 2;            // channels of the chroma plane: 2 for RGB, 3 (u, v, a) for RGBA
         const void* htab = nullptr; const void* vtab = nullptr;
         uint8_t* rgb_dst = nullptr; int rgb_dst_pitch = 0;
     };

@@ -51,7 +51,7 @@ namespace acbh
             prm.y_out = S::HEAD ? a.y_out : nullptr; prm.y_pitch = a.y_pitch;
             prm.uv_out = S::HEAD ? a.uv_out : nullptr; prm.uv_in = S::TAIL ? a.uv_in : nullptr; prm.uv_pitch = a.uv_pitch;
             prm.htab = static_cast<const Contrib*>(a.htab); prm.vtab = static_cast<const Contrib*>(a.vtab);
-            prm.rgb_dst = a.rgb_dst; prm.rgb_dst_pitch = a.rgb_dst_pitch;
+            prm.rgb_dst = a.rgb_dst; prm.rgb_dst_pitch = a.rgb_dst_pitch; prm.uvc = a.uvc;
             constexpr int SW = 32 - 2 * S::R;
             prm.strips_x = (w + SW - 1) / SW;
             prm.tiles_x = (prm.strips_x + 3) / 4;

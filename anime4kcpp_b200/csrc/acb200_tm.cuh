@@ -133,6 +133,7 @@ namespace acb
         const Contrib* htab;    // contributors of the 2x chroma resize, per output column / row
         const Contrib* vtab;
         int rgb_pitch, uv_pitch, rgb_dst_pitch, y_pitch;
+        int uvc;                // channels of the chroma plane: 2 (u, v) for RGB, 3 (u, v, a) for RGBA (the source then has four bytes per pixel)
         const uint32_t* bops;   // B operands of this segment's 3x3 convs, TM_B_WORDS_LAYER words each, in layer order
         float k[(S::HEAD ? 72 : 0) + 64 + 32];  // fp32 weights used outside the MMAs: head (72) | ARNet 1x1 (64) | legacy deconv (32)
         float b[S::NB];
@@ -361,8 +362,11 @@ namespace acb
                         const int strip = min(tile_x * 4 + q, prm.strips_x - 1);
                         const int gy = clampi(y0 - 1 + ly, 0, prm.h - 1), gx0 = strip * SW - R - 1;
                         const uint8_t* srow = prm.rgb_src + static_cast<size_t>(gy) * prm.rgb_pitch;
-                        const uint8_t* pa = srow + 3 * clampi(gx0 + lane, 0, prm.w - 1);
-                        c0[i] = __ldg(pa) | (static_cast<uint32_t>(__ldg(pa + 1)) << 8) | (static_cast<uint32_t>(__ldg(pa + 2)) << 16);
+                        const int xc = clampi(gx0 + lane, 0, prm.w - 1);
+                        const uint8_t* pa = srow + 3 * xc;
+                        // (RGBA sources are read as aligned 32-bit pixels; the host side only fuses them when rows and base are 4-byte aligned)
+                        c0[i] = prm.uvc == 3 ? __ldg(reinterpret_cast<const uint32_t*>(srow) + xc)
+                                             : __ldg(pa) | (static_cast<uint32_t>(__ldg(pa + 1)) << 8) | (static_cast<uint32_t>(__ldg(pa + 2)) << 16);
                     }
 #pragma unroll
                     for (int i = 0; i < BATCH; i++)
@@ -371,14 +375,17 @@ namespace acb
                         if (row >= 4 * (G + 2)) break;
                         const int q = row / (G + 2), ly = row - q * (G + 2);
                         float* drow = luma_all + (q * (TM_GMAX + 2) + ly) * TM_LP;
-                        uint8_t qy, qu, qv;
-                        drow[lane] = luma_from_rgb_u8(c0[i] & 0xffu, (c0[i] >> 8) & 0xffu, c0[i] >> 16, qy, qu, qv);
+                        uint8_t qy, qu, qv, qa = 0;
+                        drow[lane] = prm.uvc == 3 ? luma_from_rgba_u8(c0[i] & 0xffu, (c0[i] >> 8) & 0xffu, (c0[i] >> 16) & 0xffu, c0[i] >> 24, qy, qu, qv, qa)
+                                                  : luma_from_rgb_u8(c0[i] & 0xffu, (c0[i] >> 8) & 0xffu, (c0[i] >> 16) & 0xffu, qy, qu, qv);
                         if (S::HEAD && prm.uv_out != nullptr)
                         {
                             const int strip = tile_x * 4 + q, gy = y0 - 1 + ly, gx = strip * SW - R - 1 + lane;
                             if (strip < prm.strips_x && gy >= own_y0 && gy < own_y1 && gx >= strip * SW && gx < min(strip * SW + SW, prm.w))
                             {
-                                *reinterpret_cast<uchar2*>(prm.uv_out + static_cast<size_t>(gy) * prm.uv_pitch + 2 * gx) = make_uchar2(qu, qv);
+                                uint8_t* uvp = prm.uv_out + static_cast<size_t>(gy) * prm.uv_pitch;
+                                if (prm.uvc == 3) { uvp[3 * gx] = qu; uvp[3 * gx + 1] = qv; uvp[3 * gx + 2] = qa; }
+                                else *reinterpret_cast<uchar2*>(uvp + 2 * gx) = make_uchar2(qu, qv);
                                 if (prm.y_out != nullptr) prm.y_out[static_cast<size_t>(gy) * prm.y_pitch + gx] = qy;
                             }
                         }
@@ -391,9 +398,10 @@ namespace acb
                     const int row = t >> 1, q = row / (G + 2), ly = row - q * (G + 2);
                     const int strip = min(tile_x * 4 + q, prm.strips_x - 1);
                     const int gy = clampi(y0 - 1 + ly, 0, prm.h - 1), gx = clampi(strip * SW - R - 1 + 32 + (t & 1), 0, prm.w - 1);
-                    const uint8_t* pb = prm.rgb_src + static_cast<size_t>(gy) * prm.rgb_pitch + 3 * gx;
-                    uint8_t qy, qu, qv;
-                    luma_all[(q * (TM_GMAX + 2) + ly) * TM_LP + 32 + (t & 1)] = luma_from_rgb_u8(__ldg(pb), __ldg(pb + 1), __ldg(pb + 2), qy, qu, qv);
+                    const uint8_t* pb = prm.rgb_src + static_cast<size_t>(gy) * prm.rgb_pitch + (prm.uvc == 3 ? 4 : 3) * gx;
+                    uint8_t qy, qu, qv, qa;
+                    luma_all[(q * (TM_GMAX + 2) + ly) * TM_LP + 32 + (t & 1)] = prm.uvc == 3 ? luma_from_rgba_u8(__ldg(pb), __ldg(pb + 1), __ldg(pb + 2), __ldg(pb + 3), qy, qu, qv, qa)
+                                                                                                : luma_from_rgb_u8(__ldg(pb), __ldg(pb + 1), __ldg(pb + 2), qy, qu, qv);
                 }
             }
             else if (prm.type == ACB200_UINT8)
@@ -837,13 +845,15 @@ namespace acb
                     // (u, v) -- runs BEFORE the wait for the group's accumulators, in time the warp would otherwise spend asleep; what is kept
                     // is one word per output row: the quantised (u_a, v_a, u_b, v_b) bytes.  After the wait only the merge with the luma is left.
                     [[maybe_unused]] uint2 cq0 = make_uint2(0u, 0u), cq1 = cq0, cq2 = cq0, cq3 = cq0;
+                    [[maybe_unused]] uint2 aq0 = cq0, aq1 = cq0, aq2 = cq0, aq3 = cq0;      // RGBA: the resized alpha, same form (bytes a_a, a_a, a_b, a_b)
                     const bool fused = S::TAIL && last && prm.uv_in != nullptr;
                     if constexpr (S::TAIL)
                         if (fused)
                         {
-                            const HTaps2 hk = load_htaps2(prm.htab, 2 * min(x0 + R + lane, prm.w - 1), prm.w);
+                            const int PIX = prm.uvc;        // bytes per pixel of the chroma plane: (u, v) or (u, v, a)
+                            const HTaps2 hk = load_htaps2(prm.htab, 2 * min(x0 + R + lane, prm.w - 1), prm.w, PIX);
                             const int gy0 = y0 + yg;
-                            auto hrow_at = [&](const int gyr) { return chroma_hrow2(prm.uv_in + static_cast<size_t>(clampi(gyr, 0, prm.h - 1)) * prm.uv_pitch, hk); };
+                            auto row_ptr = [&](const int gyr) { return prm.uv_in + static_cast<size_t>(clampi(gyr, 0, prm.h - 1)) * prm.uv_pitch; };
                             auto encode4 = [](const float4 sv) {
                                 // stb encode (x 255 + 0.5, clamp, truncate): the byte is the low mantissa byte of the round-toward-zero magic sum
                                 const uint32_t b0 = __float_as_uint(__fadd_rz(fminf(fmaxf(__fadd_rn(__fmul_rn(sv.x, 255.0f), 0.5f), 0.0f), 255.0f), CM_MAGIC));
@@ -852,54 +862,66 @@ namespace acb
                                 const uint32_t b3 = __float_as_uint(__fadd_rz(fminf(fmaxf(__fadd_rn(__fmul_rn(sv.w, 255.0f), 0.5f), 0.0f), 255.0f), CM_MAGIC));
                                 return __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
                             };
-                            auto vrows = [&](const int jr, const float4& w0, const float4& w1, const float4& w2, const float4& w3, const float4& w4) {
-                                const int gy = gy0 + jr;
-                                const Contrib* vp = prm.vtab + 2 * gy;
-                                const uint4 va0 = __ldg(reinterpret_cast<const uint4*>(vp)), vb0 = __ldg(reinterpret_cast<const uint4*>(vp + 1));
-                                const float2 va1 = __ldg(reinterpret_cast<const float2*>(&vp[0].c[2])), vb1 = __ldg(reinterpret_cast<const float2*>(&vp[1].c[2]));
-                                const float ca[4] = { __uint_as_float(va0.z), __uint_as_float(va0.w), va1.x, va1.y };
-                                const float cb[4] = { __uint_as_float(vb0.z), __uint_as_float(vb0.w), vb1.x, vb1.y };
-                                float4 sa, sb;      // vertical pass: (u, v) of columns a, b in output rows 2 gy (sa) and 2 gy + 1 (sb)
-                                if (static_cast<int>(va0.x) == gy - 2 && static_cast<int>(vb0.x) == gy - 1)
-                                {
-                                    // interior rows: the window holds exactly the rows both contributors read
-                                    sa.x = tap4(ca[0], ca[1], ca[2], ca[3], w0.x, w1.x, w2.x, w3.x); sa.y = tap4(ca[0], ca[1], ca[2], ca[3], w0.y, w1.y, w2.y, w3.y);
-                                    sa.z = tap4(ca[0], ca[1], ca[2], ca[3], w0.z, w1.z, w2.z, w3.z); sa.w = tap4(ca[0], ca[1], ca[2], ca[3], w0.w, w1.w, w2.w, w3.w);
-                                    sb.x = tap4(cb[0], cb[1], cb[2], cb[3], w1.x, w2.x, w3.x, w4.x); sb.y = tap4(cb[0], cb[1], cb[2], cb[3], w1.y, w2.y, w3.y, w4.y);
-                                    sb.z = tap4(cb[0], cb[1], cb[2], cb[3], w1.z, w2.z, w3.z, w4.z); sb.w = tap4(cb[0], cb[1], cb[2], cb[3], w1.w, w2.w, w3.w, w4.w);
-                                }
-                                else
-                                {
-                                    // rows at the top image edge (folded taps start at another row): the contributors' own rows, recomputed.  Rows past
-                                    // the image carry zero coefficients and are read clamped.
-                                    float4 t[4];
+                            // the whole chroma side of the group for one pair of channels: `hrow_at(image row)` is the horizontal pass of that pair
+                            auto precompute = [&](auto hrow_at, uint2& q0, uint2& q1, uint2& q2, uint2& q3) {
+                                auto vrows = [&](const int jr, const float4& w0, const float4& w1, const float4& w2, const float4& w3, const float4& w4) {
+                                    const int gy = gy0 + jr;
+                                    const Contrib* vp = prm.vtab + 2 * gy;
+                                    const uint4 va0 = __ldg(reinterpret_cast<const uint4*>(vp)), vb0 = __ldg(reinterpret_cast<const uint4*>(vp + 1));
+                                    const float2 va1 = __ldg(reinterpret_cast<const float2*>(&vp[0].c[2])), vb1 = __ldg(reinterpret_cast<const float2*>(&vp[1].c[2]));
+                                    const float ca[4] = { __uint_as_float(va0.z), __uint_as_float(va0.w), va1.x, va1.y };
+                                    const float cb[4] = { __uint_as_float(vb0.z), __uint_as_float(vb0.w), vb1.x, vb1.y };
+                                    float4 sa, sb;      // vertical pass: the pair in columns a, b of output rows 2 gy (sa) and 2 gy + 1 (sb)
+                                    if (static_cast<int>(va0.x) == gy - 2 && static_cast<int>(vb0.x) == gy - 1)
+                                    {
+                                        // interior rows: the window holds exactly the rows both contributors read
+                                        sa.x = tap4(ca[0], ca[1], ca[2], ca[3], w0.x, w1.x, w2.x, w3.x); sa.y = tap4(ca[0], ca[1], ca[2], ca[3], w0.y, w1.y, w2.y, w3.y);
+                                        sa.z = tap4(ca[0], ca[1], ca[2], ca[3], w0.z, w1.z, w2.z, w3.z); sa.w = tap4(ca[0], ca[1], ca[2], ca[3], w0.w, w1.w, w2.w, w3.w);
+                                        sb.x = tap4(cb[0], cb[1], cb[2], cb[3], w1.x, w2.x, w3.x, w4.x); sb.y = tap4(cb[0], cb[1], cb[2], cb[3], w1.y, w2.y, w3.y, w4.y);
+                                        sb.z = tap4(cb[0], cb[1], cb[2], cb[3], w1.z, w2.z, w3.z, w4.z); sb.w = tap4(cb[0], cb[1], cb[2], cb[3], w1.w, w2.w, w3.w, w4.w);
+                                    }
+                                    else
+                                    {
+                                        // rows at the top image edge (folded taps start at another row): the contributors' own rows, recomputed.  Rows past
+                                        // the image carry zero coefficients and are read clamped.
+                                        float4 t[4];
 #pragma unroll
-                                    for (int i = 0; i < 4; i++) t[i] = hrow_at(static_cast<int>(va0.x) + i);
-                                    sa.x = tap4(ca[0], ca[1], ca[2], ca[3], t[0].x, t[1].x, t[2].x, t[3].x); sa.y = tap4(ca[0], ca[1], ca[2], ca[3], t[0].y, t[1].y, t[2].y, t[3].y);
-                                    sa.z = tap4(ca[0], ca[1], ca[2], ca[3], t[0].z, t[1].z, t[2].z, t[3].z); sa.w = tap4(ca[0], ca[1], ca[2], ca[3], t[0].w, t[1].w, t[2].w, t[3].w);
+                                        for (int i = 0; i < 4; i++) t[i] = hrow_at(static_cast<int>(va0.x) + i);
+                                        sa.x = tap4(ca[0], ca[1], ca[2], ca[3], t[0].x, t[1].x, t[2].x, t[3].x); sa.y = tap4(ca[0], ca[1], ca[2], ca[3], t[0].y, t[1].y, t[2].y, t[3].y);
+                                        sa.z = tap4(ca[0], ca[1], ca[2], ca[3], t[0].z, t[1].z, t[2].z, t[3].z); sa.w = tap4(ca[0], ca[1], ca[2], ca[3], t[0].w, t[1].w, t[2].w, t[3].w);
 #pragma unroll
-                                    for (int i = 0; i < 4; i++) t[i] = hrow_at(static_cast<int>(vb0.x) + i);
-                                    sb.x = tap4(cb[0], cb[1], cb[2], cb[3], t[0].x, t[1].x, t[2].x, t[3].x); sb.y = tap4(cb[0], cb[1], cb[2], cb[3], t[0].y, t[1].y, t[2].y, t[3].y);
-                                    sb.z = tap4(cb[0], cb[1], cb[2], cb[3], t[0].z, t[1].z, t[2].z, t[3].z); sb.w = tap4(cb[0], cb[1], cb[2], cb[3], t[0].w, t[1].w, t[2].w, t[3].w);
-                                }
-                                return make_uint2(encode4(sa), encode4(sb));
+                                        for (int i = 0; i < 4; i++) t[i] = hrow_at(static_cast<int>(vb0.x) + i);
+                                        sb.x = tap4(cb[0], cb[1], cb[2], cb[3], t[0].x, t[1].x, t[2].x, t[3].x); sb.y = tap4(cb[0], cb[1], cb[2], cb[3], t[0].y, t[1].y, t[2].y, t[3].y);
+                                        sb.z = tap4(cb[0], cb[1], cb[2], cb[3], t[0].z, t[1].z, t[2].z, t[3].z); sb.w = tap4(cb[0], cb[1], cb[2], cb[3], t[0].w, t[1].w, t[2].w, t[3].w);
+                                    }
+                                    return make_uint2(encode4(sa), encode4(sb));
+                                };
+                                // a window of five rows slides down the group (row gy needs rows gy - 2 .. gy + 2): eight horizontal passes per group
+                                float4 h0 = hrow_at(gy0 - 2), h1 = hrow_at(gy0 - 1), h2 = hrow_at(gy0), h3 = hrow_at(gy0 + 1), h4 = hrow_at(gy0 + 2);
+                                q0 = vrows(0, h0, h1, h2, h3, h4);
+                                if (k > 1) { h0 = hrow_at(gy0 + 3); q1 = vrows(1, h1, h2, h3, h4, h0); }
+                                if (k > 2) { h1 = hrow_at(gy0 + 4); q2 = vrows(2, h2, h3, h4, h0, h1); }
+                                if (k > 3) { h2 = hrow_at(gy0 + 5); q3 = vrows(3, h3, h4, h0, h1, h2); }
                             };
-                            // a window of five rows slides down the group (row gy needs rows gy - 2 .. gy + 2): eight horizontal passes per group
-                            float4 h0 = hrow_at(gy0 - 2), h1 = hrow_at(gy0 - 1), h2 = hrow_at(gy0), h3 = hrow_at(gy0 + 1), h4 = hrow_at(gy0 + 2);
-                            cq0 = vrows(0, h0, h1, h2, h3, h4);
-                            if (k > 1) { h0 = hrow_at(gy0 + 3); cq1 = vrows(1, h1, h2, h3, h4, h0); }
-                            if (k > 2) { h1 = hrow_at(gy0 + 4); cq2 = vrows(2, h2, h3, h4, h0, h1); }
-                            if (k > 3) { h2 = hrow_at(gy0 + 5); cq3 = vrows(3, h3, h4, h0, h1, h2); }
+                            if (PIX == 2) precompute([&](const int gyr) { return chroma_hrow2<0>(row_ptr(gyr), hk); }, cq0, cq1, cq2, cq3);
+                            else
+                            {
+                                precompute([&](const int gyr) { return chroma_hrow2<1>(row_ptr(gyr), hk); }, cq0, cq1, cq2, cq3);
+                                precompute([&](const int gyr) { return chroma_hrow2<2>(row_ptr(gyr), hk); }, aq0, aq1, aq2, aq3);
+                            }
                         }
                     // yl[dy * 2 + dx]: the lane's four luma results as the value BEFORE truncation to the byte (x 255 + 0.5 applied)
                     [[maybe_unused]] auto fused_store = [&](const int jr, const int gx, const int gy, const float (&yl)[4], const bool ok) {
                         const uint2 cq = jr == 0 ? cq0 : jr == 1 ? cq1 : jr == 2 ? cq2 : cq3;
-                        uint8_t* o = prm.rgb_dst + static_cast<size_t>(2 * gy) * prm.rgb_dst_pitch + 6 * gx;
+                        const bool rgba = prm.uvc == 3;
+                        const uint2 aq = jr == 0 ? aq0 : jr == 1 ? aq1 : jr == 2 ? aq2 : aq3;
+                        uint8_t* o = prm.rgb_dst + static_cast<size_t>(2 * gy) * prm.rgb_dst_pitch + (rgba ? 8 : 6) * gx;
 #pragma unroll
                         for (int dy = 0; dy < 2; dy++)
                         {
                             const uint32_t c4 = dy ? cq.y : cq.x;
                             uint32_t ch[6];
+                            uint32_t ab[2] = { 0u, 0u };
 #pragma unroll
                             for (int dx = 0; dx < 2; dx++)
                             {
@@ -908,22 +930,39 @@ namespace acb
 #if ACB_TM_CHROMA_LUT
                                 const float2 tu = *reinterpret_cast<const float2*>(smem_tm + TM_OFF_LUT + 8 * __byte_perm(c4, 0u, dx ? 0x4442 : 0x4440));
                                 const float2 tv = *reinterpret_cast<const float2*>(smem_tm + TM_OFF_LUT + 2048 + 8 * __byte_perm(c4, 0u, dx ? 0x4443 : 0x4441));
-                                const float r = __fadd_rn(yv, tv.x);
-                                const float g = __fsub_rn(__fsub_rn(yv, tu.x), tv.y);
-                                const float b = __fadd_rn(yv, tu.y);
+                                float r = __fadd_rn(yv, tv.x);
+                                float g = __fsub_rn(__fsub_rn(yv, tu.x), tv.y);
+                                float b = __fadd_rn(yv, tu.y);
 #else
                                 const float qu = unit_from_int<255>(__fsub_rn(__uint_as_float(__byte_perm(c4, 0x4B000000u, dx ? 0x7642 : 0x7640)), CM_MAGIC));
                                 const float qv = unit_from_int<255>(__fsub_rn(__uint_as_float(__byte_perm(c4, 0x4B000000u, dx ? 0x7643 : 0x7641)), CM_MAGIC));
                                 const float u = __fsub_rn(qu, 0.5f), v = __fsub_rn(qv, 0.5f);
-                                const float r = __fadd_rn(yv, __fmul_rn(1.403f, v));
-                                const float g = __fsub_rn(__fsub_rn(yv, __fmul_rn(0.344f, u)), __fmul_rn(0.714f, v));
-                                const float b = __fadd_rn(yv, __fmul_rn(1.773f, u));
+                                float r = __fadd_rn(yv, __fmul_rn(1.403f, v));
+                                float g = __fsub_rn(__fsub_rn(yv, __fmul_rn(0.344f, u)), __fmul_rn(0.714f, v));
+                                float b = __fadd_rn(yv, __fmul_rn(1.773f, u));
 #endif
+                                if (rgba)
+                                {
+                                    // yuva2rgba (ImageProcess.cpp:275-308): un-premultiply by the resized alpha, which is stored as it is
+                                    const float al = unit_from_int<255>(__fsub_rn(__uint_as_float(__byte_perm(dy ? aq.y : aq.x, 0x4B000000u, dx ? 0x7642 : 0x7640)), CM_MAGIC));
+                                    if (al > 1e-6f) { r = __fdiv_rn(r, al); g = __fdiv_rn(g, al); b = __fdiv_rn(b, al); }
+                                    else r = g = b = 0.0f;
+                                    ab[dx] = quant_u8(al);
+                                }
                                 ch[3 * dx + 0] = __float_as_uint(__fadd_rz(__fadd_rn(__fmul_rn(__saturatef(r), 255.0f), 0.5f), CM_MAGIC));
                                 ch[3 * dx + 1] = __float_as_uint(__fadd_rz(__fadd_rn(__fmul_rn(__saturatef(g), 255.0f), 0.5f), CM_MAGIC));
                                 ch[3 * dx + 2] = __float_as_uint(__fadd_rz(__fadd_rn(__fmul_rn(__saturatef(b), 255.0f), 0.5f), CM_MAGIC));
                             }
-                            if (ok) store_rgb2(o + dy * prm.rgb_dst_pitch, ch[0], ch[1], ch[2], ch[3], ch[4], ch[5]);
+                            if (ok)
+                            {
+                                if (rgba)
+                                {
+                                    uint32_t* o32 = reinterpret_cast<uint32_t*>(o + dy * prm.rgb_dst_pitch);
+                                    o32[0] = __byte_perm(__byte_perm(ch[0], ch[1], 0x0040), __byte_perm(ch[2], ab[0], 0x0040), 0x5410);
+                                    o32[1] = __byte_perm(__byte_perm(ch[3], ch[4], 0x0040), __byte_perm(ch[5], ab[1], 0x0040), 0x5410);
+                                }
+                                else store_rgb2(o + dy * prm.rgb_dst_pitch, ch[0], ch[1], ch[2], ch[3], ch[4], ch[5]);
+                            }
                         }
                     };
                     tm_wait(bar_full + 8 * (g0 + j), 0);

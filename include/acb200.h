@@ -229,8 +229,10 @@ ACB200_API int acb200_session_set_engine(acb200_session* session, int engine);
  */
 ACB200_API int acb200_session_set_tensor_impl(acb200_session* session, int impl);
 /*
- * Colour handling fused into the luma network's kernels (default on; environment: ACB200_FUSE = 0 | 1).  Where it applies --
- * 8-bit RGB, factor exactly 2, the TMEM-resident tensor implementation, models that run as two or more segments -- the RGB -> YUV
+ * Colour handling fused into the luma network's kernels: 0 off, 1 (default) 8-bit RGB, 2 8-bit RGBA as well (bit-identical too, but
+ * measured 17 % slower than the separate kernels: the alpha channel runs the chroma machinery a second time); environment:
+ * ACB200_FUSE = 0 | 1 | 2.  Where it applies --
+ * 8-bit RGB[A], factor exactly 2, the TMEM-resident tensor implementation, models that run as two or more segments -- the RGB -> YUV
  * split (core/src/ImageProcess.cpp:38-61) runs inside the first segment's tile load and the Catmull-Rom chroma resize, its
  * re-quantisation and the YUV -> RGB merge (core/src/processor/Processor.cpp:251-253) run inside the last segment's tail: two launches per
  * frame and no intermediate Y plane.  The result is bit-identical to the separate kernels (on = 0), which every other case uses.
