@@ -229,32 +229,40 @@ namespace acb
                 r2[iy][dx][2] = make_float2(v1.x, v1.y); r2[iy][dx][3] = make_float2(v1.z, v1.w);
             }
         }
+        // Output channels in groups of FOUR per (rolled) iteration: the caller stores a pixel's four channels as one float4 -- scalar
+        // stores of one channel hit every fourth bank only (a four-way conflict on each of them, 40 % of the kernel's shared-memory wavefronts).
+        static_assert(COUT % 4 == 0, "output channels are emitted in groups of four");
 #pragma unroll 1
-        for (int co = 0; co < COUT; co++)
+        for (int co4 = 0; co4 < COUT; co4 += 4)
         {
-            const float2* __restrict__ wk2 = reinterpret_cast<const float2*>(prm.k + KOFF + co * 72);
-            float2 s2[FFMA_P][4];
+            float v4[4][FFMA_P];
 #pragma unroll
-            for (int dy = 0; dy < 3; dy++)
-#pragma unroll
-                for (int dx = 0; dx < 3; dx++)
-#pragma unroll
-                    for (int c2 = 0; c2 < 4; c2++)
-                    {
-                        const float2 wgt = wk2[(dy * 3 + dx) * 4 + c2];
-#pragma unroll
-                        for (int p = 0; p < FFMA_P; p++)
-                            s2[p][c2] = fma2(r2[p + dy][dx][c2], wgt, (dy == 0 && dx == 0) ? make_float2(0.0f, 0.0f) : s2[p][c2]);
-                    }
-            float v[FFMA_P];
-            const float bias = prm.b[BOFF + co];
-#pragma unroll
-            for (int p = 0; p < FFMA_P; p++)
+            for (int j = 0; j < 4; j++)
             {
-                const float s8[8] = { s2[p][0].x, s2[p][0].y, s2[p][1].x, s2[p][1].y, s2[p][2].x, s2[p][2].y, s2[p][3].x, s2[p][3].y };
-                v[p] = __fadd_rn(bias, hsum8(s8));
+                const int co = co4 + j;
+                const float2* __restrict__ wk2 = reinterpret_cast<const float2*>(prm.k + KOFF + co * 72);
+                float2 s2[FFMA_P][4];
+#pragma unroll
+                for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+                    for (int dx = 0; dx < 3; dx++)
+#pragma unroll
+                        for (int c2 = 0; c2 < 4; c2++)
+                        {
+                            const float2 wgt = wk2[(dy * 3 + dx) * 4 + c2];
+#pragma unroll
+                            for (int p = 0; p < FFMA_P; p++)
+                                s2[p][c2] = fma2(r2[p + dy][dx][c2], wgt, (dy == 0 && dx == 0) ? make_float2(0.0f, 0.0f) : s2[p][c2]);
+                        }
+                const float bias = prm.b[BOFF + co];
+#pragma unroll
+                for (int p = 0; p < FFMA_P; p++)
+                {
+                    const float s8[8] = { s2[p][0].x, s2[p][0].y, s2[p][1].x, s2[p][1].y, s2[p][2].x, s2[p][2].y, s2[p][3].x, s2[p][3].y };
+                    v4[j][p] = __fadd_rn(bias, hsum8(s8));
+                }
             }
-            emit(co, v);
+            emit(co4, v4);
         }
         return;
 #endif
@@ -274,27 +282,36 @@ namespace acb
             }
         }
 #pragma unroll 1
-        for (int co = 0; co < COUT; co++)
+        for (int co4 = 0; co4 < COUT; co4 += 4)
         {
-            const float* __restrict__ wk = prm.k + KOFF + co * 72;
-            float s[FFMA_P][8];
+            float v4[4][FFMA_P];
+#pragma unroll 1
+            for (int j = 0; j < 4; j++)
+            {
+                const int co = co4 + j;
+                const float* __restrict__ wk = prm.k + KOFF + co * 72;
+                float s[FFMA_P][8];
 #pragma unroll
-            for (int dy = 0; dy < 3; dy++)
+                for (int dy = 0; dy < 3; dy++)
 #pragma unroll
-                for (int dx = 0; dx < 3; dx++)
+                    for (int dx = 0; dx < 3; dx++)
 #pragma unroll
-                    for (int ci = 0; ci < 8; ci++)
-                    {
-                        const float wgt = wk[(dy * 3 + dx) * 8 + ci];
+                        for (int ci = 0; ci < 8; ci++)
+                        {
+                            const float wgt = wk[(dy * 3 + dx) * 8 + ci];
 #pragma unroll
-                        for (int p = 0; p < FFMA_P; p++)
-                            s[p][ci] = fmaf(r[p + dy][dx][ci], wgt, (dy == 0 && dx == 0) ? 0.0f : s[p][ci]);
-                    }
-            float v[FFMA_P];
-            const float bias = prm.b[BOFF + co];
+                            for (int p = 0; p < FFMA_P; p++)
+                                s[p][ci] = fmaf(r[p + dy][dx][ci], wgt, (dy == 0 && dx == 0) ? 0.0f : s[p][ci]);
+                        }
+                const float bias = prm.b[BOFF + co];
 #pragma unroll
-            for (int p = 0; p < FFMA_P; p++) v[p] = __fadd_rn(bias, hsum8(s[p]));
-            emit(co, v);
+                for (int p = 0; p < FFMA_P; p++)
+                {
+                    const float t = __fadd_rn(bias, hsum8(s[p]));
+                    if (j == 0) v4[0][p] = t; else if (j == 1) v4[1][p] = t; else if (j == 2) v4[2][p] = t; else v4[3][p] = t;
+                }
+            }
+            emit(co4, v4);
         }
     }
 
@@ -312,22 +329,36 @@ namespace acb
             int qy, qx;
             rdiv.split(i, qy, qx);
             const int x = xa + qx, y = ya + FFMA_P * qy;
-            conv_cols_rolled<COUT, KOFF, BOFF>(prm, in, g, x, y, [&](const int co, const float (&v)[FFMA_P]) {
-                // channel co lives in plane co/4, component co%4 of the float4 at the pixel
-                float* dst = outf + ((co >> 2) * FT * FT + y * FT + x) * 4 + (co & 3);
-                float alpha = 0.0f;
-                if (ACT == ACT_PRELU) alpha = prm.a[AOFF + co];
+            conv_cols_rolled<COUT, KOFF, BOFF>(prm, in, g, x, y, [&](const int co4, const float (&v)[4][FFMA_P]) {
+                // channels co4 .. co4 + 3 are the float4 of plane co4 / 4 at the pixel: one 16-byte store per pixel
+                float4* dst = out + (co4 >> 2) * FT * FT + y * FT + x;
+                float alpha[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
+                if (ACT == ACT_PRELU)
+                {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) alpha[j] = prm.a[AOFF + co4 + j];
+                }
 #pragma unroll
                 for (int p = 0; p < FFMA_P; p++)
                 {
                     if (y + p >= yb) break;
-                    float s = v[p];
-                    if (ACT == ACT_RELU) s = fmaxf(s, 0.0f);
-                    else if (ACT == ACT_PRELU) s = prelu(s, alpha);
-                    if (RES) s = fmaf(s, 0.2f, dst[p * FT * 4]);
-                    dst[p * FT * 4] = s;
+                    float s[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                    {
+                        s[j] = v[j][p];
+                        if (ACT == ACT_RELU) s[j] = fmaxf(s[j], 0.0f);
+                        else if (ACT == ACT_PRELU) s[j] = prelu(s[j], alpha[j]);
+                    }
+                    if (RES)
+                    {
+                        const float4 old = dst[p * FT];
+                        s[0] = fmaf(s[0], 0.2f, old.x); s[1] = fmaf(s[1], 0.2f, old.y); s[2] = fmaf(s[2], 0.2f, old.z); s[3] = fmaf(s[3], 0.2f, old.w);
+                    }
+                    dst[p * FT] = make_float4(s[0], s[1], s[2], s[3]);
                 }
             });
+            (void)outf;
         }
     }
 
