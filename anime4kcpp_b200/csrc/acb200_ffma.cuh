@@ -208,17 +208,36 @@ namespace acb
         return *reinterpret_cast<float2*>(&rd);
     }
 
-    template<int COUT, int KOFF, int BOFF, class P, class Emit>
+    // Vertically adjacent pixels per thread for the layer whose region is (FT - 2 L)^2 (interior tiles): a layer's pixel groups are dealt
+    // over FFMA_THREADS threads in rounds, and the last round is usually partial -- 48 x 48 pixels are 576 groups of 4 rows (2.25 rounds
+    // of 256: three rounds of 4 rows) but 768 groups of 3 rows (exactly three rounds of 3 rows).  The choice with the fewest rounds x rows;
+    // ties go to the default (fewer operand loads per pixel).
+    __host__ __device__ constexpr int ffma_rows_for(int L)
+    {
+        const int side = FT - 2 * L;
+        int best = FFMA_P;
+        long best_cost = 1L << 40;
+        for (int p = 3; p <= FFMA_P; p++)
+        {
+            const long items = static_cast<long>(side) * ((side + p - 1) / p);
+            const long rounds = (items + FFMA_THREADS - 1) / FFMA_THREADS;
+            const long cost = rounds * p * 16 + (FFMA_P - p);
+            if (cost < best_cost) { best_cost = cost; best = p; }
+        }
+        return best;
+    }
+
+    template<int COUT, int KOFF, int BOFF, int PP, class P, class Emit>
     __device__ __forceinline__ void conv_cols_rolled(const P& prm, const float4* __restrict__ in, const TileGeom& g, int x, int y, Emit&& emit)
     {
 #if ACB_FFMA2
         // Packed form: input channels (2c, 2c + 1) of a pixel are one register pair, their weights one 64-bit constant load, their
         // accumulators one pair -- 36 FFMA2 instead of 72 FFMA per pixel and output channel.  Every accumulator lane still sees the same
         // products in the same order, so the sums are bit-identical to the scalar form (X86/AVX.hpp:32-58 lane for lane).
-        float2 r2[FFMA_P + 2][3][4];
+        float2 r2[PP + 2][3][4];
         const int cx2[3] = { clampi(x - 1, g.ix0, g.ix1), x, clampi(x + 1, g.ix0, g.ix1) };
 #pragma unroll
-        for (int iy = 0; iy < FFMA_P + 2; iy++)
+        for (int iy = 0; iy < PP + 2; iy++)
         {
             const int ry = clampi(y - 1 + iy, g.iy0, min(g.iy1, FT - 1)) * FT;
 #pragma unroll
@@ -235,13 +254,13 @@ namespace acb
 #pragma unroll 1
         for (int co4 = 0; co4 < COUT; co4 += 4)
         {
-            float v4[4][FFMA_P];
+            float v4[4][PP];
 #pragma unroll
             for (int j = 0; j < 4; j++)
             {
                 const int co = co4 + j;
                 const float2* __restrict__ wk2 = reinterpret_cast<const float2*>(prm.k + KOFF + co * 72);
-                float2 s2[FFMA_P][4];
+                float2 s2[PP][4];
 #pragma unroll
                 for (int dy = 0; dy < 3; dy++)
 #pragma unroll
@@ -251,12 +270,12 @@ namespace acb
                         {
                             const float2 wgt = wk2[(dy * 3 + dx) * 4 + c2];
 #pragma unroll
-                            for (int p = 0; p < FFMA_P; p++)
+                            for (int p = 0; p < PP; p++)
                                 s2[p][c2] = fma2(r2[p + dy][dx][c2], wgt, (dy == 0 && dx == 0) ? make_float2(0.0f, 0.0f) : s2[p][c2]);
                         }
                 const float bias = prm.b[BOFF + co];
 #pragma unroll
-                for (int p = 0; p < FFMA_P; p++)
+                for (int p = 0; p < PP; p++)
                 {
                     const float s8[8] = { s2[p][0].x, s2[p][0].y, s2[p][1].x, s2[p][1].y, s2[p][2].x, s2[p][2].y, s2[p][3].x, s2[p][3].y };
                     v4[j][p] = __fadd_rn(bias, hsum8(s8));
@@ -266,12 +285,12 @@ namespace acb
         }
         return;
 #endif
-        float r[FFMA_P + 2][3][8];
+        float r[PP + 2][3][8];
         const int cx[3] = { clampi(x - 1, g.ix0, g.ix1), x, clampi(x + 1, g.ix0, g.ix1) };
 #pragma unroll
-        for (int iy = 0; iy < FFMA_P + 2; iy++)
+        for (int iy = 0; iy < PP + 2; iy++)
         {
-            // (rows past the region's last group of FFMA_P feed sums that are dropped: keep their reads inside the frame)
+            // (rows past the region's last group of PP feed sums that are dropped: keep their reads inside the frame)
             const int ry = clampi(y - 1 + iy, g.iy0, min(g.iy1, FT - 1)) * FT;
 #pragma unroll
             for (int dx = 0; dx < 3; dx++)
@@ -284,13 +303,13 @@ namespace acb
 #pragma unroll 1
         for (int co4 = 0; co4 < COUT; co4 += 4)
         {
-            float v4[4][FFMA_P];
+            float v4[4][PP];
 #pragma unroll 1
             for (int j = 0; j < 4; j++)
             {
                 const int co = co4 + j;
                 const float* __restrict__ wk = prm.k + KOFF + co * 72;
-                float s[FFMA_P][8];
+                float s[PP][8];
 #pragma unroll
                 for (int dy = 0; dy < 3; dy++)
 #pragma unroll
@@ -300,12 +319,12 @@ namespace acb
                         {
                             const float wgt = wk[(dy * 3 + dx) * 8 + ci];
 #pragma unroll
-                            for (int p = 0; p < FFMA_P; p++)
+                            for (int p = 0; p < PP; p++)
                                 s[p][ci] = fmaf(r[p + dy][dx][ci], wgt, (dy == 0 && dx == 0) ? 0.0f : s[p][ci]);
                         }
                 const float bias = prm.b[BOFF + co];
 #pragma unroll
-                for (int p = 0; p < FFMA_P; p++)
+                for (int p = 0; p < PP; p++)
                 {
                     const float t = __fadd_rn(bias, hsum8(s[p]));
                     if (j == 0) v4[0][p] = t; else if (j == 1) v4[1][p] = t; else if (j == 2) v4[2][p] = t; else v4[3][p] = t;
@@ -320,16 +339,17 @@ namespace acb
     template<int L, int ACT, bool RES, int KOFF, int BOFF, int AOFF, int COUT = 8, class P>
     __device__ __forceinline__ void conv_layer(const P& prm, const float4* __restrict__ in, float4* __restrict__ out, const TileGeom& g)
     {
+        constexpr int PP = ffma_rows_for(L);
         const int xa = max(L, g.ix0), xb = min(FT - L, g.ix1 + 1), ya = max(L, g.iy0), yb = min(FT - L, g.iy1 + 1);
-        const int ncols = xb - xa, n = ncols * ((yb - ya + FFMA_P - 1) / FFMA_P);
+        const int ncols = xb - xa, n = ncols * ((yb - ya + PP - 1) / PP);
         const RegionDiv rdiv(ncols);
         float* __restrict__ outf = reinterpret_cast<float*>(out);
         for (int i = threadIdx.x; i < n; i += FFMA_THREADS)
         {
             int qy, qx;
             rdiv.split(i, qy, qx);
-            const int x = xa + qx, y = ya + FFMA_P * qy;
-            conv_cols_rolled<COUT, KOFF, BOFF>(prm, in, g, x, y, [&](const int co4, const float (&v)[4][FFMA_P]) {
+            const int x = xa + qx, y = ya + PP * qy;
+            conv_cols_rolled<COUT, KOFF, BOFF, PP>(prm, in, g, x, y, [&](const int co4, const float (&v)[4][PP]) {
                 // channels co4 .. co4 + 3 are the float4 of plane co4 / 4 at the pixel: one 16-byte store per pixel
                 float4* dst = out + (co4 >> 2) * FT * FT + y * FT + x;
                 float alpha[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
@@ -339,7 +359,7 @@ namespace acb
                     for (int j = 0; j < 4; j++) alpha[j] = prm.a[AOFF + co4 + j];
                 }
 #pragma unroll
-                for (int p = 0; p < FFMA_P; p++)
+                for (int p = 0; p < PP; p++)
                 {
                     if (y + p >= yb) break;
                     float s[4];
