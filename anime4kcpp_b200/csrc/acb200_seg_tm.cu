@@ -62,7 +62,9 @@ namespace acbh
             prm.issuers = issuers_env;
             std::memset(prm.k, 0, sizeof(prm.k));
             constexpr int K0 = S::HEAD ? 72 : 0;
-            if (S::HEAD) std::memcpy(prm.k, m.k.data() + spec.koff, sizeof(float) * 72);
+            if (S::HEAD)        // the 1 -> 8 head conv, transposed to [tap][cout] so that two couts' weights of a tap are one 64-bit operand
+                for (int co = 0; co < 8; co++)
+                    for (int p = 0; p < 9; p++) prm.k[p * 8 + co] = m.k[spec.koff + co * 9 + p];
             if (S::TAIL && S::FAM == ACB200_FAMILY_ACNET_LEGACY)
                 std::memcpy(prm.k + K0, m.k.data() + spec.koff + K0 + 576 * (S::NCONV + 1), sizeof(float) * 32);
             if (S::TAIL && S::FAM == ACB200_FAMILY_ARNET)       // the 1x1 between the tail's residual conv and the pixel-shuffle conv
@@ -72,8 +74,19 @@ namespace acbh
             else prm.a[0] = 0.0f;
             static std::atomic<unsigned long long> optin{0};
             constexpr int SMEM_MAX = S::FAM == ACB200_FAMILY_ARNET ? TM_SMEM_BYTES_ARNET : TM_SMEM_BYTES_FUSED;
-            if ((rc = smem_optin_once(s, reinterpret_cast<const void*>(segment_tm_kernel<S>), SMEM_MAX, optin)) != ACB200_OK) return rc;
             const int smem = S::FAM == ACB200_FAMILY_ARNET ? TM_SMEM_BYTES_ARNET : (prm.uv_in || ACB_TM_PROGRESS_MBAR) ? TM_SMEM_BYTES_FUSED : TM_SMEM_BYTES;
+            if constexpr (S::NEEDS_LUMA || S::TAIL)
+                if (a.uvc == 3)
+                {
+                    // four-channel images: the instantiation with the RGBA colour path
+                    static std::atomic<unsigned long long> optin4{0};
+                    if ((rc = smem_optin_once(s, reinterpret_cast<const void*>(segment_tm_kernel<S, true>), SMEM_MAX, optin4)) != ACB200_OK) return rc;
+                    segment_tm_kernel<S, true><<<prm.tiles_x * tiles_y, TM_THREADS, smem, st>>>(prm);
+                    g_launches.fetch_add(1, std::memory_order_relaxed);
+                    ACB_CUDA(s, cudaGetLastError());
+                    return ACB200_OK;
+                }
+            if ((rc = smem_optin_once(s, reinterpret_cast<const void*>(segment_tm_kernel<S>), SMEM_MAX, optin)) != ACB200_OK) return rc;
             segment_tm_kernel<S><<<prm.tiles_x * tiles_y, TM_THREADS, smem, st>>>(prm);
             g_launches.fetch_add(1, std::memory_order_relaxed);
             ACB_CUDA(s, cudaGetLastError());

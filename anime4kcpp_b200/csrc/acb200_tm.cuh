@@ -95,6 +95,9 @@ namespace acb
     constexpr int TM_SMEM_BYTES = TM_OFF_STEPS + TM_MAX_CHUNKS * TM_CHUNK_WORDS * 4;
 #endif
 
+#ifndef ACB_TM_HEAD_FFMA2
+#define ACB_TM_HEAD_FFMA2 1
+#endif
 #ifndef ACB_TM_CHROMA_LUT
 #define ACB_TM_CHROMA_LUT 1
 #endif
@@ -102,7 +105,10 @@ namespace acb
     constexpr int TM_OFF_LUT = (TM_SMEM_BYTES + 15) / 16 * 16;
     // progress barriers (ACB_TM_PROGRESS_MBAR): one one-shot mbarrier per (published layer 1 .. R, frame row), four arrivals (one per lane quadrant)
     constexpr int TM_OFF_PROG = TM_OFF_LUT + 2 * 256 * 8;
-    constexpr int TM_SMEM_BYTES_FUSED = TM_OFF_PROG + TM_MAX_R * TM_GMAX * 8;
+    // RGBA fusion: the resized alpha bytes of a tail group, one uint2 per (epilogue warp, row of the group, lane) -- parked in shared memory
+    // between the precompute and the merge so that the RGB path carries no registers for them across the wait
+    constexpr int TM_OFF_AQ = TM_OFF_PROG + TM_MAX_R * TM_GMAX * 8;
+    constexpr int TM_SMEM_BYTES_FUSED = TM_OFF_AQ + 4 * TM_SETS * 4 * 32 * 8;
     // ARNet: the block input x of the residual `conv * 0.2 + x` (CPUProcessor.cpp:1479,1483), fp32, one 32-byte slot per frame row, lane and
     // quadrant.  Written by the epilogue that produces x, read two layers later by the epilogue of the block's second conv -- two lanes to
     // the left, because the map drifts by one lane per layer.
@@ -135,7 +141,8 @@ namespace acb
         int rgb_pitch, uv_pitch, rgb_dst_pitch, y_pitch;
         int uvc;                // channels of the chroma plane: 2 (u, v) for RGB, 3 (u, v, a) for RGBA (the source then has four bytes per pixel)
         const uint32_t* bops;   // B operands of this segment's 3x3 convs, TM_B_WORDS_LAYER words each, in layer order
-        float k[(S::HEAD ? 72 : 0) + 64 + 32];  // fp32 weights used outside the MMAs: head (72) | ARNet 1x1 (64) | legacy deconv (32)
+        alignas(8) float k[(S::HEAD ? 72 : 0) + 64 + 32];  // fp32 weights used outside the MMAs: head (72, tap-major [9][8]) | ARNet 1x1 (64) | legacy deconv (32)
+        alignas(8)
         float b[S::NB];
         float a[S::NA > 0 ? S::NA : 1];
     };
@@ -267,7 +274,9 @@ namespace acb
 
     // Row bookkeeping.  The rows a layer produces are handled in GROUPS of four consecutive rows (the last group of a layer may be
     // shorter): a group is one epilogue work item and one one-shot `full` mbarrier.
-    template<class S>
+    // RGBA: the fused colour path works on four-channel images ((u, v, a) chroma plane, un-premultiplying merge); a compile-time switch so
+    // that the RGB instantiation carries none of it (as a run-time branch it cost the RGB tail 170 bytes of spills and 3.6 % of the frame)
+    template<class S, bool RGBA = false>
     __global__ void __launch_bounds__(TM_THREADS, 1) segment_tm_kernel(const __grid_constant__ TmParams<S> prm)
     {
         constexpr int R = S::R;                 // 3x3 convs of this segment (all on the tensor cores)
@@ -365,7 +374,7 @@ namespace acb
                         const int xc = clampi(gx0 + lane, 0, prm.w - 1);
                         const uint8_t* pa = srow + 3 * xc;
                         // (RGBA sources are read as aligned 32-bit pixels; the host side only fuses them when rows and base are 4-byte aligned)
-                        c0[i] = prm.uvc == 3 ? __ldg(reinterpret_cast<const uint32_t*>(srow) + xc)
+                        c0[i] = RGBA ? __ldg(reinterpret_cast<const uint32_t*>(srow) + xc)
                                              : __ldg(pa) | (static_cast<uint32_t>(__ldg(pa + 1)) << 8) | (static_cast<uint32_t>(__ldg(pa + 2)) << 16);
                     }
 #pragma unroll
@@ -376,7 +385,7 @@ namespace acb
                         const int q = row / (G + 2), ly = row - q * (G + 2);
                         float* drow = luma_all + (q * (TM_GMAX + 2) + ly) * TM_LP;
                         uint8_t qy, qu, qv, qa = 0;
-                        drow[lane] = prm.uvc == 3 ? luma_from_rgba_u8(c0[i] & 0xffu, (c0[i] >> 8) & 0xffu, (c0[i] >> 16) & 0xffu, c0[i] >> 24, qy, qu, qv, qa)
+                        drow[lane] = RGBA ? luma_from_rgba_u8(c0[i] & 0xffu, (c0[i] >> 8) & 0xffu, (c0[i] >> 16) & 0xffu, c0[i] >> 24, qy, qu, qv, qa)
                                                   : luma_from_rgb_u8(c0[i] & 0xffu, (c0[i] >> 8) & 0xffu, (c0[i] >> 16) & 0xffu, qy, qu, qv);
                         if (S::HEAD && prm.uv_out != nullptr)
                         {
@@ -384,7 +393,7 @@ namespace acb
                             if (strip < prm.strips_x && gy >= own_y0 && gy < own_y1 && gx >= strip * SW && gx < min(strip * SW + SW, prm.w))
                             {
                                 uint8_t* uvp = prm.uv_out + static_cast<size_t>(gy) * prm.uv_pitch;
-                                if (prm.uvc == 3) { uvp[3 * gx] = qu; uvp[3 * gx + 1] = qv; uvp[3 * gx + 2] = qa; }
+                                if (RGBA) { uvp[3 * gx] = qu; uvp[3 * gx + 1] = qv; uvp[3 * gx + 2] = qa; }
                                 else *reinterpret_cast<uchar2*>(uvp + 2 * gx) = make_uchar2(qu, qv);
                                 if (prm.y_out != nullptr) prm.y_out[static_cast<size_t>(gy) * prm.y_pitch + gx] = qy;
                             }
@@ -398,9 +407,9 @@ namespace acb
                     const int row = t >> 1, q = row / (G + 2), ly = row - q * (G + 2);
                     const int strip = min(tile_x * 4 + q, prm.strips_x - 1);
                     const int gy = clampi(y0 - 1 + ly, 0, prm.h - 1), gx = clampi(strip * SW - R - 1 + 32 + (t & 1), 0, prm.w - 1);
-                    const uint8_t* pb = prm.rgb_src + static_cast<size_t>(gy) * prm.rgb_pitch + (prm.uvc == 3 ? 4 : 3) * gx;
+                    const uint8_t* pb = prm.rgb_src + static_cast<size_t>(gy) * prm.rgb_pitch + (RGBA ? 4 : 3) * gx;
                     uint8_t qy, qu, qv, qa;
-                    luma_all[(q * (TM_GMAX + 2) + ly) * TM_LP + 32 + (t & 1)] = prm.uvc == 3 ? luma_from_rgba_u8(__ldg(pb), __ldg(pb + 1), __ldg(pb + 2), __ldg(pb + 3), qy, qu, qv, qa)
+                    luma_all[(q * (TM_GMAX + 2) + ly) * TM_LP + 32 + (t & 1)] = RGBA ? luma_from_rgba_u8(__ldg(pb), __ldg(pb + 1), __ldg(pb + 2), __ldg(pb + 3), qy, qu, qv, qa)
                                                                                                 : luma_from_rgb_u8(__ldg(pb), __ldg(pb + 1), __ldg(pb + 2), qy, qu, qv);
                 }
             }
@@ -738,16 +747,33 @@ namespace acb
                             for (int dy = 0; dy < 3; dy++)
 #pragma unroll
                                 for (int dx = 0; dx < 3; dx++) r9[dy * 3 + dx] = luma[(y + dy) * TM_LP + lane + dx];
+                            // two output channels per packed FMA (FFMA2; the launcher stores the head's weights tap-major: k[p * 8 + co]); every
+                            // channel still adds its nine products in tap order onto its bias
                             float v[8];
+#if ACB_TM_HEAD_FFMA2
+#pragma unroll
+                            for (int c2 = 0; c2 < 4; c2++)
+                            {
+                                float2 s = *reinterpret_cast<const float2*>(&prm.b[2 * c2]);
+#pragma unroll
+                                for (int p = 0; p < 9; p++) s = fma2(make_float2(r9[p], r9[p]), *reinterpret_cast<const float2*>(&prm.k[p * 8 + 2 * c2]), s);
+                                v[2 * c2] = s.x; v[2 * c2 + 1] = s.y;
+                            }
+#else
 #pragma unroll
                             for (int co = 0; co < 8; co++)
                             {
                                 float s = prm.b[co];
 #pragma unroll
-                                for (int p = 0; p < 9; p++) s = fmaf(r9[p], prm.k[co * 9 + p], s);
-                                if (ACT == ACT_RELU) s = fmaxf(s, 0.0f);
-                                else if (ACT == ACT_PRELU) s = prelu(s, prm.a[co]);
+                                for (int p = 0; p < 9; p++) s = fmaf(r9[p], prm.k[p * 8 + co], s);
                                 v[co] = s;
+                            }
+#endif
+#pragma unroll
+                            for (int co = 0; co < 8; co++)
+                            {
+                                if (ACT == ACT_RELU) v[co] = fmaxf(v[co], 0.0f);
+                                else if (ACT == ACT_PRELU) v[co] = prelu(v[co], prm.a[co]);
                             }
                             if constexpr (ARNET)
                             {
@@ -845,12 +871,13 @@ namespace acb
                     // (u, v) -- runs BEFORE the wait for the group's accumulators, in time the warp would otherwise spend asleep; what is kept
                     // is one word per output row: the quantised (u_a, v_a, u_b, v_b) bytes.  After the wait only the merge with the luma is left.
                     [[maybe_unused]] uint2 cq0 = make_uint2(0u, 0u), cq1 = cq0, cq2 = cq0, cq3 = cq0;
-                    [[maybe_unused]] uint2 aq0 = cq0, aq1 = cq0, aq2 = cq0, aq3 = cq0;      // RGBA: the resized alpha, same form (bytes a_a, a_a, a_b, a_b)
+                    // RGBA: the resized alpha in the same form (bytes a_a, a_a, a_b, a_b), this warp's slots: [row of the group][lane]
+                    [[maybe_unused]] uint2* const s_aq = reinterpret_cast<uint2*>(smem_tm + TM_OFF_AQ) + (warp * 4) * 32 + lane;
                     const bool fused = S::TAIL && last && prm.uv_in != nullptr;
                     if constexpr (S::TAIL)
                         if (fused)
                         {
-                            const int PIX = prm.uvc;        // bytes per pixel of the chroma plane: (u, v) or (u, v, a)
+                            constexpr int PIX = RGBA ? 3 : 2;       // bytes per pixel of the chroma plane: (u, v) or (u, v, a)
                             const HTaps2 hk = load_htaps2(prm.htab, 2 * min(x0 + R + lane, prm.w - 1), prm.w, PIX);
                             const int gy0 = y0 + yg;
                             auto row_ptr = [&](const int gyr) { return prm.uv_in + static_cast<size_t>(clampi(gyr, 0, prm.h - 1)) * prm.uv_pitch; };
@@ -903,18 +930,21 @@ namespace acb
                                 if (k > 2) { h1 = hrow_at(gy0 + 4); q2 = vrows(2, h2, h3, h4, h0, h1); }
                                 if (k > 3) { h2 = hrow_at(gy0 + 5); q3 = vrows(3, h3, h4, h0, h1, h2); }
                             };
-                            if (PIX == 2) precompute([&](const int gyr) { return chroma_hrow2<0>(row_ptr(gyr), hk); }, cq0, cq1, cq2, cq3);
+                            if constexpr (!RGBA) precompute([&](const int gyr) { return chroma_hrow2<0>(row_ptr(gyr), hk); }, cq0, cq1, cq2, cq3);
                             else
                             {
                                 precompute([&](const int gyr) { return chroma_hrow2<1>(row_ptr(gyr), hk); }, cq0, cq1, cq2, cq3);
-                                precompute([&](const int gyr) { return chroma_hrow2<2>(row_ptr(gyr), hk); }, aq0, aq1, aq2, aq3);
+                                uint2 a0 = make_uint2(0u, 0u), a1 = a0, a2 = a0, a3 = a0;
+                                precompute([&](const int gyr) { return chroma_hrow2<2>(row_ptr(gyr), hk); }, a0, a1, a2, a3);
+                                s_aq[0] = a0; s_aq[32] = a1; s_aq[64] = a2; s_aq[96] = a3;      // read back by the same thread: no synchronisation
                             }
                         }
                     // yl[dy * 2 + dx]: the lane's four luma results as the value BEFORE truncation to the byte (x 255 + 0.5 applied)
                     [[maybe_unused]] auto fused_store = [&](const int jr, const int gx, const int gy, const float (&yl)[4], const bool ok) {
                         const uint2 cq = jr == 0 ? cq0 : jr == 1 ? cq1 : jr == 2 ? cq2 : cq3;
-                        const bool rgba = prm.uvc == 3;
-                        const uint2 aq = jr == 0 ? aq0 : jr == 1 ? aq1 : jr == 2 ? aq2 : aq3;
+                        constexpr bool rgba = RGBA;
+                        uint2 aq = make_uint2(0u, 0u);
+                        if constexpr (RGBA) aq = s_aq[32 * jr];
                         uint8_t* o = prm.rgb_dst + static_cast<size_t>(2 * gy) * prm.rgb_dst_pitch + (rgba ? 8 : 6) * gx;
 #pragma unroll
                         for (int dy = 0; dy < 2; dy++)
