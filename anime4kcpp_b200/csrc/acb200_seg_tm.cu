@@ -73,8 +73,10 @@ namespace acbh
             if (S::NA > 0) std::memcpy(prm.a, m.a.data() + spec.aoff, sizeof(float) * S::NA);
             else prm.a[0] = 0.0f;
             static std::atomic<unsigned long long> optin{0};
-            constexpr int SMEM_MAX = S::FAM == ACB200_FAMILY_ARNET ? TM_SMEM_BYTES_ARNET : TM_SMEM_BYTES_FUSED;
-            const int smem = S::FAM == ACB200_FAMILY_ARNET ? TM_SMEM_BYTES_ARNET : (prm.uv_in || ACB_TM_PROGRESS_MBAR) ? TM_SMEM_BYTES_FUSED : TM_SMEM_BYTES;
+            constexpr int SMEM_MAX = S::FAM == ACB200_FAMILY_ARNET ? TM_SMEM_BYTES_ARNET_RGBA : TM_SMEM_BYTES_FUSED;
+            const int smem = S::FAM == ACB200_FAMILY_ARNET ? ((prm.uv_in && a.uvc == 3) ? TM_SMEM_BYTES_ARNET_RGBA : TM_SMEM_BYTES_ARNET)
+                                                           : (prm.uv_in && a.uvc == 3) ? TM_SMEM_BYTES_FUSED
+                                                           : (prm.uv_in || ACB_TM_PROGRESS_MBAR) ? TM_OFF_X : TM_SMEM_BYTES;
             if constexpr (S::NEEDS_LUMA || S::TAIL)
                 if (a.uvc == 3)
                 {

@@ -107,13 +107,17 @@ namespace acb
     constexpr int TM_OFF_PROG = TM_OFF_LUT + 2 * 256 * 8;
     // RGBA fusion: the resized alpha bytes of a tail group, one uint2 per (epilogue warp, row of the group, lane) -- parked in shared memory
     // between the precompute and the merge so that the RGB path carries no registers for them across the wait
-    constexpr int TM_OFF_AQ = TM_OFF_PROG + TM_MAX_R * TM_GMAX * 8;
-    constexpr int TM_SMEM_BYTES_FUSED = TM_OFF_AQ + 4 * TM_SETS * 4 * 32 * 8;
+    // (it lies BEHIND ARNet's residual store, so that only the opt-in RGBA launches of ARNet pay for both: every kilobyte of shared memory is
+    // a kilobyte less L1 for the map loads -- 16 KB more cost the ARNet chain 5 %)
+    constexpr int TM_AQ_BYTES = 4 * TM_SETS * 4 * 32 * 8;
+    constexpr int TM_OFF_X = (TM_OFF_PROG + TM_MAX_R * TM_GMAX * 8 + 127) / 128 * 128;
+    constexpr int TM_X_BYTES = 4 * (TM_GMAX + 2) * 32 * 32;
+    constexpr int TM_SMEM_BYTES_FUSED = TM_OFF_X + TM_AQ_BYTES;
     // ARNet: the block input x of the residual `conv * 0.2 + x` (CPUProcessor.cpp:1479,1483), fp32, one 32-byte slot per frame row, lane and
     // quadrant.  Written by the epilogue that produces x, read two layers later by the epilogue of the block's second conv -- two lanes to
     // the left, because the map drifts by one lane per layer.
-    constexpr int TM_OFF_X = (TM_SMEM_BYTES_FUSED + 127) / 128 * 128;
-    constexpr int TM_SMEM_BYTES_ARNET = TM_OFF_X + 4 * (TM_GMAX + 2) * 32 * 32;
+    constexpr int TM_SMEM_BYTES_ARNET = TM_OFF_X + TM_X_BYTES;
+    constexpr int TM_SMEM_BYTES_ARNET_RGBA = TM_SMEM_BYTES_ARNET + TM_AQ_BYTES;
 
     template<class S>
     struct TmParams
@@ -872,7 +876,7 @@ namespace acb
                     // is one word per output row: the quantised (u_a, v_a, u_b, v_b) bytes.  After the wait only the merge with the luma is left.
                     [[maybe_unused]] uint2 cq0 = make_uint2(0u, 0u), cq1 = cq0, cq2 = cq0, cq3 = cq0;
                     // RGBA: the resized alpha in the same form (bytes a_a, a_a, a_b, a_b), this warp's slots: [row of the group][lane]
-                    [[maybe_unused]] uint2* const s_aq = reinterpret_cast<uint2*>(smem_tm + TM_OFF_AQ) + (warp * 4) * 32 + lane;
+                    [[maybe_unused]] uint2* const s_aq = reinterpret_cast<uint2*>(smem_tm + TM_OFF_X + (ARNET ? TM_X_BYTES : 0)) + (warp * 4) * 32 + lane;
                     const bool fused = S::TAIL && last && prm.uv_in != nullptr;
                     if constexpr (S::TAIL)
                         if (fused)
