@@ -255,7 +255,8 @@ namespace acb
         for (int co4 = 0; co4 < COUT; co4 += 4)
         {
             float v4[4][PP];
-#pragma unroll
+            // (the four channels of a group run through ONE copy of the loop body: unrolled four times it is 12 % faster -- 0.760 ms for ACNetLegacy -- but the translation unit takes 14 minutes to compile, 7 minutes unrolled twice)
+#pragma unroll 1
             for (int j = 0; j < 4; j++)
             {
                 const int co = co4 + j;
@@ -278,7 +279,8 @@ namespace acb
                 for (int p = 0; p < PP; p++)
                 {
                     const float s8[8] = { s2[p][0].x, s2[p][0].y, s2[p][1].x, s2[p][1].y, s2[p][2].x, s2[p][2].y, s2[p][3].x, s2[p][3].y };
-                    v4[j][p] = __fadd_rn(bias, hsum8(s8));
+                    const float t = __fadd_rn(bias, hsum8(s8));
+                    if (j == 0) v4[0][p] = t; else if (j == 1) v4[1][p] = t; else if (j == 2) v4[2][p] = t; else v4[3][p] = t;
                 }
             }
             emit(co4, v4);
